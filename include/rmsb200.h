@@ -1,0 +1,233 @@
+/* rmsb200.h -- C ABI of librmsb200.so, the B200-native batched stiff-kinetics engine that
+ * replaces ReactionMechanismSimulator.jl's data-parallel hot path.
+ *
+ * The reference (pure Julia) has no FFI seam; the seam this library sits behind is the SciML
+ * problem/solution contract the reference builds in src/Reactor.jl:31-35,65,76
+ *   dydt(dy,y,p,t) = dydtreactor!(dy,y,t,domain,interfaces,p=p)     src/Reactor.jl:653-660
+ *   jacy!(J,y,p,t) = jacobiany!(J,y,p,t,domain,interfaces,nothing)   src/Domain.jl:2204-3091
+ *   jacp!(J,y,p,t) = jacobianp!(J,y,p,t,domain,interfaces,nothing)   src/Domain.jl:3376-3485
+ *   solve(react.ode, CVODE_BDF(); abstol, reltol) -> ODESolution     (call sites src/TestReactors.jl:22,197,305)
+ * evaluated for MANY independent reactors that share one flattened mechanism
+ * (IdealGas/IdealDiluteSolution/IdealSurface, src/Phase.jl:40-136).
+ *
+ * Conventions
+ *  - every entry point returns int: 0 = ok, <0 = error; text via rmsb_last_error() (thread local).
+ *  - all pointers in the *_batch entry points are CALLER-OWNED HOST buffers, row = reactor,
+ *    contiguous, Float64; the library owns all device memory and copies in/out itself.
+ *  - the *_dev entry points take DEVICE pointers (same layouts) and a cudaStream_t (as void*);
+ *    they only enqueue work -- no allocation of caller-visible memory, no synchronisation.
+ *  - a mechanism handle is immutable after creation and may be shared by host threads.
+ *  - species / reaction indices in the descriptor are 1-based with 0 = none, exactly the
+ *    reference's rxnarray convention (src/Phase.jl:320-348), so a Julia caller passes its arrays as is.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    RMSB_ERR_CUDA.
+ */
+#ifndef RMSB200_H
+#define RMSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMSB_VERSION 100
+
+/* ---- error codes -------------------------------------------------------------------------- */
+#define RMSB_OK             0
+#define RMSB_ERR_ARG       -1   /* bad argument / inconsistent descriptor            */
+#define RMSB_ERR_CUDA      -2   /* CUDA runtime error or no device                   */
+#define RMSB_ERR_UNSUPPORTED -3 /* feature outside the hot path      */
+#define RMSB_ERR_NOMEM     -4
+
+/* ---- phase kinds: which getC0 / calcthermo family applies (src/Phase.jl:301-307) ---------- */
+#define RMSB_PHASE_GAS      0   /* IdealGas:            C0 = 1e5/(R*T)                */
+#define RMSB_PHASE_LIQUID   1   /* IdealDiluteSolution: C0 = 1e5/(R*T), diffusion limits */
+#define RMSB_PHASE_SURFACE  2   /* IdealSurface:        C0 = sitedensity             */
+
+/* ---- domain kinds and their state / condition layouts (src/Domain.jl) ---------------------
+ *  kind            y (Ny)            cond (Ncond)   reference
+ *  CONSTANT_V      [ns; T; P] Ns+2   [V]            src/Domain.jl:120-170,1064-1113,1901-1906
+ *  CONSTANT_TP     [ns; V]    Ns+1   [T, P]         src/Domain.jl:42-102,916-966,1863-1867
+ *  CONSTANT_TV     ns         Ns     [T, V]         src/Domain.jl:500-560,1514-1561
+ *  CONSTANT_TAPHI  ns         Ns     [T, A]         src/Domain.jl:660-711,1597-1633  (phi = 0)
+ */
+#define RMSB_DOMAIN_CONSTANT_V      0
+#define RMSB_DOMAIN_CONSTANT_TP     1
+#define RMSB_DOMAIN_CONSTANT_TV     2
+#define RMSB_DOMAIN_CONSTANT_TAPHI  3
+
+/* ---- kinetics type tags (src/Calculators/Rate.jl, Ratevec.jl) -----------------------------
+ * kin_params[kin_offset[j] .. kin_offset[j+1]) holds, as doubles:
+ *  ARRHENIUS_VEC   A n Ea                         k = A*exp(n*log(T) - Ea*(1/(R*T)))   Ratevec.jl:24
+ *  ARRHENIUS       A n Ea                         k = A*T^n*exp(-Ea/(R*T))            Rate.jl:16
+ *  MULTIARRHENIUS  m, m x (A n Ea)                sum of scalar Arrhenius             Rate.jl:68-74
+ *  PLOG_VEC        nP, Ps[nP], nP x (A n Ea)      PdepArrheniusvec                    Ratevec.jl:204-215
+ *  PLOG            nP, Ps[nP], nP x {m, m x (A n Ea)}   PdepArrhenius (entries Arrhenius/MultiArrhenius) Rate.jl:48-60
+ *  MULTIPLOG       nK, nK x {PLOG block}          MultiPdepArrhenius                  Rate.jl:82-88
+ *  THIRDBODY       A n Ea                         k = Ceff*Arrhenius                  Rate.jl:98
+ *  LINDEMANN       high(A n Ea) low(A n Ea)                                           Rate.jl:109-114
+ *  TROE            high(A n Ea) low(A n Ea) a T3 T1 T2                                Rate.jl:129-147
+ *  CHEBYSHEV_VEC   Tmin Tmax Pmin Pmax nT nP coefs[nT][nP] (row major)                Ratevec.jl:89-100
+ */
+#define RMSB_KIN_ARRHENIUS_VEC   0
+#define RMSB_KIN_ARRHENIUS       1
+#define RMSB_KIN_MULTIARRHENIUS  2
+#define RMSB_KIN_PLOG_VEC        3
+#define RMSB_KIN_PLOG            4
+#define RMSB_KIN_MULTIPLOG       5
+#define RMSB_KIN_THIRDBODY       6
+#define RMSB_KIN_LINDEMANN       7
+#define RMSB_KIN_TROE            8
+#define RMSB_KIN_CHEBYSHEV_VEC   9
+
+#define RMSB_VISC_NONE     0
+#define RMSB_VISC_CONSTANT 1   /* params[0] = mu                          src/Calculators/Viscosity.jl:9-13 */
+#define RMSB_VISC_RIEDEL   2   /* params = A B C D E                      src/Calculators/Viscosity.jl:15-24 */
+
+/* Flattened mechanism, reactions in PHASE ORDER (vectorised kinetics first, src/Phase.jl:42). */
+typedef struct rmsb_mech_desc {
+    int32_t struct_size;          /* = sizeof(rmsb_mech_desc); ABI guard                                  */
+    int32_t phase_kind;           /* RMSB_PHASE_*                                                         */
+    int32_t n_species;
+    int32_t n_reactions;
+    double  sitedensity;          /* IdealSurface only (src/Phase.jl:133)                                 */
+    int32_t diffusion_limited;    /* phase.diffusionlimited (src/Phase.jl:56,95)                          */
+    int32_t nasa_max_ranges;      /* max #polynomials per species                                         */
+    const int32_t* nasa_nranges;  /* [Ns]                                                                 */
+    const int32_t* nasa_ncoef;    /* [Ns][max_ranges]  7 or 9 (src/Calculators/Thermo.jl:16-63)           */
+    const double*  nasa_tmax;     /* [Ns][max_ranges]  selectPoly: first range with T <= Tmax (:101-111)  */
+    const double*  nasa_coefs;    /* [Ns][max_ranges][9]                                                  */
+    const int32_t* rxnarray;      /* [Nr][8] 1-based, 0 = none; cols 0-3 reactants, 4-7 products          */
+    const int32_t* kin_type;      /* [Nr] RMSB_KIN_*                                                      */
+    const int32_t* kin_offset;    /* [Nr+1]                                                               */
+    const double*  kin_params;    /* [kin_offset[Nr]]                                                     */
+    const int32_t* eff_ptr;       /* [Nr+1] CSR over reactions of third-body efficiencies                 */
+    const int32_t* eff_species;   /* 1-based species index                                                */
+    const double*  eff_value;     /* efficiency - 1 (src/Parse.jl:411-413)                                */
+    const uint8_t* reversible;    /* [Nr]                                                                 */
+    const uint8_t* forwardable;   /* [Nr]                                                                 */
+    const double*  radius;        /* [Ns] species.radius (liquid, Smoluchowski), may be NULL              */
+    const double*  diff_radius;   /* [Ns] StokesDiffusivity.r; <= 0 means EmptyDiffusivity (Inf); may be NULL */
+    int32_t viscosity_kind;       /* RMSB_VISC_*  (phase.solvent.mu)                                      */
+    double  viscosity_params[5];
+} rmsb_mech_desc;
+
+typedef struct rmsb_mech rmsb_mech;    /* opaque, immutable */
+
+/* Per-reactor integration statistics (all counters are per reactor). */
+typedef struct rmsb_stats {
+    int32_t n_steps;        /* accepted steps                 */
+    int32_t n_rhs;          /* dydt evaluations               */
+    int32_t n_jac;          /* Jacobian evaluations           */
+    int32_t n_lu;           /* LU factorisations of I - c*J   */
+    int32_t n_newton_fail;  /* Newton convergence failures    */
+    int32_t n_err_fail;     /* error-test failures            */
+    int32_t last_order;
+    int32_t reserved;
+    double  last_h;
+} rmsb_stats;
+
+/* solve status per reactor */
+#define RMSB_SOLVE_OK            0
+#define RMSB_SOLVE_MAX_STEPS     1
+#define RMSB_SOLVE_STEP_TOO_SMALL 2
+#define RMSB_SOLVE_NAN           3
+
+typedef struct rmsb_solve_opts {
+    int32_t struct_size;     /* = sizeof(rmsb_solve_opts)                                          */
+    int32_t max_steps;       /* per reactor, default 500000                                        */
+    int32_t max_order;       /* 1..5, default 5                                                    */
+    int32_t idt_index;       /* 0-based y index whose max d/dt defines idt; -1 = domain default (T) */
+    double  first_step;      /* 0 = automatic                                                      */
+    int32_t warps_per_block; /* 0 = automatic                                                      */
+    int32_t reserved;
+} rmsb_solve_opts;
+
+/* ---- library ----------------------------------------------------------------------------- */
+int         rmsb_version(void);
+const char* rmsb_last_error(void);
+int         rmsb_device_count(void);
+
+/* ---- mechanism --------------------------------------------------------------------------- */
+/* Flatten once into SoA device tables on `device` (replaces the per-call object walks of
+ * src/PhaseState.jl:61-76,165-171 and the Dict iteration of :53-58). */
+int  rmsb_mech_create(const rmsb_mech_desc* desc, int device, rmsb_mech** out);
+void rmsb_mech_destroy(rmsb_mech* mech);
+int  rmsb_mech_ny(const rmsb_mech* mech, int domain_kind);     /* state length Ny    */
+int  rmsb_mech_ncond(const rmsb_mech* mech, int domain_kind);  /* #per-reactor consts */
+int  rmsb_mech_device(const rmsb_mech* mech);
+
+/* ---- batched hot-path evaluations (host buffers) ------------------------------------------
+ * y     [n][Ny]      cond [n][Ncond]
+ * p     NULL, or [Ns+Nr] shared by all reactors (p_stride = 0), or [n][Ns+Nr] (p_stride = Ns+Nr):
+ *       CONSTANT_V  : p = [dG_i ; f_j]    h/RT += dG/(RT), kf,krev *= f          src/Domain.jl:1100,1112
+ *       constant-k  : p = [G_i ; k_j]     absolute values (efficiency reactions: multiplier) :89-93,551,702
+ * const_species [n_const] 1-based species whose dydt / Jacobian rows are zeroed (:1904-1906,2318-2320)
+ */
+int rmsb_dydt_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                    const double* y, const double* cond, const double* p, int64_t p_stride,
+                    const int32_t* const_species, int32_t n_const,
+                    double* dydt /* [n][Ny] */);
+
+/* J[r] is dense COLUMN-MAJOR Ny x Ny, J[eqn + Ny*var] = d(dy_eqn/dt)/dy_var (jacobiany!). */
+int rmsb_jac_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                   const double* y, const double* cond, const double* p, int64_t p_stride,
+                   const int32_t* const_species, int32_t n_const,
+                   double* J /* [n][Ny*Ny] */);
+
+/* kf,krev as calcthermo returns them (for rops / rates accessors, src/Simulation.jl:239-254,763-778). */
+int rmsb_rates_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                     const double* y, const double* cond, const double* p, int64_t p_stride,
+                     double* kf /* [n][Nr] */, double* krev /* [n][Nr] */);
+
+/* Species Gibbs energies G[r][s] at temperatures T[r]: scalar_path != 0 -> getGibbs through
+ * getEnthalpy - T*getEntropy (src/Calculators/Thermo.jl:6-8,75-93, what the constant-T domain
+ * constructors store in p[1:Ns]); 0 -> (h/RT - s/R)*R*T of calcHSCpdless (Thermovec.jl:76-119). */
+int rmsb_gibbs_batch(const rmsb_mech* mech, int64_t n, const double* T, int scalar_path, double* G /* [n][Ns] */);
+
+/* Integrate every reactor from t = 0 to t_end[r] with a variable-order (1-5) variable-step
+ * BDF/NDF method, modified Newton, dense LU with partial pivoting, WRMS error control
+ * |e_i| / (atol + rtol*|y_i|) -- the role CVODE_BDF plays in the reference (src/Reactor.jl:76-81).
+ *  tsave  [nsave] shared output times (ascending); ysave [n][nsave][Ny] dense output (NaN past t_end)
+ *  yend   [n][Ny] state at t_end (may be NULL)
+ *  idt    [n] time of max d y[idt_index]/dt (continuous version of src/TestReactors.jl:307-308); NaN if none
+ */
+int rmsb_solve_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                     const double* y0, const double* cond, const double* p, int64_t p_stride,
+                     const int32_t* const_species, int32_t n_const,
+                     const double* t_end, double rtol, double atol,
+                     int32_t nsave, const double* tsave, double* ysave,
+                     double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                     const rmsb_solve_opts* opts);
+
+/* ---- device-resident variants (inputs/outputs already in HBM; enqueue only) ---------------- */
+int rmsb_dydt_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
+                        const double* d_y, const double* d_cond, const double* d_p, int64_t p_stride,
+                        const int32_t* d_const_species, int32_t n_const,
+                        double* d_dydt, void* stream);
+int rmsb_jac_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
+                       const double* d_y, const double* d_cond, const double* d_p, int64_t p_stride,
+                       const int32_t* d_const_species, int32_t n_const,
+                       double* d_J, void* stream);
+/* d_work: rmsb_solve_work_bytes() bytes of device scratch (work-queue counter etc.). */
+int64_t rmsb_solve_work_bytes(const rmsb_mech* mech, int domain_kind, int64_t n);
+int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
+                         const double* d_y0, const double* d_cond, const double* d_p, int64_t p_stride,
+                         const int32_t* d_const_species, int32_t n_const,
+                         const double* d_t_end, double rtol, double atol,
+                         int32_t nsave, const double* d_tsave, double* d_ysave,
+                         double* d_yend, double* d_idt, int32_t* d_status, rmsb_stats* d_stats,
+                         const rmsb_solve_opts* opts, void* d_work, void* stream);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
+int64_t rmsb_kernel_launch_count(void);
+/* FP64 FMA microbenchmark on `device`: returns sustained DFMA TFLOP/s (2 flop per FMA), <0 on error.
+ * Used as the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+double  rmsb_fp64_peak_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMSB200_H */

@@ -1,0 +1,720 @@
+// rmsb_api.cu -- C ABI of librmsb200.so (see include/rmsb200.h): mechanism flattening into SoA device
+// tables, kernel instantiations and the host/device-buffer entry points.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/rmsb200.h"
+#include "rmsb_device.cuh"
+#include "rmsb_solver.cuh"
+
+using namespace rmsb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(RMSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// mechanism handle
+// ------------------------------------------------------------------------------------------------
+struct rmsb_mech {
+    int device = 0;
+    DevMech dm{};
+    std::vector<void*> allocs;
+    int n_dt = 0, n_je = 0;
+};
+
+template <class T>
+static int upload(rmsb_mech* h, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
+    CU(cudaMalloc(&p, bytes));
+    h->allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(p);
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_version(void) { return RMSB_VERSION; }
+extern "C" const char* rmsb_last_error(void) { return g_err.c_str(); }
+extern "C" int rmsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int64_t rmsb_kernel_launch_count(void) { return g_launches.load(); }
+
+static int domain_ny(const rmsb_mech* m, int kind) {
+    switch (kind) {
+    case RMSB_DOMAIN_CONSTANT_V: return m->dm.Ns + 2;
+    case RMSB_DOMAIN_CONSTANT_TP: return m->dm.Ns + 1;
+    case RMSB_DOMAIN_CONSTANT_TV:
+    case RMSB_DOMAIN_CONSTANT_TAPHI: return m->dm.Ns;
+    }
+    return -1;
+}
+static int domain_ncond(int kind) {
+    switch (kind) {
+    case RMSB_DOMAIN_CONSTANT_V: return 1;
+    case RMSB_DOMAIN_CONSTANT_TP:
+    case RMSB_DOMAIN_CONSTANT_TV:
+    case RMSB_DOMAIN_CONSTANT_TAPHI: return 2;
+    }
+    return -1;
+}
+extern "C" int rmsb_mech_ny(const rmsb_mech* m, int kind) { return m ? domain_ny(m, kind) : -1; }
+extern "C" int rmsb_mech_ncond(const rmsb_mech* m, int kind) { return m ? domain_ncond(kind) : -1; }
+extern "C" int rmsb_mech_device(const rmsb_mech* m) { return m ? m->device : -1; }
+
+extern "C" void rmsb_mech_destroy(rmsb_mech* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
+    const int Ns = d->n_species, Nr = d->n_reactions;
+    DevMech& dm = h->dm;
+    dm.Ns = Ns; dm.Nr = Nr;
+    dm.phase_kind = d->phase_kind;
+    dm.difflim = d->diffusion_limited ? 1 : 0;
+    dm.sitedensity = d->sitedensity;
+    dm.maxr = d->nasa_max_ranges;
+    const int maxr = d->nasa_max_ranges;
+    // ---- thermo, SoA over species
+    std::vector<int> nr(Ns), nc((size_t)maxr * Ns, 7);
+    std::vector<double> tmax((size_t)maxr * Ns, 0.0), coef((size_t)maxr * 9 * Ns, 0.0);
+    for (int s = 0; s < Ns; ++s) {
+        nr[s] = d->nasa_nranges[s];
+        if (nr[s] < 1 || nr[s] > maxr) return fail(RMSB_ERR_ARG, "nasa_nranges out of range");
+        for (int r = 0; r < nr[s]; ++r) {
+            int ncf = d->nasa_ncoef[s * maxr + r];
+            if (ncf != 7 && ncf != 9) return fail(RMSB_ERR_ARG, "NASA polynomial must have 7 or 9 coefficients");
+            nc[(size_t)r * Ns + s] = ncf;
+            tmax[(size_t)r * Ns + s] = d->nasa_tmax[s * maxr + r];
+            for (int c = 0; c < ncf; ++c) coef[((size_t)r * 9 + c) * Ns + s] = d->nasa_coefs[((size_t)s * maxr + r) * 9 + c];
+        }
+    }
+    // ---- reactions
+    std::vector<int> rx((size_t)8 * Nr, -1), ktype(Nr), koff(Nr + 1), effptr(Nr + 1), effspc, effrxn;
+    std::vector<double> effval, rev(Nr), fwd(Nr);
+    for (int j = 0; j < Nr; ++j) {
+        for (int k = 0; k < 8; ++k) {
+            int v = d->rxnarray[j * 8 + k];
+            if (v < 0 || v > Ns) return fail(RMSB_ERR_ARG, "rxnarray entry out of range");
+            rx[(size_t)k * Nr + j] = v - 1;
+        }
+        if (rx[j] < 0 || rx[(size_t)4 * Nr + j] < 0) return fail(RMSB_ERR_ARG, "reaction without reactant or product");
+        for (int k = 1; k < 4; ++k)
+            if (rx[(size_t)k * Nr + j] >= 0 && rx[(size_t)(k - 1) * Nr + j] < 0) return fail(RMSB_ERR_ARG, "rxnarray slots must be packed");
+        for (int k = 5; k < 8; ++k)
+            if (rx[(size_t)k * Nr + j] >= 0 && rx[(size_t)(k - 1) * Nr + j] < 0) return fail(RMSB_ERR_ARG, "rxnarray slots must be packed");
+        ktype[j] = d->kin_type[j];
+        if (ktype[j] < 0 || ktype[j] > RMSB_KIN_CHEBYSHEV_VEC) return fail(RMSB_ERR_UNSUPPORTED, "unknown kinetics type");
+        rev[j] = d->reversible[j] ? 1.0 : 0.0;
+        fwd[j] = d->forwardable[j] ? 1.0 : 0.0;
+    }
+    for (int j = 0; j <= Nr; ++j) { koff[j] = d->kin_offset[j]; effptr[j] = d->eff_ptr ? d->eff_ptr[j] : 0; }
+    std::vector<double> kpar(d->kin_params, d->kin_params + koff[Nr]);
+    for (int k = 0; k < effptr[Nr]; ++k) {
+        int s = d->eff_species[k];
+        if (s < 1 || s > Ns) return fail(RMSB_ERR_ARG, "efficiency species out of range");
+        effspc.push_back(s - 1);
+        effval.push_back(d->eff_value[k]);
+    }
+    for (int j = 0; j < Nr; ++j) {
+        bool falloff = ktype[j] == RMSB_KIN_THIRDBODY || ktype[j] == RMSB_KIN_LINDEMANN || ktype[j] == RMSB_KIN_TROE;
+        if (effptr[j + 1] > effptr[j]) {
+            if (!falloff) return fail(RMSB_ERR_ARG, "efficiencies on a non-falloff reaction");
+            effrxn.push_back(j);
+        }
+    }
+    // ---- stoichiometric matrix rows exactly as getstoichmatrix builds them (src/Phase.jl:203-222):
+    //      slot index (1-based) > 3 is counted as a product.
+    std::vector<int> kcptr(Nr + 1, 0), kcspc;
+    std::vector<double> kccoef, nrp(Nr);
+    for (int j = 0; j < Nr; ++j) {
+        std::map<int, double> row;
+        double n = 0.0;
+        for (int k = 0; k < 8; ++k) {
+            int s = rx[(size_t)k * Nr + j];
+            if (s < 0) continue;
+            if (k + 1 > 3) { row[s] -= 1.0; n += 1.0; } else { row[s] += 1.0; n -= 1.0; }
+        }
+        nrp[j] = n;
+        for (auto& kv : row) { kcspc.push_back(kv.first); kccoef.push_back(kv.second); }
+        kcptr[j + 1] = (int)kcspc.size();
+    }
+    // ---- species -> reaction slots, reaction order (src/Reactor.jl:484-505)
+    std::vector<std::vector<int>> sr(Ns);
+    for (int j = 0; j < Nr; ++j) {
+        for (int k = 0; k < 4; ++k) { int s = rx[(size_t)k * Nr + j]; if (s >= 0) sr[s].push_back(j | (int)0x80000000); }
+        for (int k = 4; k < 8; ++k) { int s = rx[(size_t)k * Nr + j]; if (s >= 0) sr[s].push_back(j); }
+    }
+    std::vector<int> srptr(Ns + 1, 0), srrxn;
+    for (int s = 0; s < Ns; ++s) { for (int v : sr[s]) srrxn.push_back(v); srptr[s + 1] = (int)srrxn.size(); }
+    // ---- Jacobian ns-block: derivative terms + per-entry gather lists in the accumulation order of
+    //      _jacobianynswrtns! (src/Reactor.jl:899-1366): reaction ascending, forward then reverse.
+    std::vector<int> dtrxn, dtmult, dtoth, dtspc;
+    std::map<std::pair<int, int>, std::vector<int>> entries;  // (col,row) -> signed term refs
+    for (int j = 0; j < Nr; ++j) {
+        for (int dir = 0; dir < 2; ++dir) {
+            std::vector<int> slots, oslots;
+            for (int k = 0; k < 4; ++k) {
+                int a = rx[(size_t)(dir ? k + 4 : k) * Nr + j], b = rx[(size_t)(dir ? k : k + 4) * Nr + j];
+                if (a >= 0) slots.push_back(a);
+                if (b >= 0) oslots.push_back(b);
+            }
+            std::vector<int> seen;
+            for (int s : slots) {
+                bool dup = false;
+                for (int q : seen) if (q == s) dup = true;
+                if (dup) continue;
+                seen.push_back(s);
+                int mcount = 0;
+                for (int q : slots) if (q == s) ++mcount;
+                int t = (int)dtrxn.size();
+                dtrxn.push_back(j | (dir << 30));
+                dtmult.push_back(mcount);
+                dtspc.push_back(s);
+                bool removed = false;
+                int no = 0;
+                int oth[3] = {-1, -1, -1};
+                for (int q : slots) {
+                    if (q == s && !removed) { removed = true; continue; }
+                    oth[no++] = q;
+                }
+                for (int k = 0; k < 3; ++k) dtoth.push_back(oth[k]);
+                for (int q : slots) entries[{s, q}].push_back(t | (int)0x80000000);
+                for (int q : oslots) entries[{s, q}].push_back(t);
+            }
+        }
+    }
+    std::vector<int> jeptr{0}, jerow, jecol, jtidx;
+    for (auto& kv : entries) {
+        jecol.push_back(kv.first.first);
+        jerow.push_back(kv.first.second);
+        for (int v : kv.second) jtidx.push_back(v);
+        jeptr.push_back((int)jtidx.size());
+    }
+    dm.n_dt = h->n_dt = (int)dtrxn.size();
+    dm.n_je = h->n_je = (int)jerow.size();
+    dm.n_effrxn = (int)effrxn.size();
+    // ---- liquid phase data
+    std::vector<double> radius, diffr;
+    if (d->radius) radius.assign(d->radius, d->radius + Ns);
+    if (d->diff_radius) diffr.assign(d->diff_radius, d->diff_radius + Ns);
+    if (dm.difflim && (radius.empty() || diffr.empty()))
+        return fail(RMSB_ERR_ARG, "diffusion-limited phase needs radius and diff_radius");
+    dm.visc_kind = d->viscosity_kind;
+    for (int k = 0; k < 5; ++k) dm.visc[k] = d->viscosity_params[k];
+
+    int rc;
+#define UP(vec, field) if ((rc = upload(h, vec, &dm.field)) != RMSB_OK) return rc
+    UP(nr, nasa_nr); UP(nc, nasa_nc); UP(tmax, nasa_tmax); UP(coef, nasa_c);
+    UP(rx, rx); UP(ktype, ktype); UP(koff, koff); UP(kpar, kpar);
+    UP(effptr, eff_ptr); UP(effspc, eff_spc); UP(effval, eff_val); UP(effrxn, effrxn);
+    UP(rev, rev); UP(fwd, fwd);
+    UP(kcptr, kc_ptr); UP(kcspc, kc_spc); UP(kccoef, kc_coef); UP(nrp, nrp);
+    UP(srptr, sr_ptr); UP(srrxn, sr_rxn);
+    UP(dtrxn, dt_rxn); UP(dtmult, dt_mult); UP(dtoth, dt_oth); UP(dtspc, dt_spc);
+    UP(jeptr, je_ptr); UP(jerow, je_row); UP(jecol, je_col); UP(jtidx, jt_idx);
+#undef UP
+    if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
+    if (!diffr.empty()) { if ((rc = upload(h, diffr, &dm.diff_r)) != RMSB_OK) return rc; } else dm.diff_r = nullptr;
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_mech_create(const rmsb_mech_desc* desc, int device, rmsb_mech** out) {
+    if (!desc || !out) return fail(RMSB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (desc->struct_size != (int32_t)sizeof(rmsb_mech_desc)) return fail(RMSB_ERR_ARG, "rmsb_mech_desc size mismatch (ABI)");
+    if (desc->n_species < 1 || desc->n_reactions < 1) return fail(RMSB_ERR_ARG, "empty mechanism");
+    int ndev = rmsb_device_count();
+    if (ndev <= 0) return fail(RMSB_ERR_CUDA, "no CUDA device available (librmsb200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(RMSB_ERR_ARG, "device ordinal out of range");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(RMSB_ERR_CUDA, "cudaSetDevice failed");
+    rmsb_mech* h = new rmsb_mech();
+    h->device = device;
+    int rc = build_mech(desc, h);
+    if (rc != RMSB_OK) { std::string keep = g_err; rmsb_mech_destroy(h); g_err = keep; return rc; }
+    *out = h;
+    return RMSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct BatchArgs {
+    int64_t n;
+    const double* y;
+    const double* cond;
+    int ncond;
+    const double* p;
+    int64_t p_stride;
+    const int* constspc;
+    int nconst;
+    double* out;     // dydt or J
+    double* out2;    // krev (rates kernel)
+    int domain_kind;
+    int Ny;
+};
+
+template <int R>
+__device__ __forceinline__ void load_state_and_setup(const DevMech& m, const BatchArgs& a, DomainArgs& d, WarpWs& w,
+                                                     int64_t ir, int lane, double (&y)[R], const double*& cond) {
+    d.kind = a.domain_kind; d.Ny = a.Ny;
+    d.p = a.p ? a.p + ir * a.p_stride : nullptr;
+    d.constspc = a.constspc; d.nconst = a.nconst;
+    cond = a.cond + ir * a.ncond;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; y[r] = (i < a.Ny) ? a.y[ir * a.Ny + i] : 0.0; }
+    if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < m.Ns) w.ns[s] = y[r]; }
+        __syncwarp();
+        double T = cond[0], P, V;
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = cond[1]; V = bcast<double, R>(y, m.Ns); }
+        else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = cond[1]; }
+        setup_constk(m, d, w, T, P, V, lane);
+    }
+}
+
+// mode 0: dydt, 1: Jacobian, 2: kf/krev
+template <int R, int MODE>
+__global__ void __launch_bounds__(128) eval_kernel(DevMech m, BatchArgs a, int ws_per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    WarpWs w;
+    ws_carve(w, smem + (size_t)warp * ws_per_warp, m.Ns, m.Nr, a.Ny, m.n_dt, false);
+    const int64_t nw = (int64_t)gridDim.x * wpb;
+    for (int64_t ir = (int64_t)blockIdx.x * wpb + warp; ir < a.n; ir += nw) {
+        DomainArgs d;
+        double y[R];
+        const double* cond;
+        load_state_and_setup<R>(m, a, d, w, ir, lane, y, cond);
+        if (MODE == 0) {
+            double dy[R];
+            rhs_warp<double, R>(m, d, w, cond, y, dy, lane, false, nullptr);
+#pragma unroll
+            for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < a.Ny) a.out[ir * a.Ny + i] = dy[r]; }
+        } else if (MODE == 1) {
+            jac_warp<R>(m, d, w, cond, y, lane);
+            const int Ny = a.Ny, LD = w.LD;
+            double* J = a.out + (size_t)ir * Ny * Ny;
+            for (int idx = lane; idx < Ny * Ny; idx += 32) {
+                int col = idx / Ny, row = idx - col * Ny;
+                J[idx] = w.J[row + col * LD];
+            }
+        } else {
+            double dy[R];
+            rhs_warp<double, R>(m, d, w, cond, y, dy, lane, true, nullptr);
+            for (int j = lane; j < m.Nr; j += 32) { a.out[ir * m.Nr + j] = w.kf[j]; a.out2[ir * m.Nr + j] = w.kr[j]; }
+        }
+        __syncwarp();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) solve_kernel(DevMech m, SolveArgs a, int ws_per_warp) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWs w;
+    ws_carve(w, smem + (size_t)warp * ws_per_warp, m.Ns, m.Nr, a.Ny, m.n_dt, true);
+    for (;;) {
+        unsigned long long ir = 0;
+        if (lane == 0) ir = atomicAdd(a.counter, 1ULL);     // dynamic work queue: one reactor per warp at a time
+        ir = __shfl_sync(FULL, ir, 0);
+        if (ir >= (unsigned long long)a.n) break;
+        bdf_solve_warp<R>(m, a, w, (int64_t)ir, lane);
+    }
+}
+
+__global__ void gibbs_kernel(DevMech m, int64_t n, const double* T, int scalar_path, double* G) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t ir = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ir < n; ir += nw) {
+        double Tv = T[ir];
+        TPow<double> tp(Tv);
+        for (int s = lane; s < m.Ns; s += 32) {
+            double g;
+            if (scalar_path) g = gibbs_scalar(m, s, Tv);
+            else { double cp, h, sr; nasa_hscp(m, s, tp, Tv, cp, h, sr); g = (h - sr) * (RMSB_R * Tv); }
+            G[ir * m.Ns + s] = g;
+        }
+    }
+}
+
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double b = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int rows_per_lane(int Ny) { return (Ny + 31) / 32; }
+
+struct LaunchCfg { int wpb; int ws; size_t smem; int blocks_per_sm; int sms; };
+
+template <class K>
+static int config_launch(K kernel, const rmsb_mech* h, int Ny, bool solver, int want_wpb, LaunchCfg* cfg) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, solver);
+    size_t per_warp = (size_t)ws * sizeof(double);
+    size_t max_smem = prop.sharedMemPerBlockOptin;
+    if (per_warp > max_smem)
+        return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the warp-per-reactor dense kernels (per-warp workspace exceeds shared memory)");
+    int wpb = want_wpb > 0 ? want_wpb : 4;
+    if (wpb > 4) wpb = 4;
+    while (wpb > 1 && per_warp * wpb > max_smem) --wpb;
+    size_t smem = per_warp * wpb;
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, wpb * 32, smem));
+    if (bps < 1) bps = 1;
+    cfg->wpb = wpb; cfg->ws = ws; cfg->smem = smem; cfg->blocks_per_sm = bps; cfg->sms = prop.multiProcessorCount;
+    return RMSB_OK;
+}
+
+template <int R, int MODE>
+static int launch_eval_R(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+    LaunchCfg cfg;
+    int rc = config_launch(eval_kernel<R, MODE>, h, a.Ny, false, 4, &cfg);
+    if (rc != RMSB_OK) return rc;
+    int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
+    int64_t max_blocks = (int64_t)cfg.sms * cfg.blocks_per_sm * 8;   // grid-stride beyond 8 waves
+    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+    if (grid < 1) grid = 1;
+    eval_kernel<R, MODE><<<grid, cfg.wpb * 32, cfg.smem, st>>>(h->dm, a, cfg.ws);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return RMSB_OK;
+}
+
+template <int MODE>
+static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+    switch (rows_per_lane(a.Ny)) {
+    case 1: return launch_eval_R<1, MODE>(h, a, st);
+    case 2: return launch_eval_R<2, MODE>(h, a, st);
+    case 3: return launch_eval_R<3, MODE>(h, a, st);
+    case 4: return launch_eval_R<4, MODE>(h, a, st);
+    }
+    return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
+}
+
+template <int R>
+static int launch_solve_R(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
+    LaunchCfg cfg;
+    int rc = config_launch(solve_kernel<R>, h, a.Ny, true, want_wpb, &cfg);
+    if (rc != RMSB_OK) return rc;
+    int64_t resident = (int64_t)cfg.sms * cfg.blocks_per_sm;
+    int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
+    int grid = (int)(blocks_needed < resident ? blocks_needed : resident);
+    if (grid < 1) grid = 1;
+    CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+    solve_kernel<R><<<grid, cfg.wpb * 32, cfg.smem, st>>>(h->dm, a, cfg.ws);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return RMSB_OK;
+}
+
+static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
+    switch (rows_per_lane(a.Ny)) {
+    case 1: return launch_solve_R<1>(h, a, want_wpb, st);
+    case 2: return launch_solve_R<2>(h, a, want_wpb, st);
+    case 3: return launch_solve_R<3>(h, a, want_wpb, st);
+    case 4: return launch_solve_R<4>(h, a, want_wpb, st);
+    }
+    return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
+}
+
+static int check_common(const rmsb_mech* h, int kind, int64_t n, const void* y, const void* cond, int64_t p_stride, const void* p) {
+    if (!h) return fail(RMSB_ERR_ARG, "null mechanism");
+    if (domain_ny(h, kind) < 0) return fail(RMSB_ERR_ARG, "unknown domain kind");
+    if (n < 0) return fail(RMSB_ERR_ARG, "negative batch size");
+    if (n > 0 && (!y || !cond)) return fail(RMSB_ERR_ARG, "null state/condition buffer");
+    if (p && p_stride != 0 && p_stride != h->dm.Ns + h->dm.Nr) return fail(RMSB_ERR_ARG, "p_stride must be 0 or Ns+Nr");
+    if (kind == RMSB_DOMAIN_CONSTANT_V && h->dm.phase_kind != RMSB_PHASE_GAS) return fail(RMSB_ERR_ARG, "ConstantV domain needs an IdealGas phase");
+    if (kind == RMSB_DOMAIN_CONSTANT_TAPHI && h->dm.phase_kind != RMSB_PHASE_SURFACE) return fail(RMSB_ERR_ARG, "ConstantTAPhi domain needs an IdealSurface phase");
+    return RMSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------------------
+static BatchArgs make_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                            int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2) {
+    BatchArgs a;
+    a.n = n; a.y = y; a.cond = cond; a.ncond = domain_ncond(kind); a.p = p; a.p_stride = p ? p_stride : 0;
+    a.constspc = cs; a.nconst = cs ? ncs : 0; a.out = out; a.out2 = out2; a.domain_kind = kind; a.Ny = domain_ny(h, kind);
+    return a;
+}
+
+extern "C" int rmsb_dydt_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond,
+                                   const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs, double* dydt, void* stream) {
+    int rc = check_common(h, kind, n, y, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    DeviceGuard g(h->device);
+    return launch_eval<0>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr), (cudaStream_t)stream);
+}
+
+extern "C" int rmsb_jac_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond,
+                                  const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs, double* J, void* stream) {
+    int rc = check_common(h, kind, n, y, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    DeviceGuard g(h->device);
+    return launch_eval<1>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr), (cudaStream_t)stream);
+}
+
+extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech*, int, int64_t) { return 256; }
+
+static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
+    o->struct_size = sizeof(rmsb_solve_opts);
+    o->max_steps = 500000; o->max_order = 5; o->idt_index = -1; o->first_step = 0.0; o->warps_per_block = 0; o->reserved = 0;
+    if (in && in->struct_size == (int32_t)sizeof(rmsb_solve_opts)) {
+        if (in->max_steps > 0) o->max_steps = in->max_steps;
+        if (in->max_order >= 1 && in->max_order <= 5) o->max_order = in->max_order;
+        o->idt_index = in->idt_index;
+        if (in->first_step > 0.0) o->first_step = in->first_step;
+        o->warps_per_block = in->warps_per_block;
+    }
+}
+
+extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
+                                    const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
+                                    const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                                    double* ysave, double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                                    const rmsb_solve_opts* opts, void* work, void* stream) {
+    int rc = check_common(h, kind, n, y0, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    if (!t_end || !status || !work) return fail(RMSB_ERR_ARG, "t_end, status and work buffers are required");
+    if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(RMSB_ERR_ARG, "rtol must be > 0 and atol >= 0");
+    if (nsave < 0 || (nsave > 0 && !tsave)) return fail(RMSB_ERR_ARG, "bad tsave");
+    rmsb_solve_opts o;
+    default_opts(&o, opts);
+    SolveArgs a;
+    a.n = n; a.y0 = y0; a.cond = cond; a.ncond = domain_ncond(kind); a.p = p; a.p_stride = p ? p_stride : 0;
+    a.constspc = cs; a.nconst = cs ? ncs : 0; a.t_end = t_end; a.rtol = rtol; a.atol = atol;
+    a.nsave = nsave; a.tsave = tsave; a.ysave = ysave; a.yend = yend; a.idt = idt; a.status = status; a.stats = stats;
+    a.max_steps = o.max_steps; a.max_order = o.max_order; a.first_step = o.first_step;
+    a.domain_kind = kind; a.Ny = domain_ny(h, kind);
+    a.idt_index = o.idt_index >= 0 ? o.idt_index : (kind == RMSB_DOMAIN_CONSTANT_V ? h->dm.Ns : -1);
+    if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
+    a.counter = reinterpret_cast<unsigned long long*>(work);
+    DeviceGuard g(h->device);
+    return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points: copy in, run, copy out (stream-ordered pool allocations)
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct StreamGuard {
+    cudaStream_t st = nullptr;
+    ~StreamGuard() { if (st) cudaStreamDestroy(st); }
+};
+static void tune_pool(int device) {
+    static std::atomic<unsigned> done{0};
+    unsigned bit = 1u << (device & 31);
+    if (done.load() & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;   // keep freed blocks cached: repeated batch calls re-use them
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.fetch_or(bit);
+}
+
+#define H2D(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sg.st))
+#define D2H(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sg.st))
+
+static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                     int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2) {
+    int rc = check_common(h, kind, n, y, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    if (!out || (mode == 2 && !out2)) return fail(RMSB_ERR_ARG, "null output buffer");
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(RMSB_ERR_CUDA, "cudaSetDevice failed");
+    tune_pool(h->device);
+    StreamGuard sg;
+    CU(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+    const int Ny = domain_ny(h, kind), nc = domain_ncond(kind), Np = h->dm.Ns + h->dm.Nr;
+    size_t out_per = mode == 0 ? (size_t)Ny : (mode == 1 ? (size_t)Ny * Ny : (size_t)h->dm.Nr);
+    DevBuf dy(sg.st), dc(sg.st), dp(sg.st), dcs(sg.st), dout(sg.st), dout2(sg.st);
+    CU(dy.alloc(sizeof(double) * n * Ny)); CU(dc.alloc(sizeof(double) * n * nc)); CU(dout.alloc(sizeof(double) * n * out_per));
+    H2D(dy.p, y, sizeof(double) * n * Ny);
+    H2D(dc.p, cond, sizeof(double) * n * nc);
+    if (p) { size_t np = p_stride ? (size_t)n * Np : (size_t)Np; CU(dp.alloc(sizeof(double) * np)); H2D(dp.p, p, sizeof(double) * np); }
+    if (cs && ncs > 0) { CU(dcs.alloc(sizeof(int32_t) * ncs)); H2D(dcs.p, cs, sizeof(int32_t) * ncs); }
+    if (mode == 2) CU(dout2.alloc(sizeof(double) * n * out_per));
+    BatchArgs a = make_batch(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
+                             (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dout.as<double>(), dout2.as<double>());
+    if (mode == 0) rc = launch_eval<0>(h, a, sg.st);
+    else if (mode == 1) rc = launch_eval<1>(h, a, sg.st);
+    else rc = launch_eval<2>(h, a, sg.st);
+    if (rc != RMSB_OK) return rc;
+    D2H(out, dout.p, sizeof(double) * n * out_per);
+    if (mode == 2) D2H(out2, dout2.p, sizeof(double) * n * out_per);
+    CU(cudaStreamSynchronize(sg.st));
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_dydt_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                               int64_t p_stride, const int32_t* cs, int32_t ncs, double* dydt) {
+    return eval_host(0, h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr);
+}
+extern "C" int rmsb_jac_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                              int64_t p_stride, const int32_t* cs, int32_t ncs, double* J) {
+    return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr);
+}
+extern "C" int rmsb_rates_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                int64_t p_stride, double* kf, double* krev) {
+    return eval_host(2, h, kind, n, y, cond, p, p_stride, nullptr, 0, kf, krev);
+}
+
+extern "C" int rmsb_gibbs_batch(const rmsb_mech* h, int64_t n, const double* T, int scalar_path, double* G) {
+    if (!h || n < 0 || (n > 0 && (!T || !G))) return fail(RMSB_ERR_ARG, "bad argument");
+    if (n == 0) return RMSB_OK;
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(RMSB_ERR_CUDA, "cudaSetDevice failed");
+    StreamGuard sg;
+    CU(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+    DevBuf dT(sg.st), dG(sg.st);
+    CU(dT.alloc(sizeof(double) * n)); CU(dG.alloc(sizeof(double) * n * h->dm.Ns));
+    H2D(dT.p, T, sizeof(double) * n);
+    int64_t blocks = (n + 3) / 4;
+    if (blocks > 65535) blocks = 65535;
+    gibbs_kernel<<<(int)blocks, 128, 0, sg.st>>>(h->dm, n, dT.as<double>(), scalar_path, dG.as<double>());
+    ++g_launches;
+    CU(cudaGetLastError());
+    D2H(G, dG.p, sizeof(double) * n * h->dm.Ns);
+    CU(cudaStreamSynchronize(sg.st));
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                                int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
+                                int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
+                                rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    int rc = check_common(h, kind, n, y0, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    if (!t_end || !status) return fail(RMSB_ERR_ARG, "t_end and status are required");
+    if (nsave > 0 && (!tsave || !ysave)) return fail(RMSB_ERR_ARG, "tsave/ysave required when nsave > 0");
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(RMSB_ERR_CUDA, "cudaSetDevice failed");
+    tune_pool(h->device);
+    StreamGuard sg;
+    CU(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+    const int Ny = domain_ny(h, kind), nc = domain_ncond(kind), Np = h->dm.Ns + h->dm.Nr;
+    DevBuf dy(sg.st), dc(sg.st), dp(sg.st), dcs(sg.st), dte(sg.st), dts(sg.st), dys(sg.st), dye(sg.st), didt(sg.st), dst(sg.st),
+        dstats(sg.st), dwork(sg.st);
+    CU(dy.alloc(sizeof(double) * n * Ny)); H2D(dy.p, y0, sizeof(double) * n * Ny);
+    CU(dc.alloc(sizeof(double) * n * nc)); H2D(dc.p, cond, sizeof(double) * n * nc);
+    if (p) { size_t np = p_stride ? (size_t)n * Np : (size_t)Np; CU(dp.alloc(sizeof(double) * np)); H2D(dp.p, p, sizeof(double) * np); }
+    if (cs && ncs > 0) { CU(dcs.alloc(sizeof(int32_t) * ncs)); H2D(dcs.p, cs, sizeof(int32_t) * ncs); }
+    CU(dte.alloc(sizeof(double) * n)); H2D(dte.p, t_end, sizeof(double) * n);
+    if (nsave > 0) {
+        CU(dts.alloc(sizeof(double) * nsave)); H2D(dts.p, tsave, sizeof(double) * nsave);
+        CU(dys.alloc(sizeof(double) * n * nsave * Ny));
+    }
+    if (yend) CU(dye.alloc(sizeof(double) * n * Ny));
+    if (idt) CU(didt.alloc(sizeof(double) * n));
+    CU(dst.alloc(sizeof(int32_t) * n));
+    if (stats) CU(dstats.alloc(sizeof(rmsb_stats) * n));
+    CU(dwork.alloc(256));
+    rc = rmsb_solve_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
+                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
+                              nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr,
+                              yend ? dye.as<double>() : nullptr, idt ? didt.as<double>() : nullptr, dst.as<int32_t>(),
+                              stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st);
+    if (rc != RMSB_OK) return rc;
+    if (nsave > 0) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
+    if (yend) D2H(yend, dye.p, sizeof(double) * n * Ny);
+    if (idt) D2H(idt, didt.p, sizeof(double) * n);
+    D2H(status, dst.p, sizeof(int32_t) * n);
+    if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
+    CU(cudaStreamSynchronize(sg.st));
+    return RMSB_OK;
+}
+
+extern "C" double rmsb_fp64_peak_tflops(int device, int iters) {
+    if (rmsb_device_count() <= 0) { fail(RMSB_ERR_CUDA, "no CUDA device"); return -1.0; }
+    DeviceGuard g(device);
+    if (!g.ok) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    if (iters <= 0) iters = 1 << 16;
+    int threads = 256, blocks = prop.multiProcessorCount * 8;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(out, iters / 16);   // warm-up
+    ++g_launches;
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        ++g_launches;
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    return best;
+}

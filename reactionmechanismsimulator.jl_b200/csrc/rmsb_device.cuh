@@ -1,0 +1,902 @@
+// rmsb_device.cuh -- device-side mechanism tables and the warp-cooperative RHS / Jacobian.
+//
+// Execution model: ONE WARP INTEGRATES ONE REACTOR.  State component i lives in lane (i & 31),
+// register slot (i >> 5) (template parameter R = slots per lane, Ny <= 32*R).  Species-indexed
+// work (thermo, gather of reaction rates) is spread over lanes by species, reaction-indexed work
+// (rate coefficients, equilibrium constants, mass-action rates) by reaction; per-warp scratch
+// lives in shared memory.  Every warp follows its own control flow, so per-reactor adaptive
+// stepping costs no intra-warp divergence.
+//
+// What is restated here (reference = ReactionMechanismSimulator.jl, paths relative to its root):
+//   calcHSCpdless                 src/Calculators/Thermovec.jl:76-119      (vectorised thermo path)
+//   getGibbs/getEnthalpy/Entropy  src/Calculators/Thermo.jl:6-8,75-93      (scalar thermo path)
+//   rate calculators              src/Calculators/Rate.jl:10-210, Ratevec.jl:24,89-100,204-215
+//   getkf/getkfs/getKc/getKcs/getkfkrev(s)   src/PhaseState.jl:53-76,106-129,165-171,184-257
+//   calcthermo                    src/Domain.jl:916-966,1064-1113,1514-1561,1597-1633
+//   addreactionratecontributions! src/Reactor.jl:465-507
+//   calcdomainderivatives!        src/Domain.jl:1839-1842,1863-1867,1901-1906
+//   jacobiany! (+helpers)         src/Domain.jl:2151-2454,3049-3055 ; src/Reactor.jl:874-1477
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/rmsb200.h"
+
+namespace rmsb {
+
+// src/Constants.jl:1-7 (R is 8.314 exactly)
+#define RMSB_R   8.314
+#define RMSB_NA  6.022e23
+#define RMSB_KB  (8.314 / 6.022e23)
+#define RMSB_PI  3.141592653589793
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct DevMech {
+    int Ns, Nr;
+    int phase_kind;
+    int difflim;
+    double sitedensity;
+    // NASA polynomials, SoA over species: nasa_tmax[r*Ns+s], nasa_nc[r*Ns+s], nasa_c[(r*9+c)*Ns+s]
+    int maxr;
+    const int* nasa_nr;
+    const int* nasa_nc;
+    const double* nasa_tmax;
+    const double* nasa_c;
+    // reactions: rx[slot*Nr+j], 0-based, -1 = none
+    const int* rx;
+    const int* ktype;
+    const int* koff;
+    const double* kpar;
+    const int* eff_ptr;      // [Nr+1]
+    const int* eff_spc;      // 0-based
+    const double* eff_val;
+    int n_effrxn;            // reactions with >=1 efficiency AND falloff kinetics (Domain.jl:74 efficiencyinds)
+    const int* effrxn;       // their indices
+    const double* rev;       // 0/1
+    const double* fwd;       // 0/1
+    // stoichiometric matrix rows (getstoichmatrix, Phase.jl:203-222): CSR sorted by species
+    const int* kc_ptr;
+    const int* kc_spc;
+    const double* kc_coef;
+    const double* nrp;
+    // species -> (reaction, sign) in reaction order, one entry per slot occurrence
+    const int* sr_ptr;
+    const int* sr_rxn;       // rxn index; bit 31 set => reactant slot (subtract)
+    // Jacobian ns-block: derivative terms and per-entry gather lists (built on host in reference order)
+    int n_dt;
+    const int* dt_rxn;       // reaction | dir<<30 (dir 1 = reverse)
+    const int* dt_mult;      // multiplicity m
+    const int* dt_oth;       // [3*n_dt] other species of that side (-1 none)
+    const int* dt_spc;       // species differentiated against (column)
+    int n_je;
+    const int* je_ptr;       // [n_je+1]
+    const int* je_row;
+    const int* je_col;
+    const int* jt_idx;       // term index; bit 31 set => subtract
+    // liquid phase
+    const double* radius;
+    const double* diff_r;
+    int visc_kind;
+    double visc[5];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Dual numbers with two partials (d/dT, d/dP) -- the in-kernel analogue of the reference's
+// ForwardDiff pass over the complete RHS for the ConstantV T and P columns (src/Reactor.jl:1469-1477).
+// ------------------------------------------------------------------------------------------------
+struct Dual2 {
+    double v, a, b;
+    __device__ __forceinline__ Dual2() {}
+    __device__ __forceinline__ Dual2(double v_) : v(v_), a(0.0), b(0.0) {}
+    __device__ __forceinline__ Dual2(double v_, double a_, double b_) : v(v_), a(a_), b(b_) {}
+};
+__device__ __forceinline__ Dual2 operator+(Dual2 x, Dual2 y) { return Dual2(x.v + y.v, x.a + y.a, x.b + y.b); }
+__device__ __forceinline__ Dual2 operator+(Dual2 x, double y) { return Dual2(x.v + y, x.a, x.b); }
+__device__ __forceinline__ Dual2 operator+(double x, Dual2 y) { return Dual2(x + y.v, y.a, y.b); }
+__device__ __forceinline__ Dual2 operator-(Dual2 x, Dual2 y) { return Dual2(x.v - y.v, x.a - y.a, x.b - y.b); }
+__device__ __forceinline__ Dual2 operator-(Dual2 x, double y) { return Dual2(x.v - y, x.a, x.b); }
+__device__ __forceinline__ Dual2 operator-(double x, Dual2 y) { return Dual2(x - y.v, -y.a, -y.b); }
+__device__ __forceinline__ Dual2 operator-(Dual2 x) { return Dual2(-x.v, -x.a, -x.b); }
+__device__ __forceinline__ Dual2 operator*(Dual2 x, Dual2 y) { return Dual2(x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b); }
+__device__ __forceinline__ Dual2 operator*(Dual2 x, double y) { return Dual2(x.v * y, x.a * y, x.b * y); }
+__device__ __forceinline__ Dual2 operator*(double x, Dual2 y) { return Dual2(x * y.v, x * y.a, x * y.b); }
+__device__ __forceinline__ Dual2 operator/(Dual2 x, Dual2 y) {
+    double q = x.v / y.v, iy = 1.0 / y.v;
+    return Dual2(q, (x.a - q * y.a) * iy, (x.b - q * y.b) * iy);
+}
+__device__ __forceinline__ Dual2 operator/(Dual2 x, double y) { return Dual2(x.v / y, x.a / y, x.b / y); }
+__device__ __forceinline__ Dual2 operator/(double x, Dual2 y) {
+    double q = x / y.v, s = -q / y.v;
+    return Dual2(q, s * y.a, s * y.b);
+}
+__device__ __forceinline__ Dual2 dexp(Dual2 x) { double e = exp(x.v); return Dual2(e, e * x.a, e * x.b); }
+__device__ __forceinline__ double dexp(double x) { return exp(x); }
+__device__ __forceinline__ Dual2 dlog(Dual2 x) { double i = 1.0 / x.v; return Dual2(log(x.v), x.a * i, x.b * i); }
+__device__ __forceinline__ double dlog(double x) { return log(x); }
+__device__ __forceinline__ Dual2 dlog10(Dual2 x) {
+    double i = 0.4342944819032518 / x.v;  // log10(e)/x
+    return Dual2(log10(x.v), x.a * i, x.b * i);
+}
+__device__ __forceinline__ double dlog10(double x) { return log10(x); }
+__device__ __forceinline__ Dual2 dpow(Dual2 x, double n) {  // x^n, real exponent
+    double v = pow(x.v, n), d = n * v / x.v;
+    return Dual2(v, d * x.a, d * x.b);
+}
+__device__ __forceinline__ double dpow(double x, double n) { return pow(x, n); }
+__device__ __forceinline__ Dual2 dpow(Dual2 x, Dual2 n) {  // general x^n
+    double v = pow(x.v, n.v), dx = n.v * v / x.v, dn = v * log(x.v);
+    return Dual2(v, dx * x.a + dn * n.a, dx * x.b + dn * n.b);
+}
+__device__ __forceinline__ Dual2 dexp10(Dual2 x) {  // 10^x
+    double v = pow(10.0, x.v), d = v * 2.302585092994046;
+    return Dual2(v, d * x.a, d * x.b);
+}
+__device__ __forceinline__ double dexp10(double x) { return pow(10.0, x); }
+__device__ __forceinline__ double val(double x) { return x; }
+__device__ __forceinline__ double val(Dual2 x) { return x.v; }
+
+// ---- warp helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ Dual2 warp_sum(Dual2 x) { return Dual2(warp_sum(x.v), warp_sum(x.a), warp_sum(x.b)); }
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
+    return x;
+}
+__device__ __forceinline__ double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
+__device__ __forceinline__ Dual2 shfl(Dual2 x, int src) { return Dual2(shfl(x.v, src), shfl(x.a, src), shfl(x.b, src)); }
+
+// broadcast distributed component idx of y to every lane
+template <class N, int R>
+__device__ __forceinline__ N bcast(const N (&y)[R], int idx) {
+    N out = y[0];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        N t = shfl(y[r], idx & 31);
+        if ((idx >> 5) == r) out = t;
+    }
+    return out;
+}
+
+// Per-warp shared-memory workspace (all pointers into the warp's private slice).
+struct WarpWs {
+    double* ns;     // [Ns]
+    double* cs;     // [Ns]
+    double* g;      // [3*Ns]  G/(RT) (variable-k, Dual2-capable) or absolute G (constant-k domains)
+    double* q;      // [3*Nr]  net rates (Dual2-capable)
+    double* kf;     // [Nr]
+    double* kr;     // [Nr]
+    double* us;     // [Ns]
+    double* cp;     // [Ns]
+    double* dterm;  // [n_dt]
+    double* J;      // [Ny*LD]
+    double* LU;     // [Ny*LD]
+    double* dinv;   // [Ny]
+    double* xs;     // [Ny]
+    int* perm;      // [Ny]
+    int LD;
+};
+
+__host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, bool solver) {
+    int LD = Ny | 1;
+    int n = 2 * Ns + 3 * Ns + 3 * Nr + 2 * Nr + 2 * Ns + n_dt + Ny * LD + 2 * Ny + (Ny + 1) / 2 + 2;
+    if (solver) n += Ny * LD;
+    return (n + 1) & ~1;
+}
+
+__device__ inline void ws_carve(WarpWs& w, double* base, int Ns, int Nr, int Ny, int n_dt, bool solver) {
+    w.LD = Ny | 1;
+    double* p = base;
+    w.ns = p; p += Ns;
+    w.cs = p; p += Ns;
+    w.g = p; p += 3 * Ns;
+    w.q = p; p += 3 * Nr;
+    w.kf = p; p += Nr;
+    w.kr = p; p += Nr;
+    w.us = p; p += Ns;
+    w.cp = p; p += Ns;
+    w.dterm = p; p += n_dt;
+    w.J = p; p += Ny * w.LD;
+    w.dinv = p; p += Ny;
+    w.xs = p; p += Ny;
+    w.perm = reinterpret_cast<int*>(p); p += (Ny + 1) / 2 + 1;
+    w.LU = solver ? p : w.J;
+}
+
+// smem load/store of a possibly-dual value at logical index i of an array with Dual2 capacity
+template <class N> struct SmemNum;
+template <> struct SmemNum<double> {
+    static __device__ __forceinline__ void st(double* a, int i, double x) { a[i] = x; }
+    static __device__ __forceinline__ double ld(const double* a, int i) { return a[i]; }
+};
+template <> struct SmemNum<Dual2> {
+    static __device__ __forceinline__ void st(double* a, int i, Dual2 x) { a[3 * i] = x.v; a[3 * i + 1] = x.a; a[3 * i + 2] = x.b; }
+    static __device__ __forceinline__ Dual2 ld(const double* a, int i) { return Dual2(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Thermo
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int select_poly(const DevMech& m, int s, double T) {
+    // selectPoly: first range with T <= Tmax, else the last (src/Calculators/Thermo.jl:101-111)
+    int nr = m.nasa_nr[s];
+    for (int r = 0; r < nr; ++r)
+        if (T <= m.nasa_tmax[r * m.Ns + s]) return r;
+    return nr - 1;
+}
+
+template <class N>
+struct TPow {  // powers of T built exactly as Thermovec.jl:78-84 / :100-105
+    N T0, T1, T2, T3, T4, T5, T6;
+    __device__ __forceinline__ explicit TPow(N T) {
+        T0 = T; T1 = T * T; T2 = T1 * T; T3 = T2 * T; T4 = 1.0 / T; T5 = T4 * T4; T6 = dlog(T);
+    }
+};
+
+// calcHSCpdless for species s (src/Calculators/Thermovec.jl:76-119; literal 0.33333333333 kept)
+template <class N>
+__device__ __forceinline__ void nasa_hscp(const DevMech& m, int s, const TPow<N>& t, double Tv, N& cp, N& h, N& sr) {
+    int r = select_poly(m, s, Tv);
+    const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
+    const int Ns = m.Ns;
+    if (m.nasa_nc[r * Ns + s] != 7) {
+        N ct0 = c[0] * t.T5, ct1 = c[Ns] * t.T4;
+        double ct2 = c[2 * Ns];
+        N ct3 = c[3 * Ns] * t.T0, ct4 = c[4 * Ns] * t.T1, ct5 = c[5 * Ns] * t.T2, ct6 = c[6 * Ns] * t.T3;
+        cp = ct0 + ct1 + ct2 + ct3 + ct4 + ct5 + ct6;
+        h = -ct0 + t.T6 * ct1 + ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + c[7 * Ns] * t.T4;
+        sr = -0.5 * ct0 - ct1 + t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + c[8 * Ns];
+    } else {
+        double ct2 = c[0];
+        N ct3 = c[Ns] * t.T0, ct4 = c[2 * Ns] * t.T1, ct5 = c[3 * Ns] * t.T2, ct6 = c[4 * Ns] * t.T3;
+        cp = ct2 + ct3 + ct4 + ct5 + ct6;
+        h = ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + c[5 * Ns] * t.T4;
+        sr = t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + c[6 * Ns];
+    }
+}
+
+// getGibbs through the scalar path: evalpoly Horner (src/Tools.jl:13-22) with exact c_k/k
+// (src/Calculators/Thermo.jl:6-8,75-93).  Used by the constant-T domains at setup.
+__device__ inline double gibbs_scalar(const DevMech& m, int s, double T) {
+    int r = select_poly(m, s, T);
+    const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
+    const int Ns = m.Ns;
+    double H, S;
+    if (m.nasa_nc[r * Ns + s] == 7) {
+        double out = 0.0;
+        for (int i = 4; i >= 0; --i) { out += c[i * Ns] / (double)(i + 1); if (i != 0) out *= T; }
+        H = out * RMSB_R * T + c[5 * Ns] * RMSB_R;
+        out = 0.0;
+        for (int i = 3; i >= 0; --i) { out += c[(i + 1) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
+        S = (c[0] * log(T) + T * out + c[6 * Ns]) * RMSB_R;
+    } else {
+        double out = 0.0;
+        for (int i = 4; i >= 0; --i) { out += c[(i + 2) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
+        H = ((-c[0] / T + c[Ns] * log(T)) / T + out) * RMSB_R * T + c[7 * Ns] * RMSB_R;
+        out = 0.0;
+        for (int i = 3; i >= 0; --i) { out += c[(i + 3) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
+        S = ((-c[0] / (2 * T) - c[Ns]) / T + c[2 * Ns] * log(T) + T * out + c[8 * Ns]) * RMSB_R;
+    }
+    return H - T * S;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rate calculators
+// ------------------------------------------------------------------------------------------------
+template <class N>
+struct KinEnv {
+    N T, logT, invRT;   // invRT = 1.0/(R*T)  (Ratevec.jl:24)
+    N RT;               // R*T
+    N P;
+};
+
+template <class N> __device__ __forceinline__ N arr_vec(const double* a, const KinEnv<N>& e) {
+    return a[0] * dexp(a[1] * e.logT - a[2] * e.invRT);            // Ratevec.jl:24
+}
+template <class N> __device__ __forceinline__ N arr_sca(const double* a, const KinEnv<N>& e) {
+    return a[0] * dpow(e.T, a[1]) * dexp(-a[2] / e.RT);            // Rate.jl:16
+}
+
+__device__ __forceinline__ void bounding_inds(double el, const double* x, int n, int& i0, int& i1) {
+    // getBoundingIndsSorted, src/Tools.jl:26-40
+    if (el <= x[0]) { i0 = 0; i1 = -1; return; }
+    for (int i = 0; i < n; ++i) {
+        if (x[i] >= el) {
+            if (x[i] == el) { i0 = i; i1 = -1; } else { i0 = i - 1; i1 = i; }
+            return;
+        }
+    }
+    i0 = n - 1; i1 = -1;
+}
+
+template <class N> __device__ __forceinline__ N plog_interp(N lowk, N highk, N P, double Plow, double Phigh) {
+    // Rate.jl:59 : lowk*10^(log10(P/Plow)/log10(Phigh/Plow)*log10(highk/lowk))
+    return lowk * dexp10(dlog10(P / Plow) / log10(Phigh / Plow) * dlog10(highk / lowk));
+}
+
+// one PLOG block with per-pressure {m, m x Arrhenius}; returns value and advances the cursor
+template <class N> __device__ inline N plog_block(const double*& c, const KinEnv<N>& e) {
+    int nP = (int)c[0];
+    const double* Ps = c + 1;
+    const double* ent = c + 1 + nP;
+    // locate entry starts
+    int i0, i1;
+    bounding_inds(val(e.P), Ps, nP, i0, i1);
+    N lowk = 0.0, highk = 0.0;
+    const double* q = ent;
+    for (int i = 0; i < nP; ++i) {
+        int mcount = (int)q[0];
+        if (i == i0 || i == i1) {
+            N acc = 0.0;
+            if (mcount == 1) acc = arr_sca(q + 1, e);
+            else for (int k = 0; k < mcount; ++k) acc = acc + arr_sca(q + 1 + 3 * k, e);
+            if (i == i0) lowk = acc; else highk = acc;
+        }
+        q += 1 + 3 * mcount;
+    }
+    c = q;
+    if (i1 < 0) return lowk;
+    return plog_interp(lowk, highk, e.P, Ps[i0], Ps[i1]);
+}
+
+template <class N> __device__ __forceinline__ N cheb_T(int n, N x) {  // Rate.jl:158-176
+    if (n == 0) return N(1.0);
+    if (n == 1) return x;
+    N T0 = 1.0, T1 = x, Tn = 0.0;
+    for (int i = 1; i < n; ++i) { Tn = 2.0 * x * T1 - T0; T0 = T1; T1 = Tn; }
+    return Tn;
+}
+
+template <class N> __device__ inline N troe_F(const double* a, N T, N Pr) {
+    // a = [a, T3, T1, T2]; Rate.jl:134-146
+    if (a[2] == 0.0 && a[1] == 0.0) return N(1.0);
+    N Fcent = (1 - a[0]) * dexp(-T / a[1]) + a[0] * dexp(-T / a[2]);
+    if (a[3] != 0.0) Fcent = Fcent + dexp(-a[3] / T);
+    const double d = 0.14;
+    N lF = dlog10(Fcent);
+    N n = 0.75 - 1.27 * lF;
+    N c = -0.4 - 0.67 * lF;
+    N lPr = dlog10(Pr);
+    N x = (lPr + c) / (n - d * lPr);
+    return dexp10(lF / (1 + x * x));
+}
+
+// kinetics(T=T,P=P,C=C): forward rate coefficient of reaction j.  `scalar_forms` forces the scalar
+// expressions for the *_VEC types (the diffusion-limited path goes through getkf for every reaction,
+// src/PhaseState.jl:184-223,249-252).
+template <class N>
+__device__ inline N eval_kin(const DevMech& m, int j, const KinEnv<N>& e, N Ceff, bool scalar_forms) {
+    const double* a = m.kpar + m.koff[j];
+    switch (m.ktype[j]) {
+    case RMSB_KIN_ARRHENIUS_VEC:
+        return scalar_forms ? arr_sca(a, e) : arr_vec(a, e);
+    case RMSB_KIN_ARRHENIUS:
+        return arr_sca(a, e);
+    case RMSB_KIN_MULTIARRHENIUS: {  // Rate.jl:68-74
+        int mc = (int)a[0];
+        N out = 0.0;
+        for (int k = 0; k < mc; ++k) out = out + arr_sca(a + 1 + 3 * k, e);
+        return out;
+    }
+    case RMSB_KIN_PLOG_VEC: {        // Ratevec.jl:204-215 (vector form leaves) / Rate.jl:48-60
+        int nP = (int)a[0];
+        const double* Ps = a + 1;
+        const double* ar = a + 1 + nP;
+        int i0, i1;
+        bounding_inds(val(e.P), Ps, nP, i0, i1);
+        N lowk = scalar_forms ? arr_sca(ar + 3 * i0, e) : arr_vec(ar + 3 * i0, e);
+        if (i1 < 0) return lowk;
+        N highk = scalar_forms ? arr_sca(ar + 3 * i1, e) : arr_vec(ar + 3 * i1, e);
+        return plog_interp(lowk, highk, e.P, Ps[i0], Ps[i1]);
+    }
+    case RMSB_KIN_PLOG: {
+        const double* c = a;
+        return plog_block(c, e);
+    }
+    case RMSB_KIN_MULTIPLOG: {       // Rate.jl:82-88
+        int nk = (int)a[0];
+        const double* c = a + 1;
+        N out = 0.0;
+        for (int k = 0; k < nk; ++k) out = out + plog_block(c, e);
+        return out;
+    }
+    case RMSB_KIN_THIRDBODY:         // Rate.jl:98
+        return Ceff * arr_sca(a, e);
+    case RMSB_KIN_LINDEMANN: {       // Rate.jl:109-114
+        N k0 = arr_sca(a + 3, e), kinf = arr_sca(a, e);
+        N Pr = k0 * Ceff / kinf;
+        return kinf * Pr / (1.0 + Pr);
+    }
+    case RMSB_KIN_TROE: {            // Rate.jl:129-147
+        N k0 = arr_sca(a + 3, e), kinf = arr_sca(a, e);
+        N Pr = k0 * Ceff / kinf;
+        N Fv = troe_F(a + 6, e.T, Pr);
+        return kinf * (Pr / (1 + Pr)) * Fv;
+    }
+    case RMSB_KIN_CHEBYSHEV_VEC: {   // Ratevec.jl:89-100 (P outer, T inner) / Rate.jl:194-209 (T outer)
+        double Tmin = a[0], Tmax = a[1], Pmin = a[2], Pmax = a[3];
+        int nT = (int)a[4], nP = (int)a[5];
+        const double* cf = a + 6;
+        N Tred = (2.0 / e.T - 1.0 / Tmin - 1.0 / Tmax) / (1.0 / Tmax - 1.0 / Tmin);
+        N Pred = (2.0 * dlog10(e.P) - log10(Pmin) - log10(Pmax)) / (log10(Pmax) - log10(Pmin));
+        N k = 0.0;
+        if (!scalar_forms) {
+            for (int jp = 0; jp < nP; ++jp)
+                for (int it = 0; it < nT; ++it)
+                    k = k + cf[it * nP + jp] * (cheb_T(it, Tred) * cheb_T(jp, Pred));
+        } else {
+            for (int it = 0; it < nT; ++it)
+                for (int jp = 0; jp < nP; ++jp)
+                    k = k + cf[it * nP + jp] * cheb_T(it, Tred) * cheb_T(jp, Pred);
+        }
+        return dexp10(k);
+    }
+    }
+    return N(0.0);
+}
+
+// _calcdkdCeff, src/Calculators/Rate.jl:232-262
+__device__ inline double dk_dCeff(const DevMech& m, int j, const KinEnv<double>& e, double Ceff) {
+    const double* a = m.kpar + m.koff[j];
+    int kt = m.ktype[j];
+    if (kt == RMSB_KIN_THIRDBODY) return arr_sca(a, e);
+    double k0 = arr_sca(a + 3, e), kinf = arr_sca(a, e);
+    double Pr = k0 * Ceff / kinf;
+    if (kt == RMSB_KIN_LINDEMANN || (a[8] == 0.0 && a[7] == 0.0)) return k0 / ((1.0 + Pr) * (1.0 + Pr));
+    const double* t = a + 6;
+    double T = e.T;
+    double Fcent = (1 - t[0]) * exp(-T / t[1]) + t[0] * exp(-T / t[2]);
+    if (t[3] != 0.0) Fcent += exp(-t[3] / T);
+    const double d = 0.14;
+    double lF = log10(Fcent);
+    double n = 0.75 - 1.27 * lF;
+    double c = -0.4 - 0.67 * lF;
+    double lPr = log10(Pr);
+    double x = (lPr + c) / (n - d * lPr);
+    double F = pow(10.0, lF / (1.0 + x * x));
+    double dFdCeff = -log(10.0) * F * lF / ((1.0 + x * x) * (1.0 + x * x)) * 2.0 * x * 0.4342944819032518 / Pr * k0 / kinf / (n - d * lPr) * (1.0 + d * x);
+    return k0 / ((1.0 + Pr) * (1.0 + Pr)) * F + kinf * Pr / (1.0 + Pr) * dFdCeff;
+}
+
+// Ceff = C + sum_i ns[i]*(eff_i-1)/V   (src/PhaseState.jl:53-58)
+template <class N>
+__device__ __forceinline__ N ceff_of(const DevMech& m, int j, N C, const double* ns, double V) {
+    int b = m.eff_ptr[j], en = m.eff_ptr[j + 1];
+    if (b == en) return C;
+    double acc = 0.0;
+    for (int k = b; k < en; ++k) acc += ns[m.eff_spc[k]] * m.eff_val[k];
+    return C + acc / V;
+}
+
+// mass-action net rate of reaction j: src/Reactor.jl:465-483
+template <class N>
+__device__ __forceinline__ N net_rate(const DevMech& m, int j, N kf, N kr, const double* cs) {
+    const int Nr = m.Nr;
+    N fR = kf * cs[m.rx[j]];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; fR = fR * cs[s]; }
+    N rR = kr * cs[m.rx[4 * Nr + j]];
+#pragma unroll
+    for (int k = 5; k < 8; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; rR = rR * cs[s]; }
+    return fR - rR;
+}
+
+// scalar getKc (src/PhaseState.jl:106-129, phi = 0) from absolute Gibbs energies G[]
+__device__ inline double kc_scalar(const DevMech& m, int j, const double* G, double T, double C0) {
+    const int Nr = m.Nr;
+    double acc = G[m.rx[j]];
+    int nre = 1;
+    for (int k = 1; k < 4; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; acc += G[s]; ++nre; }
+    double dG = 0.0 - acc;
+    acc = G[m.rx[4 * Nr + j]];
+    int npr = 1;
+    for (int k = 5; k < 8; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; acc += G[s]; ++npr; }
+    dG += acc;
+    return exp(-(dG) / (RMSB_R * T)) * pow(C0, (double)(npr - nre));
+}
+
+// getDiffusiveRate for 1 or 2 bodies (src/PhaseState.jl:87-93); >2-body form is out of scope
+__device__ inline double diffusive_rate(const DevMech& m, int j, int side, const double* diffs) {
+    const int Nr = m.Nr;
+    int s0 = m.rx[(side * 4) * Nr + j], s1 = m.rx[(side * 4 + 1) * Nr + j];
+    if (s1 < 0) return INFINITY;
+    return 4.0 * RMSB_PI * (diffs[s0] + diffs[s1]) * (m.radius[s0] + m.radius[s1]) * RMSB_NA;
+}
+
+struct DomainArgs {
+    int kind;           // RMSB_DOMAIN_*
+    int Ny;
+    const double* p;    // nullptr or per-reactor parameter row
+    const int* constspc;  // 1-based (reference convention)
+    int nconst;
+};
+
+struct RhsAux {   // by-products the Jacobian needs
+    double T, P, V, N, C, Cv, dotUsdn;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Constant-k domain setup (TP / TV / TAPhi ctors, src/Domain.jl:42-102,500-560,660-711):
+// Gs via the scalar thermo path, kfs/krevs once per reactor.  w.g <- absolute G, w.kf/w.kr <- k's.
+// `ns0` (in w.ns) / V are the initial amounts (only efficiency reactions look at them, and those are
+// re-evaluated on every RHS call for TP).
+// ------------------------------------------------------------------------------------------------
+__device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpWs& w, double T, double P, double V, int lane) {
+    const int Ns = m.Ns, Nr = m.Nr;
+    const double* p = d.p;
+    for (int s = lane; s < Ns; s += 32) w.g[s] = p ? p[s] : gibbs_scalar(m, s, T);
+    // diffusivities (Stokes, src/Calculators/Diffusion.jl:19) into w.us (free in constant-k domains)
+    if (m.difflim) {
+        double mu = 0.0;
+        if (m.visc_kind == RMSB_VISC_RIEDEL)
+            mu = exp(m.visc[0] + m.visc[1] / T + m.visc[2] * log(T) + m.visc[3] * pow(T, m.visc[4]));
+        else if (m.visc_kind == RMSB_VISC_CONSTANT)
+            mu = m.visc[0];
+        for (int s = lane; s < Ns; s += 32) {
+            double r = m.diff_r ? m.diff_r[s] : 0.0;
+            w.us[s] = (r > 0.0) ? RMSB_KB * T / (6 * RMSB_PI * mu * r) : INFINITY;
+        }
+    }
+    __syncwarp();
+    KinEnv<double> e;
+    e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+    double C0 = (m.phase_kind == RMSB_PHASE_SURFACE) ? m.sitedensity : 1.0e5 / (RMSB_R * T);
+    double logC0 = log(C0);
+    double N = 0.0;
+    for (int s = 0; s < Ns; ++s) N += w.ns[s];
+    double C = (d.kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (d.kind == RMSB_DOMAIN_CONSTANT_TV ? N / V : 0.0);
+    bool is_eff_dom = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
+    for (int j = lane; j < Nr; j += 32) {
+        double kf, kr;
+        bool eff = (m.eff_ptr[j + 1] > m.eff_ptr[j]);
+        if (!m.difflim) {
+            // getkfkrevs vector path: getkfs + getKcs (src/PhaseState.jl:226-233)
+            if (p && !(is_eff_dom && eff)) kf = p[Ns + j];
+            else {
+                double Ceff = ceff_of(m, j, C, w.ns, V);
+                kf = eval_kin(m, j, e, Ceff, false);
+            }
+            double ex = 0.0;
+            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex += m.kc_coef[k] * (w.g[m.kc_spc[k]] / (RMSB_R * T));
+            ex += m.nrp[j] * logC0;
+            kr = kf / exp(ex);
+        } else {
+            // getkfkrev per reaction (src/PhaseState.jl:184-223): scalar forms, scalar Kc, diffusion limits
+            if (p) kf = p[Ns + j];
+            else {
+                double Ceff = ceff_of(m, j, C, w.ns, V);
+                kf = eval_kin(m, j, e, Ceff, true);
+            }
+            double Kc = kc_scalar(m, j, w.g, T, C0);
+            kr = kf / Kc;
+            int nre = 0, npr = 0;
+            for (int k = 0; k < 4; ++k) { if (m.rx[k * Nr + j] >= 0) ++nre; if (m.rx[(k + 4) * Nr + j] >= 0) ++npr; }
+            const double* diffs = w.us;
+            if (nre == 1) {
+                if (npr > 1) {
+                    double krd = diffusive_rate(m, j, 1, diffs);
+                    kr = kr * krd / (kr + krd);
+                    kf = Kc * kr;
+                }
+            } else if (npr == 1) {
+                double kfd = diffusive_rate(m, j, 0, diffs);
+                kf = kf * kfd / (kf + kfd);
+                kr = kf / Kc;
+            } else if (npr == nre) {
+                double kfd = diffusive_rate(m, j, 0, diffs);
+                double krd = diffusive_rate(m, j, 1, diffs);
+                double kff = kf * kfd / (kf + kfd);
+                double krevr = kr * krd / (kr + krd);
+                double kfr = Kc * krevr;
+                if (kff > kfr) { kf = kfr; kr = krevr; }
+                else { kf = kff; kr = kf / Kc; }
+            }
+            kf *= m.fwd[j]; kr *= m.rev[j];   // inside getkfkrev (:220-221) ...
+        }
+        kf *= m.fwd[j]; kr *= m.rev[j];       // ... and again in getkfkrevs (:254-255)
+        w.kf[j] = kf; w.kr[j] = kr;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// dydtreactor! for one reactor (src/Reactor.jl:653-660).
+//   y   : distributed state (N = double or Dual2)
+//   dy  : distributed result
+//   store_k : also leave kf/kr/us/cp (values) in the workspace for the Jacobian
+// For constant-k domains setup_constk() must have filled w.g / w.kf / w.kr.
+// ------------------------------------------------------------------------------------------------
+template <class N, int R>
+__device__ inline void rhs_warp(const DevMech& m, const DomainArgs& d, WarpWs& w, const double* cond,
+                                const N (&y)[R], N (&dy)[R], int lane, bool store_k, RhsAux* aux) {
+    const int Ns = m.Ns, Nr = m.Nr;
+    const double* p = d.p;
+    typedef SmemNum<N> SM;
+    // species amounts to smem
+#pragma unroll
+    for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) w.ns[s] = val(y[r]); }
+
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
+        N T = bcast<N, R>(y, Ns), P = bcast<N, R>(y, Ns + 1);
+        const double V = cond[0];
+        N RT = RMSB_R * T;
+        N Nt = P * V / RT;            // N = P*V/(R*T)  (Domain.jl:1068)
+        N C = Nt / V;
+        TPow<N> tp(T);
+        N us[R];
+        N cpns = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int s = r * 32 + lane;
+            us[r] = 0.0;
+            if (s < Ns) {
+                N cp, h, sr;
+                nasa_hscp(m, s, tp, val(T), cp, h, sr);
+                if (p) h = h + p[s] / RT;                   // Domain.jl:1100
+                N G = (h - sr) * RT;                        // :1101
+                us[r] = (h - 1.0) * RT;                     // :1102
+                SM::st(w.g, s, G / RT);                     // getKcs uses Gs./(R*T) (PhaseState.jl:166)
+                w.cs[s] = val(y[r]) / V;
+                cpns = cpns + cp * y[r];
+                if (store_k) { w.us[s] = val(us[r]); w.cp[s] = val(cp); }
+            }
+        }
+        N Cv = warp_sum(cpns);                              // dot(cpdivR, ns)
+        Cv = Cv * (RMSB_R / Nt);
+        Cv = Cv - RMSB_R;
+        __syncwarp();
+        KinEnv<N> e;
+        e.T = T; e.logT = tp.T6; e.RT = RT; e.invRT = 1.0 / RT; e.P = P;
+        N logC0 = dlog(1.0e5 / RT);
+        for (int j = lane; j < Nr; j += 32) {
+            N Ceff = ceff_of(m, j, C, w.ns, V);
+            N kf = eval_kin(m, j, e, Ceff, false);
+            N ex = 0.0;
+            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex = ex + m.kc_coef[k] * SM::ld(w.g, m.kc_spc[k]);
+            ex = ex + m.nrp[j] * logC0;
+            N kr = kf / dexp(ex);
+            kf = kf * m.fwd[j]; kr = kr * m.rev[j];
+            if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }   // Domain.jl:1112
+            if (store_k) { w.kf[j] = val(kf); w.kr[j] = val(kr); }
+            SM::st(w.q, j, net_rate(m, j, kf, kr, w.cs));
+        }
+        __syncwarp();
+        N usum = 0.0, nsum = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int s = r * 32 + lane;
+            dy[r] = 0.0;
+            if (s < Ns) {
+                N acc = 0.0;
+                for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
+                    int jr = m.sr_rxn[k];
+                    N qv = SM::ld(w.q, jr & 0x7fffffff);
+                    acc = (jr < 0) ? acc - qv : acc + qv;
+                }
+                N dn = acc * V;                              // dydt .*= V
+                dy[r] = dn;
+                usum = usum + us[r] * dn;
+                nsum = nsum + dn;
+            }
+        }
+        N dotU = warp_sum(usum), sumn = warp_sum(nsum);
+        N dT = -dotU / (Nt * Cv);                            // Domain.jl:1902
+        N dP = sumn * RMSB_R * T / V + P / T * dT;           // :1903
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = r * 32 + lane;
+            if (i == Ns) dy[r] = dT;
+            if (i == Ns + 1) dy[r] = dP;
+        }
+        if (aux) { aux->T = val(T); aux->P = val(P); aux->V = V; aux->N = val(Nt); aux->C = val(C); aux->Cv = val(Cv); aux->dotUsdn = val(dotU); }
+    } else {
+        // constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns)
+        double T = cond[0];
+        double P, V;
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = cond[1]; V = val(bcast<N, R>(y, Ns)); }
+        else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = cond[1]; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) w.cs[s] = val(y[r]) / V; }
+        __syncwarp();
+        double Nt, C;
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { Nt = P * V / (RMSB_R * T); C = Nt / V; }
+        else {
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) a += val(y[r]); }
+            Nt = warp_sum(a); C = Nt / V;
+        }
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP && m.n_effrxn > 0) {
+            // efficiency reactions are re-evaluated each call through getkfkrev (Domain.jl:924,943-945)
+            KinEnv<double> e;
+            e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+            double C0 = 1.0e5 / (RMSB_R * T);
+            for (int q = lane; q < m.n_effrxn; q += 32) {
+                int j = m.effrxn[q];
+                double Ceff = ceff_of(m, j, C, w.ns, V);
+                double kf = eval_kin(m, j, e, Ceff, false);
+                if (d.p) kf = kf * d.p[Ns + j];
+                double Kc = kc_scalar(m, j, w.g, T, C0);
+                double kr = kf / Kc;
+                w.kf[j] = kf * m.fwd[j]; w.kr[j] = kr * m.rev[j];
+            }
+            __syncwarp();
+        }
+        for (int j = lane; j < Nr; j += 32) w.q[j] = net_rate<double>(m, j, w.kf[j], w.kr[j], w.cs);
+        __syncwarp();
+        double nsum = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int s = r * 32 + lane;
+            dy[r] = 0.0;
+            if (s < Ns) {
+                double acc = 0.0;
+                for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
+                    int jr = m.sr_rxn[k];
+                    double qv = w.q[jr & 0x7fffffff];
+                    acc = (jr < 0) ? acc - qv : acc + qv;
+                }
+                double dn = acc * V;
+                dy[r] = dn;
+                nsum += dn;
+            }
+        }
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
+            double dV = warp_sum(nsum) * RMSB_R * T / P;     // Domain.jl:1864
+#pragma unroll
+            for (int r = 0; r < R; ++r) if (r * 32 + lane == Ns) dy[r] = dV;
+        }
+        if (aux) { aux->T = T; aux->P = P; aux->V = V; aux->N = Nt; aux->C = C; aux->Cv = 0.0; aux->dotUsdn = 0.0; }
+    }
+    // constant species (Domain.jl:1840-1842,1865-1867,1904-1906)
+    for (int k = 0; k < d.nconst; ++k) {
+        int s = d.constspc[k] - 1;  // API indices are 1-based
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (r * 32 + lane == s) dy[r] = 0.0;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// jacobiany! for one reactor: dense column-major Ny x LD matrix in w.J.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__device__ inline void jac_warp(const DevMech& m, const DomainArgs& d, WarpWs& w, const double* cond,
+                                const double (&y)[R], int lane) {
+    const int Ns = m.Ns, Nr = m.Nr, Ny = d.Ny, LD = w.LD;
+    double dy[R];
+    RhsAux ax;
+    rhs_warp<double, R>(m, d, w, cond, y, dy, lane, true, &ax);
+    double dn[R];   // V*rates before constant-species zeroing (jacobiany! recomputes dydt, Domain.jl:2301-2303)
+#pragma unroll
+    for (int r = 0; r < R; ++r) dn[r] = dy[r];
+    for (int i = lane; i < Ny * LD; i += 32) w.J[i] = 0.0;
+    // (1) derivative terms  m*k*prod(other cs)   (src/Reactor.jl:899-1366)
+    for (int t = lane; t < m.n_dt; t += 32) {
+        int jr = m.dt_rxn[t];
+        int j = jr & 0x3fffffff;
+        double v = (double)m.dt_mult[t] * ((jr >> 30) ? w.kr[j] : w.kf[j]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { int s = m.dt_oth[3 * t + k]; if (s < 0) break; v *= w.cs[s]; }
+        w.dterm[t] = v;
+    }
+    __syncwarp();
+    // (2) gather into entries, in the reference's accumulation order
+    for (int e = lane; e < m.n_je; e += 32) {
+        double acc = 0.0;
+        for (int k = m.je_ptr[e]; k < m.je_ptr[e + 1]; ++k) {
+            int ti = m.jt_idx[k];
+            double v = w.dterm[ti & 0x7fffffff];
+            acc = (ti < 0) ? acc - v : acc + v;
+        }
+        w.J[m.je_row[e] + m.je_col[e] * LD] = acc;
+    }
+    __syncwarp();
+    const bool hasV = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
+    // (3) V column of the ns block (src/Reactor.jl:1368-1413) -- lanes over species rows
+    if (hasV) {
+        for (int s = lane; s < Ns; s += 32) {
+            double acc = 0.0;
+            for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
+                int jr = m.sr_rxn[k];
+                int j = jr & 0x7fffffff;
+                // forward / reverse -(order-1)*k*prod(cs)
+                double df = 0.0, dr = 0.0;
+                int nre = 0, npr = 0;
+                double pf = w.kf[j], pr = w.kr[j];
+                for (int q = 0; q < 4; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pf *= w.cs[sp]; ++nre; }
+                for (int q = 4; q < 8; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pr *= w.cs[sp]; ++npr; }
+                if (nre > 1) df = -(double)(nre - 1) * pf;
+                if (npr > 1) dr = -(double)(npr - 1) * pr;
+                if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
+            }
+            w.J[s + Ns * LD] = acc;
+        }
+        __syncwarp();
+    }
+    // (4) efficiency reactions: dk/dn_i = dk/dCeff*(eff_i-1)/V (+ dk/dV for V-state domains)
+    //     (src/Domain.jl:2151-2167, src/Reactor.jl:1418-1467).  One reaction at a time (uniform loop).
+    if (m.n_effrxn > 0 && d.kind != RMSB_DOMAIN_CONSTANT_TAPHI) {
+        KinEnv<double> e;
+        e.T = ax.T; e.logT = log(ax.T); e.RT = RMSB_R * ax.T; e.invRT = 1.0 / (RMSB_R * ax.T); e.P = ax.P;
+        for (int q = 0; q < m.n_effrxn; ++q) {
+            int j = m.effrxn[q];
+            double Kc = w.kf[j] / w.kr[j];
+            double acc = 0.0;
+            for (int k = m.eff_ptr[j]; k < m.eff_ptr[j + 1]; ++k) acc += w.cs[m.eff_spc[k]] * m.eff_val[k];
+            double Ceff = ax.C + acc;
+            double dkdC = dk_dCeff(m, j, e, Ceff);
+            double pf = ax.V, pr = ax.V;   // prod(cs)*V per side
+            {
+                double a = 1.0, b = 1.0;
+                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; a *= w.cs[sp]; }
+                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; b *= w.cs[sp]; }
+                pf = a * ax.V; pr = b * ax.V;
+            }
+            int ne = m.eff_ptr[j + 1] - m.eff_ptr[j];
+            int ncol = ne + (hasV ? 1 : 0);
+            for (int c = lane; c < ncol; c += 32) {
+                int col; double dkf;
+                if (c < ne) { col = m.eff_spc[m.eff_ptr[j] + c]; dkf = dkdC * (m.eff_val[m.eff_ptr[j] + c] / ax.V); }
+                else { col = Ns; dkf = dkdC * (ax.C - Ceff) / ax.V; }
+                double dkr = dkf / Kc;
+                double dvf = dkf * pf, dvr = dkr * pr;
+                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] -= dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] += dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] -= dvr; }
+                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] += dvr; }
+            }
+            __syncwarp();
+        }
+    }
+    // (5) thermodynamic-variable rows
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
+        double f = RMSB_R * ax.T / ax.P;
+        for (int c = lane; c <= Ns; c += 32) {           // Domain.jl:2211-2214
+            double a = 0.0;
+            for (int i = 0; i < Ns; ++i) a += w.J[i + c * LD];
+            w.J[Ns + c * LD] = a * RMSB_R * ax.T / ax.P;
+        }
+        (void)f;
+    } else if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
+        for (int c = lane; c < Ns; c += 32) {            // Domain.jl:2312-2316
+            double dCv = w.cp[c] * RMSB_R / ax.N;
+            double a = 0.0, sm = 0.0;
+            for (int i = 0; i < Ns; ++i) { double v = w.J[i + c * LD]; a += w.us[i] * v; sm += v; }
+            double jt = -a / (ax.N * ax.Cv) + ax.dotUsdn / (ax.N * ax.Cv * ax.Cv) * dCv;
+            w.J[Ns + c * LD] = jt;
+            w.J[Ns + 1 + c * LD] = sm * RMSB_R * ax.T / ax.V + ax.P / ax.T * jt;
+        }
+    }
+    __syncwarp();
+    // (6) constant species rows (Domain.jl:2216-2218,2318-2320,3053-3055)
+    for (int k = 0; k < d.nconst; ++k) {
+        int s = d.constspc[k] - 1;  // API indices are 1-based
+        for (int c = lane; c < Ny; c += 32) w.J[s + c * LD] = 0.0;
+    }
+    __syncwarp();
+    // (7) ConstantV: T and P columns = derivative of the complete RHS (src/Reactor.jl:1469-1477)
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
+        Dual2 yd[R], dyd[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = r * 32 + lane;
+            yd[r] = Dual2(y[r], i == Ns ? 1.0 : 0.0, i == Ns + 1 ? 1.0 : 0.0);
+        }
+        rhs_warp<Dual2, R>(m, d, w, cond, yd, dyd, lane, false, nullptr);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = r * 32 + lane;
+            if (i < Ny) { w.J[i + Ns * LD] = dyd[r].a; w.J[i + (Ns + 1) * LD] = dyd[r].b; }
+        }
+        __syncwarp();
+    }
+    (void)dn;
+}
+
+}  // namespace rmsb

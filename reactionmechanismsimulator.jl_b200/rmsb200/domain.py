@@ -1,0 +1,213 @@
+"""Domains: the reference's ConstantVDomain / ConstantTPDomain / ConstantTVDomain / ConstantTAPhiDomain
+constructors (src/Domain.jl:42-102,120-170,500-560,660-711) returning ``(domain, y0, p)``, plus array
+constructors that build a whole ensemble of conditions at once (the reference parses one Dict per
+reactor; an ensemble of 100k conditions is built here from arrays without a Python loop).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .mechanism import R
+from .phase import Phase
+
+
+class Domain:
+    """One condition (n = 1) or an ensemble (n > 1) of reactors of the same kind sharing a phase."""
+
+    def __init__(self, kind: int, phase: Phase, y0: np.ndarray, cond: np.ndarray, constantspecies: Sequence[str] = ()):
+        self.kind, self.phase = kind, phase
+        self.y0 = np.ascontiguousarray(np.atleast_2d(y0), dtype=float)
+        self.cond = np.ascontiguousarray(np.atleast_2d(cond), dtype=float)
+        self.n = self.y0.shape[0]
+        Ns, Nr = phase.Ns, phase.Nr
+        self.Ny = self.y0.shape[1]
+        self.constantspeciesinds = np.array([phase.spcdict[k] for k in constantspecies], dtype=np.int32)
+        self.parameterindexes = [1, Ns + Nr]
+        self.efficiencyinds = list(phase.efficiencyinds)
+        if kind == L.DOMAIN_CONSTANT_V:
+            self.indexes = [1, Ns, Ns + 1, Ns + 2]
+            self.thermovariabledict = {"T": Ns + 1, "P": Ns + 2}
+        elif kind == L.DOMAIN_CONSTANT_TP:
+            self.indexes = [1, Ns, Ns + 1]
+            self.thermovariabledict = {"V": Ns + 1}
+        else:
+            self.indexes = [1, Ns]
+            self.thermovariabledict = {}
+        self.p: Optional[np.ndarray] = None
+        self._p_default: Optional[np.ndarray] = None
+
+    # -- names mirrored from the reference structs ---------------------------------------------
+    @property
+    def T(self):
+        return None if self.kind == L.DOMAIN_CONSTANT_V else _scalar(self.cond[:, 0])
+
+    @property
+    def P(self):
+        return _scalar(self.cond[:, 1]) if self.kind == L.DOMAIN_CONSTANT_TP else None
+
+    @property
+    def V(self):
+        if self.kind == L.DOMAIN_CONSTANT_V:
+            return _scalar(self.cond[:, 0])
+        return _scalar(self.cond[:, 1]) if self.kind == L.DOMAIN_CONSTANT_TV else None
+
+    @property
+    def A(self):
+        return _scalar(self.cond[:, 1]) if self.kind == L.DOMAIN_CONSTANT_TAPHI else None
+
+    def _p_for_device(self, p):
+        """None when p is the constructor default (the device then evaluates its own tables, the
+        'nothermochg && nokfchg' branch of calcthermo, src/Domain.jl:941-946,1532-1533)."""
+        if p is None:
+            return None, 0
+        p = np.ascontiguousarray(p, dtype=float)
+        if self._p_default is not None and p.shape == self._p_default.shape and np.array_equal(p, self._p_default):
+            return None, 0
+        Np = self.phase.Ns + self.phase.Nr
+        if p.ndim == 1:
+            assert p.size == Np
+            return p, 0
+        assert p.shape == (self.n, Np)
+        return p, Np
+
+    # -- batched hot-path calls ------------------------------------------------------------------
+    def dydt(self, y=None, p=None):
+        """dydtreactor! for every reactor of the ensemble (src/Reactor.jl:653-660)."""
+        y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
+        pp, ps = self._p_for_device(p)
+        out = np.empty_like(y)
+        cs = self.constantspeciesinds
+        L.check(L.lib().rmsb_dydt_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
+        return out
+
+    def jacobiany(self, y=None, p=None):
+        """jacobiany! for every reactor -> [n][Ny][Ny] with J[r, eqn, var] (src/Domain.jl:2204-3091)."""
+        y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
+        pp, ps = self._p_for_device(p)
+        out = np.empty((y.shape[0], self.Ny * self.Ny))
+        cs = self.constantspeciesinds
+        L.check(L.lib().rmsb_jac_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+                                       L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
+        return out.reshape(y.shape[0], self.Ny, self.Ny).transpose(0, 2, 1)   # column-major -> [eqn, var]
+
+    def rates(self, y=None, p=None):
+        """(kfs, krevs) as calcthermo returns them -> two [n][Nr] arrays."""
+        y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
+        pp, ps = self._p_for_device(p)
+        kf = np.empty((y.shape[0], self.phase.Nr))
+        kr = np.empty_like(kf)
+        L.check(L.lib().rmsb_rates_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+                                         L.ptr(kf), L.ptr(kr)))
+        return kf, kr
+
+
+def _scalar(a):
+    return float(a[0]) if a.size == 1 else a
+
+
+def _parse(phase: Phase, initialconds: Dict[str, float], special: Sequence[str]):
+    vals = {k: 0.0 for k in special}
+    ns = np.zeros(phase.Ns)
+    for key, val in initialconds.items():
+        if key in vals:
+            vals[key] = float(val)
+        else:
+            assert key in phase.spcdict, f"{key} not found in species list: {phase.names}"
+            ns[phase.spcdict[key] - 1] = float(val)
+    return vals, ns
+
+
+def _finish_constk(dom: Domain, efficiency_to_one: bool):
+    """p = [Gs; kfs] of the constant-k domains (src/Domain.jl:88-93,549-551,700-702)."""
+    ph = dom.phase
+    Gs = ph.gibbs(dom.cond[:, 0])
+    kf, kr = dom.rates()
+    dom.kfs, dom.krevs, dom.Gs = kf, kr, Gs
+    kfp = kf.copy()
+    if efficiency_to_one:
+        for ind in ph.efficiencyinds:
+            kfp[:, ind - 1] = 1.0
+    p = np.concatenate([Gs, kfp], axis=1)
+    dom.p = p[0] if dom.n == 1 else p
+    dom._p_default = dom.p.copy()
+
+
+# ---- reference-style constructors: one condition from a Dict ------------------------------------
+def ConstantVDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """src/Domain.jl:120-170 -> (domain, y0, p); y0 = [ns; T; P], p = [zeros(Ns); ones(Nr)]."""
+    assert phase.kind == L.PHASE_GAS
+    v, ns = _parse(phase, initialconds, ("T", "P", "V"))
+    T, P, V = v["T"], v["P"], v["V"]
+    assert V != 0.0 or (T != 0.0 and P != 0.0)
+    N = ns.sum()
+    if V == 0.0:
+        V = N * R * T / P
+    elif T == 0.0:
+        T = P * V / (R * N)
+    elif P == 0.0:
+        P = N * R * T / V
+    else:
+        raise ValueError("ConstantVDomain overspecified with T,P and V")
+    dom = Domain(L.DOMAIN_CONSTANT_V, phase, np.concatenate([ns, [T, P]]), np.array([V]), constantspecies)
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, dom.y0[0].copy(), dom.p
+
+
+def ConstantTPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """src/Domain.jl:42-102 -> (domain, y0, p); y0 = [ns; V], p = [Gs; kfs (efficiency reactions -> 1.0)]."""
+    v, ns = _parse(phase, initialconds, ("T", "P"))
+    T, P = v["T"], v["P"]
+    assert T != 0.0 and P != 0.0
+    V = ns.sum() * R * T / P
+    dom = Domain(L.DOMAIN_CONSTANT_TP, phase, np.concatenate([ns, [V]]), np.array([T, P]), constantspecies)
+    _finish_constk(dom, True)
+    return dom, dom.y0[0].copy(), dom.p
+
+
+def ConstantTVDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """src/Domain.jl:500-560 -> (domain, y0, p); y0 = ns."""
+    assert "P" not in initialconds, "ConstantTVDomain cannot specify P"
+    v, ns = _parse(phase, initialconds, ("T", "V", "Phi"))
+    assert v["T"] != 0.0 and v["V"] != 0.0 and v["Phi"] == 0.0
+    dom = Domain(L.DOMAIN_CONSTANT_TV, phase, ns, np.array([v["T"], v["V"]]), constantspecies)
+    _finish_constk(dom, False)
+    return dom, dom.y0[0].copy(), dom.p
+
+
+def ConstantTAPhiDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """src/Domain.jl:660-711 -> (domain, y0, p); y0 = ns, 'V' is the area A (phi = 0 only)."""
+    v, ns = _parse(phase, initialconds, ("T", "A", "Phi"))
+    assert v["T"] != 0.0 and v["A"] != 0.0 and v["Phi"] == 0.0
+    dom = Domain(L.DOMAIN_CONSTANT_TAPHI, phase, ns, np.array([v["T"], v["A"]]), constantspecies)
+    _finish_constk(dom, False)
+    return dom, dom.y0[0].copy(), dom.p
+
+
+# ---- ensemble constructors: arrays of conditions -------------------------------------------------
+def ConstantVEnsemble(phase: Phase, T, P, ns, constantspecies: Sequence[str] = ()) -> Domain:
+    """n ConstantV reactors: T[n], P[n] initial temperature/pressure, ns[n][Ns] initial moles;
+    V = N*R*T/P per reactor as in src/Domain.jl:143-145."""
+    T, P = np.asarray(T, dtype=float), np.asarray(P, dtype=float)
+    ns = np.atleast_2d(np.asarray(ns, dtype=float))
+    V = ns.sum(axis=1) * R * T / P
+    dom = Domain(L.DOMAIN_CONSTANT_V, phase, np.concatenate([ns, T[:, None], P[:, None]], axis=1), V[:, None], constantspecies)
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom
+
+
+def ConstantTPEnsemble(phase: Phase, T, P, ns, constantspecies: Sequence[str] = ()) -> Domain:
+    T, P = np.asarray(T, dtype=float), np.asarray(P, dtype=float)
+    ns = np.atleast_2d(np.asarray(ns, dtype=float))
+    V = ns.sum(axis=1) * R * T / P
+    return Domain(L.DOMAIN_CONSTANT_TP, phase, np.concatenate([ns, V[:, None]], axis=1), np.stack([T, P], axis=1), constantspecies)
+
+
+def ConstantTVEnsemble(phase: Phase, T, V, ns, constantspecies: Sequence[str] = ()) -> Domain:
+    T, V = np.asarray(T, dtype=float), np.asarray(V, dtype=float)
+    return Domain(L.DOMAIN_CONSTANT_TV, phase, np.atleast_2d(np.asarray(ns, dtype=float)), np.stack([T, V], axis=1), constantspecies)

@@ -1,0 +1,119 @@
+"""Reactor + solve: the reference's `Reactor(domain, y0, tspan; p)` / `solve(react.ode, CVODE_BDF();
+abstol, reltol)` surface (src/Reactor.jl:30-98; call sites src/TestReactors.jl:22,197,305) for one
+reactor or an ensemble.  `solve` runs the whole ensemble in ONE call to `rmsb_solve_batch`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .domain import Domain
+
+
+class RMSB200:
+    """Algorithm tag standing where CVODE_BDF() stands in the reference (`react.recommendedsolver`)."""
+
+    def __init__(self, max_steps=500000, max_order=5, first_step=0.0, warps_per_block=0):
+        self.max_steps, self.max_order, self.first_step, self.warps_per_block = max_steps, max_order, first_step, warps_per_block
+
+
+class Reactor:
+    """Reactor(domain, y0, tspan; p) (src/Reactor.jl:13-28,30-98).  `domain` may hold an ensemble."""
+
+    def __init__(self, domain: Domain, y0=None, tspan: Tuple[float, float] = (0.0, 1.0), interfaces: Sequence = (), p=None,
+                 forwardsensitivities: bool = False):
+        if interfaces:
+            raise NotImplementedError("interfaces are outside the accelerated hot path in this round (DESIGN.md)")
+        if forwardsensitivities:
+            raise NotImplementedError("forward sensitivities: SURVEY section 8 row a19, not built in this round")
+        self.domain = domain
+        self.y0 = domain.y0 if y0 is None else np.ascontiguousarray(np.atleast_2d(y0), dtype=float)
+        assert tspan[0] == 0.0, "integration starts at t = 0"
+        self.tspan = (float(tspan[0]), tspan[1])
+        self.p = domain.p if p is None else p
+        self.interfaces = list(interfaces)
+        self.recommendedsolver = RMSB200()
+        self.forwardsensitivities = False
+
+    @property
+    def ode(self):          # `solve(react.ode, ...)` reads naturally
+        return self
+
+
+class Solution:
+    """What comes back from `solve`: the role of the ODESolution the reference's Simulation consumes
+    (src/Simulation.jl:25-39): saved times `t`, states `u[r, k, :]`, final state, status and per-reactor
+    integrator statistics; `sol(t)` interpolates (cubic Hermite on the saved points, like the
+    Sundials.jl solution object, when derivatives were requested; linear otherwise)."""
+
+    def __init__(self, reactor, t, u, yend, idt, status, stats, t_end):
+        self.reactor, self.t, self.u, self.yend = reactor, t, u, yend
+        self.idt, self.status, self.stats, self.t_end = idt, status, stats, t_end
+        self._du = None
+
+    @property
+    def retcode(self):
+        return ["Success" if s == L.SOLVE_OK else {1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}[int(s)] for s in self.status]
+
+    def derivatives(self):
+        """du/dt at the saved points (one batched dydt call)."""
+        if self._du is None:
+            dom = self.reactor.domain
+            n, k, Ny = self.u.shape
+            du = np.empty_like(self.u)
+            for j in range(k):
+                yj = np.ascontiguousarray(self.u[:, j, :])
+                ok = np.isfinite(yj).all(axis=1)
+                d = np.full_like(yj, np.nan)
+                if ok.all():
+                    d = dom.dydt(yj, self.reactor.p)
+                du[:, j, :] = d
+            self._du = du
+        return self._du
+
+    def __call__(self, tq, r: int = 0, hermite: bool = True):
+        """State of reactor r at time tq."""
+        t = self.t
+        if tq <= t[0]:
+            return self.u[r, 0].copy()
+        if tq >= t[-1]:
+            return self.u[r, -1].copy()
+        k = int(np.searchsorted(t, tq, side="right")) - 1
+        h = t[k + 1] - t[k]
+        s = (tq - t[k]) / h
+        y0, y1 = self.u[r, k], self.u[r, k + 1]
+        if not hermite:
+            return (1 - s) * y0 + s * y1
+        du = self.derivatives()
+        d0, d1 = du[r, k], du[r, k + 1]
+        h00, h10 = 2 * s ** 3 - 3 * s ** 2 + 1, s ** 3 - 2 * s ** 2 + s
+        h01, h11 = -2 * s ** 3 + 3 * s ** 2, s ** 3 - s ** 2
+        return h00 * y0 + h10 * h * d0 + h01 * y1 + h11 * h * d1
+
+
+def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6, reltol: float = 1e-3,
+          saveat: Optional[Sequence[float]] = None, idt_index: int = -1, t_end=None) -> Solution:
+    """solve(react.ode, alg; abstol, reltol[, saveat]) -- default tolerances are SciML's (1e-6, 1e-3)."""
+    alg = alg or react.recommendedsolver
+    dom = react.domain
+    y0 = react.y0
+    n, Ny = y0.shape
+    te = react.tspan[1] if t_end is None else t_end
+    te = np.ascontiguousarray(np.broadcast_to(np.asarray(te, dtype=float), (n,)))
+    tsave = None if saveat is None else np.ascontiguousarray(np.asarray(saveat, dtype=float))
+    nsave = 0 if tsave is None else tsave.size
+    ysave = np.empty((n, nsave, Ny)) if nsave else None
+    yend = np.empty((n, Ny))
+    idt = np.empty(n)
+    status = np.empty(n, dtype=np.int32)
+    stats = np.zeros(n, dtype=L.STATS_DTYPE)
+    pp, ps = dom._p_for_device(react.p)
+    cs = dom.constantspeciesinds
+    opts = L.SolveOpts(C.sizeof(L.SolveOpts), alg.max_steps, alg.max_order, idt_index, alg.first_step, alg.warps_per_block, 0)
+    L.check(L.lib().rmsb_solve_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                     L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                     L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
+    return Solution(react, tsave, ysave, yend, idt, status, stats, te)
