@@ -70,12 +70,13 @@ class Simulation:
         return c if name is None else c[self.spcindex(name)]
 
     def rates(self, t):
-        """Net rate of every reaction at time t (getrates, src/Reactor.jl:435-462; src/Simulation.jl:763-778)."""
+        """rates(sim, t): getrate(rxn, cs, kfs, krevs) * V for every reaction, mol/s (src/Simulation.jl:763-767)."""
         d = self.domain
         y = self.y(t)[None, :]
         sub = _single(d, self.r)
         kf, kr = sub.rates(y, self.p)
-        cs = y[0, :d.phase.Ns] / self._TPV(y[0])[2]
+        V = self._TPV(y[0])[2]
+        cs = y[0, :d.phase.Ns] / V
         ra = d.phase.rxnarray
         out = np.zeros(d.phase.Nr)
         for j in range(d.phase.Nr):
@@ -85,11 +86,11 @@ class Simulation:
                     f *= cs[ra[j, k] - 1]
                 if ra[j, 4 + k] > 0:
                     b *= cs[ra[j, 4 + k] - 1]
-            out[j] = f - b
+            out[j] = (f - b) * V
         return out
 
     def rops(self, name, t):
-        """Rate of production of species `name` by every reaction (src/Simulation.jl:357-373), mol/(m^3 s)."""
+        """rops(sim, name, t): (#product - #reactant occurrences) * rate * V per reaction (src/Simulation.jl:357-373)."""
         d = self.domain
         rts = self.rates(t)
         s = self.spcindex(name) + 1

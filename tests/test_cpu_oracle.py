@@ -1,0 +1,66 @@
+"""The C++ CPU port (oracle/cpu/rms_cpu.cpp: fast checker + CPU baseline) against the NumPy oracle's committed
+vectors and against scipy.integrate.BDF, the independent implementation of the same NDF/BDF algorithm."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import cpu_oracle as co
+from oracle import integrate as oi
+
+G = np.load(cases.ROOT / "tests" / "golden" / "parity_vectors.npz")
+
+
+@pytest.mark.parametrize("case", list(cases.CASES))
+def test_cpp_rhs_and_jacobian_match_numpy_oracle(case):
+    dom = cases.oracle_domain(case)
+    cm = co.CpuMech(dom.phase)
+    ys = G[f"{case}/y"]
+    p = dom.p if dom.kind == "ConstantV" else None
+    f = cm.dydt(dom.kind, ys, dom.cond, p, dom.constantspeciesinds)
+    J = cm.jac(dom.kind, ys, dom.cond, p, dom.constantspeciesinds)
+    for k in range(len(ys)):
+        assert cases.err_dydt(f[k], G[f"{case}/f"][k]) < 1e-12
+        assert cases.err_jac(J[k], G[f"{case}/J"][k]) < 1e-12
+    if dom.kind == "ConstantV":
+        fp = cm.dydt(dom.kind, ys, dom.cond, G[f"{case}/p"], dom.constantspeciesinds)
+        for k in range(len(ys)):
+            assert cases.err_dydt(fp[k], G[f"{case}/f_p"][k]) < 1e-12
+
+
+def test_cpp_bdf_tracks_scipy_bdf():
+    """Same algorithm, independent code: step / Jacobian / LU counts within 15 % and the same solution."""
+    dom = cases.oracle_domain("superminimal_V")
+    cm = co.CpuMech(dom.phase)
+    r = cm.solve("ConstantV", dom.y0, dom.cond, 0.101, 1e-6, 1e-16, tsave=G["superminimal_V/tq"])
+    s = oi.solve(dom, (0, 0.101), p=dom.p, rtol=1e-6, atol=1e-16)
+    st = r["stats"][0]
+    assert r["status"][0] == 0
+    assert abs(st["n_steps"] - (s.t.size - 1)) <= 0.15 * (s.t.size - 1)
+    assert abs(st["n_lu"] - s.nlu) <= 0.15 * s.nlu
+    assert abs(st["n_rhs"] - s.nfev) <= 0.15 * s.nfev
+    yq = G["superminimal_V/yq"]
+    big = np.abs(yq) > 1e-9
+    assert np.max(np.abs(r["ysave"][0] - yq)[big] / np.abs(yq)[big]) < 5e-3      # loose tolerance run vs tight oracle
+
+
+def test_cpp_bdf_tight_tolerance_trajectories():
+    """C1 / C2 at rtol 1e-10 against the NumPy-oracle trajectories (golden points of src/TestReactors.jl:193-213,301-310)."""
+    for case, kind, tend in (("superminimal_V", "ConstantV", 0.101), ("superminimal_TP", "ConstantTP", 150.11094)):
+        dom = cases.oracle_domain(case)
+        cm = co.CpuMech(dom.phase)
+        r = cm.solve(kind, dom.y0, dom.cond, tend, 1e-10, 1e-20, tsave=G[f"{case}/tq"])
+        yq = G[f"{case}/yq"]
+        big = np.abs(yq) > 1e-12 * np.max(np.abs(yq[:, :12]))
+        assert r["status"][0] == 0
+        assert np.max(np.abs(r["ysave"][0] - yq)[big] / np.abs(yq)[big]) < 1e-6
+    assert abs(r["ysave"][0][1, dom.phase.names.index("H2")] / (dom.P * r["ysave"][0][1, -1] / (8.314 * dom.T)) - 0.412883111) < 1e-4 * 0.41
+
+
+def test_cpp_idt_golden_grid():
+    dom = cases.oracle_domain("superminimal_V")
+    cm = co.CpuMech(dom.phase)
+    ts = np.exp(np.linspace(np.log(1e-15), np.log(0.1), 10000))
+    r = cm.solve("ConstantV", dom.y0, dom.cond, 0.101, 1e-8, 1e-20, tsave=ts)
+    idt = ts[np.argmax(np.diff(r["ysave"][0][:, 12]))]
+    assert idt == pytest.approx(0.038384723436228063, rel=1e-5)                 # src/TestReactors.jl:310
+    assert r["idt"][0] == pytest.approx(idt, rel=4e-3)                          # continuous definition, within one grid cell

@@ -1,0 +1,116 @@
+"""Host-side logic of the product (parser, flattening, descriptor packing, C-ABI surface) -- CPU only, no
+compute calls.  The product's flattening is compared with the oracle's independent one."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import rmsb200 as rb
+from oracle import cpu_oracle as co
+from oracle import rms_oracle as ro
+from rmsb200 import _lib as L
+from rmsb200 import phase as ph
+
+
+def test_library_exports_every_header_symbol():
+    header = (cases.ROOT / "include" / "rmsb200.h").read_text()
+    declared = set(re.findall(r"\b(rmsb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"librmsb200.so does not export {name}"
+    assert set(L.EXPORTS) == declared
+    assert lib.rmsb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(L.Stats) == 40 and C.sizeof(L.SolveOpts) == 32
+    assert C.sizeof(L.MechDesc) == C.sizeof(co.Desc)
+
+
+def test_no_gpu_fails_loudly():
+    lib = L.lib()
+    if lib.rmsb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    d = rb.readinput(cases.fixture("superminimal"))
+    ig = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"])
+    with pytest.raises(rb.RMSBError, match="no CUDA device"):
+        _ = ig.handle
+    assert lib.rmsb_fp64_peak_tflops(0, 16) < 0
+
+
+@pytest.mark.parametrize("fx,key", [("superminimal", "phase"), ("ethane", "phase"), ("propane", "phase"), ("liquid_phase", "phase"),
+                                   ("minimal_edge", "phase"), ("ch4o2cat", "gas"), ("ch4o2cat", "surface")])
+def test_flattening_agrees_with_oracle(fx, key):
+    do, dp = ro.readinput(cases.fixture(fx)), rb.readinput(cases.fixture(fx))
+    if fx == "liquid_phase":
+        po = ro.IdealDiluteSolution(do[key]["Species"], do[key]["Reactions"], do["Solvents"][0])
+        pp = rb.IdealDiluteSolution(dp[key]["Species"], dp[key]["Reactions"], dp["Solvents"][0])
+    elif key == "surface":
+        po = ro.IdealSurface(do[key]["Species"], do[key]["Reactions"], 2.486e-5)
+        pp = rb.IdealSurface(dp[key]["Species"], dp[key]["Reactions"], 2.486e-5)
+    else:
+        po, pp = ro.IdealGas(do[key]["Species"], do[key]["Reactions"]), rb.IdealGas(dp[key]["Species"], dp[key]["Reactions"])
+    assert (po.Ns, po.Nr, po.nvec) == (pp.Ns, pp.Nr, pp.nvec)
+    np.testing.assert_array_equal(po.rxnarray.T + 1, pp.rxnarray)                    # reaction reordering (src/Phase.jl:42)
+    assert [i + 1 for i in po.efficiencyinds] == pp.efficiencyinds
+    cm = co.CpuMech(po)                                                            # independent packing of the same descriptor
+    for name in ("kt", "ko", "ep", "es"):
+        np.testing.assert_array_equal(cm._keep[name], getattr(pp, {"kt": "_ktype", "ko": "_koff", "ep": "_effptr", "es": "_effspc"}[name]))
+    np.testing.assert_array_equal(cm._keep["kp"], pp._kpar)
+    np.testing.assert_array_equal(cm._keep["coef"], pp._coefs)
+    np.testing.assert_allclose(cm._keep["rad"], pp._radius, rtol=1e-15)
+    np.testing.assert_allclose(cm._keep["dr"], pp._diffr, rtol=1e-15)
+
+
+def test_reaction_order_vectorised_first():
+    d = rb.readinput(cases.fixture("ethane"))
+    ig = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"])
+    types = [r.kinetics["type"] for r in ig.reactions]
+    assert all(t in ("Arrhenius", "PdepArrhenius", "Chebyshev") for t in types[:ig.nvec])
+    assert all(t in ("MultiArrhenius", "MultiPdepArrhenius", "ThirdBody", "Lindemann", "Troe", "PdepArrhenius") for t in types[ig.nvec:])
+    assert ig.veckineticsinds[-1] == ig.nvec
+    assert [r.index for r in ig.reactions] == list(range(1, ig.Nr + 1))
+    eff = [r for r in ig.reactions if r.kinetics.get("efficiencies")]
+    assert len(eff) == 7 and all(v >= -1.0 for r in eff for v in r.kinetics["efficiencies"].values())   # stored as eff-1
+
+
+def test_kinetics_packing_layout():
+    a = {"type": "Arrhenius", "A": 1.0, "n": 2.0, "Ea": 3.0}
+    assert ph.pack_kinetics(a, True) == (L.KIN_ARRHENIUS_VEC, [1.0, 2.0, 3.0])
+    assert ph.pack_kinetics(a, False) == (L.KIN_ARRHENIUS, [1.0, 2.0, 3.0])
+    pl = {"type": "PdepArrhenius", "Ps": [1e4, 1e6], "arrs": [a, {"type": "MultiArrhenius", "arrs": [a, a]}]}
+    assert ph.pack_kinetics(pl, False) == (L.KIN_PLOG, [2.0, 1e4, 1e6, 1.0, 1.0, 2.0, 3.0, 2.0, 1.0, 2.0, 3.0, 1.0, 2.0, 3.0])
+    tr = {"type": "Troe", "arrhigh": a, "arrlow": a, "a": 0.5, "T3": 10.0, "T1": 20.0, "T2": 0.0, "efficiencies": {}}
+    assert ph.pack_kinetics(tr, False) == (L.KIN_TROE, [1.0, 2.0, 3.0, 1.0, 2.0, 3.0, 0.5, 10.0, 20.0, 0.0])
+    with pytest.raises(NotImplementedError):
+        ph.pack_kinetics({"type": "Arrheniusq"}, False)
+
+
+def test_molecule_counts():
+    from rmsb200.mechanism import getspeciesradius, molecule_counts
+    assert molecule_counts("CCCCCCCC")[:2] == ({"C": 8, "H": 18}, 25)
+    assert molecule_counts("[O]O")[:2] == ({"O": 2, "H": 1}, 2)
+    assert molecule_counts("CCCCC(CCC)O[O]")[:2] == ({"C": 8, "H": 17, "O": 2}, 26)
+    assert molecule_counts("[H][H]")[:2] == ({"H": 2}, 1)
+    assert molecule_counts("O=C=O")[2] == pytest.approx(0.044009, rel=1e-4)
+    with pytest.raises(KeyError):
+        molecule_counts("[Pt]")
+    assert getspeciesradius({"C": 8, "H": 18}, 25) == pytest.approx(3.659e-10, rel=1e-3)
+
+
+def test_domain_constructors_host_side():
+    d = rb.readinput(cases.fixture("superminimal"))
+    ig = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"], name="phase")
+    dom, y0, p = rb.ConstantVDomain(phase=ig, initialconds={"T": 1000.0, "P": 10e5, "H2": 0.67, "O2": 0.33})
+    assert y0.shape == (14,) and p.shape == (29,)
+    assert dom.V == pytest.approx(8.314 * 1000.0 / 10e5)                  # V = N*R*T/P  (src/Domain.jl:143-145)
+    assert dom.thermovariabledict == {"T": 13, "P": 14} and dom.indexes == [1, 12, 13, 14]
+    with pytest.raises(ValueError):
+        rb.ConstantVDomain(phase=ig, initialconds={"T": 1000.0, "P": 1e5, "V": 1.0, "H2": 1.0})
+    with pytest.raises(AssertionError):
+        rb.ConstantVDomain(phase=ig, initialconds={"T": 1000.0, "P": 1e5, "XYZ": 1.0})
+    ens = rb.ConstantVEnsemble(ig, [1000.0, 1200.0], [1e5, 2e5], np.array([[0, 0, 0, 0, 0.67, 0.33] + [0] * 6] * 2))
+    assert ens.n == 2 and ens.cond.shape == (2, 1) and ens.y0.shape == (2, 14)
