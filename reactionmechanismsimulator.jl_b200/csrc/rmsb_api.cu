@@ -289,67 +289,56 @@ struct BatchArgs {
     int Ny;
 };
 
-template <int R>
-__device__ __forceinline__ void load_state_and_setup(const DevMech& m, const BatchArgs& a, DomainArgs& d, WarpWs& w,
-                                                     int64_t ir, int lane, double (&y)[R], const double*& cond) {
-    d.kind = a.domain_kind; d.Ny = a.Ny;
-    d.p = a.p ? a.p + ir * a.p_stride : nullptr;
-    d.constspc = a.constspc; d.nconst = a.nconst;
-    cond = a.cond + ir * a.ncond;
-#pragma unroll
-    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; y[r] = (i < a.Ny) ? a.y[ir * a.Ny + i] : 0.0; }
-    if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < m.Ns) w.ns[s] = y[r]; }
-        __syncwarp();
-        double T = cond[0], P, V;
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = cond[1]; V = bcast<double, R>(y, m.Ns); }
-        else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = cond[1]; }
-        setup_constk(m, d, w, T, P, V, lane);
-    }
+__device__ __forceinline__ Ws make_ws(double* base, const DevMech& m, int Ny) {
+    Ws w;
+    w.base = base; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = m.n_dt; w.LD = Ny | 1;
+    return w;
 }
 
-// mode 0: dydt, 1: Jacobian, 2: kf/krev
-template <int R, int MODE>
-__global__ void __launch_bounds__(128) eval_kernel(DevMech m, BatchArgs a, int ws_per_warp) {
+// mode 0: dydt, 1: Jacobian, 2: kf/krev.  One warp per reactor, grid-stride over the batch.
+template <int MODE>
+__global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMech m, const __grid_constant__ BatchArgs a, int ws_per_warp) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    WarpWs w;
-    ws_carve(w, smem + (size_t)warp * ws_per_warp, m.Ns, m.Nr, a.Ny, m.n_dt, false);
+    const Ws w = make_ws(smem + (size_t)warp * ws_per_warp, m, a.Ny);
+    const int Ny = a.Ny;
     const int64_t nw = (int64_t)gridDim.x * wpb;
     for (int64_t ir = (int64_t)blockIdx.x * wpb + warp; ir < a.n; ir += nw) {
         DomainArgs d;
-        double y[R];
-        const double* cond;
-        load_state_and_setup<R>(m, a, d, w, ir, lane, y, cond);
+        d.kind = a.domain_kind;
+        d.p = a.p ? a.p + ir * a.p_stride : nullptr;
+        d.constspc = a.constspc; d.nconst = a.nconst;
+        d.cond = a.cond + ir * a.ncond;
+        double* yb = w.ybuf();
+        for (int i = lane; i < Ny; i += 32) yb[i] = a.y[ir * Ny + i];
+        rhs_prepare(d, w, lane);
+        if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(m, d, w, lane);
         if (MODE == 0) {
-            double dy[R];
-            rhs_warp<double, R>(m, d, w, cond, y, dy, lane, false, nullptr);
-#pragma unroll
-            for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < a.Ny) a.out[ir * a.Ny + i] = dy[r]; }
+            rhs_warp(m, d, w, lane, false);
+            const double* fb = w.fbuf();
+            for (int i = lane; i < Ny; i += 32) a.out[ir * Ny + i] = fb[i];
         } else if (MODE == 1) {
-            jac_warp<R>(m, d, w, cond, y, lane);
-            const int Ny = a.Ny, LD = w.LD;
+            jac_warp(m, d, w, lane);
+            const int LD = w.LD;
+            const double* Js = w.J();
             double* J = a.out + (size_t)ir * Ny * Ny;
             for (int idx = lane; idx < Ny * Ny; idx += 32) {
                 int col = idx / Ny, row = idx - col * Ny;
-                J[idx] = w.J[row + col * LD];
+                J[idx] = Js[row + col * LD];
             }
         } else {
-            double dy[R];
-            rhs_warp<double, R>(m, d, w, cond, y, dy, lane, true, nullptr);
-            for (int j = lane; j < m.Nr; j += 32) { a.out[ir * m.Nr + j] = w.kf[j]; a.out2[ir * m.Nr + j] = w.kr[j]; }
+            rhs_warp(m, d, w, lane, true);
+            for (int j = lane; j < m.Nr; j += 32) { a.out[ir * m.Nr + j] = w.kf()[j]; a.out2[ir * m.Nr + j] = w.kr()[j]; }
         }
         __syncwarp();
     }
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) solve_kernel(DevMech m, SolveArgs a, int ws_per_warp) {
+__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevMech m, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWs w;
-    ws_carve(w, smem + (size_t)warp * ws_per_warp, m.Ns, m.Nr, a.Ny, m.n_dt, true);
+    const Ws w = make_ws(smem + (size_t)warp * ws_per_warp, m, a.Ny);
     for (;;) {
         unsigned long long ir = 0;
         if (lane == 0) ir = atomicAdd(a.counter, 1ULL);     // dynamic work queue: one reactor per warp at a time
@@ -413,30 +402,19 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, bool solver, int 
     return RMSB_OK;
 }
 
-template <int R, int MODE>
-static int launch_eval_R(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+template <int MODE>
+static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
     LaunchCfg cfg;
-    int rc = config_launch(eval_kernel<R, MODE>, h, a.Ny, false, 4, &cfg);
+    int rc = config_launch(eval_kernel<MODE>, h, a.Ny, false, 4, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
     int64_t max_blocks = (int64_t)cfg.sms * cfg.blocks_per_sm * 8;   // grid-stride beyond 8 waves
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
-    eval_kernel<R, MODE><<<grid, cfg.wpb * 32, cfg.smem, st>>>(h->dm, a, cfg.ws);
+    eval_kernel<MODE><<<grid, cfg.wpb * 32, cfg.smem, st>>>(h->dm, a, cfg.ws);
     ++g_launches;
     CU(cudaGetLastError());
     return RMSB_OK;
-}
-
-template <int MODE>
-static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
-    switch (rows_per_lane(a.Ny)) {
-    case 1: return launch_eval_R<1, MODE>(h, a, st);
-    case 2: return launch_eval_R<2, MODE>(h, a, st);
-    case 3: return launch_eval_R<3, MODE>(h, a, st);
-    case 4: return launch_eval_R<4, MODE>(h, a, st);
-    }
-    return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
 }
 
 template <int R>

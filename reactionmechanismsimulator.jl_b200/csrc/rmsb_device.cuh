@@ -1,11 +1,14 @@
 // rmsb_device.cuh -- device-side mechanism tables and the warp-cooperative RHS / Jacobian.
 //
-// Execution model: ONE WARP INTEGRATES ONE REACTOR.  State component i lives in lane (i & 31),
-// register slot (i >> 5) (template parameter R = slots per lane, Ny <= 32*R).  Species-indexed
-// work (thermo, gather of reaction rates) is spread over lanes by species, reaction-indexed work
-// (rate coefficients, equilibrium constants, mass-action rates) by reaction; per-warp scratch
-// lives in shared memory.  Every warp follows its own control flow, so per-reactor adaptive
-// stepping costs no intra-warp divergence.
+// Execution model: ONE WARP INTEGRATES ONE REACTOR.  Species-indexed work (thermo, gather of reaction
+// rates) is spread over lanes by species, reaction-indexed work (rate coefficients, equilibrium
+// constants, mass-action rates) by reaction; per-warp scratch lives in the warp's private slice of
+// shared memory.  Every warp follows its own control flow, so per-reactor adaptive stepping costs no
+// intra-warp divergence.
+//
+// Code-size discipline (round-1 ncu finding: a fully inlined kernel was 95k SASS instructions and stalled
+// on instruction fetch): the RHS, Jacobian, LU and setup routines are NOT inlined; they exchange vectors
+// through the shared-memory slice (ybuf -> fbuf) so no register array crosses a call boundary.
 //
 // What is restated here (reference = ReactionMechanismSimulator.jl, paths relative to its root):
 //   calcHSCpdless                 src/Calculators/Thermovec.jl:76-119      (vectorised thermo path)
@@ -124,10 +127,6 @@ __device__ __forceinline__ Dual2 dpow(Dual2 x, double n) {  // x^n, real exponen
     return Dual2(v, d * x.a, d * x.b);
 }
 __device__ __forceinline__ double dpow(double x, double n) { return pow(x, n); }
-__device__ __forceinline__ Dual2 dpow(Dual2 x, Dual2 n) {  // general x^n
-    double v = pow(x.v, n.v), dx = n.v * v / x.v, dn = v * log(x.v);
-    return Dual2(v, dx * x.a + dn * n.a, dx * x.b + dn * n.b);
-}
 __device__ __forceinline__ Dual2 dexp10(Dual2 x) {  // 10^x
     double v = pow(10.0, x.v), d = v * 2.302585092994046;
     return Dual2(v, d * x.a, d * x.b);
@@ -135,6 +134,10 @@ __device__ __forceinline__ Dual2 dexp10(Dual2 x) {  // 10^x
 __device__ __forceinline__ double dexp10(double x) { return pow(10.0, x); }
 __device__ __forceinline__ double val(double x) { return x; }
 __device__ __forceinline__ double val(Dual2 x) { return x.v; }
+// seed the thermodynamic state variables: which = 0 -> d/dT = 1, which = 1 -> d/dP = 1
+template <class N> __device__ __forceinline__ N seed(double v, int which);
+template <> __device__ __forceinline__ double seed<double>(double v, int) { return v; }
+template <> __device__ __forceinline__ Dual2 seed<Dual2>(double v, int which) { return Dual2(v, which == 0 ? 1.0 : 0.0, which == 1 ? 1.0 : 0.0); }
 
 // ---- warp helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double x) {
@@ -143,69 +146,39 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 __device__ __forceinline__ Dual2 warp_sum(Dual2 x) { return Dual2(warp_sum(x.v), warp_sum(x.a), warp_sum(x.b)); }
-__device__ __forceinline__ double warp_max(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
-    return x;
-}
-__device__ __forceinline__ double shfl(double x, int src) { return __shfl_sync(FULL, x, src); }
-__device__ __forceinline__ Dual2 shfl(Dual2 x, int src) { return Dual2(shfl(x.v, src), shfl(x.a, src), shfl(x.b, src)); }
 
-// broadcast distributed component idx of y to every lane
-template <class N, int R>
-__device__ __forceinline__ N bcast(const N (&y)[R], int idx) {
-    N out = y[0];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        N t = shfl(y[r], idx & 31);
-        if ((idx >> 5) == r) out = t;
-    }
-    return out;
-}
-
-// Per-warp shared-memory workspace (all pointers into the warp's private slice).
-struct WarpWs {
-    double* ns;     // [Ns]
-    double* cs;     // [Ns]
-    double* g;      // [3*Ns]  G/(RT) (variable-k, Dual2-capable) or absolute G (constant-k domains)
-    double* q;      // [3*Nr]  net rates (Dual2-capable)
-    double* kf;     // [Nr]
-    double* kr;     // [Nr]
-    double* us;     // [Ns]
-    double* cp;     // [Ns]
-    double* dterm;  // [n_dt]
-    double* J;      // [Ny*LD]
-    double* LU;     // [Ny*LD]
-    double* dinv;   // [Ny]
-    double* xs;     // [Ny]
-    int* perm;      // [Ny]
-    int LD;
+// ------------------------------------------------------------------------------------------------
+// Per-warp shared-memory workspace.  A small by-value view (base pointer + sizes); sub-arrays are
+// located by integer offsets so that the struct travels in registers across non-inlined calls.
+// ------------------------------------------------------------------------------------------------
+struct Ws {
+    double* base;
+    int Ns, Nr, Ny, ndt, LD;
+    __device__ __forceinline__ double* cs() const { return base; }                                  // [Ns]   concentrations
+    __device__ __forceinline__ double* g() const { return base + Ns; }                              // [3Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
+    __device__ __forceinline__ double* un() const { return base + 4 * Ns; }                         // [3Ns]  internal energies U_i (Dual2-capable) | diffusivities (liquid setup)
+    __device__ __forceinline__ double* q() const { return base + 7 * Ns; }                          // [3Nr]  net rates (Dual2-capable)
+    __device__ __forceinline__ double* kf() const { return base + 7 * Ns + 3 * Nr; }                // [Nr]
+    __device__ __forceinline__ double* kr() const { return base + 7 * Ns + 4 * Nr; }                // [Nr]
+    __device__ __forceinline__ double* us() const { return base + 7 * Ns + 5 * Nr; }                // [Ns]   U_i values (Jacobian)
+    __device__ __forceinline__ double* cp() const { return base + 8 * Ns + 5 * Nr; }                // [Ns]   cp_i/R values (Jacobian)
+    __device__ __forceinline__ double* dterm() const { return base + 9 * Ns + 5 * Nr; }             // [ndt]
+    __device__ __forceinline__ double* ybuf() const { return dterm() + ndt; }                       // [Ny]   RHS / Jacobian input state
+    __device__ __forceinline__ double* fbuf() const { return ybuf() + Ny; }                         // [3Ny]  RHS output (Dual2-capable)
+    __device__ __forceinline__ double* aux() const { return fbuf() + 3 * Ny; }                      // [8]    T P V N C Cv dot(U,dn)
+    __device__ __forceinline__ double* ru() const { return aux() + 8; }                             // [36]   change_D matrix
+    __device__ __forceinline__ double* dinv() const { return ru() + 36; }                           // [Ny]   1/U_kk
+    __device__ __forceinline__ double* xs() const { return dinv() + Ny; }                           // [Ny]   linear-solve vector
+    __device__ __forceinline__ int* perm() const { return reinterpret_cast<int*>(xs() + Ny); }      // [Ny]   row permutation
+    __device__ __forceinline__ double* J() const { return xs() + Ny + (Ny + 1) / 2 + 1; }           // [Ny*LD] Jacobian, column-major
+    __device__ __forceinline__ double* LU() const { return J() + Ny * LD; }                         // [Ny*LD] factors of I - c*J (solver only)
 };
 
 __host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, bool solver) {
     int LD = Ny | 1;
-    int n = 2 * Ns + 3 * Ns + 3 * Nr + 2 * Nr + 2 * Ns + n_dt + Ny * LD + 2 * Ny + (Ny + 1) / 2 + 2;
+    int n = 9 * Ns + 5 * Nr + n_dt + Ny + 3 * Ny + 8 + 36 + Ny + Ny + (Ny + 1) / 2 + 1 + Ny * LD;
     if (solver) n += Ny * LD;
     return (n + 1) & ~1;
-}
-
-__device__ inline void ws_carve(WarpWs& w, double* base, int Ns, int Nr, int Ny, int n_dt, bool solver) {
-    w.LD = Ny | 1;
-    double* p = base;
-    w.ns = p; p += Ns;
-    w.cs = p; p += Ns;
-    w.g = p; p += 3 * Ns;
-    w.q = p; p += 3 * Nr;
-    w.kf = p; p += Nr;
-    w.kr = p; p += Nr;
-    w.us = p; p += Ns;
-    w.cp = p; p += Ns;
-    w.dterm = p; p += n_dt;
-    w.J = p; p += Ny * w.LD;
-    w.dinv = p; p += Ny;
-    w.xs = p; p += Ny;
-    w.perm = reinterpret_cast<int*>(p); p += (Ny + 1) / 2 + 1;
-    w.LU = solver ? p : w.J;
 }
 
 // smem load/store of a possibly-dual value at logical index i of an array with Dual2 capacity
@@ -262,7 +235,7 @@ __device__ __forceinline__ void nasa_hscp(const DevMech& m, int s, const TPow<N>
 
 // getGibbs through the scalar path: evalpoly Horner (src/Tools.jl:13-22) with exact c_k/k
 // (src/Calculators/Thermo.jl:6-8,75-93).  Used by the constant-T domains at setup.
-__device__ inline double gibbs_scalar(const DevMech& m, int s, double T) {
+__device__ __noinline__ double gibbs_scalar(const DevMech& m, int s, double T) {
     int r = select_poly(m, s, T);
     const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
     const int Ns = m.Ns;
@@ -324,7 +297,6 @@ template <class N> __device__ inline N plog_block(const double*& c, const KinEnv
     int nP = (int)c[0];
     const double* Ps = c + 1;
     const double* ent = c + 1 + nP;
-    // locate entry starts
     int i0, i1;
     bounding_inds(val(e.P), Ps, nP, i0, i1);
     N lowk = 0.0, highk = 0.0;
@@ -366,11 +338,12 @@ template <class N> __device__ inline N troe_F(const double* a, N T, N Pr) {
     return dexp10(lF / (1 + x * x));
 }
 
-// kinetics(T=T,P=P,C=C): forward rate coefficient of reaction j.  `scalar_forms` forces the scalar
-// expressions for the *_VEC types (the diffusion-limited path goes through getkf for every reaction,
-// src/PhaseState.jl:184-223,249-252).
+// kinetics(T=T,P=P,C=C) for every type except the vectorised-Arrhenius fast path handled by callers.
+// `scalar_forms` forces the scalar expressions for the *_VEC types (the diffusion-limited path goes through
+// getkf for every reaction, src/PhaseState.jl:184-223,249-252).  Not inlined: keeps the hot RHS loop small.
 template <class N>
-__device__ inline N eval_kin(const DevMech& m, int j, const KinEnv<N>& e, N Ceff, bool scalar_forms) {
+__device__ __noinline__ N eval_kin(const DevMech& m, int j, const KinEnv<N>* ep, N Ceff, bool scalar_forms) {
+    const KinEnv<N>& e = *ep;
     const double* a = m.kpar + m.koff[j];
     switch (m.ktype[j]) {
     case RMSB_KIN_ARRHENIUS_VEC:
@@ -441,7 +414,8 @@ __device__ inline N eval_kin(const DevMech& m, int j, const KinEnv<N>& e, N Ceff
 }
 
 // _calcdkdCeff, src/Calculators/Rate.jl:232-262
-__device__ inline double dk_dCeff(const DevMech& m, int j, const KinEnv<double>& e, double Ceff) {
+__device__ __noinline__ double dk_dCeff(const DevMech& m, int j, const KinEnv<double>* ep, double Ceff) {
+    const KinEnv<double>& e = *ep;
     const double* a = m.kpar + m.koff[j];
     int kt = m.ktype[j];
     if (kt == RMSB_KIN_THIRDBODY) return arr_sca(a, e);
@@ -478,16 +452,14 @@ template <class N>
 __device__ __forceinline__ N net_rate(const DevMech& m, int j, N kf, N kr, const double* cs) {
     const int Nr = m.Nr;
     N fR = kf * cs[m.rx[j]];
-#pragma unroll
     for (int k = 1; k < 4; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; fR = fR * cs[s]; }
     N rR = kr * cs[m.rx[4 * Nr + j]];
-#pragma unroll
     for (int k = 5; k < 8; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; rR = rR * cs[s]; }
     return fR - rR;
 }
 
 // scalar getKc (src/PhaseState.jl:106-129, phi = 0) from absolute Gibbs energies G[]
-__device__ inline double kc_scalar(const DevMech& m, int j, const double* G, double T, double C0) {
+__device__ __noinline__ double kc_scalar(const DevMech& m, int j, const double* G, double T, double C0) {
     const int Nr = m.Nr;
     double acc = G[m.rx[j]];
     int nre = 1;
@@ -501,7 +473,7 @@ __device__ inline double kc_scalar(const DevMech& m, int j, const double* G, dou
 }
 
 // getDiffusiveRate for 1 or 2 bodies (src/PhaseState.jl:87-93); >2-body form is out of scope
-__device__ inline double diffusive_rate(const DevMech& m, int j, int side, const double* diffs) {
+__device__ __forceinline__ double diffusive_rate(const DevMech& m, int j, int side, const double* diffs) {
     const int Nr = m.Nr;
     int s0 = m.rx[(side * 4) * Nr + j], s1 = m.rx[(side * 4 + 1) * Nr + j];
     if (s1 < 0) return INFINITY;
@@ -509,29 +481,31 @@ __device__ inline double diffusive_rate(const DevMech& m, int j, int side, const
 }
 
 struct DomainArgs {
-    int kind;           // RMSB_DOMAIN_*
-    int Ny;
-    const double* p;    // nullptr or per-reactor parameter row
-    const int* constspc;  // 1-based (reference convention)
+    int kind;             // RMSB_DOMAIN_*
     int nconst;
-};
-
-struct RhsAux {   // by-products the Jacobian needs
-    double T, P, V, N, C, Cv, dotUsdn;
+    const double* p;      // nullptr or per-reactor parameter row
+    const int* constspc;  // 1-based (reference convention)
+    const double* cond;   // per-reactor constants
 };
 
 // ------------------------------------------------------------------------------------------------
 // Constant-k domain setup (TP / TV / TAPhi ctors, src/Domain.jl:42-102,500-560,660-711):
 // Gs via the scalar thermo path, kfs/krevs once per reactor.  w.g <- absolute G, w.kf/w.kr <- k's.
-// `ns0` (in w.ns) / V are the initial amounts (only efficiency reactions look at them, and those are
+// The initial amounts are read from w.ybuf (only efficiency reactions look at them, and those are
 // re-evaluated on every RHS call for TP).
 // ------------------------------------------------------------------------------------------------
-__device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpWs& w, double T, double P, double V, int lane) {
+__device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, int lane) {
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
-    for (int s = lane; s < Ns; s += 32) w.g[s] = p ? p[s] : gibbs_scalar(m, s, T);
-    // diffusivities (Stokes, src/Calculators/Diffusion.jl:19) into w.us (free in constant-k domains)
-    if (m.difflim) {
+    const double* ns = w.ybuf();
+    double* G = w.g();
+    double* diffs = w.un();
+    const double T = d.cond[0];
+    double P, V;
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = ns[Ns]; }
+    else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
+    for (int s = lane; s < Ns; s += 32) G[s] = p ? p[s] : gibbs_scalar(m, s, T);
+    if (m.difflim) {   // Stokes diffusivities, src/Calculators/Diffusion.jl:19, Viscosity.jl:24
         double mu = 0.0;
         if (m.visc_kind == RMSB_VISC_RIEDEL)
             mu = exp(m.visc[0] + m.visc[1] / T + m.visc[2] * log(T) + m.visc[3] * pow(T, m.visc[4]));
@@ -539,7 +513,7 @@ __device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpW
             mu = m.visc[0];
         for (int s = lane; s < Ns; s += 32) {
             double r = m.diff_r ? m.diff_r[s] : 0.0;
-            w.us[s] = (r > 0.0) ? RMSB_KB * T / (6 * RMSB_PI * mu * r) : INFINITY;
+            diffs[s] = (r > 0.0) ? RMSB_KB * T / (6 * RMSB_PI * mu * r) : INFINITY;
         }
     }
     __syncwarp();
@@ -548,7 +522,7 @@ __device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpW
     double C0 = (m.phase_kind == RMSB_PHASE_SURFACE) ? m.sitedensity : 1.0e5 / (RMSB_R * T);
     double logC0 = log(C0);
     double N = 0.0;
-    for (int s = 0; s < Ns; ++s) N += w.ns[s];
+    for (int s = 0; s < Ns; ++s) N += ns[s];
     double C = (d.kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (d.kind == RMSB_DOMAIN_CONSTANT_TV ? N / V : 0.0);
     bool is_eff_dom = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
     for (int j = lane; j < Nr; j += 32) {
@@ -557,26 +531,19 @@ __device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpW
         if (!m.difflim) {
             // getkfkrevs vector path: getkfs + getKcs (src/PhaseState.jl:226-233)
             if (p && !(is_eff_dom && eff)) kf = p[Ns + j];
-            else {
-                double Ceff = ceff_of(m, j, C, w.ns, V);
-                kf = eval_kin(m, j, e, Ceff, false);
-            }
+            else kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, ns, V), false);
             double ex = 0.0;
-            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex += m.kc_coef[k] * (w.g[m.kc_spc[k]] / (RMSB_R * T));
+            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex += m.kc_coef[k] * (G[m.kc_spc[k]] / (RMSB_R * T));
             ex += m.nrp[j] * logC0;
             kr = kf / exp(ex);
         } else {
             // getkfkrev per reaction (src/PhaseState.jl:184-223): scalar forms, scalar Kc, diffusion limits
             if (p) kf = p[Ns + j];
-            else {
-                double Ceff = ceff_of(m, j, C, w.ns, V);
-                kf = eval_kin(m, j, e, Ceff, true);
-            }
-            double Kc = kc_scalar(m, j, w.g, T, C0);
+            else kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, ns, V), true);
+            double Kc = kc_scalar(m, j, G, T, C0);
             kr = kf / Kc;
             int nre = 0, npr = 0;
             for (int k = 0; k < 4; ++k) { if (m.rx[k * Nr + j] >= 0) ++nre; if (m.rx[(k + 4) * Nr + j] >= 0) ++npr; }
-            const double* diffs = w.us;
             if (nre == 1) {
                 if (npr > 1) {
                     double krd = diffusive_rate(m, j, 1, diffs);
@@ -596,194 +563,201 @@ __device__ inline void setup_constk(const DevMech& m, const DomainArgs& d, WarpW
                 if (kff > kfr) { kf = kfr; kr = krevr; }
                 else { kf = kff; kr = kf / Kc; }
             }
-            kf *= m.fwd[j]; kr *= m.rev[j];   // inside getkfkrev (:220-221) ...
         }
-        kf *= m.fwd[j]; kr *= m.rev[j];       // ... and again in getkfkrevs (:254-255)
-        w.kf[j] = kf; w.kr[j] = kr;
+        w.kf()[j] = kf * m.fwd[j];          // forwardability / reversibility masks (:220-221, :254-255)
+        w.kr()[j] = kr * m.rev[j];
     }
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // dydtreactor! for one reactor (src/Reactor.jl:653-660).
-//   y   : distributed state (N = double or Dual2)
-//   dy  : distributed result
-//   store_k : also leave kf/kr/us/cp (values) in the workspace for the Jacobian
-// For constant-k domains setup_constk() must have filled w.g / w.kf / w.kr.
+//   in : w.ybuf   state values (the Dual2 instantiation seeds dT = 1 on T and dP = 1 on P itself)
+//        w.aux[7] 1/V (ConstantV) -- per-reactor constant, set once by the caller
+//   out: w.fbuf   dy/dt (N-capable); w.aux[0..6] <- T P V N C Cv dot(U,dn) (Cv only with store_k);
+//        with store_k also kf/kr/us/cp for the Jacobian
+// Arithmetic note (DESIGN.md "floating-point contract"): the reference is compiled under @fastmath and is
+// itself reproducible only to a few ulp; this kernel keeps the reference's formulas but replaces divisions by
+// a shared reciprocal where the reference divides by the same quantity (1/T, 1/(R*T), 1/V) and evaluates
+// kf/Kc as kf*exp(-x).  Measured agreement with the oracle: <= 1e-13 relative (tests/test_gpu_parity.py).
 // ------------------------------------------------------------------------------------------------
-template <class N, int R>
-__device__ inline void rhs_warp(const DevMech& m, const DomainArgs& d, WarpWs& w, const double* cond,
-                                const N (&y)[R], N (&dy)[R], int lane, bool store_k, RhsAux* aux) {
+#define RMSB_INV_R (1.0 / 8.314)
+#define RMSB_LOG_1E5_OVER_R 9.394984624139783   /* log(1.0e5/8.314) */
+
+template <class N>
+__device__ __noinline__ void rhs_v(const DevMech& m, DomainArgs d, Ws w, int lane, bool store_k) {
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
     typedef SmemNum<N> SM;
-    // species amounts to smem
-#pragma unroll
-    for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) w.ns[s] = val(y[r]); }
-
-    if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
-        N T = bcast<N, R>(y, Ns), P = bcast<N, R>(y, Ns + 1);
-        const double V = cond[0];
-        N RT = RMSB_R * T;
-        N Nt = P * V / RT;            // N = P*V/(R*T)  (Domain.jl:1068)
-        N C = Nt / V;
-        TPow<N> tp(T);
-        N us[R];
-        N cpns = 0.0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int s = r * 32 + lane;
-            us[r] = 0.0;
-            if (s < Ns) {
-                N cp, h, sr;
-                nasa_hscp(m, s, tp, val(T), cp, h, sr);
-                if (p) h = h + p[s] / RT;                   // Domain.jl:1100
-                N G = (h - sr) * RT;                        // :1101
-                us[r] = (h - 1.0) * RT;                     // :1102
-                SM::st(w.g, s, G / RT);                     // getKcs uses Gs./(R*T) (PhaseState.jl:166)
-                w.cs[s] = val(y[r]) / V;
-                cpns = cpns + cp * y[r];
-                if (store_k) { w.us[s] = val(us[r]); w.cp[s] = val(cp); }
-            }
-        }
-        N Cv = warp_sum(cpns);                              // dot(cpdivR, ns)
-        Cv = Cv * (RMSB_R / Nt);
-        Cv = Cv - RMSB_R;
-        __syncwarp();
-        KinEnv<N> e;
-        e.T = T; e.logT = tp.T6; e.RT = RT; e.invRT = 1.0 / RT; e.P = P;
-        N logC0 = dlog(1.0e5 / RT);
-        for (int j = lane; j < Nr; j += 32) {
-            N Ceff = ceff_of(m, j, C, w.ns, V);
-            N kf = eval_kin(m, j, e, Ceff, false);
-            N ex = 0.0;
-            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex = ex + m.kc_coef[k] * SM::ld(w.g, m.kc_spc[k]);
-            ex = ex + m.nrp[j] * logC0;
-            N kr = kf / dexp(ex);
-            kf = kf * m.fwd[j]; kr = kr * m.rev[j];
-            if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }   // Domain.jl:1112
-            if (store_k) { w.kf[j] = val(kf); w.kr[j] = val(kr); }
-            SM::st(w.q, j, net_rate(m, j, kf, kr, w.cs));
-        }
-        __syncwarp();
-        N usum = 0.0, nsum = 0.0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int s = r * 32 + lane;
-            dy[r] = 0.0;
-            if (s < Ns) {
-                N acc = 0.0;
-                for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
-                    int jr = m.sr_rxn[k];
-                    N qv = SM::ld(w.q, jr & 0x7fffffff);
-                    acc = (jr < 0) ? acc - qv : acc + qv;
-                }
-                N dn = acc * V;                              // dydt .*= V
-                dy[r] = dn;
-                usum = usum + us[r] * dn;
-                nsum = nsum + dn;
-            }
-        }
-        N dotU = warp_sum(usum), sumn = warp_sum(nsum);
-        N dT = -dotU / (Nt * Cv);                            // Domain.jl:1902
-        N dP = sumn * RMSB_R * T / V + P / T * dT;           // :1903
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int i = r * 32 + lane;
-            if (i == Ns) dy[r] = dT;
-            if (i == Ns + 1) dy[r] = dP;
-        }
-        if (aux) { aux->T = val(T); aux->P = val(P); aux->V = V; aux->N = val(Nt); aux->C = val(C); aux->Cv = val(Cv); aux->dotUsdn = val(dotU); }
-    } else {
-        // constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns)
-        double T = cond[0];
-        double P, V;
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = cond[1]; V = val(bcast<N, R>(y, Ns)); }
-        else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = cond[1]; }
-#pragma unroll
-        for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) w.cs[s] = val(y[r]) / V; }
-        __syncwarp();
-        double Nt, C;
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { Nt = P * V / (RMSB_R * T); C = Nt / V; }
-        else {
-            double a = 0.0;
-#pragma unroll
-            for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < Ns) a += val(y[r]); }
-            Nt = warp_sum(a); C = Nt / V;
-        }
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP && m.n_effrxn > 0) {
-            // efficiency reactions are re-evaluated each call through getkfkrev (Domain.jl:924,943-945)
-            KinEnv<double> e;
-            e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
-            double C0 = 1.0e5 / (RMSB_R * T);
-            for (int q = lane; q < m.n_effrxn; q += 32) {
-                int j = m.effrxn[q];
-                double Ceff = ceff_of(m, j, C, w.ns, V);
-                double kf = eval_kin(m, j, e, Ceff, false);
-                if (d.p) kf = kf * d.p[Ns + j];
-                double Kc = kc_scalar(m, j, w.g, T, C0);
-                double kr = kf / Kc;
-                w.kf[j] = kf * m.fwd[j]; w.kr[j] = kr * m.rev[j];
-            }
-            __syncwarp();
-        }
-        for (int j = lane; j < Nr; j += 32) w.q[j] = net_rate<double>(m, j, w.kf[j], w.kr[j], w.cs);
-        __syncwarp();
-        double nsum = 0.0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int s = r * 32 + lane;
-            dy[r] = 0.0;
-            if (s < Ns) {
-                double acc = 0.0;
-                for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
-                    int jr = m.sr_rxn[k];
-                    double qv = w.q[jr & 0x7fffffff];
-                    acc = (jr < 0) ? acc - qv : acc + qv;
-                }
-                double dn = acc * V;
-                dy[r] = dn;
-                nsum += dn;
-            }
-        }
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
-            double dV = warp_sum(nsum) * RMSB_R * T / P;     // Domain.jl:1864
-#pragma unroll
-            for (int r = 0; r < R; ++r) if (r * 32 + lane == Ns) dy[r] = dV;
-        }
-        if (aux) { aux->T = T; aux->P = P; aux->V = V; aux->N = Nt; aux->C = C; aux->Cv = 0.0; aux->dotUsdn = 0.0; }
+    const double* yb = w.ybuf();
+    double* cs = w.cs();
+    double* fb = w.fbuf();
+    double* qb = w.q();
+    double* gb = w.g();
+    double* ub = w.un();
+    const double V = d.cond[0];
+    const double invV = w.aux()[7];
+    N T = seed<N>(yb[Ns], 0), P = seed<N>(yb[Ns + 1], 1);
+    TPow<N> tp(T);                       // T4 = 1/T, T6 = log(T)
+    N RT = RMSB_R * T;
+    N invRT = tp.T4 * RMSB_INV_R;        // 1/(R*T)
+    N Nt = P * V * invRT;                // N = P*V/(R*T)  (Domain.jl:1068)
+    N C = P * invRT;                     // C = N/V
+    N cpns = 0.0;
+    for (int s = lane; s < Ns; s += 32) {
+        N cp, h, sr;
+        nasa_hscp(m, s, tp, val(T), cp, h, sr);
+        if (p) h = h + p[s] * invRT;                    // Domain.jl:1100
+        N U = (h - 1.0) * RT;                           // :1102
+        SM::st(gb, s, h - sr);                          // G/(R*T) with G = (h-s)*R*T (:1101, PhaseState.jl:166)
+        SM::st(ub, s, U);
+        double nsv = yb[s];
+        cs[s] = nsv * invV;
+        cpns = cpns + cp * nsv;
+        if (store_k) { w.us()[s] = val(U); w.cp()[s] = val(cp); }
     }
-    // constant species (Domain.jl:1840-1842,1865-1867,1904-1906)
-    for (int k = 0; k < d.nconst; ++k) {
-        int s = d.constspc[k] - 1;  // API indices are 1-based
-#pragma unroll
-        for (int r = 0; r < R; ++r) if (r * 32 + lane == s) dy[r] = 0.0;
+    N cpsum = warp_sum(cpns);                           // dot(cpdivR, ns)
+    __syncwarp();
+    KinEnv<N> e;
+    e.T = T; e.logT = tp.T6; e.RT = RT; e.invRT = invRT; e.P = P;
+    N logC0 = RMSB_LOG_1E5_OVER_R - tp.T6;              // log(1e5/(R*T))
+    for (int j = lane; j < Nr; j += 32) {
+        N kf;
+        if (m.ktype[j] == RMSB_KIN_ARRHENIUS_VEC) kf = arr_vec(m.kpar + m.koff[j], e);
+        else kf = eval_kin<N>(m, j, &e, ceff_of(m, j, C, yb, V), false);
+        N ex = 0.0;
+        for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex = ex + m.kc_coef[k] * SM::ld(gb, m.kc_spc[k]);
+        ex = ex + m.nrp[j] * logC0;
+        N kr = kf * dexp(-ex);                          // kf/Kc, Kc = exp(ex)  (PhaseState.jl:165-167,230)
+        kf = kf * m.fwd[j]; kr = kr * m.rev[j];
+        if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }   // Domain.jl:1112
+        if (store_k) { w.kf()[j] = val(kf); w.kr()[j] = val(kr); }
+        SM::st(qb, j, net_rate(m, j, kf, kr, cs));
     }
+    __syncwarp();
+    N usum = 0.0, nsum = 0.0;
+    for (int s = lane; s < Ns; s += 32) {
+        N acc = 0.0;
+        for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
+            int jr = m.sr_rxn[k];
+            N qv = SM::ld(qb, jr & 0x7fffffff);
+            acc = (jr < 0) ? acc - qv : acc + qv;
+        }
+        N dn = acc * V;                                  // dydt .*= V
+        SM::st(fb, s, dn);
+        usum = usum + SM::ld(ub, s) * dn;
+        nsum = nsum + dn;
+    }
+    N dotU = warp_sum(usum), sumn = warp_sum(nsum);
+    // dT/dt = -dot(Us,dn)/(N*Cv) with N*Cv = R*(dot(cp/R,ns) - N)     (Domain.jl:1103-1105,1902)
+    N dT = -dotU / (RMSB_R * (cpsum - Nt));
+    N dP = sumn * RT * invV + P * tp.T4 * dT;            // :1903
+    if (lane == 0) {
+        SM::st(fb, Ns, dT);
+        SM::st(fb, Ns + 1, dP);
+        double* ax = w.aux();
+        ax[0] = val(T); ax[1] = val(P); ax[2] = V; ax[3] = val(Nt); ax[4] = val(C); ax[6] = val(dotU);
+        if (store_k) ax[5] = val(cpsum) * (RMSB_R / val(Nt)) - RMSB_R;   // Cvave
+    }
+    __syncwarp();
+    for (int k = lane; k < d.nconst; k += 32) SM::st(fb, d.constspc[k] - 1, N(0.0));   // Domain.jl:1904-1906
     __syncwarp();
 }
 
+// constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns).  setup_constk() must have filled w.g / w.kf / w.kr.
+__device__ __noinline__ void rhs_ck(const DevMech& m, DomainArgs d, Ws w, int lane) {
+    const int Ns = m.Ns, Nr = m.Nr;
+    const double* p = d.p;
+    const double* yb = w.ybuf();
+    double* cs = w.cs();
+    double* fb = w.fbuf();
+    double* qb = w.q();
+    const double T = d.cond[0];
+    double P, V;
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = yb[Ns]; }
+    else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
+    const double invV = 1.0 / V;
+    double a = 0.0;
+    for (int s = lane; s < Ns; s += 32) { double nsv = yb[s]; cs[s] = nsv * invV; a += nsv; }
+    double Nt, C;
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { Nt = P * V / (RMSB_R * T); C = Nt * invV; }
+    else { Nt = warp_sum(a); C = Nt * invV; }
+    __syncwarp();
+    double* kfb = w.kf();
+    double* krb = w.kr();
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP && m.n_effrxn > 0) {
+        // efficiency reactions are re-evaluated each call through getkfkrev (Domain.jl:924,943-945)
+        KinEnv<double> e;
+        e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+        double C0 = 1.0e5 / (RMSB_R * T);
+        for (int q = lane; q < m.n_effrxn; q += 32) {
+            int j = m.effrxn[q];
+            double kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, yb, V), false);
+            if (p) kf = kf * p[Ns + j];
+            double kr = kf / kc_scalar(m, j, w.g(), T, C0);
+            kfb[j] = kf * m.fwd[j]; krb[j] = kr * m.rev[j];
+        }
+        __syncwarp();
+    }
+    for (int j = lane; j < Nr; j += 32) qb[j] = net_rate<double>(m, j, kfb[j], krb[j], cs);
+    __syncwarp();
+    double nsum = 0.0;
+    for (int s = lane; s < Ns; s += 32) {
+        double acc = 0.0;
+        for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
+            int jr = m.sr_rxn[k];
+            double qv = qb[jr & 0x7fffffff];
+            acc = (jr < 0) ? acc - qv : acc + qv;
+        }
+        double dn = acc * V;
+        fb[s] = dn;
+        nsum += dn;
+    }
+    if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
+        double dV = warp_sum(nsum) * RMSB_R * T / P;     // Domain.jl:1864
+        if (lane == 0) fb[Ns] = dV;
+    }
+    if (lane == 0) {
+        double* ax = w.aux();
+        ax[0] = T; ax[1] = P; ax[2] = V; ax[3] = Nt; ax[4] = C; ax[5] = 0.0; ax[6] = 0.0;
+    }
+    __syncwarp();
+    for (int k = lane; k < d.nconst; k += 32) fb[d.constspc[k] - 1] = 0.0;   // Domain.jl:1840-1842,1865-1867
+    __syncwarp();
+}
+
+// per-reactor constants the RHS reads from the workspace (call once per reactor, before the first RHS)
+__device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, int lane) {
+    if (lane == 0) w.aux()[7] = (d.kind == RMSB_DOMAIN_CONSTANT_V) ? 1.0 / d.cond[0] : 0.0;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void rhs_warp(const DevMech& m, const DomainArgs& d, const Ws& w, int lane, bool store_k) {
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(m, d, w, lane, store_k);
+    else rhs_ck(m, d, w, lane);
+}
+
 // ------------------------------------------------------------------------------------------------
-// jacobiany! for one reactor: dense column-major Ny x LD matrix in w.J.
+// jacobiany! for one reactor: in w.ybuf, out dense column-major Ny x LD matrix in w.J.
 // ------------------------------------------------------------------------------------------------
-template <int R>
-__device__ inline void jac_warp(const DevMech& m, const DomainArgs& d, WarpWs& w, const double* cond,
-                                const double (&y)[R], int lane) {
-    const int Ns = m.Ns, Nr = m.Nr, Ny = d.Ny, LD = w.LD;
-    double dy[R];
-    RhsAux ax;
-    rhs_warp<double, R>(m, d, w, cond, y, dy, lane, true, &ax);
-    double dn[R];   // V*rates before constant-species zeroing (jacobiany! recomputes dydt, Domain.jl:2301-2303)
-#pragma unroll
-    for (int r = 0; r < R; ++r) dn[r] = dy[r];
-    for (int i = lane; i < Ny * LD; i += 32) w.J[i] = 0.0;
+__device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int lane) {
+    const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, LD = w.LD;
+    rhs_warp(m, d, w, lane, true);
+    double* J = w.J();
+    const double* cs = w.cs();
+    const double* kfb = w.kf();
+    const double* krb = w.kr();
+    double* dterm = w.dterm();
+    const double* ax = w.aux();
+    const double aT = ax[0], aP = ax[1], aV = ax[2], aN = ax[3], aC = ax[4], aCv = ax[5], adotU = ax[6];
+    for (int i = lane; i < Ny * LD; i += 32) J[i] = 0.0;
     // (1) derivative terms  m*k*prod(other cs)   (src/Reactor.jl:899-1366)
     for (int t = lane; t < m.n_dt; t += 32) {
         int jr = m.dt_rxn[t];
         int j = jr & 0x3fffffff;
-        double v = (double)m.dt_mult[t] * ((jr >> 30) ? w.kr[j] : w.kf[j]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { int s = m.dt_oth[3 * t + k]; if (s < 0) break; v *= w.cs[s]; }
-        w.dterm[t] = v;
+        double v = (double)m.dt_mult[t] * ((jr >> 30) ? krb[j] : kfb[j]);
+        for (int k = 0; k < 3; ++k) { int s = m.dt_oth[3 * t + k]; if (s < 0) break; v *= cs[s]; }
+        dterm[t] = v;
     }
     __syncwarp();
     // (2) gather into entries, in the reference's accumulation order
@@ -791,10 +765,10 @@ __device__ inline void jac_warp(const DevMech& m, const DomainArgs& d, WarpWs& w
         double acc = 0.0;
         for (int k = m.je_ptr[e]; k < m.je_ptr[e + 1]; ++k) {
             int ti = m.jt_idx[k];
-            double v = w.dterm[ti & 0x7fffffff];
+            double v = dterm[ti & 0x7fffffff];
             acc = (ti < 0) ? acc - v : acc + v;
         }
-        w.J[m.je_row[e] + m.je_col[e] * LD] = acc;
+        J[m.je_row[e] + m.je_col[e] * LD] = acc;
     }
     __syncwarp();
     const bool hasV = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
@@ -805,17 +779,16 @@ __device__ inline void jac_warp(const DevMech& m, const DomainArgs& d, WarpWs& w
             for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
                 int jr = m.sr_rxn[k];
                 int j = jr & 0x7fffffff;
-                // forward / reverse -(order-1)*k*prod(cs)
                 double df = 0.0, dr = 0.0;
                 int nre = 0, npr = 0;
-                double pf = w.kf[j], pr = w.kr[j];
-                for (int q = 0; q < 4; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pf *= w.cs[sp]; ++nre; }
-                for (int q = 4; q < 8; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pr *= w.cs[sp]; ++npr; }
+                double pf = kfb[j], pr = krb[j];
+                for (int q = 0; q < 4; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pf *= cs[sp]; ++nre; }
+                for (int q = 4; q < 8; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pr *= cs[sp]; ++npr; }
                 if (nre > 1) df = -(double)(nre - 1) * pf;
                 if (npr > 1) dr = -(double)(npr - 1) * pr;
                 if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
             }
-            w.J[s + Ns * LD] = acc;
+            J[s + Ns * LD] = acc;
         }
         __syncwarp();
     }
@@ -823,80 +796,67 @@ __device__ inline void jac_warp(const DevMech& m, const DomainArgs& d, WarpWs& w
     //     (src/Domain.jl:2151-2167, src/Reactor.jl:1418-1467).  One reaction at a time (uniform loop).
     if (m.n_effrxn > 0 && d.kind != RMSB_DOMAIN_CONSTANT_TAPHI) {
         KinEnv<double> e;
-        e.T = ax.T; e.logT = log(ax.T); e.RT = RMSB_R * ax.T; e.invRT = 1.0 / (RMSB_R * ax.T); e.P = ax.P;
+        e.T = aT; e.logT = log(aT); e.RT = RMSB_R * aT; e.invRT = 1.0 / (RMSB_R * aT); e.P = aP;
         for (int q = 0; q < m.n_effrxn; ++q) {
             int j = m.effrxn[q];
-            double Kc = w.kf[j] / w.kr[j];
+            double Kc = kfb[j] / krb[j];
             double acc = 0.0;
-            for (int k = m.eff_ptr[j]; k < m.eff_ptr[j + 1]; ++k) acc += w.cs[m.eff_spc[k]] * m.eff_val[k];
-            double Ceff = ax.C + acc;
-            double dkdC = dk_dCeff(m, j, e, Ceff);
-            double pf = ax.V, pr = ax.V;   // prod(cs)*V per side
-            {
-                double a = 1.0, b = 1.0;
-                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; a *= w.cs[sp]; }
-                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; b *= w.cs[sp]; }
-                pf = a * ax.V; pr = b * ax.V;
-            }
+            for (int k = m.eff_ptr[j]; k < m.eff_ptr[j + 1]; ++k) acc += cs[m.eff_spc[k]] * m.eff_val[k];
+            double Ceff = aC + acc;
+            double dkdC = dk_dCeff(m, j, &e, Ceff);
+            double a = 1.0, b = 1.0;
+            for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; a *= cs[sp]; }
+            for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; b *= cs[sp]; }
+            double pf = a * aV, pr = b * aV;
             int ne = m.eff_ptr[j + 1] - m.eff_ptr[j];
             int ncol = ne + (hasV ? 1 : 0);
             for (int c = lane; c < ncol; c += 32) {
                 int col; double dkf;
-                if (c < ne) { col = m.eff_spc[m.eff_ptr[j] + c]; dkf = dkdC * (m.eff_val[m.eff_ptr[j] + c] / ax.V); }
-                else { col = Ns; dkf = dkdC * (ax.C - Ceff) / ax.V; }
+                if (c < ne) { col = m.eff_spc[m.eff_ptr[j] + c]; dkf = dkdC * (m.eff_val[m.eff_ptr[j] + c] / aV); }
+                else { col = Ns; dkf = dkdC * (aC - Ceff) / aV; }
                 double dkr = dkf / Kc;
                 double dvf = dkf * pf, dvr = dkr * pr;
-                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] -= dvf; }
-                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] += dvf; }
-                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] -= dvr; }
-                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; w.J[sp + col * LD] += dvr; }
+                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] -= dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] += dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] -= dvr; }
+                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] += dvr; }
             }
             __syncwarp();
         }
     }
     // (5) thermodynamic-variable rows
     if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
-        double f = RMSB_R * ax.T / ax.P;
         for (int c = lane; c <= Ns; c += 32) {           // Domain.jl:2211-2214
             double a = 0.0;
-            for (int i = 0; i < Ns; ++i) a += w.J[i + c * LD];
-            w.J[Ns + c * LD] = a * RMSB_R * ax.T / ax.P;
+            for (int i = 0; i < Ns; ++i) a += J[i + c * LD];
+            J[Ns + c * LD] = a * RMSB_R * aT / aP;
         }
-        (void)f;
     } else if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
+        const double* us = w.us();
+        const double* cpb = w.cp();
         for (int c = lane; c < Ns; c += 32) {            // Domain.jl:2312-2316
-            double dCv = w.cp[c] * RMSB_R / ax.N;
+            double dCv = cpb[c] * RMSB_R / aN;
             double a = 0.0, sm = 0.0;
-            for (int i = 0; i < Ns; ++i) { double v = w.J[i + c * LD]; a += w.us[i] * v; sm += v; }
-            double jt = -a / (ax.N * ax.Cv) + ax.dotUsdn / (ax.N * ax.Cv * ax.Cv) * dCv;
-            w.J[Ns + c * LD] = jt;
-            w.J[Ns + 1 + c * LD] = sm * RMSB_R * ax.T / ax.V + ax.P / ax.T * jt;
+            for (int i = 0; i < Ns; ++i) { double v = J[i + c * LD]; a += us[i] * v; sm += v; }
+            double jt = -a / (aN * aCv) + adotU / (aN * aCv * aCv) * dCv;
+            J[Ns + c * LD] = jt;
+            J[Ns + 1 + c * LD] = sm * RMSB_R * aT / aV + aP / aT * jt;
         }
     }
     __syncwarp();
     // (6) constant species rows (Domain.jl:2216-2218,2318-2320,3053-3055)
     for (int k = 0; k < d.nconst; ++k) {
-        int s = d.constspc[k] - 1;  // API indices are 1-based
-        for (int c = lane; c < Ny; c += 32) w.J[s + c * LD] = 0.0;
+        int s = d.constspc[k] - 1;
+        for (int c = lane; c < Ny; c += 32) J[s + c * LD] = 0.0;
     }
     __syncwarp();
     // (7) ConstantV: T and P columns = derivative of the complete RHS (src/Reactor.jl:1469-1477)
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
-        Dual2 yd[R], dyd[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int i = r * 32 + lane;
-            yd[r] = Dual2(y[r], i == Ns ? 1.0 : 0.0, i == Ns + 1 ? 1.0 : 0.0);
-        }
-        rhs_warp<Dual2, R>(m, d, w, cond, yd, dyd, lane, false, nullptr);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int i = r * 32 + lane;
-            if (i < Ny) { w.J[i + Ns * LD] = dyd[r].a; w.J[i + (Ns + 1) * LD] = dyd[r].b; }
-        }
+        rhs_v<Dual2>(m, d, w, lane, false);
+        const double* fb = w.fbuf();
+        for (int i = lane; i < Ny; i += 32) { J[i + Ns * LD] = fb[3 * i + 1]; J[i + (Ns + 1) * LD] = fb[3 * i + 2]; }
         __syncwarp();
     }
-    (void)dn;
 }
 
 }  // namespace rmsb

@@ -10,9 +10,11 @@
 // The same algorithm is available on the CPU as scipy.integrate.BDF, which the tests use as an
 // independent cross-check of step counts and solution values.
 //
-// Data placement: state vectors (y, D[0..7], scale, psi, d) are distributed over the warp's registers;
-// J and the LU factors of I - c*J live in the warp's shared-memory slice (column-major, odd leading
-// dimension); HBM is touched only for the initial state, the saved outputs and the final statistics.
+// Data placement: state vectors (y, D[0..7], scale, psi, d) are distributed over the warp's registers
+// (component i -> lane i&31, slot i>>5); J and the LU factors of I - c*J live in the warp's shared-memory
+// slice (column-major, odd leading dimension); vectors cross into the non-inlined RHS / Jacobian / LU
+// routines through that slice.  HBM is touched only for the initial state, the saved outputs and the
+// final statistics.
 #pragma once
 #include "rmsb_device.cuh"
 
@@ -22,6 +24,26 @@ constexpr int BDF_MAX_ORDER = 5;
 constexpr int NEWTON_MAXITER = 4;
 constexpr double BDF_MIN_FACTOR = 0.2;
 constexpr double BDF_MAX_FACTOR = 10.0;
+
+// NDF constants (Shampine-Reichelt kappa; gamma_k = sum_{j<=k} 1/j accumulated left to right)
+#define RMSB_G1 (1.0)
+#define RMSB_G2 (RMSB_G1 + 1.0 / 2.0)
+#define RMSB_G3 (RMSB_G2 + 1.0 / 3.0)
+#define RMSB_G4 (RMSB_G3 + 1.0 / 4.0)
+#define RMSB_G5 (RMSB_G4 + 1.0 / 5.0)
+#define RMSB_K1 (-0.1850)
+#define RMSB_K2 (-1.0 / 9.0)
+#define RMSB_K3 (-0.0823)
+#define RMSB_K4 (-0.0415)
+__constant__ double c_gamma[6] = {0.0, RMSB_G1, RMSB_G2, RMSB_G3, RMSB_G4, RMSB_G5};
+__constant__ double c_alpha[6] = {0.0, (1.0 - RMSB_K1) * RMSB_G1, (1.0 - RMSB_K2) * RMSB_G2, (1.0 - RMSB_K3) * RMSB_G3,
+                                  (1.0 - RMSB_K4) * RMSB_G4, (1.0 - 0.0) * RMSB_G5};
+__constant__ double c_ec[6] = {1.0, RMSB_K1 * RMSB_G1 + 1.0 / 2.0, RMSB_K2 * RMSB_G2 + 1.0 / 3.0, RMSB_K3 * RMSB_G3 + 1.0 / 4.0,
+                               RMSB_K4 * RMSB_G4 + 1.0 / 5.0, 0.0 * RMSB_G5 + 1.0 / 6.0};
+// U = R(factor = 1): U[k][j] = prod_{l=1..k} (l-1-j)/l = (-1)^k C(j,k)
+__constant__ double c_U[36] = {1, 1, 1, 1, 1, 1,   0, -1, -2, -3, -4, -5,   0, 0, 1, 3, 6, 10,
+                               0, 0, 0, -1, -4, -10,   0, 0, 0, 0, 1, 5,   0, 0, 0, 0, 0, -1};
+__constant__ double c_invl[6] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0};
 
 struct SolveArgs {
     int64_t n;
@@ -70,23 +92,66 @@ __device__ __forceinline__ bool all_finite(const double (&x)[R], int Ny, int lan
     return __all_sync(FULL, ok);
 }
 
-// ---- dense LU with partial pivoting of A = I - c*J in shared memory ------------------------------
-// Rows are owned by lanes (row i -> lane i&31), columns are walked sequentially; row k is broadcast.
-// Returns false if a zero pivot is met.
 template <int R>
-__device__ inline bool lu_factor_warp(WarpWs& w, int Ny, double c, int lane) {
-    const int LD = w.LD;
-    double* A = w.LU;
+__device__ __forceinline__ void to_smem(double* dst, const double (&x)[R], int Ny, int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) dst[i] = x[r]; }
+    __syncwarp();
+}
+template <int R>
+__device__ __forceinline__ void from_smem(double (&x)[R], const double* src, int Ny, int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; x[r] = (i < Ny) ? src[i] : 0.0; }
+}
+
+// f(y): state through w.ybuf, result through w.fbuf
+template <int R>
+__device__ __forceinline__ void eval_rhs(const DevMech& m, const DomainArgs& d, const Ws& w, const double (&y)[R], double (&f)[R], int lane) {
+    to_smem<R>(w.ybuf(), y, w.Ny, lane);
+    rhs_warp(m, d, w, lane, false);
+    from_smem<R>(f, w.fbuf(), w.Ny, lane);
+}
+
+// WRMS norm with precomputed reciprocal weights: sqrt(sum((x_i*iw_i)^2)/Ny)
+template <int R>
+__device__ __forceinline__ double rms_norm_w(const double (&x)[R], const double (&iw)[R], int Ny, int lane) {
+    double a = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = r * 32 + lane;
+        if (i < Ny) { double q = x[r] * iw[r]; a += q * q; }
+    }
+    return sqrt(warp_sum(a) / (double)Ny);
+}
+
+// x^e for the step-size heuristics (safety factors): single precision is ample and ~20x cheaper than pow()
+__device__ __forceinline__ double fast_pow(double x, float e) {
+    if (!(x > 0.0)) return INFINITY;            // 0^(-e)
+    if (isinf(x)) return 0.0;
+    return (double)exp2f(e * log2f((float)fmin(fmax(x, 1e-37), 1e37)));
+}
+
+// ---- explicit inverse of A = I - c*J by in-place Gauss-Jordan with partial pivoting ----------------
+// Rows are owned by lanes (row i -> lane i&31); the result (column-major, leading dimension LD) replaces
+// w.LU.  Each simplified-Newton iteration is then one 2*Ny^2-flop mat-vec instead of two dependent
+// triangular sweeps.  Rounding in the explicit inverse only affects the Newton contraction rate, never
+// the converged solution (the residual c*f(y) - psi - d is evaluated exactly each iteration).
+// Returns false if a zero / non-finite pivot is met.
+template <int R>
+__device__ __noinline__ bool inv_factor_warp(Ws w, double c, int lane) {
+    const int LD = w.LD, Ny = w.Ny;
+    double* A = w.LU();
+    const double* J = w.J();
+    int* piv = w.perm();
     for (int idx = lane; idx < Ny * LD; idx += 32) {
         int col = idx / LD, row = idx - col * LD;
-        if (row < Ny) A[idx] = ((row == col) ? 1.0 : 0.0) - c * w.J[idx];
+        if (row < Ny) A[idx] = ((row == col) ? 1.0 : 0.0) - c * J[idx];
     }
-    for (int i = lane; i < Ny; i += 32) w.perm[i] = i;
     bool ok = true;
     for (int k = 0; k < Ny; ++k) {
         __syncwarp();
         // pivot search on the high word of |a_ik| (ordering of non-negative doubles == ordering of their bits;
-        // ties within 2^-20 relative are equally good pivots)
+        // candidates within 2^-20 relative of the maximum are equally good pivots)
         unsigned best = 0; int bi = -1;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -98,32 +163,45 @@ __device__ inline bool lu_factor_warp(WarpWs& w, int Ny, double c, int lane) {
         }
         unsigned mx = __reduce_max_sync(FULL, best);
         unsigned vote = __ballot_sync(FULL, best == mx && bi >= 0);
-        int src = __ffs(vote) - 1;
-        int pr = __shfl_sync(FULL, bi, src);
-        if (pr != k) {
-            for (int j = lane; j < Ny; j += 32) {
-                double t = A[k + j * LD]; A[k + j * LD] = A[pr + j * LD]; A[pr + j * LD] = t;
-            }
-            if (lane == 0) { int t = w.perm[k]; w.perm[k] = w.perm[pr]; w.perm[pr] = t; }
-            __syncwarp();
+        int pr = __shfl_sync(FULL, bi, __ffs(vote) - 1);
+        if (lane == 0) piv[k] = pr;
+        double piv_v = A[pr + k * LD];
+        if (piv_v == 0.0 || !isfinite(piv_v)) { ok = false; piv_v = 1.0; }
+        const double inv = 1.0 / piv_v;
+        // swap rows k <-> pr and scale the new row k by 1/pivot (lanes over columns); a_kk := 1 first
+        for (int j = lane; j < Ny; j += 32) {
+            double akj = A[k + j * LD], apj = A[pr + j * LD];
+            if (j == k) apj = 1.0;
+            A[k + j * LD] = apj * inv;
+            if (pr != k) A[pr + j * LD] = akj;
         }
-        double piv = A[k + k * LD];
-        if (piv == 0.0 || !isfinite(piv)) { ok = false; piv = 1.0; }
-        double inv = 1.0 / piv;
-        if (lane == 0) w.dinv[k] = inv;
-        double l[R];
+        __syncwarp();
+        // eliminate column k from every other row (own rows only): a_ik := 0, row_i -= f * row_k
+        double f[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int i = r * 32 + lane;
-            l[r] = 0.0;
-            if (i > k && i < Ny) { l[r] = A[i + k * LD] * inv; A[i + k * LD] = l[r]; }
+            f[r] = 0.0;
+            if (i < Ny && i != k) { f[r] = A[i + k * LD]; A[i + k * LD] = 0.0; }
         }
-        for (int j = k + 1; j < Ny; ++j) {
+        for (int j = 0; j < Ny; ++j) {
             double akj = A[k + j * LD];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 int i = r * 32 + lane;
-                if (i > k && i < Ny) A[i + j * LD] -= l[r] * akj;
+                if (i < Ny && i != k) A[i + j * LD] -= f[r] * akj;
+            }
+        }
+    }
+    __syncwarp();
+    // undo the row interchanges: column swaps in reverse order (each lane touches only its own rows)
+    for (int k = Ny - 1; k >= 0; --k) {
+        int pr = piv[k];
+        if (pr != k) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int i = r * 32 + lane;
+                if (i < Ny) { double t = A[i + k * LD]; A[i + k * LD] = A[i + pr * LD]; A[i + pr * LD] = t; }
             }
         }
     }
@@ -131,44 +209,20 @@ __device__ inline bool lu_factor_warp(WarpWs& w, int Ny, double c, int lane) {
     return ok;
 }
 
-// Solve (I - cJ) x = b with the factors above; b distributed in registers, overwritten with x.
+// x = Ainv * b with b in w.xs (already synchronised); result distributed in registers
 template <int R>
-__device__ inline void lu_solve_warp(const WarpWs& w, int Ny, double (&b)[R], int lane) {
-    const int LD = w.LD;
-    const double* A = w.LU;
-    // apply the row permutation through the warp's scratch vector
+__device__ __forceinline__ void inv_apply(const Ws& w, double (&x)[R], int lane) {
+    const int LD = w.LD, Ny = w.Ny;
+    const double* A = w.LU();
+    const double* b = w.xs();
 #pragma unroll
-    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) w.xs[i] = b[r]; }
-    __syncwarp();
+    for (int r = 0; r < R; ++r) x[r] = 0.0;
+    for (int j = 0; j < Ny; ++j) {
+        double bj = b[j];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) b[r] = w.xs[w.perm[i]]; }
-    // forward substitution (unit lower)
-#pragma unroll
-    for (int kr = 0; kr < R; ++kr) {
-        for (int kl = 0; kl < 32; ++kl) {
-            int k = kr * 32 + kl;
-            if (k >= Ny - 1) break;
-            double xk = __shfl_sync(FULL, b[kr], kl);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int i = r * 32 + lane;
-                if (i > k && i < Ny) b[r] -= A[i + k * LD] * xk;
-            }
-        }
-    }
-    // backward substitution
-#pragma unroll
-    for (int kr = R - 1; kr >= 0; --kr) {
-        for (int kl = 31; kl >= 0; --kl) {
-            int k = kr * 32 + kl;
-            if (k >= Ny) continue;
-            if (lane == kl) b[kr] *= w.dinv[k];
-            double xk = __shfl_sync(FULL, b[kr], kl);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int i = r * 32 + lane;
-                if (i < k) b[r] -= A[i + k * LD] * xk;
-            }
+        for (int r = 0; r < R; ++r) {
+            int i = r * 32 + lane;
+            if (i < Ny) x[r] += A[i + j * LD] * bj;
         }
     }
     __syncwarp();
@@ -176,39 +230,42 @@ __device__ inline void lu_solve_warp(const WarpWs& w, int Ny, double (&b)[R], in
 
 // ---- change_D: rescale the backward differences for a step-size ratio `factor` -------------------
 // D_new[j] = sum_i (R(factor) U)[i][j] D[i], R[i][k] = prod_{l=1..i} (l-1-factor*k)/l, U = R(1).
-template <int R>
-__device__ inline void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int order, double factor) {
-    double Rm[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1], Um[BDF_MAX_ORDER + 1][BDF_MAX_ORDER + 1];
-#pragma unroll
-    for (int k = 0; k <= BDF_MAX_ORDER; ++k) { Rm[0][k] = 1.0; Um[0][k] = 1.0; }
-#pragma unroll
-    for (int i = 1; i <= BDF_MAX_ORDER; ++i) {
-#pragma unroll
-        for (int k = 0; k <= BDF_MAX_ORDER; ++k) {
-            if (k == 0) { Rm[i][k] = 0.0; Um[i][k] = 0.0; }
+// The 6x6 product is formed cooperatively (one entry per lane) in w.ru.
+__device__ __noinline__ void compute_ru(Ws w, double factor, int lane) {
+    double* ru = w.ru();
+    for (int e = lane; e < 36; e += 32) {
+        int i = e / 6, j = e - 6 * i;
+        double acc = 0.0;
+        for (int k = 0; k <= j; ++k) {
+            double rik;
+            if (k == 0) rik = (i == 0) ? 1.0 : 0.0;
             else {
-                Rm[i][k] = Rm[i - 1][k] * (((double)(i - 1) - factor * (double)k) / (double)i);
-                Um[i][k] = Um[i - 1][k] * (((double)(i - 1) - (double)k) / (double)i);
+                rik = 1.0;
+                for (int l = 1; l <= i; ++l) rik *= ((double)(l - 1) - factor * (double)k) * c_invl[l];
             }
+            acc += rik * c_U[k * 6 + j];
         }
+        ru[e] = acc;
     }
+    __syncwarp();
+}
+
+template <int R>
+__device__ __forceinline__ void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int order, double factor, const Ws& w, int lane) {
+    compute_ru(w, factor, lane);
+    const double* ru = w.ru();
     double Dn[BDF_MAX_ORDER + 1][R];
 #pragma unroll
     for (int j = 1; j <= BDF_MAX_ORDER; ++j) {
-        double ru[BDF_MAX_ORDER + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) Dn[j][r] = 0.0;
 #pragma unroll
         for (int i = 0; i <= BDF_MAX_ORDER; ++i) {
-            double a = 0.0;
+            if (i <= order) {
+                double c = ru[i * 6 + j];
 #pragma unroll
-            for (int k = 0; k <= BDF_MAX_ORDER; ++k) if (k <= j) a += Rm[i][k] * Um[k][j];
-            ru[i] = a;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double a = 0.0;
-#pragma unroll
-            for (int i = 0; i <= BDF_MAX_ORDER; ++i) if (i <= order) a += ru[i] * D[i][r];
-            Dn[j][r] = a;
+                for (int r = 0; r < R; ++r) Dn[j][r] += c * D[i][r];
+            }
         }
     }
 #pragma unroll
@@ -217,38 +274,27 @@ __device__ inline void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int order, do
 #pragma unroll
             for (int r = 0; r < R; ++r) D[j][r] = Dn[j][r];
         }
+    __syncwarp();
 }
 
 // ---- the integrator ---------------------------------------------------------------------------
 template <int R>
-__device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, int64_t ir, int lane) {
+__device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w, int64_t ir, int lane) {
     const int Ny = a.Ny;
     DomainArgs d;
-    d.kind = a.domain_kind; d.Ny = Ny;
+    d.kind = a.domain_kind;
     d.p = a.p ? a.p + ir * a.p_stride : nullptr;
     d.constspc = a.constspc; d.nconst = a.nconst;
-    const double* cond = a.cond + ir * a.ncond;
+    d.cond = a.cond + ir * a.ncond;
     const double rtol = a.rtol, atol = a.atol;
     const double t_end = a.t_end[ir];
-
-    // BDF constants (Shampine-Reichelt NDF kappa; gamma_k = sum_{j<=k} 1/j)
-    const double kappa[BDF_MAX_ORDER + 1] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
-    double gamma[BDF_MAX_ORDER + 1], alpha[BDF_MAX_ORDER + 1], error_const[BDF_MAX_ORDER + 1];
-    gamma[0] = 0.0;
-#pragma unroll
-    for (int k = 1; k <= BDF_MAX_ORDER; ++k) gamma[k] = gamma[k - 1] + 1.0 / (double)k;
-#pragma unroll
-    for (int k = 0; k <= BDF_MAX_ORDER; ++k) {
-        alpha[k] = (1.0 - kappa[k]) * gamma[k];
-        error_const[k] = kappa[k] * gamma[k] + 1.0 / (double)(k + 1);
-    }
 
     double D[BDF_MAX_ORDER + 3][R];
 #pragma unroll
     for (int j = 0; j < BDF_MAX_ORDER + 3; ++j)
 #pragma unroll
         for (int r = 0; r < R; ++r) D[j][r] = 0.0;
-    double y[R], f[R], scale[R];
+    double y[R], f[R], scale[R];   // scale holds the RECIPROCAL weights 1/(atol + rtol*|y_i|)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         int i = r * 32 + lane;
@@ -257,15 +303,11 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
     int n_rhs = 0, n_jac = 0, n_lu = 0, n_steps = 0, n_nfail = 0, n_efail = 0;
     int status = RMSB_SOLVE_OK;
 
+    rhs_prepare(d, w, lane);
     // constant-k domains: rate coefficients once per reactor
     if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) { int s = r * 32 + lane; if (s < m.Ns) w.ns[s] = y[r]; }
-        __syncwarp();
-        double T = cond[0], P, V;
-        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = cond[1]; V = bcast<double, R>(y, m.Ns); }
-        else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = cond[1]; }
-        setup_constk(m, d, w, T, P, V, lane);
+        to_smem<R>(w.ybuf(), y, Ny, lane);
+        setup_constk(m, d, w, lane);
     }
 
     // output bookkeeping
@@ -281,31 +323,31 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
         ++isave;
     }
 
-    // f0 and initial Jacobian
-    rhs_warp<double, R>(m, d, w, cond, y, f, lane, false, nullptr); ++n_rhs;
+    // f0, initial step, initial Jacobian
+    eval_rhs<R>(m, d, w, y, f, lane); ++n_rhs;
     double t = 0.0;
     double h_abs;
-    bool finite_ok = all_finite<R>(f, Ny, lane);
-    if (!finite_ok) status = RMSB_SOLVE_NAN;
+    if (!all_finite<R>(f, Ny, lane)) status = RMSB_SOLVE_NAN;
     if (a.first_step > 0.0) h_abs = a.first_step;
     else {
         // select_initial_step (Hairer-Norsett-Wanner II.4), order = 1
 #pragma unroll
-        for (int r = 0; r < R; ++r) scale[r] = atol + fabs(y[r]) * rtol;
-        double d0 = rms_norm_scaled<R>(y, scale, Ny, lane);
-        double d1 = rms_norm_scaled<R>(f, scale, Ny, lane);
+        for (int r = 0; r < R; ++r) scale[r] = 1.0 / (atol + fabs(y[r]) * rtol);
+        double d0 = rms_norm_w<R>(y, scale, Ny, lane);
+        double d1 = rms_norm_w<R>(f, scale, Ny, lane);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        double y1[R], f1[R], df[R];
+        double y1[R], f1[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) y1[r] = y[r] + h0 * f[r];
-        rhs_warp<double, R>(m, d, w, cond, y1, f1, lane, false, nullptr); ++n_rhs;
+        eval_rhs<R>(m, d, w, y1, f1, lane); ++n_rhs;
 #pragma unroll
-        for (int r = 0; r < R; ++r) df[r] = f1[r] - f[r];
-        double d2 = rms_norm_scaled<R>(df, scale, Ny, lane) / h0;
-        double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.5);
+        for (int r = 0; r < R; ++r) f1[r] = f1[r] - f[r];
+        double d2 = rms_norm_w<R>(f1, scale, Ny, lane) / h0;
+        double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : sqrt(0.01 / fmax(d1, d2));
         h_abs = fmin(fmin(100.0 * h0, h1), t_end);
     }
-    jac_warp<R>(m, d, w, cond, y, lane); ++n_jac;
+    to_smem<R>(w.ybuf(), y, Ny, lane);
+    jac_warp(m, d, w, lane); ++n_jac;
     bool lu_valid = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) { D[0][r] = y[r]; D[1][r] = f[r] * h_abs; }
@@ -315,9 +357,9 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
 
     while (status == RMSB_SOLVE_OK && t < t_end) {
         if (n_steps >= a.max_steps) { status = RMSB_SOLVE_MAX_STEPS; break; }
-        const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+        const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*(nextafter(t,inf)-t)
         if (h_abs < min_step) {
-            change_D<R>(D, order, min_step / h_abs);
+            change_D<R>(D, order, min_step / h_abs, w, lane);
             h_abs = min_step; n_equal = 0; lu_valid = false;
         }
         bool accepted = false, current_jac = false;
@@ -328,28 +370,29 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
             t_new = t + h_abs;
             if (t_new - t_end > 0.0) {
                 t_new = t_end;
-                change_D<R>(D, order, fabs(t_new - t) / h_abs);
+                change_D<R>(D, order, fabs(t_new - t) / h_abs, w, lane);
                 n_equal = 0; lu_valid = false;
             }
             h = t_new - t; h_abs = fabs(h);
             double ypred[R], psi[R];
+            const double alpha_o = c_alpha[order];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double s = 0.0, ps = 0.0;
 #pragma unroll
                 for (int j = 0; j <= BDF_MAX_ORDER; ++j) if (j <= order) s += D[j][r];
 #pragma unroll
-                for (int j = 1; j <= BDF_MAX_ORDER; ++j) if (j <= order) ps += D[j][r] * gamma[j];
+                for (int j = 1; j <= BDF_MAX_ORDER; ++j) if (j <= order) ps += D[j][r] * c_gamma[j];
                 ypred[r] = s;
-                psi[r] = ps / alpha[order];
-                scale[r] = atol + rtol * fabs(s);
+                psi[r] = ps / alpha_o;
+                scale[r] = 1.0 / (atol + rtol * fabs(s));
             }
-            const double c = h / alpha[order];
+            const double c = h / alpha_o;
             bool converged = false;
             int n_iter = 0;
             while (!converged) {
                 bool lu_ok = true;
-                if (!lu_valid) { lu_ok = lu_factor_warp<R>(w, Ny, c, lane); lu_valid = true; ++n_lu; }
+                if (!lu_valid) { lu_ok = inv_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; }
                 // ---- solve_bdf_system: simplified Newton on y = ypred + d, c*f(y) - psi - d = 0
 #pragma unroll
                 for (int r = 0; r < R; ++r) { dvec[r] = 0.0; ynew[r] = ypred[r]; }
@@ -357,16 +400,21 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
                 if (lu_ok) {
                     for (int k = 0; k < NEWTON_MAXITER; ++k) {
                         n_iter = k + 1;
-                        rhs_warp<double, R>(m, d, w, cond, ynew, f, lane, false, nullptr); ++n_rhs;
+                        eval_rhs<R>(m, d, w, ynew, f, lane); ++n_rhs;
                         if (!all_finite<R>(f, Ny, lane)) break;
                         double dy[R];
 #pragma unroll
                         for (int r = 0; r < R; ++r) dy[r] = c * f[r] - psi[r] - dvec[r];
-                        lu_solve_warp<R>(w, Ny, dy, lane);
-                        double dy_norm = rms_norm_scaled<R>(dy, scale, Ny, lane);
+                        to_smem<R>(w.xs(), dy, Ny, lane);
+                        inv_apply<R>(w, dy, lane);
+                        double dy_norm = rms_norm_w<R>(dy, scale, Ny, lane);
                         double rate = (dy_norm_old < 0.0) ? -1.0 : dy_norm / dy_norm_old;
                         if (!(dy_norm == dy_norm)) break;   // NaN
-                        if (rate >= 0.0 && (rate >= 1.0 || pow(rate, (double)(NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > newton_tol)) break;
+                        if (rate >= 0.0) {
+                            double rp = rate;                                  // rate^(NEWTON_MAXITER - k)
+                            for (int q = 1; q < NEWTON_MAXITER - k; ++q) rp *= rate;
+                            if (rate >= 1.0 || rp / (1.0 - rate) * dy_norm > newton_tol) break;
+                        }
 #pragma unroll
                         for (int r = 0; r < R; ++r) { ynew[r] += dy[r]; dvec[r] += dy[r]; }
                         if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
@@ -375,27 +423,29 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
                 }
                 if (!converged) {
                     if (current_jac) break;
-                    jac_warp<R>(m, d, w, cond, ypred, lane); ++n_jac;
+                    to_smem<R>(w.ybuf(), ypred, Ny, lane);
+                    jac_warp(m, d, w, lane); ++n_jac;
                     lu_valid = false; current_jac = true;
                 }
             }
             if (!converged) {
                 ++n_nfail;
                 h_abs *= 0.5;
-                change_D<R>(D, order, 0.5);
+                change_D<R>(D, order, 0.5, w, lane);
                 n_equal = 0; lu_valid = false;
                 continue;
             }
             safety = 0.9 * (2.0 * NEWTON_MAXITER + 1.0) / (2.0 * NEWTON_MAXITER + (double)n_iter);
             double err[R];
+            const double ec_o = c_ec[order];
 #pragma unroll
-            for (int r = 0; r < R; ++r) { scale[r] = atol + rtol * fabs(ynew[r]); err[r] = error_const[order] * dvec[r]; }
-            error_norm = rms_norm_scaled<R>(err, scale, Ny, lane);
+            for (int r = 0; r < R; ++r) { scale[r] = 1.0 / (atol + rtol * fabs(ynew[r])); err[r] = ec_o * dvec[r]; }
+            error_norm = rms_norm_w<R>(err, scale, Ny, lane);
             if (error_norm > 1.0) {
                 ++n_efail;
-                double factor = fmax(BDF_MIN_FACTOR, safety * pow(error_norm, -1.0 / (double)(order + 1)));
+                double factor = fmax(BDF_MIN_FACTOR, safety * fast_pow(error_norm, -1.0f / (float)(order + 1)));
                 h_abs *= factor;
-                change_D<R>(D, order, factor);
+                change_D<R>(D, order, factor, w, lane);
                 n_equal = 0; lu_valid = false;
             } else accepted = true;
         }
@@ -433,30 +483,38 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
             }
             ++isave;
         }
-        // ---- ignition-delay tracker: max over the step of d/dt of component idt_index, 32 samples per step
+        // ---- ignition-delay tracker: max over the step of d/dt of component idt_index (32 samples of the
+        //      interpolant's derivative).  Steps whose mean slope D1/h is far below the running maximum are skipped:
+        //      within an error-controlled step the derivative of the order<=5 interpolant stays within 8x of its mean.
         if (idt_index >= 0) {
-            double Dk[BDF_MAX_ORDER + 1];
+            double d1k = 0.0;
 #pragma unroll
-            for (int j = 0; j <= BDF_MAX_ORDER; ++j) Dk[j] = bcast<double, R>(D[j], idt_index);
-            double ts = t_old + h * (double)(lane + 1) * (1.0 / 32.0);
-            double pj = 1.0, dpj = 0.0, der = 0.0;
+            for (int r = 0; r < R; ++r) { double tv = __shfl_sync(FULL, D[1][r], idt_index & 31); if ((idt_index >> 5) == r) d1k = tv; }
+            const double invh = 1.0 / h;
+            if (8.0 * d1k * invh > idt_best) {
+                double ts = t_old + h * (double)(lane + 1) * (1.0 / 32.0);
+                double pj = 1.0, dpj = 0.0, der = 0.0;
 #pragma unroll
-            for (int j = 1; j <= BDF_MAX_ORDER; ++j) {
-                if (j <= order) {
-                    double den = h * (double)j;
-                    double x = (ts - (t - (double)(j - 1) * h)) / den;
-                    dpj = dpj * x + pj / den;
-                    pj = pj * x;
-                    der += Dk[j] * dpj;
+                for (int j = 1; j <= BDF_MAX_ORDER; ++j) {
+                    if (j <= order) {
+                        double dk = 0.0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { double tv = __shfl_sync(FULL, D[j][r], idt_index & 31); if ((idt_index >> 5) == r) dk = tv; }
+                        double iden = invh * c_invl[j];                       // 1/(h*j)
+                        double x = (ts - (t - (double)(j - 1) * h)) * iden;
+                        dpj = dpj * x + pj * iden;
+                        pj = pj * x;
+                        der += dk * dpj;
+                    }
                 }
-            }
-            double best = der; double bt = ts;
+                double best = der; double bt = ts;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ob = __shfl_xor_sync(FULL, best, o), ot = __shfl_xor_sync(FULL, bt, o);
-                if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ob = __shfl_xor_sync(FULL, best, o), ot = __shfl_xor_sync(FULL, bt, o);
+                    if (ob > best || (ob == best && ot < bt)) { best = ob; bt = ot; }
+                }
+                if (best > idt_best) { idt_best = best; idt_time = bt; }
             }
-            if (best > idt_best) { idt_best = best; idt_time = bt; }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) y[r] = D[0][r];
@@ -465,28 +523,30 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
         double e_m = INFINITY, e_p = INFINITY;
         double tmp[R];
         if (order > 1) {
+            const double ecm = c_ec[order - 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double v = 0.0;
 #pragma unroll
                 for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) if (j == order) v = D[j][r];
-                tmp[r] = error_const[order - 1] * v;
+                tmp[r] = ecm * v;
             }
-            e_m = rms_norm_scaled<R>(tmp, scale, Ny, lane);
+            e_m = rms_norm_w<R>(tmp, scale, Ny, lane);
         }
         if (order < max_order) {
+            const double ecp = c_ec[order + 1];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 double v = 0.0;
 #pragma unroll
                 for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) if (j == order + 2) v = D[j][r];
-                tmp[r] = error_const[order + 1] * v;
+                tmp[r] = ecp * v;
             }
-            e_p = rms_norm_scaled<R>(tmp, scale, Ny, lane);
+            e_p = rms_norm_w<R>(tmp, scale, Ny, lane);
         }
-        double fm = pow(e_m, -1.0 / (double)order);
-        double f0 = pow(error_norm, -1.0 / (double)(order + 1));
-        double fp = pow(e_p, -1.0 / (double)(order + 2));
+        double fm = fast_pow(e_m, -1.0f / (float)order);
+        double f0 = fast_pow(error_norm, -1.0f / (float)(order + 1));
+        double fp = fast_pow(e_p, -1.0f / (float)(order + 2));
         int delta; double fmax_;   // np.argmax([fm, f0, fp]) - 1: the first maximum wins
         if (fm >= f0 && fm >= fp) { delta = -1; fmax_ = fm; }
         else if (f0 >= fp) { delta = 0; fmax_ = f0; }
@@ -494,7 +554,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, WarpWs& w, 
         order += delta;
         double factor = fmin(BDF_MAX_FACTOR, safety * fmax_);
         h_abs *= factor;
-        change_D<R>(D, order, factor);
+        change_D<R>(D, order, factor, w, lane);
         n_equal = 0; lu_valid = false;
     }
 
