@@ -289,19 +289,28 @@ struct BatchArgs {
     int Ny;
 };
 
-__device__ __forceinline__ Ws make_ws(double* base, const DevMech& m, int Ny) {
+// Stage the mechanism descriptor at the start of the block's dynamic shared memory (see mech()).
+__device__ __forceinline__ void stage_mech(const DevMech& mp) {
+    const int* src = reinterpret_cast<const int*>(&mp);
+    int* dst = reinterpret_cast<int*>(smem_ws);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevMech) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ Ws make_ws(int warp, int ws_per_warp, int Ny) {
+    const DevMech& m = mech();
     Ws w;
-    w.base = base; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = m.n_dt; w.LD = Ny | 1;
+    w.off = MECH_DOUBLES + warp * ws_per_warp; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = m.n_dt; w.LD = Ny | 1;
     return w;
 }
 
 // mode 0: dydt, 1: Jacobian, 2: kf/krev.  One warp per reactor, grid-stride over the batch.
 template <int MODE>
-__global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMech m, const __grid_constant__ BatchArgs a, int ws_per_warp) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a, int ws_per_warp) {
+    stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const Ws w = make_ws(smem + (size_t)warp * ws_per_warp, m, a.Ny);
-    const int Ny = a.Ny;
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny);
+    const int Ny = a.Ny, Nr = w.Nr;
     const int64_t nw = (int64_t)gridDim.x * wpb;
     for (int64_t ir = (int64_t)blockIdx.x * wpb + warp; ir < a.n; ir += nw) {
         DomainArgs d;
@@ -312,13 +321,13 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
         double* yb = w.ybuf();
         for (int i = lane; i < Ny; i += 32) yb[i] = a.y[ir * Ny + i];
         rhs_prepare(d, w, lane);
-        if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(m, d, w, lane);
+        if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(d, w, lane);
         if (MODE == 0) {
-            rhs_warp(m, d, w, lane, false);
+            rhs_warp(d, w, lane, false);
             const double* fb = w.fbuf();
             for (int i = lane; i < Ny; i += 32) a.out[ir * Ny + i] = fb[i];
         } else if (MODE == 1) {
-            jac_warp(m, d, w, lane);
+            jac_warp(d, w, lane);
             const int LD = w.LD;
             const double* Js = w.J();
             double* J = a.out + (size_t)ir * Ny * Ny;
@@ -327,38 +336,40 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
                 J[idx] = Js[row + col * LD];
             }
         } else {
-            rhs_warp(m, d, w, lane, true);
-            for (int j = lane; j < m.Nr; j += 32) { a.out[ir * m.Nr + j] = w.kf()[j]; a.out2[ir * m.Nr + j] = w.kr()[j]; }
+            rhs_warp(d, w, lane, true);
+            for (int j = lane; j < Nr; j += 32) { a.out[ir * Nr + j] = w.kf()[j]; a.out2[ir * Nr + j] = w.kr()[j]; }
         }
         __syncwarp();
     }
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevMech m, const __grid_constant__ SolveArgs a, int ws_per_warp) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
+    stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Ws w = make_ws(smem + (size_t)warp * ws_per_warp, m, a.Ny);
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny);
     for (;;) {
         unsigned long long ir = 0;
         if (lane == 0) ir = atomicAdd(a.counter, 1ULL);     // dynamic work queue: one reactor per warp at a time
         ir = __shfl_sync(FULL, ir, 0);
         if (ir >= (unsigned long long)a.n) break;
-        bdf_solve_warp<R>(m, a, w, (int64_t)ir, lane);
+        bdf_solve_warp<R>(a, w, (int64_t)ir, lane);
     }
 }
 
-__global__ void gibbs_kernel(DevMech m, int64_t n, const double* T, int scalar_path, double* G) {
+__global__ void gibbs_kernel(const __grid_constant__ DevMech mp, int64_t n, const double* T, int scalar_path, double* G) {
+    stage_mech(mp);
+    const int Ns = mech().Ns;
     const int lane = threadIdx.x & 31;
     const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t ir = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ir < n; ir += nw) {
         double Tv = T[ir];
         TPow<double> tp(Tv);
-        for (int s = lane; s < m.Ns; s += 32) {
+        for (int s = lane; s < Ns; s += 32) {
             double g;
-            if (scalar_path) g = gibbs_scalar(m, s, Tv);
-            else { double cp, h, sr; nasa_hscp(m, s, tp, Tv, cp, h, sr); g = (h - sr) * (RMSB_R * Tv); }
-            G[ir * m.Ns + s] = g;
+            if (scalar_path) g = gibbs_scalar(s, Tv);
+            else { double cp, h, sr; nasa_hscp(s, tp, Tv, cp, h, sr); g = (h - sr) * (RMSB_R * Tv); }
+            G[ir * Ns + s] = g;
         }
     }
 }
@@ -387,13 +398,14 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, bool solver, int 
     CU(cudaGetDeviceProperties(&prop, h->device));
     int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, solver);
     size_t per_warp = (size_t)ws * sizeof(double);
-    size_t max_smem = prop.sharedMemPerBlockOptin;
+    const size_t mech_bytes = (size_t)MECH_DOUBLES * sizeof(double);
+    size_t max_smem = prop.sharedMemPerBlockOptin - mech_bytes;
     if (per_warp > max_smem)
         return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the warp-per-reactor dense kernels (per-warp workspace exceeds shared memory)");
     int wpb = want_wpb > 0 ? want_wpb : 4;
     if (wpb > 4) wpb = 4;
     while (wpb > 1 && per_warp * wpb > max_smem) --wpb;
-    size_t smem = per_warp * wpb;
+    size_t smem = per_warp * wpb + mech_bytes;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, wpb * 32, smem));
@@ -610,7 +622,7 @@ extern "C" int rmsb_gibbs_batch(const rmsb_mech* h, int64_t n, const double* T, 
     H2D(dT.p, T, sizeof(double) * n);
     int64_t blocks = (n + 3) / 4;
     if (blocks > 65535) blocks = 65535;
-    gibbs_kernel<<<(int)blocks, 128, 0, sg.st>>>(h->dm, n, dT.as<double>(), scalar_path, dG.as<double>());
+    gibbs_kernel<<<(int)blocks, 128, (size_t)MECH_DOUBLES * sizeof(double), sg.st>>>(h->dm, n, dT.as<double>(), scalar_path, dG.as<double>());
     ++g_launches;
     CU(cudaGetLastError());
     D2H(G, dG.p, sizeof(double) * n * h->dm.Ns);

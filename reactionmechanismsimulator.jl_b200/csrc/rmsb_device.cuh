@@ -151,28 +151,37 @@ __device__ __forceinline__ Dual2 warp_sum(Dual2 x) { return Dual2(warp_sum(x.v),
 // Per-warp shared-memory workspace.  A small by-value view (base pointer + sizes); sub-arrays are
 // located by integer offsets so that the struct travels in registers across non-inlined calls.
 // ------------------------------------------------------------------------------------------------
+extern __shared__ double smem_ws[];     // [DevMech copy | warp 0 slice | warp 1 slice | ...]
+
 struct Ws {
-    double* base;
+    int off;                                  // offset (in doubles) of this warp's slice inside smem_ws
     int Ns, Nr, Ny, ndt, LD;
-    __device__ __forceinline__ double* cs() const { return base; }                                  // [Ns]   concentrations
-    __device__ __forceinline__ double* g() const { return base + Ns; }                              // [3Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
-    __device__ __forceinline__ double* un() const { return base + 4 * Ns; }                         // [3Ns]  internal energies U_i (Dual2-capable) | diffusivities (liquid setup)
-    __device__ __forceinline__ double* q() const { return base + 7 * Ns; }                          // [3Nr]  net rates (Dual2-capable)
-    __device__ __forceinline__ double* kf() const { return base + 7 * Ns + 3 * Nr; }                // [Nr]
-    __device__ __forceinline__ double* kr() const { return base + 7 * Ns + 4 * Nr; }                // [Nr]
-    __device__ __forceinline__ double* us() const { return base + 7 * Ns + 5 * Nr; }                // [Ns]   U_i values (Jacobian)
-    __device__ __forceinline__ double* cp() const { return base + 8 * Ns + 5 * Nr; }                // [Ns]   cp_i/R values (Jacobian)
-    __device__ __forceinline__ double* dterm() const { return base + 9 * Ns + 5 * Nr; }             // [ndt]
+    __device__ __forceinline__ double* at(int o) const { return smem_ws + off + o; }
+    __device__ __forceinline__ double* cs() const { return at(0); }                                 // [Ns]   concentrations
+    __device__ __forceinline__ double* g() const { return at(Ns); }                                 // [3Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
+    __device__ __forceinline__ double* un() const { return at(4 * Ns); }                            // [3Ns]  internal energies U_i (Dual2-capable) | diffusivities (liquid setup)
+    __device__ __forceinline__ double* q() const { return at(7 * Ns); }                             // [3Nr]  net rates (Dual2-capable)
+    __device__ __forceinline__ double* kf() const { return at(7 * Ns + 3 * Nr); }                   // [Nr]
+    __device__ __forceinline__ double* kr() const { return at(7 * Ns + 4 * Nr); }                   // [Nr]
+    __device__ __forceinline__ double* us() const { return at(7 * Ns + 5 * Nr); }                   // [Ns]   U_i values (Jacobian)
+    __device__ __forceinline__ double* cp() const { return at(8 * Ns + 5 * Nr); }                   // [Ns]   cp_i/R values (Jacobian)
+    __device__ __forceinline__ double* dterm() const { return at(9 * Ns + 5 * Nr); }                // [ndt]
     __device__ __forceinline__ double* ybuf() const { return dterm() + ndt; }                       // [Ny]   RHS / Jacobian input state
     __device__ __forceinline__ double* fbuf() const { return ybuf() + Ny; }                         // [3Ny]  RHS output (Dual2-capable)
-    __device__ __forceinline__ double* aux() const { return fbuf() + 3 * Ny; }                      // [8]    T P V N C Cv dot(U,dn)
+    __device__ __forceinline__ double* aux() const { return fbuf() + 3 * Ny; }                      // [8]    T P V N C Cv dot(U,dn) 1/V
     __device__ __forceinline__ double* ru() const { return aux() + 8; }                             // [36]   change_D matrix
-    __device__ __forceinline__ double* dinv() const { return ru() + 36; }                           // [Ny]   1/U_kk
+    __device__ __forceinline__ double* dinv() const { return ru() + 36; }                           // [Ny]   spare
     __device__ __forceinline__ double* xs() const { return dinv() + Ny; }                           // [Ny]   linear-solve vector
-    __device__ __forceinline__ int* perm() const { return reinterpret_cast<int*>(xs() + Ny); }      // [Ny]   row permutation
+    __device__ __forceinline__ int* perm() const { return reinterpret_cast<int*>(xs() + Ny); }      // [Ny]   pivot rows
     __device__ __forceinline__ double* J() const { return xs() + Ny + (Ny + 1) / 2 + 1; }           // [Ny*LD] Jacobian, column-major
-    __device__ __forceinline__ double* LU() const { return J() + Ny * LD; }                         // [Ny*LD] factors of I - c*J (solver only)
+    __device__ __forceinline__ double* LU() const { return J() + Ny * LD; }                         // [Ny*LD] inverse of I - c*J (solver only)
 };
+
+// The mechanism descriptor lives at the start of the block's dynamic shared memory: every routine reads it
+// through a pointer of known address space (LDS with immediate offsets), never through a generic reference.
+constexpr int MECH_DOUBLES = (int)((sizeof(DevMech) + 15) / 16 * 2);
+__device__ __forceinline__ const DevMech& mech() { return *reinterpret_cast<const DevMech*>(smem_ws); }
+#define G(ptr, idx) __ldg((ptr) + (idx))   /* mechanism tables are immutable global memory: read-only path */
 
 __host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, bool solver) {
     int LD = Ny | 1;
@@ -195,11 +204,12 @@ template <> struct SmemNum<Dual2> {
 // ------------------------------------------------------------------------------------------------
 // Thermo
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int select_poly(const DevMech& m, int s, double T) {
+__device__ __forceinline__ int select_poly(int s, double T) {
+    const DevMech& m = mech();
     // selectPoly: first range with T <= Tmax, else the last (src/Calculators/Thermo.jl:101-111)
-    int nr = m.nasa_nr[s];
+    int nr = G(m.nasa_nr, s);
     for (int r = 0; r < nr; ++r)
-        if (T <= m.nasa_tmax[r * m.Ns + s]) return r;
+        if (T <= G(m.nasa_tmax, r * m.Ns + s)) return r;
     return nr - 1;
 }
 
@@ -213,47 +223,49 @@ struct TPow {  // powers of T built exactly as Thermovec.jl:78-84 / :100-105
 
 // calcHSCpdless for species s (src/Calculators/Thermovec.jl:76-119; literal 0.33333333333 kept)
 template <class N>
-__device__ __forceinline__ void nasa_hscp(const DevMech& m, int s, const TPow<N>& t, double Tv, N& cp, N& h, N& sr) {
-    int r = select_poly(m, s, Tv);
+__device__ __forceinline__ void nasa_hscp(int s, const TPow<N>& t, double Tv, N& cp, N& h, N& sr) {
+    const DevMech& m = mech();
+    int r = select_poly(s, Tv);
     const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
     const int Ns = m.Ns;
-    if (m.nasa_nc[r * Ns + s] != 7) {
-        N ct0 = c[0] * t.T5, ct1 = c[Ns] * t.T4;
-        double ct2 = c[2 * Ns];
-        N ct3 = c[3 * Ns] * t.T0, ct4 = c[4 * Ns] * t.T1, ct5 = c[5 * Ns] * t.T2, ct6 = c[6 * Ns] * t.T3;
+    if (G(m.nasa_nc, r * Ns + s) != 7) {
+        N ct0 = G(c, 0) * t.T5, ct1 = G(c, Ns) * t.T4;
+        double ct2 = G(c, 2 * Ns);
+        N ct3 = G(c, 3 * Ns) * t.T0, ct4 = G(c, 4 * Ns) * t.T1, ct5 = G(c, 5 * Ns) * t.T2, ct6 = G(c, 6 * Ns) * t.T3;
         cp = ct0 + ct1 + ct2 + ct3 + ct4 + ct5 + ct6;
-        h = -ct0 + t.T6 * ct1 + ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + c[7 * Ns] * t.T4;
-        sr = -0.5 * ct0 - ct1 + t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + c[8 * Ns];
+        h = -ct0 + t.T6 * ct1 + ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + G(c, 7 * Ns) * t.T4;
+        sr = -0.5 * ct0 - ct1 + t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + G(c, 8 * Ns);
     } else {
-        double ct2 = c[0];
-        N ct3 = c[Ns] * t.T0, ct4 = c[2 * Ns] * t.T1, ct5 = c[3 * Ns] * t.T2, ct6 = c[4 * Ns] * t.T3;
+        double ct2 = G(c, 0);
+        N ct3 = G(c, Ns) * t.T0, ct4 = G(c, 2 * Ns) * t.T1, ct5 = G(c, 3 * Ns) * t.T2, ct6 = G(c, 4 * Ns) * t.T3;
         cp = ct2 + ct3 + ct4 + ct5 + ct6;
-        h = ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + c[5 * Ns] * t.T4;
-        sr = t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + c[6 * Ns];
+        h = ct2 + 0.5 * ct3 + 0.33333333333 * ct4 + 0.25 * ct5 + 0.2 * ct6 + G(c, 5 * Ns) * t.T4;
+        sr = t.T6 * ct2 + ct3 + 0.5 * ct4 + 0.33333333333 * ct5 + 0.25 * ct6 + G(c, 6 * Ns);
     }
 }
 
 // getGibbs through the scalar path: evalpoly Horner (src/Tools.jl:13-22) with exact c_k/k
 // (src/Calculators/Thermo.jl:6-8,75-93).  Used by the constant-T domains at setup.
-__device__ __noinline__ double gibbs_scalar(const DevMech& m, int s, double T) {
-    int r = select_poly(m, s, T);
+__device__ __noinline__ double gibbs_scalar(int s, double T) {
+    const DevMech& m = mech();
+    int r = select_poly(s, T);
     const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
     const int Ns = m.Ns;
     double H, S;
-    if (m.nasa_nc[r * Ns + s] == 7) {
+    if (G(m.nasa_nc, r * Ns + s) == 7) {
         double out = 0.0;
-        for (int i = 4; i >= 0; --i) { out += c[i * Ns] / (double)(i + 1); if (i != 0) out *= T; }
-        H = out * RMSB_R * T + c[5 * Ns] * RMSB_R;
+        for (int i = 4; i >= 0; --i) { out += G(c, i * Ns) / (double)(i + 1); if (i != 0) out *= T; }
+        H = out * RMSB_R * T + G(c, 5 * Ns) * RMSB_R;
         out = 0.0;
-        for (int i = 3; i >= 0; --i) { out += c[(i + 1) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
-        S = (c[0] * log(T) + T * out + c[6 * Ns]) * RMSB_R;
+        for (int i = 3; i >= 0; --i) { out += G(c, (i + 1) * Ns) / (double)(i + 1); if (i != 0) out *= T; }
+        S = (G(c, 0) * log(T) + T * out + G(c, 6 * Ns)) * RMSB_R;
     } else {
         double out = 0.0;
-        for (int i = 4; i >= 0; --i) { out += c[(i + 2) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
-        H = ((-c[0] / T + c[Ns] * log(T)) / T + out) * RMSB_R * T + c[7 * Ns] * RMSB_R;
+        for (int i = 4; i >= 0; --i) { out += G(c, (i + 2) * Ns) / (double)(i + 1); if (i != 0) out *= T; }
+        H = ((-G(c, 0) / T + G(c, Ns) * log(T)) / T + out) * RMSB_R * T + G(c, 7 * Ns) * RMSB_R;
         out = 0.0;
-        for (int i = 3; i >= 0; --i) { out += c[(i + 3) * Ns] / (double)(i + 1); if (i != 0) out *= T; }
-        S = ((-c[0] / (2 * T) - c[Ns]) / T + c[2 * Ns] * log(T) + T * out + c[8 * Ns]) * RMSB_R;
+        for (int i = 3; i >= 0; --i) { out += G(c, (i + 3) * Ns) / (double)(i + 1); if (i != 0) out *= T; }
+        S = ((-G(c, 0) / (2 * T) - G(c, Ns)) / T + G(c, 2 * Ns) * log(T) + T * out + G(c, 8 * Ns)) * RMSB_R;
     }
     return H - T * S;
 }
@@ -269,10 +281,10 @@ struct KinEnv {
 };
 
 template <class N> __device__ __forceinline__ N arr_vec(const double* a, const KinEnv<N>& e) {
-    return a[0] * dexp(a[1] * e.logT - a[2] * e.invRT);            // Ratevec.jl:24
+    return G(a, 0) * dexp(G(a, 1) * e.logT - G(a, 2) * e.invRT);            // Ratevec.jl:24
 }
 template <class N> __device__ __forceinline__ N arr_sca(const double* a, const KinEnv<N>& e) {
-    return a[0] * dpow(e.T, a[1]) * dexp(-a[2] / e.RT);            // Rate.jl:16
+    return G(a, 0) * dpow(e.T, G(a, 1)) * dexp(-G(a, 2) / e.RT);            // Rate.jl:16
 }
 
 __device__ __forceinline__ void bounding_inds(double el, const double* x, int n, int& i0, int& i1) {
@@ -342,10 +354,11 @@ template <class N> __device__ inline N troe_F(const double* a, N T, N Pr) {
 // `scalar_forms` forces the scalar expressions for the *_VEC types (the diffusion-limited path goes through
 // getkf for every reaction, src/PhaseState.jl:184-223,249-252).  Not inlined: keeps the hot RHS loop small.
 template <class N>
-__device__ __noinline__ N eval_kin(const DevMech& m, int j, const KinEnv<N>* ep, N Ceff, bool scalar_forms) {
+__device__ __noinline__ N eval_kin(int j, const KinEnv<N>* ep, N Ceff, bool scalar_forms) {
+    const DevMech& m = mech();
     const KinEnv<N>& e = *ep;
-    const double* a = m.kpar + m.koff[j];
-    switch (m.ktype[j]) {
+    const double* a = m.kpar + G(m.koff, j);
+    switch (G(m.ktype, j)) {
     case RMSB_KIN_ARRHENIUS_VEC:
         return scalar_forms ? arr_sca(a, e) : arr_vec(a, e);
     case RMSB_KIN_ARRHENIUS:
@@ -414,10 +427,11 @@ __device__ __noinline__ N eval_kin(const DevMech& m, int j, const KinEnv<N>* ep,
 }
 
 // _calcdkdCeff, src/Calculators/Rate.jl:232-262
-__device__ __noinline__ double dk_dCeff(const DevMech& m, int j, const KinEnv<double>* ep, double Ceff) {
+__device__ __noinline__ double dk_dCeff(int j, const KinEnv<double>* ep, double Ceff) {
+    const DevMech& m = mech();
     const KinEnv<double>& e = *ep;
-    const double* a = m.kpar + m.koff[j];
-    int kt = m.ktype[j];
+    const double* a = m.kpar + G(m.koff, j);
+    int kt = G(m.ktype, j);
     if (kt == RMSB_KIN_THIRDBODY) return arr_sca(a, e);
     double k0 = arr_sca(a + 3, e), kinf = arr_sca(a, e);
     double Pr = k0 * Ceff / kinf;
@@ -439,45 +453,49 @@ __device__ __noinline__ double dk_dCeff(const DevMech& m, int j, const KinEnv<do
 
 // Ceff = C + sum_i ns[i]*(eff_i-1)/V   (src/PhaseState.jl:53-58)
 template <class N>
-__device__ __forceinline__ N ceff_of(const DevMech& m, int j, N C, const double* ns, double V) {
-    int b = m.eff_ptr[j], en = m.eff_ptr[j + 1];
+__device__ __forceinline__ N ceff_of(int j, N C, const double* ns, double V) {
+    const DevMech& m = mech();
+    int b = G(m.eff_ptr, j), en = G(m.eff_ptr, j + 1);
     if (b == en) return C;
     double acc = 0.0;
-    for (int k = b; k < en; ++k) acc += ns[m.eff_spc[k]] * m.eff_val[k];
+    for (int k = b; k < en; ++k) acc += ns[G(m.eff_spc, k)] * G(m.eff_val, k);
     return C + acc / V;
 }
 
 // mass-action net rate of reaction j: src/Reactor.jl:465-483
 template <class N>
-__device__ __forceinline__ N net_rate(const DevMech& m, int j, N kf, N kr, const double* cs) {
+__device__ __forceinline__ N net_rate(int j, N kf, N kr, const double* cs) {
+    const DevMech& m = mech();
     const int Nr = m.Nr;
-    N fR = kf * cs[m.rx[j]];
-    for (int k = 1; k < 4; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; fR = fR * cs[s]; }
-    N rR = kr * cs[m.rx[4 * Nr + j]];
-    for (int k = 5; k < 8; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; rR = rR * cs[s]; }
+    N fR = kf * cs[G(m.rx, j)];
+    for (int k = 1; k < 4; ++k) { int s = G(m.rx, k * Nr + j); if (s < 0) break; fR = fR * cs[s]; }
+    N rR = kr * cs[G(m.rx, 4 * Nr + j)];
+    for (int k = 5; k < 8; ++k) { int s = G(m.rx, k * Nr + j); if (s < 0) break; rR = rR * cs[s]; }
     return fR - rR;
 }
 
 // scalar getKc (src/PhaseState.jl:106-129, phi = 0) from absolute Gibbs energies G[]
-__device__ __noinline__ double kc_scalar(const DevMech& m, int j, const double* G, double T, double C0) {
+__device__ __noinline__ double kc_scalar(int j, const double* G, double T, double C0) {
+    const DevMech& m = mech();
     const int Nr = m.Nr;
-    double acc = G[m.rx[j]];
+    double acc = G[G(m.rx, j)];
     int nre = 1;
-    for (int k = 1; k < 4; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; acc += G[s]; ++nre; }
+    for (int k = 1; k < 4; ++k) { int s = G(m.rx, k * Nr + j); if (s < 0) break; acc += G[s]; ++nre; }
     double dG = 0.0 - acc;
-    acc = G[m.rx[4 * Nr + j]];
+    acc = G[G(m.rx, 4 * Nr + j)];
     int npr = 1;
-    for (int k = 5; k < 8; ++k) { int s = m.rx[k * Nr + j]; if (s < 0) break; acc += G[s]; ++npr; }
+    for (int k = 5; k < 8; ++k) { int s = G(m.rx, k * Nr + j); if (s < 0) break; acc += G[s]; ++npr; }
     dG += acc;
     return exp(-(dG) / (RMSB_R * T)) * pow(C0, (double)(npr - nre));
 }
 
 // getDiffusiveRate for 1 or 2 bodies (src/PhaseState.jl:87-93); >2-body form is out of scope
-__device__ __forceinline__ double diffusive_rate(const DevMech& m, int j, int side, const double* diffs) {
+__device__ __forceinline__ double diffusive_rate(int j, int side, const double* diffs) {
+    const DevMech& m = mech();
     const int Nr = m.Nr;
-    int s0 = m.rx[(side * 4) * Nr + j], s1 = m.rx[(side * 4 + 1) * Nr + j];
+    int s0 = G(m.rx, (side * 4) * Nr + j), s1 = G(m.rx, (side * 4 + 1) * Nr + j);
     if (s1 < 0) return INFINITY;
-    return 4.0 * RMSB_PI * (diffs[s0] + diffs[s1]) * (m.radius[s0] + m.radius[s1]) * RMSB_NA;
+    return 4.0 * RMSB_PI * (diffs[s0] + diffs[s1]) * (G(m.radius, s0) + G(m.radius, s1)) * RMSB_NA;
 }
 
 struct DomainArgs {
@@ -494,7 +512,8 @@ struct DomainArgs {
 // The initial amounts are read from w.ybuf (only efficiency reactions look at them, and those are
 // re-evaluated on every RHS call for TP).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, int lane) {
+__device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
     const double* ns = w.ybuf();
@@ -504,7 +523,7 @@ __device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, 
     double P, V;
     if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = ns[Ns]; }
     else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
-    for (int s = lane; s < Ns; s += 32) G[s] = p ? p[s] : gibbs_scalar(m, s, T);
+    for (int s = lane; s < Ns; s += 32) G[s] = p ? p[s] : gibbs_scalar(s, T);
     if (m.difflim) {   // Stokes diffusivities, src/Calculators/Diffusion.jl:19, Viscosity.jl:24
         double mu = 0.0;
         if (m.visc_kind == RMSB_VISC_RIEDEL)
@@ -512,7 +531,7 @@ __device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, 
         else if (m.visc_kind == RMSB_VISC_CONSTANT)
             mu = m.visc[0];
         for (int s = lane; s < Ns; s += 32) {
-            double r = m.diff_r ? m.diff_r[s] : 0.0;
+            double r = m.diff_r ? G(m.diff_r, s) : 0.0;
             diffs[s] = (r > 0.0) ? RMSB_KB * T / (6 * RMSB_PI * mu * r) : INFINITY;
         }
     }
@@ -527,36 +546,36 @@ __device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, 
     bool is_eff_dom = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
     for (int j = lane; j < Nr; j += 32) {
         double kf, kr;
-        bool eff = (m.eff_ptr[j + 1] > m.eff_ptr[j]);
+        bool eff = (G(m.eff_ptr, j + 1) > G(m.eff_ptr, j));
         if (!m.difflim) {
             // getkfkrevs vector path: getkfs + getKcs (src/PhaseState.jl:226-233)
             if (p && !(is_eff_dom && eff)) kf = p[Ns + j];
-            else kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, ns, V), false);
+            else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), false);
             double ex = 0.0;
-            for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex += m.kc_coef[k] * (G[m.kc_spc[k]] / (RMSB_R * T));
-            ex += m.nrp[j] * logC0;
+            for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex += G(m.kc_coef, k) * (G[G(m.kc_spc, k)] / (RMSB_R * T));
+            ex += G(m.nrp, j) * logC0;
             kr = kf / exp(ex);
         } else {
             // getkfkrev per reaction (src/PhaseState.jl:184-223): scalar forms, scalar Kc, diffusion limits
             if (p) kf = p[Ns + j];
-            else kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, ns, V), true);
-            double Kc = kc_scalar(m, j, G, T, C0);
+            else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), true);
+            double Kc = kc_scalar(j, G, T, C0);
             kr = kf / Kc;
             int nre = 0, npr = 0;
-            for (int k = 0; k < 4; ++k) { if (m.rx[k * Nr + j] >= 0) ++nre; if (m.rx[(k + 4) * Nr + j] >= 0) ++npr; }
+            for (int k = 0; k < 4; ++k) { if (G(m.rx, k * Nr + j) >= 0) ++nre; if (G(m.rx, (k + 4) * Nr + j) >= 0) ++npr; }
             if (nre == 1) {
                 if (npr > 1) {
-                    double krd = diffusive_rate(m, j, 1, diffs);
+                    double krd = diffusive_rate(j, 1, diffs);
                     kr = kr * krd / (kr + krd);
                     kf = Kc * kr;
                 }
             } else if (npr == 1) {
-                double kfd = diffusive_rate(m, j, 0, diffs);
+                double kfd = diffusive_rate(j, 0, diffs);
                 kf = kf * kfd / (kf + kfd);
                 kr = kf / Kc;
             } else if (npr == nre) {
-                double kfd = diffusive_rate(m, j, 0, diffs);
-                double krd = diffusive_rate(m, j, 1, diffs);
+                double kfd = diffusive_rate(j, 0, diffs);
+                double krd = diffusive_rate(j, 1, diffs);
                 double kff = kf * kfd / (kf + kfd);
                 double krevr = kr * krd / (kr + krd);
                 double kfr = Kc * krevr;
@@ -564,8 +583,8 @@ __device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, 
                 else { kf = kff; kr = kf / Kc; }
             }
         }
-        w.kf()[j] = kf * m.fwd[j];          // forwardability / reversibility masks (:220-221, :254-255)
-        w.kr()[j] = kr * m.rev[j];
+        w.kf()[j] = kf * G(m.fwd, j);          // forwardability / reversibility masks (:220-221, :254-255)
+        w.kr()[j] = kr * G(m.rev, j);
     }
     __syncwarp();
 }
@@ -585,7 +604,8 @@ __device__ __noinline__ void setup_constk(const DevMech& m, DomainArgs d, Ws w, 
 #define RMSB_LOG_1E5_OVER_R 9.394984624139783   /* log(1.0e5/8.314) */
 
 template <class N>
-__device__ __noinline__ void rhs_v(const DevMech& m, DomainArgs d, Ws w, int lane, bool store_k) {
+__device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
+    const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
     typedef SmemNum<N> SM;
@@ -606,7 +626,7 @@ __device__ __noinline__ void rhs_v(const DevMech& m, DomainArgs d, Ws w, int lan
     N cpns = 0.0;
     for (int s = lane; s < Ns; s += 32) {
         N cp, h, sr;
-        nasa_hscp(m, s, tp, val(T), cp, h, sr);
+        nasa_hscp(s, tp, val(T), cp, h, sr);
         if (p) h = h + p[s] * invRT;                    // Domain.jl:1100
         N U = (h - 1.0) * RT;                           // :1102
         SM::st(gb, s, h - sr);                          // G/(R*T) with G = (h-s)*R*T (:1101, PhaseState.jl:166)
@@ -623,23 +643,23 @@ __device__ __noinline__ void rhs_v(const DevMech& m, DomainArgs d, Ws w, int lan
     N logC0 = RMSB_LOG_1E5_OVER_R - tp.T6;              // log(1e5/(R*T))
     for (int j = lane; j < Nr; j += 32) {
         N kf;
-        if (m.ktype[j] == RMSB_KIN_ARRHENIUS_VEC) kf = arr_vec(m.kpar + m.koff[j], e);
-        else kf = eval_kin<N>(m, j, &e, ceff_of(m, j, C, yb, V), false);
+        if (G(m.ktype, j) == RMSB_KIN_ARRHENIUS_VEC) kf = arr_vec(m.kpar + G(m.koff, j), e);
+        else kf = eval_kin<N>(j, &e, ceff_of(j, C, yb, V), false);
         N ex = 0.0;
-        for (int k = m.kc_ptr[j]; k < m.kc_ptr[j + 1]; ++k) ex = ex + m.kc_coef[k] * SM::ld(gb, m.kc_spc[k]);
-        ex = ex + m.nrp[j] * logC0;
+        for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex = ex + G(m.kc_coef, k) * SM::ld(gb, G(m.kc_spc, k));
+        ex = ex + G(m.nrp, j) * logC0;
         N kr = kf * dexp(-ex);                          // kf/Kc, Kc = exp(ex)  (PhaseState.jl:165-167,230)
-        kf = kf * m.fwd[j]; kr = kr * m.rev[j];
+        kf = kf * G(m.fwd, j); kr = kr * G(m.rev, j);
         if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }   // Domain.jl:1112
         if (store_k) { w.kf()[j] = val(kf); w.kr()[j] = val(kr); }
-        SM::st(qb, j, net_rate(m, j, kf, kr, cs));
+        SM::st(qb, j, net_rate(j, kf, kr, cs));
     }
     __syncwarp();
     N usum = 0.0, nsum = 0.0;
     for (int s = lane; s < Ns; s += 32) {
         N acc = 0.0;
-        for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
-            int jr = m.sr_rxn[k];
+        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+            int jr = G(m.sr_rxn, k);
             N qv = SM::ld(qb, jr & 0x7fffffff);
             acc = (jr < 0) ? acc - qv : acc + qv;
         }
@@ -665,7 +685,8 @@ __device__ __noinline__ void rhs_v(const DevMech& m, DomainArgs d, Ws w, int lan
 }
 
 // constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns).  setup_constk() must have filled w.g / w.kf / w.kr.
-__device__ __noinline__ void rhs_ck(const DevMech& m, DomainArgs d, Ws w, int lane) {
+__device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
     const double* yb = w.ybuf();
@@ -691,21 +712,21 @@ __device__ __noinline__ void rhs_ck(const DevMech& m, DomainArgs d, Ws w, int la
         e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
         double C0 = 1.0e5 / (RMSB_R * T);
         for (int q = lane; q < m.n_effrxn; q += 32) {
-            int j = m.effrxn[q];
-            double kf = eval_kin<double>(m, j, &e, ceff_of(m, j, C, yb, V), false);
+            int j = G(m.effrxn, q);
+            double kf = eval_kin<double>(j, &e, ceff_of(j, C, yb, V), false);
             if (p) kf = kf * p[Ns + j];
-            double kr = kf / kc_scalar(m, j, w.g(), T, C0);
-            kfb[j] = kf * m.fwd[j]; krb[j] = kr * m.rev[j];
+            double kr = kf / kc_scalar(j, w.g(), T, C0);
+            kfb[j] = kf * G(m.fwd, j); krb[j] = kr * G(m.rev, j);
         }
         __syncwarp();
     }
-    for (int j = lane; j < Nr; j += 32) qb[j] = net_rate<double>(m, j, kfb[j], krb[j], cs);
+    for (int j = lane; j < Nr; j += 32) qb[j] = net_rate<double>(j, kfb[j], krb[j], cs);
     __syncwarp();
     double nsum = 0.0;
     for (int s = lane; s < Ns; s += 32) {
         double acc = 0.0;
-        for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
-            int jr = m.sr_rxn[k];
+        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+            int jr = G(m.sr_rxn, k);
             double qv = qb[jr & 0x7fffffff];
             acc = (jr < 0) ? acc - qv : acc + qv;
         }
@@ -732,17 +753,18 @@ __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, in
     __syncwarp();
 }
 
-__device__ __forceinline__ void rhs_warp(const DevMech& m, const DomainArgs& d, const Ws& w, int lane, bool store_k) {
-    if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(m, d, w, lane, store_k);
-    else rhs_ck(m, d, w, lane);
+__device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int lane, bool store_k) {
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(d, w, lane, store_k);
+    else rhs_ck(d, w, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
 // jacobiany! for one reactor: in w.ybuf, out dense column-major Ny x LD matrix in w.J.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int lane) {
+__device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, LD = w.LD;
-    rhs_warp(m, d, w, lane, true);
+    rhs_warp(d, w, lane, true);
     double* J = w.J();
     const double* cs = w.cs();
     const double* kfb = w.kf();
@@ -753,22 +775,22 @@ __device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int 
     for (int i = lane; i < Ny * LD; i += 32) J[i] = 0.0;
     // (1) derivative terms  m*k*prod(other cs)   (src/Reactor.jl:899-1366)
     for (int t = lane; t < m.n_dt; t += 32) {
-        int jr = m.dt_rxn[t];
+        int jr = G(m.dt_rxn, t);
         int j = jr & 0x3fffffff;
-        double v = (double)m.dt_mult[t] * ((jr >> 30) ? krb[j] : kfb[j]);
-        for (int k = 0; k < 3; ++k) { int s = m.dt_oth[3 * t + k]; if (s < 0) break; v *= cs[s]; }
+        double v = (double)G(m.dt_mult, t) * ((jr >> 30) ? krb[j] : kfb[j]);
+        for (int k = 0; k < 3; ++k) { int s = G(m.dt_oth, 3 * t + k); if (s < 0) break; v *= cs[s]; }
         dterm[t] = v;
     }
     __syncwarp();
     // (2) gather into entries, in the reference's accumulation order
     for (int e = lane; e < m.n_je; e += 32) {
         double acc = 0.0;
-        for (int k = m.je_ptr[e]; k < m.je_ptr[e + 1]; ++k) {
-            int ti = m.jt_idx[k];
+        for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
+            int ti = G(m.jt_idx, k);
             double v = dterm[ti & 0x7fffffff];
             acc = (ti < 0) ? acc - v : acc + v;
         }
-        J[m.je_row[e] + m.je_col[e] * LD] = acc;
+        J[G(m.je_row, e) + G(m.je_col, e) * LD] = acc;
     }
     __syncwarp();
     const bool hasV = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
@@ -776,14 +798,14 @@ __device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int 
     if (hasV) {
         for (int s = lane; s < Ns; s += 32) {
             double acc = 0.0;
-            for (int k = m.sr_ptr[s]; k < m.sr_ptr[s + 1]; ++k) {
-                int jr = m.sr_rxn[k];
+            for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+                int jr = G(m.sr_rxn, k);
                 int j = jr & 0x7fffffff;
                 double df = 0.0, dr = 0.0;
                 int nre = 0, npr = 0;
                 double pf = kfb[j], pr = krb[j];
-                for (int q = 0; q < 4; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pf *= cs[sp]; ++nre; }
-                for (int q = 4; q < 8; ++q) { int sp = m.rx[q * Nr + j]; if (sp < 0) break; pr *= cs[sp]; ++npr; }
+                for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; ++nre; }
+                for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; ++npr; }
                 if (nre > 1) df = -(double)(nre - 1) * pf;
                 if (npr > 1) dr = -(double)(npr - 1) * pr;
                 if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
@@ -798,28 +820,28 @@ __device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int 
         KinEnv<double> e;
         e.T = aT; e.logT = log(aT); e.RT = RMSB_R * aT; e.invRT = 1.0 / (RMSB_R * aT); e.P = aP;
         for (int q = 0; q < m.n_effrxn; ++q) {
-            int j = m.effrxn[q];
+            int j = G(m.effrxn, q);
             double Kc = kfb[j] / krb[j];
             double acc = 0.0;
-            for (int k = m.eff_ptr[j]; k < m.eff_ptr[j + 1]; ++k) acc += cs[m.eff_spc[k]] * m.eff_val[k];
+            for (int k = G(m.eff_ptr, j); k < G(m.eff_ptr, j + 1); ++k) acc += cs[G(m.eff_spc, k)] * G(m.eff_val, k);
             double Ceff = aC + acc;
-            double dkdC = dk_dCeff(m, j, &e, Ceff);
+            double dkdC = dk_dCeff(j, &e, Ceff);
             double a = 1.0, b = 1.0;
-            for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; a *= cs[sp]; }
-            for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; b *= cs[sp]; }
+            for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; a *= cs[sp]; }
+            for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; b *= cs[sp]; }
             double pf = a * aV, pr = b * aV;
-            int ne = m.eff_ptr[j + 1] - m.eff_ptr[j];
+            int ne = G(m.eff_ptr, j + 1) - G(m.eff_ptr, j);
             int ncol = ne + (hasV ? 1 : 0);
             for (int c = lane; c < ncol; c += 32) {
                 int col; double dkf;
-                if (c < ne) { col = m.eff_spc[m.eff_ptr[j] + c]; dkf = dkdC * (m.eff_val[m.eff_ptr[j] + c] / aV); }
+                if (c < ne) { col = G(m.eff_spc, G(m.eff_ptr, j) + c); dkf = dkdC * (G(m.eff_val, G(m.eff_ptr, j) + c) / aV); }
                 else { col = Ns; dkf = dkdC * (aC - Ceff) / aV; }
                 double dkr = dkf / Kc;
                 double dvf = dkf * pf, dvr = dkr * pr;
-                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] -= dvf; }
-                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] += dvf; }
-                for (int k = 4; k < 8; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] -= dvr; }
-                for (int k = 0; k < 4; ++k) { int sp = m.rx[k * Nr + j]; if (sp < 0) break; J[sp + col * LD] += dvr; }
+                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * LD] -= dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * LD] += dvf; }
+                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * LD] -= dvr; }
+                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * LD] += dvr; }
             }
             __syncwarp();
         }
@@ -852,7 +874,7 @@ __device__ __noinline__ void jac_warp(const DevMech& m, DomainArgs d, Ws w, int 
     __syncwarp();
     // (7) ConstantV: T and P columns = derivative of the complete RHS (src/Reactor.jl:1469-1477)
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
-        rhs_v<Dual2>(m, d, w, lane, false);
+        rhs_v<Dual2>(d, w, lane, false);
         const double* fb = w.fbuf();
         for (int i = lane; i < Ny; i += 32) { J[i + Ns * LD] = fb[3 * i + 1]; J[i + (Ns + 1) * LD] = fb[3 * i + 2]; }
         __syncwarp();

@@ -106,9 +106,9 @@ __device__ __forceinline__ void from_smem(double (&x)[R], const double* src, int
 
 // f(y): state through w.ybuf, result through w.fbuf
 template <int R>
-__device__ __forceinline__ void eval_rhs(const DevMech& m, const DomainArgs& d, const Ws& w, const double (&y)[R], double (&f)[R], int lane) {
+__device__ __forceinline__ void eval_rhs(const DomainArgs& d, const Ws& w, const double (&y)[R], double (&f)[R], int lane) {
     to_smem<R>(w.ybuf(), y, w.Ny, lane);
-    rhs_warp(m, d, w, lane, false);
+    rhs_warp(d, w, lane, false);
     from_smem<R>(f, w.fbuf(), w.Ny, lane);
 }
 
@@ -279,7 +279,7 @@ __device__ __forceinline__ void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int 
 
 // ---- the integrator ---------------------------------------------------------------------------
 template <int R>
-__device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w, int64_t ir, int lane) {
+__device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int lane) {
     const int Ny = a.Ny;
     DomainArgs d;
     d.kind = a.domain_kind;
@@ -307,7 +307,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
     // constant-k domains: rate coefficients once per reactor
     if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
         to_smem<R>(w.ybuf(), y, Ny, lane);
-        setup_constk(m, d, w, lane);
+        setup_constk(d, w, lane);
     }
 
     // output bookkeeping
@@ -324,7 +324,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
     }
 
     // f0, initial step, initial Jacobian
-    eval_rhs<R>(m, d, w, y, f, lane); ++n_rhs;
+    eval_rhs<R>(d, w, y, f, lane); ++n_rhs;
     double t = 0.0;
     double h_abs;
     if (!all_finite<R>(f, Ny, lane)) status = RMSB_SOLVE_NAN;
@@ -339,7 +339,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
         double y1[R], f1[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) y1[r] = y[r] + h0 * f[r];
-        eval_rhs<R>(m, d, w, y1, f1, lane); ++n_rhs;
+        eval_rhs<R>(d, w, y1, f1, lane); ++n_rhs;
 #pragma unroll
         for (int r = 0; r < R; ++r) f1[r] = f1[r] - f[r];
         double d2 = rms_norm_w<R>(f1, scale, Ny, lane) / h0;
@@ -347,7 +347,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
         h_abs = fmin(fmin(100.0 * h0, h1), t_end);
     }
     to_smem<R>(w.ybuf(), y, Ny, lane);
-    jac_warp(m, d, w, lane); ++n_jac;
+    jac_warp(d, w, lane); ++n_jac;
     bool lu_valid = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) { D[0][r] = y[r]; D[1][r] = f[r] * h_abs; }
@@ -400,7 +400,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
                 if (lu_ok) {
                     for (int k = 0; k < NEWTON_MAXITER; ++k) {
                         n_iter = k + 1;
-                        eval_rhs<R>(m, d, w, ynew, f, lane); ++n_rhs;
+                        eval_rhs<R>(d, w, ynew, f, lane); ++n_rhs;
                         if (!all_finite<R>(f, Ny, lane)) break;
                         double dy[R];
 #pragma unroll
@@ -424,7 +424,7 @@ __device__ void bdf_solve_warp(const DevMech& m, const SolveArgs& a, const Ws& w
                 if (!converged) {
                     if (current_jac) break;
                     to_smem<R>(w.ybuf(), ypred, Ny, lane);
-                    jac_warp(m, d, w, lane); ++n_jac;
+                    jac_warp(d, w, lane); ++n_jac;
                     lu_valid = false; current_jac = true;
                 }
             }
