@@ -343,8 +343,11 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
     }
 }
 
+#ifndef RMSB_SOLVE_MINBLOCKS
+#define RMSB_SOLVE_MINBLOCKS 1
+#endif
 template <int R>
-__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
+__global__ void __launch_bounds__(128, RMSB_SOLVE_MINBLOCKS) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Ws w = make_ws(warp, ws_per_warp, a.Ny);

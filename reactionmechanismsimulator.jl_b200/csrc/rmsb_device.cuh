@@ -598,7 +598,7 @@ __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
 // Arithmetic note (DESIGN.md "floating-point contract"): the reference is compiled under @fastmath and is
 // itself reproducible only to a few ulp; this kernel keeps the reference's formulas but replaces divisions by
 // a shared reciprocal where the reference divides by the same quantity (1/T, 1/(R*T), 1/V) and evaluates
-// kf/Kc as kf*exp(-x).  Measured agreement with the oracle: <= 1e-13 relative (tests/test_gpu_parity.py).
+// kf/Kc as kf*exp(-x).  Measured agreement with the CPU restatement: <= 1e-13 relative (tests/test_gpu_parity.py).
 // ------------------------------------------------------------------------------------------------
 #define RMSB_INV_R (1.0 / 8.314)
 #define RMSB_LOG_1E5_OVER_R 9.394984624139783   /* log(1.0e5/8.314) */

@@ -1,0 +1,195 @@
+# RMSB200.jl -- Julia host shim for librmsb200.so (include/rmsb200.h).
+#
+# STATUS: written against the C ABI, NOT EXECUTED in the build image (no `julia` binary there; SURVEY.md
+# "Container facts").  The executable host mirror used by the tests is the Python package `rmsb200/`; this file is
+# the binding a ReactionMechanismSimulator.jl maintainer would load.  It keeps the reference API surface:
+# `readinput`-parsed `Species`/`ElementaryReaction`, `IdealGas`, `ConstantVDomain`/`ConstantTPDomain`/
+# `ConstantTVDomain`, `Reactor`, `solve`, `Simulation` all stay RMS's own; only the hot path moves:
+#
+#     sols = solve(reactors::Vector{<:Reactor}, RMSB200(); abstol=1e-16, reltol=1e-6)   # one kernel launch
+#     sol  = solve(react.ode, RMSB200(react); abstol, reltol)                          # drop-in for CVODE_BDF()
+#
+# Every `ccall` below names the header entry point it binds; layouts are row = reactor, Float64, 1-based
+# species indices exactly as `phase.rxnarray` stores them (src/Phase.jl:320-348).
+module RMSB200Shim
+
+using ReactionMechanismSimulator
+using SciMLBase
+const RMS = ReactionMechanismSimulator
+
+const LIB = get(ENV, "RMSB200_LIB", joinpath(@__DIR__, "..", "csrc", "librmsb200.so"))
+
+# ---- mirrors of the C structs (include/rmsb200.h) -------------------------------------------------
+struct MechDesc
+    struct_size::Int32; phase_kind::Int32; n_species::Int32; n_reactions::Int32
+    sitedensity::Float64; diffusion_limited::Int32; nasa_max_ranges::Int32
+    nasa_nranges::Ptr{Int32}; nasa_ncoef::Ptr{Int32}; nasa_tmax::Ptr{Float64}; nasa_coefs::Ptr{Float64}
+    rxnarray::Ptr{Int32}; kin_type::Ptr{Int32}; kin_offset::Ptr{Int32}; kin_params::Ptr{Float64}
+    eff_ptr::Ptr{Int32}; eff_species::Ptr{Int32}; eff_value::Ptr{Float64}
+    reversible::Ptr{UInt8}; forwardable::Ptr{UInt8}; radius::Ptr{Float64}; diff_radius::Ptr{Float64}
+    viscosity_kind::Int32; viscosity_params::NTuple{5,Float64}
+end
+
+struct Stats
+    n_steps::Int32; n_rhs::Int32; n_jac::Int32; n_lu::Int32; n_newton_fail::Int32; n_err_fail::Int32
+    last_order::Int32; reserved::Int32; last_h::Float64
+end
+
+struct SolveOpts
+    struct_size::Int32; max_steps::Int32; max_order::Int32; idt_index::Int32
+    first_step::Float64; warps_per_block::Int32; reserved::Int32
+end
+
+const PHASE_GAS, PHASE_LIQUID, PHASE_SURFACE = Int32(0), Int32(1), Int32(2)
+const DOMAIN_V, DOMAIN_TP, DOMAIN_TV, DOMAIN_TAPHI = Int32(0), Int32(1), Int32(2), Int32(3)
+const KIN = (ARRHENIUS_VEC=0, ARRHENIUS=1, MULTIARRHENIUS=2, PLOG_VEC=3, PLOG=4, MULTIPLOG=5, THIRDBODY=6, LINDEMANN=7, TROE=8, CHEBYSHEV_VEC=9)
+
+lasterror() = unsafe_string(ccall((:rmsb_last_error, LIB), Cstring, ()))
+check(rc) = rc == 0 || error("librmsb200 error $rc: $(lasterror())")
+
+# ---- flattening: phase (already flattened by RMS, src/Phase.jl:40-57) -> descriptor -------------------
+arr(a::Arrhenius) = Float64[a.A, a.n, a.Ea]
+function plogblock(k::PdepArrhenius)
+    out = Float64[length(k.Ps); k.Ps]
+    for a in k.arrs
+        a isa Arrhenius ? append!(out, [1.0; arr(a)]) : append!(out, [Float64(length(a.arrs)); vcat(arr.(a.arrs)...)])
+    end
+    out
+end
+"(tag, params) in the layout documented in include/rmsb200.h; `vec` = reaction lies in a vectorised group (index <= veckineticsinds[end])"
+function packkinetics(k, vec::Bool)
+    k isa Arrhenius && return (vec ? KIN.ARRHENIUS_VEC : KIN.ARRHENIUS, arr(k))
+    k isa MultiArrhenius && return (KIN.MULTIARRHENIUS, [Float64(length(k.arrs)); vcat(arr.(k.arrs)...)])
+    k isa PdepArrhenius && return vec ? (KIN.PLOG_VEC, [Float64(length(k.Ps)); k.Ps; vcat(arr.(k.arrs)...)]) : (KIN.PLOG, plogblock(k))
+    k isa MultiPdepArrhenius && return (KIN.MULTIPLOG, [Float64(length(k.parrs)); vcat(plogblock.(k.parrs)...)])
+    k isa ThirdBody && return (KIN.THIRDBODY, arr(k.arr))
+    k isa Lindemann && return (KIN.LINDEMANN, [arr(k.arrhigh); arr(k.arrlow)])
+    k isa Troe && return (KIN.TROE, [arr(k.arrhigh); arr(k.arrlow); k.a; k.T3; k.T1; k.T2])
+    k isa Chebyshev && return (KIN.CHEBYSHEV_VEC, [k.Tmin; k.Tmax; k.Pmin; k.Pmax; Float64.(size(k.coefs))...; vec(permutedims(k.coefs))])
+    error("kinetics type $(typeof(k)) is outside the accelerated hot path")
+end
+
+mutable struct Mech
+    handle::Ptr{Cvoid}
+    keep::Vector{Any}          # arrays the descriptor points into
+    Ns::Int; Nr::Int
+end
+
+function Mech(phase; device::Integer=0)
+    Ns, Nr = length(phase.species), length(phase.reactions)
+    maxr = maximum(length(s.thermo.polys) for s in phase.species)
+    nr = Int32[length(s.thermo.polys) for s in phase.species]
+    nc = fill(Int32(7), maxr, Ns); tmax = zeros(maxr, Ns); coefs = zeros(9, maxr, Ns)        # column-major == C [Ns][maxr][9]
+    for (i, s) in enumerate(phase.species), (r, p) in enumerate(s.thermo.polys)
+        nc[r, i] = length(p.coefs); tmax[r, i] = p.Tmax; coefs[1:length(p.coefs), r, i] = p.coefs
+    end
+    rx = Int32.(phase.rxnarray)                                                               # 8 x Nr column-major == C [Nr][8]
+    nvec = isempty(phase.veckineticsinds) ? 0 : phase.veckineticsinds[end]
+    ktype = Int32[]; koff = Int32[0]; kpar = Float64[]; effptr = Int32[0]; effspc = Int32[]; effval = Float64[]
+    for (j, rxn) in enumerate(phase.reactions)
+        tag, pars = packkinetics(rxn.kinetics, j <= nvec)
+        push!(ktype, tag); append!(kpar, pars); push!(koff, length(kpar))
+        if hasproperty(rxn.kinetics, :efficiencies)
+            for i in sort(collect(keys(rxn.kinetics.efficiencies)))
+                push!(effspc, i); push!(effval, rxn.kinetics.efficiencies[i])                 # already eff-1 (src/Parse.jl:411-413)
+            end
+        end
+        push!(effptr, length(effspc))
+    end
+    rev = UInt8.(phase.reversibility); fwd = UInt8.(phase.forwardability)
+    radius = Float64[s.radius for s in phase.species]
+    diffr = Float64[s.diffusion isa StokesDiffusivity ? s.diffusion.r : -1.0 for s in phase.species]
+    kind = phase isa IdealSurface ? PHASE_SURFACE : (phase isa IdealDiluteSolution ? PHASE_LIQUID : PHASE_GAS)
+    visc, vp = Int32(0), (0.0, 0.0, 0.0, 0.0, 0.0)
+    if hasproperty(phase, :solvent) && phase.solvent.mu isa RiedelViscosity
+        mu = phase.solvent.mu; visc, vp = Int32(2), (mu.A, mu.B, mu.C, mu.D, mu.E)
+    end
+    isempty(kpar) && push!(kpar, 0.0); isempty(effspc) && push!(effspc, 0); isempty(effval) && push!(effval, 0.0)
+    keep = Any[nr, nc, tmax, coefs, rx, ktype, koff, kpar, effptr, effspc, effval, rev, fwd, radius, diffr]
+    desc = Ref(MechDesc(sizeof(MechDesc), kind, Ns, Nr, hasproperty(phase, :sitedensity) ? phase.sitedensity : 0.0,
+        Int32(phase.diffusionlimited), maxr, pointer(nr), pointer(nc), pointer(tmax), pointer(coefs), pointer(rx), pointer(ktype),
+        pointer(koff), pointer(kpar), pointer(effptr), pointer(effspc), pointer(effval), pointer(rev), pointer(fwd),
+        pointer(radius), pointer(diffr), visc, vp))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:rmsb_mech_create, LIB), Cint, (Ref{MechDesc}, Cint, Ref{Ptr{Cvoid}}), desc, device, h))   # rmsb_mech_create
+    m = Mech(h[], keep, Ns, Nr)
+    finalizer(x -> ccall((:rmsb_mech_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), m)                                       # rmsb_mech_destroy
+    m
+end
+
+# ---- domain -> (kind, cond, constant species) -----------------------------------------------------------
+domainkind(d::ConstantVDomain) = (DOMAIN_V, Float64[d.V])
+domainkind(d::ConstantTPDomain) = (DOMAIN_TP, Float64[d.T, d.P])
+domainkind(d::ConstantTVDomain) = (DOMAIN_TV, Float64[d.T, d.V])
+domainkind(d::ConstantTAPhiDomain) = (DOMAIN_TAPHI, Float64[d.T, d.A])
+
+"p is passed to the device only when it differs from the domain's own default (the nothermochg && nokfchg branch, src/Domain.jl:941-946)"
+devicep(d, p) = (p isa SciMLBase.NullParameters || p == d.p) ? (C_NULL, 0) : (pointer(p), 0)
+
+# ---- batched hot-path evaluations ---------------------------------------------------------------------------
+"dydt for n states of reactors sharing `domain`'s phase: Y is Ny x n (column = reactor)"
+function dydt_batch(mech::Mech, domain, Y::Matrix{Float64}, cond::Matrix{Float64}; p=SciMLBase.NullParameters())
+    kind, _ = domainkind(domain)
+    out = similar(Y); pp, ps = devicep(domain, p)
+    cs = Int32.(domain.constantspeciesinds)
+    GC.@preserve p check(ccall((:rmsb_dydt_batch, LIB), Cint,                                                                 # rmsb_dydt_batch
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}),
+        mech.handle, kind, size(Y, 2), Y, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), out))
+    out
+end
+
+"dense Jacobians, Ny x Ny x n, J[eqn, var, r] (column-major per reactor == jacobiany!'s layout)"
+function jac_batch(mech::Mech, domain, Y::Matrix{Float64}, cond::Matrix{Float64}; p=SciMLBase.NullParameters())
+    kind, _ = domainkind(domain)
+    Ny, n = size(Y); out = zeros(Ny, Ny, n); pp, ps = devicep(domain, p)
+    cs = Int32.(domain.constantspeciesinds)
+    GC.@preserve p check(ccall((:rmsb_jac_batch, LIB), Cint,                                                                  # rmsb_jac_batch
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}),
+        mech.handle, kind, n, Y, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), out))
+    out
+end
+
+# ---- solve ------------------------------------------------------------------------------------------------------
+struct RMSB200 <: SciMLBase.AbstractODEAlgorithm
+    max_steps::Int32; max_order::Int32; device::Int
+end
+RMSB200(; max_steps=500000, max_order=5, device=0) = RMSB200(max_steps, max_order, device)
+
+const MECHCACHE = IdDict{Any,Mech}()
+mechfor(phase, device) = get!(() -> Mech(phase; device=device), MECHCACHE, phase)
+
+"""
+Integrate many reactors that share one phase and domain type in ONE call (rmsb_solve_batch).  Returns one
+`ODESolution` per reactor built exactly as the reference itself fabricates solutions
+(`SciMLBase.build_solution(prob, alg, t, u; interp, retcode)`, src/Simulation.jl:72, src/ThreadedSensitivities.jl:165):
+cubic Hermite interpolation over the saved (t, u, du), so `Simulation(sol, domain)` works unchanged.
+"""
+function SciMLBase.solve(reactors::Vector{<:RMS.Reactor}, alg::RMSB200; abstol=1e-6, reltol=1e-3, saveat=Float64[])
+    r1 = reactors[1]; dom = r1.domain; mech = mechfor(dom.phase, alg.device)
+    kind, _ = domainkind(dom)
+    n, Ny = length(reactors), length(r1.y0)
+    Y0 = hcat((r.y0 for r in reactors)...)
+    cond = hcat((domainkind(r.domain)[2] for r in reactors)...)
+    tend = Float64[r.tspan[2] for r in reactors]
+    ts = isempty(saveat) ? collect(range(0.0, maximum(tend), length=201)) : collect(Float64, saveat)
+    nsave = length(ts)
+    ysave = zeros(Ny, nsave, n); yend = zeros(Ny, n); idt = zeros(n); status = zeros(Int32, n); stats = Vector{Stats}(undef, n)
+    opts = Ref(SolveOpts(sizeof(SolveOpts), alg.max_steps, alg.max_order, -1, 0.0, 0, 0))
+    cs = Int32.(dom.constantspeciesinds); pp, ps = devicep(dom, r1.p)
+    GC.@preserve r1 check(ccall((:rmsb_solve_batch, LIB), Cint,                                                                 # rmsb_solve_batch
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Float64, Float64,
+         Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Stats}, Ref{SolveOpts}),
+        mech.handle, kind, n, Y0, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), tend, reltol, abstol,
+        nsave, ts, ysave, yend, idt, status, stats, opts))
+    map(1:n) do i
+        keepidx = findall(t -> t <= tend[i], ts)
+        u = [ysave[:, k, i] for k in keepidx]
+        du = [similar(x) for x in u]
+        for (x, dx) in zip(u, du); RMS.dydtreactor!(dx, x, 0.0, reactors[i].domain, reactors[i].interfaces; p=reactors[i].p); end
+        interp = SciMLBase.HermiteInterpolation(ts[keepidx], u, du)
+        SciMLBase.build_solution(reactors[i].ode, alg, ts[keepidx], u; interp=interp,
+                                 retcode=status[i] == 0 ? SciMLBase.ReturnCode.Success : SciMLBase.ReturnCode.Failure)
+    end
+end
+
+end # module

@@ -10,6 +10,7 @@ from ._lib import (DOMAIN_CONSTANT_TAPHI, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV
                    lib)
 from .domain import (ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
                      ConstantVDomain, ConstantVEnsemble, Domain)
+from .ensemble import shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)
 from .phase import IdealDiluteSolution, IdealGas, IdealSurface, Phase
 from .reactor import RMSB200, Reactor, Solution, solve

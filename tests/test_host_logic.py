@@ -114,3 +114,11 @@ def test_domain_constructors_host_side():
         rb.ConstantVDomain(phase=ig, initialconds={"T": 1000.0, "P": 1e5, "XYZ": 1.0})
     ens = rb.ConstantVEnsemble(ig, [1000.0, 1200.0], [1e5, 2e5], np.array([[0, 0, 0, 0, 0.67, 0.33] + [0] * 6] * 2))
     assert ens.n == 2 and ens.cond.shape == (2, 1) and ens.y0.shape == (2, 14)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import, load or execute it."""
+    pkg = cases.ROOT / "reactionmechanismsimulator.jl_b200"
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.jl")):
+        text = path.read_text()
+        assert "oracle" not in text, f"{path} mentions the oracle"
