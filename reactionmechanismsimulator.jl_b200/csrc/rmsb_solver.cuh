@@ -131,22 +131,25 @@ __device__ __forceinline__ double fast_pow(double x, float e) {
     return (double)exp2f(e * log2f((float)fmin(fmax(x, 1e-37), 1e37)));
 }
 
-// ---- explicit inverse of A = I - c*J by in-place Gauss-Jordan with partial pivoting ----------------
-// Rows are owned by lanes (row i -> lane i&31); the result (column-major, leading dimension LD) replaces
-// w.LU.  Each simplified-Newton iteration is then one 2*Ny^2-flop mat-vec instead of two dependent
-// triangular sweeps.  Rounding in the explicit inverse only affects the Newton contraction rate, never
-// the converged solution (the residual c*f(y) - psi - d is evaluated exactly each iteration).
+// ---- dense LU with partial pivoting of A = I - c*J in the warp's shared-memory slice -------------------
+// Rows are owned by lanes (row i -> lane i&31), columns are walked sequentially; row k is broadcast.
+// (An explicit Gauss-Jordan inverse + mat-vec per Newton iteration was tried in round 1: 4x fewer instructions per
+// solve, but on the ill-conditioned post-ignition matrices its residual is cond*eps*|b| instead of eps*|A||x|, Newton
+// "converged" falsely at rtol 1e-6 and the ideal-gas invariant drifted by 1 % -- caught by
+// tests/test_gpu_parity.py::test_ensemble_properties_at_scale.  Substitution with the LU factors is backward stable.)
 // Returns false if a zero / non-finite pivot is met.
 template <int R>
-__device__ __noinline__ bool inv_factor_warp(Ws w, double c, int lane) {
+__device__ __noinline__ bool lu_factor_warp(Ws w, double c, int lane) {
     const int LD = w.LD, Ny = w.Ny;
     double* A = w.LU();
     const double* J = w.J();
-    int* piv = w.perm();
+    int* perm = w.perm();
+    double* dinv = w.dinv();
     for (int idx = lane; idx < Ny * LD; idx += 32) {
         int col = idx / LD, row = idx - col * LD;
         if (row < Ny) A[idx] = ((row == col) ? 1.0 : 0.0) - c * J[idx];
     }
+    for (int i = lane; i < Ny; i += 32) perm[i] = i;
     bool ok = true;
     for (int k = 0; k < Ny; ++k) {
         __syncwarp();
@@ -164,44 +167,30 @@ __device__ __noinline__ bool inv_factor_warp(Ws w, double c, int lane) {
         unsigned mx = __reduce_max_sync(FULL, best);
         unsigned vote = __ballot_sync(FULL, best == mx && bi >= 0);
         int pr = __shfl_sync(FULL, bi, __ffs(vote) - 1);
-        if (lane == 0) piv[k] = pr;
-        double piv_v = A[pr + k * LD];
-        if (piv_v == 0.0 || !isfinite(piv_v)) { ok = false; piv_v = 1.0; }
-        const double inv = 1.0 / piv_v;
-        // swap rows k <-> pr and scale the new row k by 1/pivot (lanes over columns); a_kk := 1 first
-        for (int j = lane; j < Ny; j += 32) {
-            double akj = A[k + j * LD], apj = A[pr + j * LD];
-            if (j == k) apj = 1.0;
-            A[k + j * LD] = apj * inv;
-            if (pr != k) A[pr + j * LD] = akj;
+        if (pr != k) {
+            for (int j = lane; j < Ny; j += 32) {
+                double t = A[k + j * LD]; A[k + j * LD] = A[pr + j * LD]; A[pr + j * LD] = t;
+            }
+            if (lane == 0) { int t = perm[k]; perm[k] = perm[pr]; perm[pr] = t; }
+            __syncwarp();
         }
-        __syncwarp();
-        // eliminate column k from every other row (own rows only): a_ik := 0, row_i -= f * row_k
-        double f[R];
+        double piv = A[k + k * LD];
+        if (piv == 0.0 || !isfinite(piv)) { ok = false; piv = 1.0; }
+        double inv = 1.0 / piv;
+        if (lane == 0) dinv[k] = inv;
+        double l[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int i = r * 32 + lane;
-            f[r] = 0.0;
-            if (i < Ny && i != k) { f[r] = A[i + k * LD]; A[i + k * LD] = 0.0; }
+            l[r] = 0.0;
+            if (i > k && i < Ny) { l[r] = A[i + k * LD] * inv; A[i + k * LD] = l[r]; }
         }
-        for (int j = 0; j < Ny; ++j) {
+        for (int j = k + 1; j < Ny; ++j) {
             double akj = A[k + j * LD];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 int i = r * 32 + lane;
-                if (i < Ny && i != k) A[i + j * LD] -= f[r] * akj;
-            }
-        }
-    }
-    __syncwarp();
-    // undo the row interchanges: column swaps in reverse order (each lane touches only its own rows)
-    for (int k = Ny - 1; k >= 0; --k) {
-        int pr = piv[k];
-        if (pr != k) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                int i = r * 32 + lane;
-                if (i < Ny) { double t = A[i + k * LD]; A[i + k * LD] = A[i + pr * LD]; A[i + pr * LD] = t; }
+                if (i > k && i < Ny) A[i + j * LD] -= l[r] * akj;
             }
         }
     }
@@ -209,22 +198,49 @@ __device__ __noinline__ bool inv_factor_warp(Ws w, double c, int lane) {
     return ok;
 }
 
-// x = Ainv * b with b in w.xs (already synchronised); result distributed in registers
+// Solve (I - cJ) x = b with the factors above; b in w.xs on entry (synchronised), x returned in registers.
 template <int R>
-__device__ __forceinline__ void inv_apply(const Ws& w, double (&x)[R], int lane) {
+__device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
     const int LD = w.LD, Ny = w.Ny;
     const double* A = w.LU();
-    const double* b = w.xs();
+    const double* dinv = w.dinv();
+    const int* perm = w.perm();
+    double* xs = w.xs();
+    double b[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) x[r] = 0.0;
-    for (int j = 0; j < Ny; ++j) {
-        double bj = b[j];
+    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; b[r] = (i < Ny) ? xs[perm[i]] : 0.0; }
+    // forward substitution (unit lower)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int i = r * 32 + lane;
-            if (i < Ny) x[r] += A[i + j * LD] * bj;
+    for (int kr = 0; kr < R; ++kr) {
+        for (int kl = 0; kl < 32; ++kl) {
+            int k = kr * 32 + kl;
+            if (k >= Ny - 1) break;
+            double xk = __shfl_sync(FULL, b[kr], kl);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int i = r * 32 + lane;
+                if (i > k && i < Ny) b[r] -= A[i + k * LD] * xk;
+            }
         }
     }
+    // backward substitution
+#pragma unroll
+    for (int kr = R - 1; kr >= 0; --kr) {
+        for (int kl = 31; kl >= 0; --kl) {
+            int k = kr * 32 + kl;
+            if (k >= Ny) continue;
+            if (lane == kl) b[kr] *= dinv[k];
+            double xk = __shfl_sync(FULL, b[kr], kl);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int i = r * 32 + lane;
+                if (i < k) b[r] -= A[i + k * LD] * xk;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) xs[i] = b[r]; }
     __syncwarp();
 }
 
@@ -392,7 +408,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
             int n_iter = 0;
             while (!converged) {
                 bool lu_ok = true;
-                if (!lu_valid) { lu_ok = inv_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; }
+                if (!lu_valid) { lu_ok = lu_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; }
                 // ---- solve_bdf_system: simplified Newton on y = ypred + d, c*f(y) - psi - d = 0
 #pragma unroll
                 for (int r = 0; r < R; ++r) { dvec[r] = 0.0; ynew[r] = ypred[r]; }
@@ -406,7 +422,8 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
 #pragma unroll
                         for (int r = 0; r < R; ++r) dy[r] = c * f[r] - psi[r] - dvec[r];
                         to_smem<R>(w.xs(), dy, Ny, lane);
-                        inv_apply<R>(w, dy, lane);
+                        lu_solve_warp<R>(w, lane);
+                        from_smem<R>(dy, w.xs(), Ny, lane);
                         double dy_norm = rms_norm_w<R>(dy, scale, Ny, lane);
                         double rate = (dy_norm_old < 0.0) ? -1.0 : dy_norm / dy_norm_old;
                         if (!(dy_norm == dy_norm)) break;   // NaN

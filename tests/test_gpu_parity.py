@@ -152,6 +152,26 @@ def test_ensemble_vs_cpu_oracle_idt():
     assert np.max(np.abs(sol.yend - ref["yend"])[big] / np.abs(ref["yend"])[big]) < 1e-6
 
 
+def test_ensemble_loose_tolerance_vs_tight_cpu_oracle():
+    """2 000 conditions at the THROUGHPUT tolerances (rtol 1e-6, atol 1e-16) against the C++ CPU oracle at rtol 1e-10:
+    ignition delay within 0.1 % (north_star), final temperature within 1e-4."""
+    gdom, _, _ = cases.product_domain("superminimal_V")
+    ig = gdom.phase
+    T0, P0, ns = sweep(ig, 2000)
+    ens = rb.ConstantVEnsemble(ig, T0, P0, ns)
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 0.1)), abstol=1e-16, reltol=1e-6)
+    odom = cases.oracle_domain("superminimal_V")
+    ref = co.CpuMech(odom.phase).solve("ConstantV", ens.y0, ens.cond, 0.1, 1e-10, 1e-20)
+    assert np.all(sol.status == 0)
+    ign = (ref["yend"][:, ig.Ns] - ens.y0[:, ig.Ns]) > 400.0
+    assert ign.sum() > 1000
+    np.testing.assert_allclose(sol.idt[ign], ref["idt"][ign], rtol=1e-3)
+    np.testing.assert_allclose(sol.yend[:, ig.Ns], ref["yend"][:, ig.Ns], rtol=1e-4)
+    # step counts stay in the same ballpark as the CPU implementation of the same algorithm at the same tolerance
+    ref6 = co.CpuMech(odom.phase).solve("ConstantV", ens.y0[:200], ens.cond[:200], 0.1, 1e-6, 1e-16)
+    assert abs(sol.stats["n_steps"][:200].mean() / ref6["stats"]["n_steps"].mean() - 1.0) < 0.15
+
+
 def test_ensemble_properties_at_scale():
     """Size-independent properties on a 20 000-reactor ensemble at the throughput tolerances (rtol 1e-6, atol 1e-16):
     element conservation, batch-order independence, determinism, agreement of duplicates."""
@@ -167,17 +187,19 @@ def test_ensemble_properties_at_scale():
     # H and O atoms are conserved by every reaction: check the element balance of the final state
     names = ig.names
     nH = np.array([{"H2": 2, "H": 1, "OH": 1, "HO2": 1, "H2O2": 2, "H2O": 2}.get(s, 0) for s in names], dtype=float)
-    nO = np.array([{"O2": 2, "O": 1, "OH": 1, "HO2": 2, "H2O2": 2, "H2O": 1}.get(s, 0) for s in names], dtype=float)
-    for nel in (nH, nO):
+    nO = np.array([{"O2": 2, "O(T)": 1, "OH": 1, "HO2": 2, "H2O2": 2, "H2O": 1}.get(s, 0) for s in names], dtype=float)
+    for nel in (nH, nO):       # linear invariants are preserved by BDF + exact linear solves to rounding
         a0, a1 = ens.y0[:, :ig.Ns] @ nel, sol.yend[:, :ig.Ns] @ nel
-        np.testing.assert_allclose(a1, a0, rtol=1e-5)
+        np.testing.assert_allclose(a1, a0, rtol=1e-12)
     # reversed batch order gives bitwise the same per-reactor results (no cross-reactor coupling, deterministic kernels)
     rev = rb.ConstantVEnsemble(ig, T0[::-1].copy(), P0[::-1].copy(), ns[::-1].copy())
     sol2 = rb.solve(rb.Reactor(rev, None, (0.0, 0.1)), abstol=1e-16, reltol=1e-6)
     assert np.array_equal(sol2.yend[::-1], sol.yend) and np.array_equal(sol2.idt[::-1], sol.idt, equal_nan=True)
-    # ignited reactors end hot, ideal-gas law holds: P*V = N*R*T with N = P V/(RT) consistent with sum(ns) (closed system)
+    # the ideal-gas law is an invariant of the ConstantV equations (dP/dt is derived from it, Domain.jl:1903):
+    # P*V/(R*T) must track sum(ns) to integration accuracy (the CPU port drifts by 6e-7 at these tolerances).
+    # This is the check that exposed false Newton convergence of an explicit-inverse linear solve in round 1.
     Ni = sol.yend[:, ig.Ns + 1] * ens.cond[:, 0] / (8.314 * sol.yend[:, ig.Ns])
-    np.testing.assert_allclose(Ni, sol.yend[:, :ig.Ns].sum(axis=1), rtol=1e-4)
+    np.testing.assert_allclose(Ni, sol.yend[:, :ig.Ns].sum(axis=1), rtol=1e-5)
 
 
 def test_edge_cases():
