@@ -185,7 +185,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
-    opts = L.SolveOpts(C.sizeof(L.SolveOpts), 500000, 5, -1, 0.0, args.warps_per_block, 0)
+    opts = L.SolveOpts(C.sizeof(L.SolveOpts), 500000, 5, -1, 0.0, args.warps_per_block, args.flags)
     g_idt = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     g_st = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--warps-per-block", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="integrator flags (rmsb_solve_opts.reserved); 0 = defaults")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

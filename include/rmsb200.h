@@ -141,7 +141,7 @@ typedef struct rmsb_solve_opts {
     int32_t idt_index;       /* 0-based y index whose max d/dt defines idt; -1 = domain default (T) */
     double  first_step;      /* 0 = automatic                                                      */
     int32_t warps_per_block; /* 0 = automatic                                                      */
-    int32_t reserved;
+    int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis */
 } rmsb_solve_opts;
 
 /* ---- library ----------------------------------------------------------------------------- */

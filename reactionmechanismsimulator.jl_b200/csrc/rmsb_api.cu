@@ -509,6 +509,7 @@ static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
         o->idt_index = in->idt_index;
         if (in->first_step > 0.0) o->first_step = in->first_step;
         o->warps_per_block = in->warps_per_block;
+        o->reserved = in->reserved;
     }
 }
 
@@ -530,7 +531,7 @@ extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, con
     a.constspc = cs; a.nconst = cs ? ncs : 0; a.t_end = t_end; a.rtol = rtol; a.atol = atol;
     a.nsave = nsave; a.tsave = tsave; a.ysave = ysave; a.yend = yend; a.idt = idt; a.status = status; a.stats = stats;
     a.max_steps = o.max_steps; a.max_order = o.max_order; a.first_step = o.first_step;
-    a.domain_kind = kind; a.Ny = domain_ny(h, kind);
+    a.domain_kind = kind; a.Ny = domain_ny(h, kind); a.flags = o.reserved;
     a.idt_index = o.idt_index >= 0 ? o.idt_index : (kind == RMSB_DOMAIN_CONSTANT_V ? h->dm.Ns : -1);
     if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
     a.counter = reinterpret_cast<unsigned long long*>(work);

@@ -70,6 +70,8 @@ struct SolveArgs {
     unsigned long long* counter;
     int domain_kind;
     int Ny;
+    int flags;      // bit 0: scipy-style Newton test (every step >= 2 iterations, tolerance min(0.03, sqrt(rtol)));
+                    // bit 1: no step-size hysteresis.  0 = production defaults (CVODE-style test, hysteresis)
 };
 
 // ---- distributed vector helpers -----------------------------------------------------------------
@@ -370,6 +372,13 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     int order = 1, n_equal = 0;
     const int max_order = a.max_order;
     const double newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
+    const bool scipy_newton = (a.flags & 1) != 0, hysteresis = (a.flags & 2) == 0;
+    double crate = 1.0;     // Newton convergence-rate estimate carried across steps (CVODE), reset with every new LU
+    // Newton tolerance coefficient: CVODE's nlscoef = 0.1 made this NDF error estimator fail 4.6x more often
+    // (profiles/r01_newton_sweep.txt); 0.1/8 gives the fewest RHS evaluations at unchanged accuracy.
+    // bits 8..15 of flags = v: 0 -> default 0.1/8, otherwise 0.1 / 2^(v-1).
+    const int nls_v = (a.flags >> 8) & 0xff;
+    const double nls_coef = ldexp(0.1, -(nls_v == 0 ? 3 : nls_v - 1));
 
     while (status == RMSB_SOLVE_OK && t < t_end) {
         if (n_steps >= a.max_steps) { status = RMSB_SOLVE_MAX_STEPS; break; }
@@ -408,7 +417,9 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
             int n_iter = 0;
             while (!converged) {
                 bool lu_ok = true;
-                if (!lu_valid) { lu_ok = lu_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; }
+                if (!lu_valid) { lu_ok = lu_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; crate = 1.0; }
+                // CVODE's nonlinear tolerance: the Newton error may contribute 0.1 to the (<= 1) local error test
+                const double nl_tol = scipy_newton ? newton_tol : fmax(newton_tol, nls_coef / c_ec[order]);
                 // ---- solve_bdf_system: simplified Newton on y = ypred + d, c*f(y) - psi - d = 0
 #pragma unroll
                 for (int r = 0; r < R; ++r) { dvec[r] = 0.0; ynew[r] = ypred[r]; }
@@ -430,11 +441,14 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
                         if (rate >= 0.0) {
                             double rp = rate;                                  // rate^(NEWTON_MAXITER - k)
                             for (int q = 1; q < NEWTON_MAXITER - k; ++q) rp *= rate;
-                            if (rate >= 1.0 || rp / (1.0 - rate) * dy_norm > newton_tol) break;
+                            if (rate >= 1.0 || rp / (1.0 - rate) * dy_norm > nl_tol) break;
+                            crate = fmax(0.3 * crate, rate);
                         }
 #pragma unroll
                         for (int r = 0; r < R; ++r) { ynew[r] += dy[r]; dvec[r] += dy[r]; }
-                        if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
+                        if (scipy_newton) {
+                            if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < nl_tol)) { converged = true; break; }
+                        } else if (dy_norm * fmin(1.0, crate) <= nl_tol) { converged = true; break; }   // cvNlsNewton: del*min(1,crate)/tq4 <= 1
                         dy_norm_old = dy_norm;
                     }
                 }
@@ -568,8 +582,10 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
         if (fm >= f0 && fm >= fp) { delta = -1; fmax_ = fm; }
         else if (f0 >= fp) { delta = 0; fmax_ = f0; }
         else { delta = 1; fmax_ = fp; }
-        order += delta;
         double factor = fmin(BDF_MAX_FACTOR, safety * fmax_);
+        // hysteresis: a proposed growth below 20 % at unchanged order is not worth a new LU (ode15s / CVODE practice)
+        if (hysteresis && delta == 0 && factor >= 1.0 && factor < 1.2) continue;
+        order += delta;
         h_abs *= factor;
         change_D<R>(D, order, factor, w, lane);
         n_equal = 0; lu_valid = false;

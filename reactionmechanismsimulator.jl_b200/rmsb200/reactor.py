@@ -16,8 +16,11 @@ from .domain import Domain
 class RMSB200:
     """Algorithm tag standing where CVODE_BDF() stands in the reference (`react.recommendedsolver`)."""
 
-    def __init__(self, max_steps=500000, max_order=5, first_step=0.0, warps_per_block=0):
+    def __init__(self, max_steps=500000, max_order=5, first_step=0.0, warps_per_block=0, flags=0):
+        """flags: 0 = production defaults (CVODE-style Newton convergence test, step-size hysteresis);
+        bit 0 = scipy-style Newton test; bit 1 = no hysteresis (3 reproduces scipy.integrate.BDF's step logic)."""
         self.max_steps, self.max_order, self.first_step, self.warps_per_block = max_steps, max_order, first_step, warps_per_block
+        self.flags = flags
 
 
 class Reactor:
@@ -112,7 +115,7 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
     stats = np.zeros(n, dtype=L.STATS_DTYPE)
     pp, ps = dom._p_for_device(react.p)
     cs = dom.constantspeciesinds
-    opts = L.SolveOpts(C.sizeof(L.SolveOpts), alg.max_steps, alg.max_order, idt_index, alg.first_step, alg.warps_per_block, 0)
+    opts = L.SolveOpts(C.sizeof(L.SolveOpts), alg.max_steps, alg.max_order, idt_index, alg.first_step, alg.warps_per_block, alg.flags)
     L.check(L.lib().rmsb_solve_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
                                      L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
                                      L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
