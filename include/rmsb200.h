@@ -51,11 +51,15 @@ extern "C" {
  *  CONSTANT_TP     [ns; V]    Ns+1   [T, P]         src/Domain.jl:42-102,916-966,1863-1867
  *  CONSTANT_TV     ns         Ns     [T, V]         src/Domain.jl:500-560,1514-1561
  *  CONSTANT_TAPHI  ns         Ns     [T, A]         src/Domain.jl:660-711,1597-1633  (phi = 0)
+ *  COUPLED_TP_TAPHI [ns_bulk; ns_surf; V] Ns+1  [T, P, A]   ConstantTP gas + ConstantTAPhi surface + ReactiveInternalInterfaceConstantTPhi
+ *                                                 in one system: src/Reactor.jl:99-258,662-725, src/Interface.jl:71-133 (needs a
+ *                                                 two-phase descriptor: species_phase / rxn_domain below)
  */
 #define RMSB_DOMAIN_CONSTANT_V      0
 #define RMSB_DOMAIN_CONSTANT_TP     1
 #define RMSB_DOMAIN_CONSTANT_TV     2
 #define RMSB_DOMAIN_CONSTANT_TAPHI  3
+#define RMSB_DOMAIN_COUPLED_TP_TAPHI 4
 
 /* ---- kinetics type tags (src/Calculators/Rate.jl, Ratevec.jl) -----------------------------
  * kin_params[kin_offset[j] .. kin_offset[j+1]) holds, as doubles:
@@ -111,6 +115,10 @@ typedef struct rmsb_mech_desc {
     const double*  diff_radius;   /* [Ns] StokesDiffusivity.r; <= 0 means EmptyDiffusivity (Inf); may be NULL */
     int32_t viscosity_kind;       /* RMSB_VISC_*  (phase.solvent.mu)                                      */
     double  viscosity_params[5];
+    /* two-phase (gas + surface) systems only, NULL otherwise: species of the bulk phase first, then the surface phase */
+    const int32_t* species_phase; /* [Ns] 0 = bulk phase (concentration = n/V), 1 = surface phase (n/A)              */
+    const int32_t* rxn_domain;    /* [Nr] 0 = bulk reaction (rate*V), 1 = surface reaction (rate*A),                 */
+                                  /*      2 = interface reaction (rate*A, constant k, two-phase Kc; src/Interface.jl:89-108) */
 } rmsb_mech_desc;
 
 typedef struct rmsb_mech rmsb_mech;    /* opaque, immutable */

@@ -29,7 +29,8 @@ class Desc(C.Structure):   # rmsb_mech_desc
                 ("nasa_nranges", _pi), ("nasa_ncoef", _pi), ("nasa_tmax", _pd), ("nasa_coefs", _pd),
                 ("rxnarray", _pi), ("kin_type", _pi), ("kin_offset", _pi), ("kin_params", _pd),
                 ("eff_ptr", _pi), ("eff_species", _pi), ("eff_value", _pd), ("reversible", _pu8), ("forwardable", _pu8),
-                ("radius", _pd), ("diff_radius", _pd), ("viscosity_kind", C.c_int32), ("viscosity_params", C.c_double * 5)]
+                ("radius", _pd), ("diff_radius", _pd), ("viscosity_kind", C.c_int32), ("viscosity_params", C.c_double * 5),
+                ("species_phase", _pi), ("rxn_domain", _pi)]
 
 
 STATS = np.dtype([("n_steps", "i4"), ("n_rhs", "i4"), ("n_jac", "i4"), ("n_lu", "i4"), ("n_newton_fail", "i4"),

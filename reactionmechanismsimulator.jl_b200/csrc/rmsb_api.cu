@@ -74,7 +74,8 @@ extern "C" int64_t rmsb_kernel_launch_count(void) { return g_launches.load(); }
 static int domain_ny(const rmsb_mech* m, int kind) {
     switch (kind) {
     case RMSB_DOMAIN_CONSTANT_V: return m->dm.Ns + 2;
-    case RMSB_DOMAIN_CONSTANT_TP: return m->dm.Ns + 1;
+    case RMSB_DOMAIN_CONSTANT_TP:
+    case RMSB_DOMAIN_COUPLED_TP_TAPHI: return m->dm.Ns + 1;
     case RMSB_DOMAIN_CONSTANT_TV:
     case RMSB_DOMAIN_CONSTANT_TAPHI: return m->dm.Ns;
     }
@@ -86,6 +87,7 @@ static int domain_ncond(int kind) {
     case RMSB_DOMAIN_CONSTANT_TP:
     case RMSB_DOMAIN_CONSTANT_TV:
     case RMSB_DOMAIN_CONSTANT_TAPHI: return 2;
+    case RMSB_DOMAIN_COUPLED_TP_TAPHI: return 3;
     }
     return -1;
 }
@@ -228,6 +230,35 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     dm.n_dt = h->n_dt = (int)dtrxn.size();
     dm.n_je = h->n_je = (int)jerow.size();
     dm.n_effrxn = (int)effrxn.size();
+    // ---- two-phase systems: phase of every species, domain of every reaction, C0 exponents per phase
+    std::vector<int> rxdom(Nr, 0), srmid(Ns, 0);
+    std::vector<double> nrp2(Nr, 0.0);
+    dm.coupled = (d->species_phase && d->rxn_domain) ? 1 : 0;
+    dm.n_bulk = Ns;
+    if (dm.coupled) {
+        int nb = 0;
+        while (nb < Ns && d->species_phase[nb] == 0) ++nb;
+        for (int s = nb; s < Ns; ++s) if (d->species_phase[s] != 1) return fail(RMSB_ERR_ARG, "species_phase must be 0...0 1...1");
+        dm.n_bulk = nb;
+        for (int j = 0; j < Nr; ++j) {
+            rxdom[j] = d->rxn_domain[j];
+            if (rxdom[j] < 0 || rxdom[j] > 2 || (j > 0 && rxdom[j] < rxdom[j - 1])) return fail(RMSB_ERR_ARG, "rxn_domain must be sorted 0..0 1..1 2..2");
+            double nb_ = 0.0, ns_ = 0.0;
+            for (int k = 0; k < 8; ++k) {
+                int sp = rx[(size_t)k * Nr + j];
+                if (sp < 0) continue;
+                double sgn = (k < 4) ? -1.0 : 1.0;
+                if (sp < nb) nb_ += sgn; else ns_ += sgn;
+            }
+            nrp[j] = nb_; nrp2[j] = ns_;
+            if (effptr[j + 1] > effptr[j]) return fail(RMSB_ERR_UNSUPPORTED, "third-body efficiencies in a coupled gas-surface system");
+        }
+        for (int s = 0; s < Ns; ++s) {
+            int mid = srptr[s + 1];
+            for (int k = srptr[s]; k < srptr[s + 1]; ++k) if (rxdom[srrxn[k] & 0x7fffffff] == 2) { mid = k; break; }
+            srmid[s] = mid;
+        }
+    }
     // ---- liquid phase data
     std::vector<double> radius, diffr;
     if (d->radius) radius.assign(d->radius, d->radius + Ns);
@@ -247,6 +278,7 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     UP(srptr, sr_ptr); UP(srrxn, sr_rxn);
     UP(dtrxn, dt_rxn); UP(dtmult, dt_mult); UP(dtoth, dt_oth); UP(dtspc, dt_spc);
     UP(jeptr, je_ptr); UP(jerow, je_row); UP(jecol, je_col); UP(jtidx, jt_idx);
+    UP(rxdom, rx_dom); UP(nrp2, nrp2); UP(srmid, sr_mid);
 #undef UP
     if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
     if (!diffr.empty()) { if ((rc = upload(h, diffr, &dm.diff_r)) != RMSB_OK) return rc; } else dm.diff_r = nullptr;
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
         double* yb = w.ybuf();
         for (int i = lane; i < Ny; i += 32) yb[i] = a.y[ir * Ny + i];
         rhs_prepare(d, w, lane);
-        if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(d, w, lane);
+        setup_domain(d, w, lane);
         if (MODE == 0) {
             rhs_warp(d, w, lane, false);
             const double* fb = w.fbuf();
@@ -466,6 +498,7 @@ static int check_common(const rmsb_mech* h, int kind, int64_t n, const void* y, 
     if (p && p_stride != 0 && p_stride != h->dm.Ns + h->dm.Nr) return fail(RMSB_ERR_ARG, "p_stride must be 0 or Ns+Nr");
     if (kind == RMSB_DOMAIN_CONSTANT_V && h->dm.phase_kind != RMSB_PHASE_GAS) return fail(RMSB_ERR_ARG, "ConstantV domain needs an IdealGas phase");
     if (kind == RMSB_DOMAIN_CONSTANT_TAPHI && h->dm.phase_kind != RMSB_PHASE_SURFACE) return fail(RMSB_ERR_ARG, "ConstantTAPhi domain needs an IdealSurface phase");
+    if ((kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) != (h->dm.coupled != 0)) return fail(RMSB_ERR_ARG, "the coupled gas-surface domain and two-phase mechanisms go together");
     return RMSB_OK;
 }
 

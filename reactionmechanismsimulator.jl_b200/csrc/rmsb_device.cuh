@@ -82,6 +82,11 @@ struct DevMech {
     const double* diff_r;
     int visc_kind;
     double visc[5];
+    // two-phase (bulk + surface + interface) systems: species [0,n_bulk) live in the bulk phase
+    int coupled, n_bulk;
+    const int* rx_dom;       // [Nr] 0 bulk reaction, 1 surface reaction, 2 interface reaction (sorted ascending)
+    const double* nrp2;      // [Nr] surface-phase exponent of C0 in Kc (nrp is the bulk-phase exponent)
+    const int* sr_mid;       // [Ns] first interface entry of the species' slot list
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -747,6 +752,154 @@ __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coupled ConstantTP gas + ConstantTAPhi surface + ReactiveInternalInterfaceConstantTPhi (config C4):
+// y = [ns_bulk; ns_surf; V], cond = [T, P, A].  Multi-domain dydtreactor! src/Reactor.jl:662-725; interface
+// construction src/Interface.jl:89-108; two-phase getKc src/PhaseState.jl:131-162.  All rate coefficients are
+// constants of the reactor (T fixed) and are computed once by setup_coupled.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void setup_coupled(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr;
+    double* Gb = w.g();
+    const double T = d.cond[0], P = d.cond[1];
+    for (int s = lane; s < Ns; s += 32) Gb[s] = gibbs_scalar(s, T);       // calcgibbs of both constant-T domains
+    __syncwarp();
+    KinEnv<double> e;
+    e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+    const double C0g = 1.0e5 / (RMSB_R * T), sig = m.sitedensity;
+    const double logC0g = log(C0g), logsig = log(sig);
+    for (int j = lane; j < Nr; j += 32) {
+        const int dom = G(m.rx_dom, j);
+        double kf, kr;
+        if (dom == 2) {
+            // interface: kfs = getkf(rxn, nothing, T, ...), Kc = exp(-dG/RT)*C0_1^dN1*C0_2^dN2, krevs = kfs./Kc
+            kf = eval_kin<double>(j, &e, 0.0, true);
+            double dG = 0.0;
+            for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; dG -= Gb[sp]; }
+            for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; dG += Gb[sp]; }
+            double Kc = exp(-(dG) / (RMSB_R * T)) * pow(C0g, G(m.nrp, j)) * pow(sig, G(m.nrp2, j));
+            kr = kf / Kc;
+        } else {
+            // single-phase reactions of the TP / TAPhi domains: getkfs + getKcs (src/PhaseState.jl:226-233)
+            kf = eval_kin<double>(j, &e, dom == 0 ? P / (RMSB_R * T) : 0.0, false);
+            double ex = 0.0;
+            for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex += G(m.kc_coef, k) * (Gb[G(m.kc_spc, k)] / (RMSB_R * T));
+            ex += (dom == 0) ? G(m.nrp, j) * logC0g : G(m.nrp2, j) * logsig;
+            kr = kf / exp(ex);
+        }
+        w.kf()[j] = kf * G(m.fwd, j);
+        w.kr()[j] = kr * G(m.rev, j);
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr, Nb = m.n_bulk;
+    const double* yb = w.ybuf();
+    double* cs = w.cs();
+    double* fb = w.fbuf();
+    double* qb = w.q();
+    const double T = d.cond[0], P = d.cond[1], A = d.cond[2];
+    const double V = yb[Ns];
+    for (int s = lane; s < Ns; s += 32) cs[s] = yb[s] / (s < Nb ? V : A);
+    __syncwarp();
+    const double* kfb = w.kf();
+    const double* krb = w.kr();
+    for (int j = lane; j < Nr; j += 32) {
+        double q = net_rate<double>(j, kfb[j], krb[j], cs);
+        if (G(m.rx_dom, j) == 2) q *= A;                                   // evaluate(): R = (fR - rR)*A
+        qb[j] = q;
+    }
+    __syncwarp();
+    double nsum = 0.0;
+    for (int s = lane; s < Ns; s += 32) {
+        double acc = 0.0;
+        const int k0 = G(m.sr_ptr, s), k1 = G(m.sr_mid, s), k2 = G(m.sr_ptr, s + 1);
+        for (int k = k0; k < k1; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
+        acc *= (s < Nb ? V : A);                                           // dydt[block] .*= V (or A)
+        for (int k = k1; k < k2; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
+        fb[s] = acc;
+        if (s < Nb) nsum += acc;
+    }
+    double dV = warp_sum(nsum) * RMSB_R * T / P;                           // Domain.jl:1864 on the gas block
+    if (lane == 0) {
+        fb[Ns] = dV;
+        double* ax = w.aux();
+        ax[0] = T; ax[1] = P; ax[2] = V; ax[3] = P * V / (RMSB_R * T); ax[4] = P / (RMSB_R * T); ax[5] = A; ax[6] = 0.0;
+    }
+    __syncwarp();
+    for (int k = lane; k < d.nconst; k += 32) fb[d.constspc[k] - 1] = 0.0;
+    __syncwarp();
+}
+
+// Analytic Jacobian of the coupled system (the reference differentiates the whole RHS with ForwardDiff, src/Reactor.jl:203).
+__device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr, Nb = m.n_bulk, Ny = w.Ny, LD = w.LD;
+    rhs_coupled(d, w, lane);
+    double* J = w.J();
+    const double* cs = w.cs();
+    const double* kfb = w.kf();
+    const double* krb = w.kr();
+    double* dterm = w.dterm();
+    const double T = d.cond[0], P = d.cond[1], A = d.cond[2];
+    const double V = w.aux()[2];
+    for (int i = lane; i < Ny * LD; i += 32) J[i] = 0.0;
+    for (int t = lane; t < m.n_dt; t += 32) {
+        int jr = G(m.dt_rxn, t);
+        int j = jr & 0x3fffffff;
+        double v = (double)G(m.dt_mult, t) * ((jr >> 30) ? krb[j] : kfb[j]);
+        for (int k = 0; k < 3; ++k) { int s = G(m.dt_oth, 3 * t + k); if (s < 0) break; v *= cs[s]; }
+        const double scale = (G(m.rx_dom, j) == 0) ? V : A;               // rate * domain size ...
+        const double size = (G(m.dt_spc, t) < Nb) ? V : A;                // ... d(c_k)/d(n_k) = 1/size_k
+        dterm[t] = v * scale / size;
+    }
+    __syncwarp();
+    for (int e = lane; e < m.n_je; e += 32) {
+        double acc = 0.0;
+        for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
+            int ti = G(m.jt_idx, k);
+            double v = dterm[ti & 0x7fffffff];
+            acc = (ti < 0) ? acc - v : acc + v;
+        }
+        J[G(m.je_row, e) + G(m.je_col, e) * LD] = acc;
+    }
+    __syncwarp();
+    // V column: d(scale_j * k prod c)/dV = (k prod c) * ([bulk reaction] - scale_j * (#bulk species in the side)/V)
+    for (int s = lane; s < Ns; s += 32) {
+        double acc = 0.0;
+        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+            int jr = G(m.sr_rxn, k);
+            int j = jr & 0x7fffffff;
+            const int dom = G(m.rx_dom, j);
+            const double scale = (dom == 0) ? V : A;
+            double pf = kfb[j], pr = krb[j];
+            int gf = 0, gr = 0;
+            for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; if (sp < Nb) ++gf; }
+            for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; if (sp < Nb) ++gr; }
+            double df = pf * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gf / V);
+            double dr = pr * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gr / V);
+            double dq = df - dr;
+            acc = (jr < 0) ? acc - dq : acc + dq;
+        }
+        J[s + Ns * LD] = acc;
+    }
+    __syncwarp();
+    for (int c = lane; c <= Ns; c += 32) {                                   // V row from the gas block
+        double a = 0.0;
+        for (int i = 0; i < Nb; ++i) a += J[i + c * LD];
+        J[Ns + c * LD] = a * RMSB_R * T / P;
+    }
+    __syncwarp();
+    for (int k = 0; k < d.nconst; ++k) {
+        int s = d.constspc[k] - 1;
+        for (int c = lane; c < Ny; c += 32) J[s + c * LD] = 0.0;
+    }
+    __syncwarp();
+}
+
 // per-reactor constants the RHS reads from the workspace (call once per reactor, before the first RHS)
 __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, int lane) {
     if (lane == 0) w.aux()[7] = (d.kind == RMSB_DOMAIN_CONSTANT_V) ? 1.0 / d.cond[0] : 0.0;
@@ -755,7 +908,14 @@ __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, in
 
 __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int lane, bool store_k) {
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(d, w, lane, store_k);
+    else if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) rhs_coupled(d, w, lane);
     else rhs_ck(d, w, lane);
+}
+
+// once per reactor for every domain whose rate coefficients are constants of the reactor
+__device__ __forceinline__ void setup_domain(const DomainArgs& d, const Ws& w, int lane) {
+    if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) setup_coupled(d, w, lane);
+    else if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(d, w, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -764,6 +924,7 @@ __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int l
 __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, LD = w.LD;
+    if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) { jac_coupled(d, w, lane); return; }
     rhs_warp(d, w, lane, true);
     double* J = w.J();
     const double* cs = w.cs();

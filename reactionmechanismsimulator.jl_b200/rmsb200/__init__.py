@@ -8,6 +8,8 @@ to the CUDA library and raises if it is missing.
 """
 from ._lib import (DOMAIN_CONSTANT_TAPHI, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_V, LIB_PATH, RMSBError,
                    lib)
+from .coupled import CoupledEnsemble, CoupledPhase, SystemSimulation, coupled_domain
+from .coupled import make_interface as ReactiveInternalInterfaceConstantTPhi
 from .domain import (ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
                      ConstantVDomain, ConstantVEnsemble, Domain)
 from .ensemble import shard_bounds, shard_domain, solve_sharded

@@ -14,7 +14,7 @@ LIB_PATH = Path(os.environ.get("RMSB200_LIB", _HERE.parent / "csrc" / "librmsb20
 # ---- constants mirrored from include/rmsb200.h -------------------------------------------------
 RMSB_OK = 0
 PHASE_GAS, PHASE_LIQUID, PHASE_SURFACE = 0, 1, 2
-DOMAIN_CONSTANT_V, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_TAPHI = 0, 1, 2, 3
+DOMAIN_CONSTANT_V, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_TAPHI, DOMAIN_COUPLED_TP_TAPHI = 0, 1, 2, 3, 4
 (KIN_ARRHENIUS_VEC, KIN_ARRHENIUS, KIN_MULTIARRHENIUS, KIN_PLOG_VEC, KIN_PLOG, KIN_MULTIPLOG,
  KIN_THIRDBODY, KIN_LINDEMANN, KIN_TROE, KIN_CHEBYSHEV_VEC) = range(10)
 VISC_NONE, VISC_CONSTANT, VISC_RIEDEL = 0, 1, 2
@@ -34,6 +34,7 @@ class MechDesc(C.Structure):
         ("eff_ptr", _pi), ("eff_species", _pi), ("eff_value", _pd),
         ("reversible", _pu8), ("forwardable", _pu8), ("radius", _pd), ("diff_radius", _pd),
         ("viscosity_kind", C.c_int32), ("viscosity_params", C.c_double * 5),
+        ("species_phase", _pi), ("rxn_domain", _pi),
     ]
 
 

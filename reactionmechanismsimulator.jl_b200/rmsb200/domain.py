@@ -66,6 +66,8 @@ class Domain:
         p = np.ascontiguousarray(p, dtype=float)
         if self._p_default is not None and p.shape == self._p_default.shape and np.array_equal(p, self._p_default):
             return None, 0
+        if self.kind == L.DOMAIN_COUPLED_TP_TAPHI:
+            raise NotImplementedError("non-default parameters for coupled gas-surface systems (DESIGN.md, 'next')")
         Np = self.phase.Ns + self.phase.Nr
         if p.ndim == 1:
             assert p.size == Np

@@ -119,6 +119,9 @@ class Phase:
         self.efficiencyinds = [r.index for r in self.reactions
                                if r.kinetics["type"] in ("ThirdBody", "Lindemann", "Troe") and r.kinetics["efficiencies"]]
         self._device = device
+        self._vectorised = [j < self.nvec for j in range(self.Nr)]
+        self._species_phase = None      # two-phase systems only (rmsb200/coupled.py)
+        self._rxn_domain = None
         self._handle = None
         self._build_desc()
 
@@ -137,7 +140,7 @@ class Phase:
                 self._coefs[i, r, :len(p.coefs)] = p.coefs
         ktype, koff, kpar, effptr, effspc, effval = [], [0], [], [0], [], []
         for j, r in enumerate(self.reactions):
-            tag, pars = pack_kinetics(r.kinetics, vectorised=(j < self.nvec))
+            tag, pars = pack_kinetics(r.kinetics, vectorised=self._vectorised[j])
             ktype.append(tag)
             kpar += [float(v) for v in pars]
             koff.append(len(kpar))
@@ -165,6 +168,8 @@ class Phase:
         d.reversible, d.forwardable = pu(self.reversibility), pu(self.forwardability)
         d.radius, d.diff_radius = pd(self._radius), pd(self._diffr)
         d.viscosity_kind = L.VISC_NONE
+        if self._species_phase is not None:
+            d.species_phase, d.rxn_domain = pi(self._species_phase), pi(self._rxn_domain)
         if self.solvent is not None:
             mu = self.solvent.mu
             if mu["type"] == "RiedelViscosity":

@@ -26,6 +26,24 @@ class RMSB200:
 class Reactor:
     """Reactor(domain, y0, tspan; p) (src/Reactor.jl:13-28,30-98).  `domain` may hold an ensemble."""
 
+    def __new__(cls, domain, y0=None, tspan=(0.0, 1.0), interfaces=(), p=None, **kw):
+        """Reactor((domaingas, domaincat), (y0gas, y0cat), tspan, (inter,), (pgas, pcat, pinter)) -> (react, y0, p):
+        the multi-domain constructor of the reference (src/Reactor.jl:99-258) for one ConstantTP gas domain, one
+        ConstantTAPhi surface domain and one ReactiveInternalInterfaceConstantTPhi."""
+        if isinstance(domain, (tuple, list)):
+            from .coupled import ReactiveInternalInterfaceConstantTPhi, coupled_domain
+            if len(domain) != 2 or len(interfaces) != 1 or not isinstance(interfaces[0], ReactiveInternalInterfaceConstantTPhi):
+                raise NotImplementedError("multi-domain systems other than gas(TP) + surface(TAPhi) + ReactiveInternalInterfaceConstantTPhi "
+                                          "are outside the accelerated hot path (DESIGN.md)")
+            dom = coupled_domain(interfaces[0])
+            pall = None if p is None else np.concatenate([np.ravel(np.asarray(x, dtype=float)) for x in p])   # src/Reactor.jl:135-200
+            dom.p, dom._p_default = pall, (None if pall is None else pall.copy())
+            react = object.__new__(cls)
+            Reactor.__init__(react, dom, None, tspan, (), pall)
+            react.interfaces = list(interfaces)
+            return react, dom.y0[0].copy(), pall
+        return object.__new__(cls)
+
     def __init__(self, domain: Domain, y0=None, tspan: Tuple[float, float] = (0.0, 1.0), interfaces: Sequence = (), p=None,
                  forwardsensitivities: bool = False):
         if interfaces:

@@ -122,3 +122,27 @@ def test_product_never_touches_the_oracle():
     for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.jl")):
         text = path.read_text()
         assert "oracle" not in text, f"{path} mentions the oracle"
+
+
+def test_coupled_descriptor_host_side():
+    """C4: the merged two-phase descriptor (rmsb200/coupled.py) -- species order, reaction blocks, sticking -> Arrhenius."""
+    from oracle import coupled as oc
+    from rmsb200.coupled import CoupledPhase, stickingcoefficient2arrhenius
+    d = rb.readinput(cases.fixture("ch4o2cat"))
+    ig = rb.IdealGas(d["gas"]["Species"], d["gas"]["Reactions"], name="gas")
+    cat = rb.IdealSurface(d["surface"]["Species"], d["surface"]["Reactions"], 2.486e-5, name="surface")
+    cp = CoupledPhase(ig, cat, d[frozenset(("gas", "surface"))]["Reactions"])
+    assert (cp.Ns, cp.Nr, cp.n_gas_rxn, cp.n_surf_rxn, cp.n_iface_rxn) == (41, 222, 3, 198, 21)
+    assert list(cp._species_phase) == [0] * 12 + [1] * 29 and list(cp._rxn_domain) == [0] * 3 + [1] * 198 + [2] * 21
+    osys = oc.ch4o2cat_system(cases.fixture("ch4o2cat"))
+    assert cp.names == osys.names
+    np.testing.assert_array_equal(cp.rxnarray[-21:] - 1, osys.irxnarray.T)
+    for r_p, r_o in zip(cp.reactions[-21:], osys.irxns):                      # closed-form sticking conversion agrees
+        assert r_p.kinetics["type"] == "Arrhenius"
+        for key in ("A", "n", "Ea"):
+            assert r_p.kinetics[key] == pytest.approx(r_o.kinetics[key], rel=1e-14)
+    with pytest.raises(NotImplementedError):
+        stickingcoefficient2arrhenius({"A": 5.0, "n": 0.0, "Ea": 0.0}, 2.486e-5, 1, 0.016)
+    # molecular weights come from the SMILES (RDKit MolWt in the reference, src/Parse.jl:143)
+    mw = {s.name: s.molecularweight for s in ig.species}
+    assert mw["CH4"] == pytest.approx(0.016043, rel=1e-4) and mw["CO2"] == pytest.approx(0.044009, rel=1e-4)
