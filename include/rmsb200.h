@@ -184,10 +184,23 @@ int rmsb_jac_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
                    const int32_t* const_species, int32_t n_const,
                    double* J /* [n][Ny*Ny] */);
 
+/* Jp[r] is dense COLUMN-MAJOR Ny x (Ns+Nr), Jp[eqn + Ny*par] = d(dy_eqn/dt)/dp_par (jacobianp!,
+ * src/Domain.jl:3095-3485): par < Ns -> G_par, par = Ns+j -> k_j (or its multiplier, see p above).
+ * CONSTANT_TV needs an explicit p (chain rule through the diffusion limit, :3290-3317). */
+int rmsb_jacp_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                    const double* y, const double* cond, const double* p, int64_t p_stride,
+                    const int32_t* const_species, int32_t n_const,
+                    double* Jp /* [n][Ny*(Ns+Nr)] */);
+
 /* kf,krev as calcthermo returns them (for rops / rates accessors, src/Simulation.jl:239-254,763-778). */
 int rmsb_rates_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
                      const double* y, const double* cond, const double* p, int64_t p_stride,
                      double* kf /* [n][Nr] */, double* krev /* [n][Nr] */);
+
+/* getkfs (src/PhaseState.jl:165-171): forward rate coefficients BEFORE diffusion limitation -- what the constant-k
+ * domain constructors store in p[Ns..] (kfsnondiff for liquid phases, src/Domain.jl:549-551). */
+int rmsb_kfs_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                   const double* y, const double* cond, double* kf /* [n][Nr] */);
 
 /* Species Gibbs energies G[r][s] at temperatures T[r]: scalar_path != 0 -> getGibbs through
  * getEnthalpy - T*getEntropy (src/Calculators/Thermo.jl:6-8,75-93, what the constant-T domain
@@ -209,6 +222,22 @@ int rmsb_solve_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
                      double* yend, double* idt, int32_t* status, rmsb_stats* stats,
                      const rmsb_solve_opts* opts);
 
+/* Forward sensitivities S = dy/dp of every reactor w.r.t. all Ns+Nr parameters, integrated together with the
+ * state: the role of `Reactor(...; forwardsensitivities=true)` + ODEForwardSensitivityProblem
+ * (src/Reactor.jl:63-75) and of threadedsensitivities (src/ThreadedSensitivities.jl:15-79).  Staggered direct
+ * method: after each accepted BDF step of the state, the linear sensitivity corrector
+ * (I - c*J(y_new)) dS = c*(J(y_new)*S_pred + Jp(y_new)) - psi_S is solved for all parameters with one fresh LU
+ * (one lane per parameter column); sensitivities follow the state's step/order sequence and are not in its
+ * error test (CVODES errconS = false).  S(0) = 0.
+ *  ssave [n][nsave][Ns+Nr][Ny] (NaN past t_end), send [n][Ns+Nr][Ny]; either may be NULL. */
+int rmsb_sens_batch(const rmsb_mech* mech, int domain_kind, int64_t n,
+                    const double* y0, const double* cond, const double* p, int64_t p_stride,
+                    const int32_t* const_species, int32_t n_const,
+                    const double* t_end, double rtol, double atol,
+                    int32_t nsave, const double* tsave, double* ysave, double* ssave,
+                    double* yend, double* send, int32_t* status, rmsb_stats* stats,
+                    const rmsb_solve_opts* opts);
+
 /* ---- device-resident variants (inputs/outputs already in HBM; enqueue only) ---------------- */
 int rmsb_dydt_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
                         const double* d_y, const double* d_cond, const double* d_p, int64_t p_stride,
@@ -218,6 +247,20 @@ int rmsb_jac_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
                        const double* d_y, const double* d_cond, const double* d_p, int64_t p_stride,
                        const int32_t* d_const_species, int32_t n_const,
                        double* d_J, void* stream);
+int rmsb_jacp_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
+                        const double* d_y, const double* d_cond, const double* d_p, int64_t p_stride,
+                        const int32_t* d_const_species, int32_t n_const,
+                        double* d_Jp, void* stream);
+/* d_work: rmsb_sens_work_bytes() bytes of device scratch (work-queue counter + the backward-difference
+ * history of the sensitivities of every resident warp). */
+int64_t rmsb_sens_work_bytes(const rmsb_mech* mech, int domain_kind, int64_t n);
+int rmsb_sens_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
+                        const double* d_y0, const double* d_cond, const double* d_p, int64_t p_stride,
+                        const int32_t* d_const_species, int32_t n_const,
+                        const double* d_t_end, double rtol, double atol,
+                        int32_t nsave, const double* d_tsave, double* d_ysave, double* d_ssave,
+                        double* d_yend, double* d_send, int32_t* d_status, rmsb_stats* d_stats,
+                        const rmsb_solve_opts* opts, void* d_work, void* stream);
 /* d_work: rmsb_solve_work_bytes() bytes of device scratch (work-queue counter etc.). */
 int64_t rmsb_solve_work_bytes(const rmsb_mech* mech, int domain_kind, int64_t n);
 int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,

@@ -14,6 +14,8 @@
 // scipy.integrate.BDF -- with the reference's analytic Jacobian; same WRMS error control.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -497,6 +499,8 @@ void jacobian(const Mech& m, const Dom& d, Work& w, const double* y) {
 }
 
 // ---- dense LU (partial pivoting), column-major -----------------------------------------------------
+int g_flags = 0;   // integrator flags, same meaning as rmsb_solve_opts.reserved (0 = the CUDA path's defaults)
+
 bool lu_factor(double* A, int n, int* piv) {
     for (int k = 0; k < n; ++k) {
         int p = k; double best = std::fabs(A[k + (size_t)k * n]);
@@ -581,9 +585,33 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
     }
     jacobian(m, d, w, y.data()); ++st.n_jac;
     bool lu_valid = false;
+    double c_jac = 0.0;   // c = h/alpha at the last Jacobian evaluation (0: not yet used)
+    // A Jacobian evaluated at a step size 100x smaller (or larger) is refreshed before the next factorisation: with a stale J and
+    // c -> large the modified Newton iteration looks converged in the weighted norm while the state coasts along the
+    // equilibrium manifold (its energy-conservation null vector is the stale one); seen as a T drift of 1e-4 in the
+    // post-ignition tail of 2.6 % of the C2 sweep.  Costs +4 Jacobians per solve.
+    const double jac_ratio = getenv("RMSO_JRATIO") ? atof(getenv("RMSO_JRATIO")) : 100.0;
     for (int i = 0; i < n; ++i) { D[i] = y[i]; D[n + i] = f[i] * h_abs; }
     int order = 1, n_equal = 0;
     const double newton_tol = std::max(10.0 * 2.220446049250313e-16 / rtol, std::min(0.03, std::sqrt(rtol)));
+    const bool scipy_newton = (g_flags & 1) != 0, hysteresis = (g_flags & 2) == 0;
+    const int nls_v = (g_flags >> 8) & 0xff;
+    const double nls_coef = std::ldexp(0.1, -(nls_v == 0 ? 3 : nls_v - 1));
+    double crate = 1.0;
+    // species no reaction changes (net stoichiometry zero everywhere) and constant species: dy_i/dt == 0, zero Jacobian row
+    std::vector<char> unit_row(n, 0);
+    std::vector<double> rhs_keep(n);
+    for (int s = 0; s < m.Ns; ++s) unit_row[s] = 1;
+    for (int j = 0; j < m.Nr; ++j) {
+        const int* r = &m.rx[j * 8];
+        for (int a = 0; a < 8; ++a) {
+            if (r[a] < 0) continue;
+            int net = 0;
+            for (int b = 0; b < 8; ++b) if (r[b] == r[a]) net += (b < 4) ? -1 : 1;
+            if (net != 0) unit_row[r[a]] = 0;
+        }
+    }
+    for (int k = 0; k < d.nconst; ++k) unit_row[d.constspc[k] - 1] = 1;
     double idt_best = -std::numeric_limits<double>::infinity(), idt_time = std::numeric_limits<double>::quiet_NaN();
     int status = RMSB_SOLVE_OK;
     for (int i = 0; i < n; ++i) if (!std::isfinite(f[i])) status = RMSB_SOLVE_NAN;
@@ -596,8 +624,16 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
         while (!accepted) {
             if (h_abs < min_step) { status = RMSB_SOLVE_STEP_TOO_SMALL; break; }
             t_new = t + h_abs;
-            if (t_new - t_end > 0.0) { t_new = t_end; change_D(D, n, order, std::fabs(t_new - t) / h_abs); n_equal = 0; lu_valid = false; }
-            h = t_new - t; h_abs = std::fabs(h);
+            // the step the differences D are scaled for is h_abs itself; recomputing it as fl(t + h_abs) - t (scipy) makes the
+            // formula inconsistent by ulp(t)*|dy/dt|, an error floor that rtol = 1e-12 hits during ignition (autonomous RHS:
+            // the rounding of t itself is harmless)
+            if (t_new - t_end > 0.0) {
+                t_new = t_end;
+                double hc = t_end - t;
+                change_D(D, n, order, hc / h_abs); n_equal = 0; lu_valid = false;
+                h_abs = hc;
+            }
+            h = h_abs;
             for (int i = 0; i < n; ++i) {
                 double s = 0.0, ps = 0.0;
                 for (int j = 0; j <= order; ++j) s += D[(size_t)j * n + i];
@@ -610,9 +646,14 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
             while (!converged) {
                 bool lu_ok = true;
                 if (!lu_valid) {
+                    if (c_jac == 0.0) c_jac = c;
+                    else if (jac_ratio > 0.0 && !current_jac && (c > jac_ratio * c_jac || c * jac_ratio < c_jac)) {
+                        jacobian(m, d, w, ypred.data()); ++st.n_jac; current_jac = true; c_jac = c;
+                    }
                     for (int cc = 0; cc < n; ++cc) for (int r = 0; r < n; ++r) w.lu[r + (size_t)cc * n] = (r == cc ? 1.0 : 0.0) - c * w.jac[r + (size_t)cc * n];
-                    lu_ok = lu_factor(w.lu.data(), n, w.piv.data()); lu_valid = true; ++st.n_lu;
+                    lu_ok = lu_factor(w.lu.data(), n, w.piv.data()); lu_valid = true; ++st.n_lu; crate = 1.0;
                 }
+                const double nl_tol = scipy_newton ? newton_tol : std::max(newton_tol, nls_coef / ec[order]);
                 std::fill(dvec.begin(), dvec.end(), 0.0);
                 ynew = ypred;
                 double dy_norm_old = -1.0;
@@ -624,18 +665,30 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
                         for (int i = 0; i < n; ++i) if (!std::isfinite(f[i])) fin = false;
                         if (!fin) break;
                         for (int i = 0; i < n; ++i) dy[i] = c * f[i] - psi[i] - dvec[i];
+                        for (int i = 0; i < n; ++i) rhs_keep[i] = dy[i];
                         lu_solve(w.lu.data(), n, w.piv.data(), dy.data());
+                        for (int i = 0; i < n; ++i) if (unit_row[i]) dy[i] = rhs_keep[i];   // row i of I - c*J is a unit row: x_i = b_i exactly
                         double dy_norm = rms(dy.data(), scale.data(), n);
                         double rate = dy_norm_old < 0.0 ? -1.0 : dy_norm / dy_norm_old;
                         if (!(dy_norm == dy_norm)) break;
-                        if (rate >= 0.0 && (rate >= 1.0 || std::pow(rate, NEWTON_MAXITER - k) / (1.0 - rate) * dy_norm > newton_tol)) break;
+                        if (current_jac && getenv("RMSO_DEBUG") && rate >= 0.0 && (rate >= 1.0 || std::pow(rate, NEWTON_MAXITER - k) / (1.0 - rate) * dy_norm > newton_tol)) {
+                            int im = 0; double em = 0; for (int i = 0; i < n; ++i) { double e = std::fabs(dy[i] / scale[i]); if (e > em) { em = e; im = i; } }
+                            fprintf(stderr, "nfail t=%.10g h=%.3e order=%d k=%d dy_norm=%.3e rate=%.3e worst %d (y=%.4e dy=%.3e scale=%.3e) T=%.2f\n", t, h_abs, order, k, dy_norm, rate, im, ynew[im], dy[im], scale[im], ynew[n-2]);
+                        }
+                        if (rate >= 0.0) {
+                            if (rate >= 1.0 || std::pow(rate, NEWTON_MAXITER - k) / (1.0 - rate) * dy_norm > nl_tol) break;
+                            crate = std::max(0.3 * crate, rate);
+                        }
                         for (int i = 0; i < n; ++i) { ynew[i] += dy[i]; dvec[i] += dy[i]; }
-                        if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < newton_tol)) { converged = true; break; }
+                        if (getenv("RMSO_TRACE")) fprintf(stderr, "   it t=%.6e h=%.3e o=%d k=%d dy_norm=%.3e rate=%.3e crate=%.3e\n", t, h_abs, order, k, dy_norm, rate, crate);
+                        if (scipy_newton) {
+                            if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < nl_tol)) { converged = true; break; }
+                        } else if (dy_norm * std::min(1.0, crate) <= nl_tol) { converged = true; break; }
                         dy_norm_old = dy_norm;
                     }
                 if (!converged) {
                     if (current_jac) break;
-                    jacobian(m, d, w, ypred.data()); ++st.n_jac;
+                    jacobian(m, d, w, ypred.data()); ++st.n_jac; c_jac = c;
                     lu_valid = false; current_jac = true;
                 }
             }
@@ -644,6 +697,10 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
             for (int i = 0; i < n; ++i) { scale[i] = atol + rtol * std::fabs(ynew[i]); err[i] = ec[order] * dvec[i]; }
             error_norm = rms(err.data(), scale.data(), n);
             if (error_norm > 1.0) {
+                if (getenv("RMSO_DEBUG")) {
+                    int im = 0; double em = 0; for (int i = 0; i < n; ++i) { double e = std::fabs(err[i] / scale[i]); if (e > em) { em = e; im = i; } }
+                    fprintf(stderr, "efail t=%.17g h=%.3e order=%d err=%.3e worst comp %d (y=%.6e d=%.3e D1=%.3e) iters=%d\n", t, h_abs, order, error_norm, im, ynew[im], dvec[im], D[1 * n + im], n_iter);
+                }
                 ++st.n_err_fail;
                 double factor = std::max(0.2, safety * std::pow(error_norm, -1.0 / (order + 1)));
                 h_abs *= factor; change_D(D, n, order, factor); n_equal = 0; lu_valid = false;
@@ -651,6 +708,10 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
         }
         if (!accepted) break;
         ++n_equal; ++st.n_steps;
+        if (getenv("RMSO_TRACE")) {
+            double sn = 0; for (int i = 0; i < m.Ns; ++i) sn += ynew[i];
+            fprintf(stderr, "ACC t=%.6e h=%.3e o=%d err=%.3e T=%.6f inv=%.3e lu_valid=%d\n", t_new, h_abs, order, error_norm, ynew[m.Ns], ynew[m.Ns + 1] * d.cond[0] / (8.314 * ynew[m.Ns]) / sn - 1.0, (int)lu_valid);
+        }
         double t_old = t;
         t = t_new;
         for (int i = 0; i < n; ++i) {
@@ -686,8 +747,9 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
         double fm = std::pow(e_m, -1.0 / order), f0 = std::pow(error_norm, -1.0 / (order + 1)), fp = std::pow(e_p, -1.0 / (order + 2));
         int delta; double fmx;
         if (fm >= f0 && fm >= fp) { delta = -1; fmx = fm; } else if (f0 >= fp) { delta = 0; fmx = f0; } else { delta = 1; fmx = fp; }
-        order += delta;
         double factor = std::min(10.0, safety * fmx);
+        if (hysteresis && delta == 0 && factor >= 1.0 && factor < 1.2) continue;
+        order += delta;
         h_abs *= factor; change_D(D, n, order, factor); n_equal = 0; lu_valid = false;
     }
     if (yend) std::copy(y.begin(), y.end(), yend);
@@ -791,6 +853,8 @@ int rmso_eval(void* h, int mode, int kind, int64_t n, const double* y, const dou
     }
     return 0;
 }
+
+void rmso_set_flags(int flags) { g_flags = flags; }
 
 int rmso_solve(void* h, int kind, int64_t n, const double* y0, const double* cond, const double* p, int64_t p_stride,
                const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,

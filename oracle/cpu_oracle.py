@@ -191,7 +191,8 @@ class CpuMech:
         assert rc == 0
         return out.reshape(n, Ny, Ny).transpose(0, 2, 1)
 
-    def solve(self, kind, y0, cond, t_end, rtol, atol, p=None, constspc=(), tsave=None, max_steps=500000, idt_index=-1, nthreads=0):
+    def solve(self, kind, y0, cond, t_end, rtol, atol, p=None, constspc=(), tsave=None, max_steps=500000, idt_index=-1, nthreads=0, flags=0):
+        lib().rmso_set_flags(int(flags))     # same meaning as RMSB200(flags=...): 0 = the CUDA path's defaults, 3 = scipy.integrate.BDF's step logic
         y0, cond, p, ps, cs = self._common(kind, y0, cond, p, constspc)
         n, Ny = y0.shape
         te = np.ascontiguousarray(np.broadcast_to(np.asarray(t_end, dtype=float), (n,)))

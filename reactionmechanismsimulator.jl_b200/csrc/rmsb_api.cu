@@ -181,6 +181,13 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
         for (int k = 0; k < 4; ++k) { int s = rx[(size_t)k * Nr + j]; if (s >= 0) sr[s].push_back(j | (int)0x80000000); }
         for (int k = 4; k < 8; ++k) { int s = rx[(size_t)k * Nr + j]; if (s >= 0) sr[s].push_back(j); }
     }
+    // species whose net stoichiometry is zero in every reaction: their dn/dt and Jacobian rows are exact zeros
+    std::vector<int> inert(Ns, 1);
+    for (int j = 0; j < Nr; ++j) {
+        std::map<int, int> net;
+        for (int k = 0; k < 8; ++k) { int s = rx[(size_t)k * Nr + j]; if (s >= 0) net[s] += (k < 4) ? -1 : 1; }
+        for (auto& kv : net) if (kv.second != 0) inert[kv.first] = 0;
+    }
     std::vector<int> srptr(Ns + 1, 0), srrxn;
     for (int s = 0; s < Ns; ++s) { for (int v : sr[s]) srrxn.push_back(v); srptr[s + 1] = (int)srrxn.size(); }
     // ---- Jacobian ns-block: derivative terms + per-entry gather lists in the accumulation order of
@@ -278,7 +285,7 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     UP(srptr, sr_ptr); UP(srrxn, sr_rxn);
     UP(dtrxn, dt_rxn); UP(dtmult, dt_mult); UP(dtoth, dt_oth); UP(dtspc, dt_spc);
     UP(jeptr, je_ptr); UP(jerow, je_row); UP(jecol, je_col); UP(jtidx, jt_idx);
-    UP(rxdom, rx_dom); UP(nrp2, nrp2); UP(srmid, sr_mid);
+    UP(rxdom, rx_dom); UP(nrp2, nrp2); UP(srmid, sr_mid); UP(inert, inert);
 #undef UP
     if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
     if (!diffr.empty()) { if ((rc = upload(h, diffr, &dm.diff_r)) != RMSB_OK) return rc; } else dm.diff_r = nullptr;
@@ -329,19 +336,20 @@ __device__ __forceinline__ void stage_mech(const DevMech& mp) {
     __syncthreads();
 }
 
-__device__ __forceinline__ Ws make_ws(int warp, int ws_per_warp, int Ny) {
+__device__ __forceinline__ Ws make_ws(int warp, int ws_per_warp, int Ny, int mode = 0) {
     const DevMech& m = mech();
     Ws w;
     w.off = MECH_DOUBLES + warp * ws_per_warp; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = m.n_dt; w.LD = Ny | 1;
+    w.jpo = ws_jp_offset(m.Ns, m.Nr, Ny, m.n_dt, mode);
     return w;
 }
 
-// mode 0: dydt, 1: Jacobian, 2: kf/krev.  One warp per reactor, grid-stride over the batch.
+// mode 0: dydt, 1: Jacobian, 2: kf/krev, 3: parameter Jacobian, 4: kf before diffusion limitation.  One warp per reactor, grid-stride over the batch.
 template <int MODE>
 __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const Ws w = make_ws(warp, ws_per_warp, a.Ny);
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny, MODE == 3 ? 3 : 0);
     const int Ny = a.Ny, Nr = w.Nr;
     const int64_t nw = (int64_t)gridDim.x * wpb;
     for (int64_t ir = (int64_t)blockIdx.x * wpb + warp; ir < a.n; ir += nw) {
@@ -367,6 +375,21 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
                 int col = idx / Ny, row = idx - col * Ny;
                 J[idx] = Js[row + col * LD];
             }
+        } else if (MODE == 3) {
+            const int Np = w.Ns + Nr;
+            double* Jp = a.out + (size_t)ir * Ny * Np;      // column-major Ny x Np
+            for (int c0 = 0; c0 < Np; c0 += JP_CHUNK) {
+                jacp_warp(d, w, lane, c0, c0 == 0);
+                const double* jc = w.jp();
+                for (int idx = lane; idx < Ny * JP_CHUNK; idx += 32) {
+                    int cl = idx / Ny, row = idx - cl * Ny;
+                    if (c0 + cl < Np) Jp[(size_t)(c0 + cl) * Ny + row] = jc[row * JP_CHUNK + cl];
+                }
+                __syncwarp();
+            }
+        } else if (MODE == 4) {
+            kfs_intrinsic(d, w, lane);
+            for (int j = lane; j < Nr; j += 32) a.out[ir * Nr + j] = w.kf()[j];
         } else {
             rhs_warp(d, w, lane, true);
             for (int j = lane; j < Nr; j += 32) { a.out[ir * Nr + j] = w.kf()[j]; a.out2[ir * Nr + j] = w.kr()[j]; }
@@ -389,6 +412,21 @@ __global__ void __launch_bounds__(128, RMSB_SOLVE_MINBLOCKS) solve_kernel(const 
         ir = __shfl_sync(FULL, ir, 0);
         if (ir >= (unsigned long long)a.n) break;
         bdf_solve_warp<R>(a, w, (int64_t)ir, lane);
+    }
+}
+
+// forward sensitivities ride on the same integrator (bdf_solve_warp<R, true>)
+template <int R>
+__global__ void __launch_bounds__(128, 1) sens_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
+    stage_mech(mp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny, 2);
+    for (;;) {
+        unsigned long long ir = 0;
+        if (lane == 0) ir = atomicAdd(a.counter, 1ULL);
+        ir = __shfl_sync(FULL, ir, 0);
+        if (ir >= (unsigned long long)a.n) break;
+        bdf_solve_warp<R, true>(a, w, (int64_t)ir, lane);
     }
 }
 
@@ -428,10 +466,10 @@ static int rows_per_lane(int Ny) { return (Ny + 31) / 32; }
 struct LaunchCfg { int wpb; int ws; size_t smem; int blocks_per_sm; int sms; };
 
 template <class K>
-static int config_launch(K kernel, const rmsb_mech* h, int Ny, bool solver, int want_wpb, LaunchCfg* cfg) {
+static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int want_wpb, LaunchCfg* cfg) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
-    int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, solver);
+    int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, mode);
     size_t per_warp = (size_t)ws * sizeof(double);
     const size_t mech_bytes = (size_t)MECH_DOUBLES * sizeof(double);
     size_t max_smem = prop.sharedMemPerBlockOptin - mech_bytes;
@@ -452,7 +490,7 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, bool solver, int 
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
     LaunchCfg cfg;
-    int rc = config_launch(eval_kernel<MODE>, h, a.Ny, false, 4, &cfg);
+    int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
     int64_t max_blocks = (int64_t)cfg.sms * cfg.blocks_per_sm * 8;   // grid-stride beyond 8 waves
@@ -467,7 +505,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
 template <int R>
 static int launch_solve_R(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
     LaunchCfg cfg;
-    int rc = config_launch(solve_kernel<R>, h, a.Ny, true, want_wpb, &cfg);
+    int rc = config_launch(solve_kernel<R>, h, a.Ny, 1, want_wpb, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t resident = (int64_t)cfg.sms * cfg.blocks_per_sm;
     int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
@@ -478,6 +516,39 @@ static int launch_solve_R(const rmsb_mech* h, const SolveArgs& a, int want_wpb, 
     ++g_launches;
     CU(cudaGetLastError());
     return RMSB_OK;
+}
+
+constexpr size_t SENS_WORK_HEADER = 256;
+static int sens_npp(const rmsb_mech* h) { return (h->dm.Ns + h->dm.Nr + 31) & ~31; }
+
+// resident warps of the sensitivity kernel and the scratch they need; launches when `a` is given
+template <int R>
+static int sens_R(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
+    LaunchCfg cfg;
+    int rc = config_launch(sens_kernel<R>, h, Ny, 2, want_wpb, &cfg);
+    if (rc != RMSB_OK) return rc;
+    int64_t resident = (int64_t)cfg.sms * cfg.blocks_per_sm;
+    int64_t blocks_needed = (n + cfg.wpb - 1) / cfg.wpb;
+    int grid = (int)(blocks_needed < resident ? blocks_needed : resident);
+    if (grid < 1) grid = 1;
+    size_t per_warp = sizeof(double) * (size_t)(BDF_MAX_ORDER + 3) * Ny * sens_npp(h);
+    if (work_bytes) *work_bytes = SENS_WORK_HEADER + per_warp * (size_t)grid * cfg.wpb;
+    if (!a) return RMSB_OK;
+    CU(cudaMemsetAsync(a->counter, 0, sizeof(unsigned long long), st));
+    sens_kernel<R><<<grid, cfg.wpb * 32, cfg.smem, st>>>(h->dm, *a, cfg.ws);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return RMSB_OK;
+}
+
+static int sens_dispatch(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
+    switch (rows_per_lane(Ny)) {
+    case 1: return sens_R<1>(h, Ny, n, want_wpb, work_bytes, a, st);
+    case 2: return sens_R<2>(h, Ny, n, want_wpb, work_bytes, a, st);
+    case 3: return sens_R<3>(h, Ny, n, want_wpb, work_bytes, a, st);
+    case 4: return sens_R<4>(h, Ny, n, want_wpb, work_bytes, a, st);
+    }
+    return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
 }
 
 static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
@@ -531,6 +602,23 @@ extern "C" int rmsb_jac_batch_dev(const rmsb_mech* h, int kind, int64_t n, const
     return launch_eval<1>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr), (cudaStream_t)stream);
 }
 
+static int check_jacp(const rmsb_mech* h, int kind, const double* p) {
+    if (kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "parameter Jacobian of the coupled gas-surface system is not built");
+    if (kind == RMSB_DOMAIN_CONSTANT_TV && !p) return fail(RMSB_ERR_ARG, "ConstantTV parameter Jacobian needs the explicit parameter vector p (chain rule through the diffusion limit)");
+    (void)h;
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_jacp_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond,
+                                   const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs, double* Jp, void* stream) {
+    int rc = check_common(h, kind, n, y, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if ((rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    DeviceGuard g(h->device);
+    return launch_eval<3>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr), (cudaStream_t)stream);
+}
+
 extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech*, int, int64_t) { return 256; }
 
 static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
@@ -546,13 +634,14 @@ static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
     }
 }
 
-extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
-                                    const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
-                                    const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
-                                    double* ysave, double* yend, double* idt, int32_t* status, rmsb_stats* stats,
-                                    const rmsb_solve_opts* opts, void* work, void* stream) {
+static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
+                          const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
+                          const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                          double* ysave, double* ssave, double* yend, double* send, double* idt, int32_t* status, rmsb_stats* stats,
+                          const rmsb_solve_opts* opts, void* work, void* stream) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
+    if (sens && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!t_end || !status || !work) return fail(RMSB_ERR_ARG, "t_end, status and work buffers are required");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(RMSB_ERR_ARG, "rtol must be > 0 and atol >= 0");
@@ -568,8 +657,38 @@ extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, con
     a.idt_index = o.idt_index >= 0 ? o.idt_index : (kind == RMSB_DOMAIN_CONSTANT_V ? h->dm.Ns : -1);
     if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
     a.counter = reinterpret_cast<unsigned long long*>(work);
+    a.ssave = ssave; a.send = send; a.sens_hist = nullptr; a.Npp = sens_npp(h);
     DeviceGuard g(h->device);
-    return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
+    if (!sens) return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
+    a.idt_index = -1; a.idt = nullptr;
+    a.sens_hist = reinterpret_cast<double*>(static_cast<char*>(work) + SENS_WORK_HEADER);
+    return sens_dispatch(h, a.Ny, n, o.warps_per_block, nullptr, &a, (cudaStream_t)stream);
+}
+
+extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
+                                    const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
+                                    const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                                    double* ysave, double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                                    const rmsb_solve_opts* opts, void* work, void* stream) {
+    return solve_dev_impl(false, h, kind, n, y0, cond, p, p_stride, cs, ncs, t_end, rtol, atol, nsave, tsave, ysave, nullptr,
+                          yend, nullptr, idt, status, stats, opts, work, stream);
+}
+
+extern "C" int64_t rmsb_sens_work_bytes(const rmsb_mech* h, int kind, int64_t n) {
+    if (!h || domain_ny(h, kind) < 0) { fail(RMSB_ERR_ARG, "bad mechanism / domain kind"); return -1; }
+    DeviceGuard g(h->device);
+    size_t bytes = 0;
+    if (sens_dispatch(h, domain_ny(h, kind), n > 0 ? n : 1, 0, &bytes, nullptr, nullptr) != RMSB_OK) return -1;
+    return (int64_t)bytes;
+}
+
+extern "C" int rmsb_sens_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
+                                   const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
+                                   const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                                   double* ysave, double* ssave, double* yend, double* send, int32_t* status, rmsb_stats* stats,
+                                   const rmsb_solve_opts* opts, void* work, void* stream) {
+    return solve_dev_impl(true, h, kind, n, y0, cond, p, p_stride, cs, ncs, t_end, rtol, atol, nsave, tsave, ysave, ssave,
+                          yend, send, nullptr, status, stats, opts, work, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -606,6 +725,7 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
                      int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2) {
     int rc = check_common(h, kind, n, y, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
+    if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!out || (mode == 2 && !out2)) return fail(RMSB_ERR_ARG, "null output buffer");
     DeviceGuard g(h->device);
@@ -614,7 +734,7 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     StreamGuard sg;
     CU(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
     const int Ny = domain_ny(h, kind), nc = domain_ncond(kind), Np = h->dm.Ns + h->dm.Nr;
-    size_t out_per = mode == 0 ? (size_t)Ny : (mode == 1 ? (size_t)Ny * Ny : (size_t)h->dm.Nr);
+    size_t out_per = mode == 0 ? (size_t)Ny : (mode == 1 ? (size_t)Ny * Ny : (mode == 3 ? (size_t)Ny * Np : (size_t)h->dm.Nr));
     DevBuf dy(sg.st), dc(sg.st), dp(sg.st), dcs(sg.st), dout(sg.st), dout2(sg.st);
     CU(dy.alloc(sizeof(double) * n * Ny)); CU(dc.alloc(sizeof(double) * n * nc)); CU(dout.alloc(sizeof(double) * n * out_per));
     H2D(dy.p, y, sizeof(double) * n * Ny);
@@ -626,6 +746,8 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dout.as<double>(), dout2.as<double>());
     if (mode == 0) rc = launch_eval<0>(h, a, sg.st);
     else if (mode == 1) rc = launch_eval<1>(h, a, sg.st);
+    else if (mode == 3) rc = launch_eval<3>(h, a, sg.st);
+    else if (mode == 4) rc = launch_eval<4>(h, a, sg.st);
     else rc = launch_eval<2>(h, a, sg.st);
     if (rc != RMSB_OK) return rc;
     D2H(out, dout.p, sizeof(double) * n * out_per);
@@ -642,9 +764,18 @@ extern "C" int rmsb_jac_batch(const rmsb_mech* h, int kind, int64_t n, const dou
                               int64_t p_stride, const int32_t* cs, int32_t ncs, double* J) {
     return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr);
 }
+extern "C" int rmsb_jacp_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                               int64_t p_stride, const int32_t* cs, int32_t ncs, double* Jp) {
+    return eval_host(3, h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr);
+}
 extern "C" int rmsb_rates_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                 int64_t p_stride, double* kf, double* krev) {
     return eval_host(2, h, kind, n, y, cond, p, p_stride, nullptr, 0, kf, krev);
+}
+
+extern "C" int rmsb_kfs_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, double* kf) {
+    if (kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "rmsb_kfs_batch: single-phase domains only");
+    return eval_host(4, h, kind, n, y, cond, nullptr, 0, nullptr, 0, kf, nullptr);
 }
 
 extern "C" int rmsb_gibbs_batch(const rmsb_mech* h, int64_t n, const double* T, int scalar_path, double* G) {
@@ -707,6 +838,58 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
     if (nsave > 0) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
     if (yend) D2H(yend, dye.p, sizeof(double) * n * Ny);
     if (idt) D2H(idt, didt.p, sizeof(double) * n);
+    D2H(status, dst.p, sizeof(int32_t) * n);
+    if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
+    CU(cudaStreamSynchronize(sg.st));
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                               int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
+                               int32_t nsave, const double* tsave, double* ysave, double* ssave, double* yend, double* send,
+                               int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    int rc = check_common(h, kind, n, y0, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    if (!t_end || !status) return fail(RMSB_ERR_ARG, "t_end and status are required");
+    if (nsave > 0 && !tsave) return fail(RMSB_ERR_ARG, "tsave required when nsave > 0");
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(RMSB_ERR_CUDA, "cudaSetDevice failed");
+    tune_pool(h->device);
+    StreamGuard sg;
+    CU(cudaStreamCreateWithFlags(&sg.st, cudaStreamNonBlocking));
+    const int Ny = domain_ny(h, kind), nc = domain_ncond(kind), Np = h->dm.Ns + h->dm.Nr;
+    const size_t sper = (size_t)Ny * Np;
+    int64_t wb = rmsb_sens_work_bytes(h, kind, n);
+    if (wb < 0) return RMSB_ERR_UNSUPPORTED;
+    DevBuf dy(sg.st), dc(sg.st), dp(sg.st), dcs(sg.st), dte(sg.st), dts(sg.st), dys(sg.st), dss(sg.st), dye(sg.st), dse(sg.st),
+        dst(sg.st), dstats(sg.st), dwork(sg.st);
+    CU(dy.alloc(sizeof(double) * n * Ny)); H2D(dy.p, y0, sizeof(double) * n * Ny);
+    CU(dc.alloc(sizeof(double) * n * nc)); H2D(dc.p, cond, sizeof(double) * n * nc);
+    if (p) { size_t np = p_stride ? (size_t)n * Np : (size_t)Np; CU(dp.alloc(sizeof(double) * np)); H2D(dp.p, p, sizeof(double) * np); }
+    if (cs && ncs > 0) { CU(dcs.alloc(sizeof(int32_t) * ncs)); H2D(dcs.p, cs, sizeof(int32_t) * ncs); }
+    CU(dte.alloc(sizeof(double) * n)); H2D(dte.p, t_end, sizeof(double) * n);
+    if (nsave > 0) {
+        CU(dts.alloc(sizeof(double) * nsave)); H2D(dts.p, tsave, sizeof(double) * nsave);
+        if (ysave) CU(dys.alloc(sizeof(double) * n * nsave * Ny));
+        if (ssave) CU(dss.alloc(sizeof(double) * n * nsave * sper));
+    }
+    if (yend) CU(dye.alloc(sizeof(double) * n * Ny));
+    if (send) CU(dse.alloc(sizeof(double) * n * sper));
+    CU(dst.alloc(sizeof(int32_t) * n));
+    if (stats) CU(dstats.alloc(sizeof(rmsb_stats) * n));
+    CU(dwork.alloc((size_t)wb));
+    rc = rmsb_sens_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
+                             (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
+                             nsave > 0 ? dts.as<double>() : nullptr, (nsave > 0 && ysave) ? dys.as<double>() : nullptr,
+                             (nsave > 0 && ssave) ? dss.as<double>() : nullptr, yend ? dye.as<double>() : nullptr,
+                             send ? dse.as<double>() : nullptr, dst.as<int32_t>(), stats ? dstats.as<rmsb_stats>() : nullptr, opts,
+                             dwork.p, sg.st);
+    if (rc != RMSB_OK) return rc;
+    if (nsave > 0 && ysave) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
+    if (nsave > 0 && ssave) D2H(ssave, dss.p, sizeof(double) * n * nsave * sper);
+    if (yend) D2H(yend, dye.p, sizeof(double) * n * Ny);
+    if (send) D2H(send, dse.p, sizeof(double) * n * sper);
     D2H(status, dst.p, sizeof(int32_t) * n);
     if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
     CU(cudaStreamSynchronize(sg.st));

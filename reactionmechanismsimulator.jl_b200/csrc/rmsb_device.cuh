@@ -87,6 +87,7 @@ struct DevMech {
     const int* rx_dom;       // [Nr] 0 bulk reaction, 1 surface reaction, 2 interface reaction (sorted ascending)
     const double* nrp2;      // [Nr] surface-phase exponent of C0 in Kc (nrp is the bulk-phase exponent)
     const int* sr_mid;       // [Ns] first interface entry of the species' slot list
+    const int* inert;        // [Ns] 1 = no reaction changes the species (absent, or written on both sides everywhere): dn/dt == 0 exactly
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -161,6 +162,7 @@ extern __shared__ double smem_ws[];     // [DevMech copy | warp 0 slice | warp 1
 struct Ws {
     int off;                                  // offset (in doubles) of this warp's slice inside smem_ws
     int Ns, Nr, Ny, ndt, LD;
+    int jpo;                                  // offset of the parameter-Jacobian tile inside the slice (mode 2: after LU; mode 3: on J)
     __device__ __forceinline__ double* at(int o) const { return smem_ws + off + o; }
     __device__ __forceinline__ double* cs() const { return at(0); }                                 // [Ns]   concentrations
     __device__ __forceinline__ double* g() const { return at(Ns); }                                 // [3Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
@@ -179,7 +181,9 @@ struct Ws {
     __device__ __forceinline__ double* xs() const { return dinv() + Ny; }                           // [Ny]   linear-solve vector
     __device__ __forceinline__ int* perm() const { return reinterpret_cast<int*>(xs() + Ny); }      // [Ny]   pivot rows
     __device__ __forceinline__ double* J() const { return xs() + Ny + (Ny + 1) / 2 + 1; }           // [Ny*LD] Jacobian, column-major
-    __device__ __forceinline__ double* LU() const { return J() + Ny * LD; }                         // [Ny*LD] inverse of I - c*J (solver only)
+    __device__ __forceinline__ double* LU() const { return J() + Ny * LD; }                         // [Ny*LD] LU factors of I - c*J (solver only)
+    __device__ __forceinline__ double* jp() const { return at(jpo); }                        // [Ny*32] 32 columns of d(dy/dt)/dp, [row][lane] (sensitivities only)
+    __device__ __forceinline__ double* xm() const { return jp() + Ny * 32; }                        // [Ny*32] per-lane sensitivity work vectors, [row][lane]
 };
 
 // The mechanism descriptor lives at the start of the block's dynamic shared memory: every routine reads it
@@ -188,11 +192,23 @@ constexpr int MECH_DOUBLES = (int)((sizeof(DevMech) + 15) / 16 * 2);
 __device__ __forceinline__ const DevMech& mech() { return *reinterpret_cast<const DevMech*>(smem_ws); }
 #define G(ptr, idx) __ldg((ptr) + (idx))   /* mechanism tables are immutable global memory: read-only path */
 
-__host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, bool solver) {
+// mode 0: RHS / Jacobian evaluation, 1: solver (+ LU), 2: forward sensitivities (+ LU, Jp tile, work tile),
+// 3: parameter-Jacobian evaluation (the Jp tile takes the place of J)
+__host__ __device__ inline int ws_fixed_doubles(int Ns, int Nr, int Ny, int n_dt) {
+    return 9 * Ns + 5 * Nr + n_dt + Ny + 3 * Ny + 8 + 36 + Ny + Ny + (Ny + 1) / 2 + 1;
+}
+__host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, int mode) {
     int LD = Ny | 1;
-    int n = 9 * Ns + 5 * Nr + n_dt + Ny + 3 * Ny + 8 + 36 + Ny + Ny + (Ny + 1) / 2 + 1 + Ny * LD;
-    if (solver) n += Ny * LD;
+    int n = ws_fixed_doubles(Ns, Nr, Ny, n_dt);
+    if (mode == 3) n += (Ny * LD > Ny * 32) ? Ny * LD : Ny * 32;
+    else n += Ny * LD;
+    if (mode == 1 || mode == 2) n += Ny * LD;
+    if (mode == 2) n += 2 * Ny * 32;
     return (n + 1) & ~1;
+}
+__host__ __device__ inline int ws_jp_offset(int Ns, int Nr, int Ny, int n_dt, int mode) {
+    int LD = Ny | 1;
+    return ws_fixed_doubles(Ns, Nr, Ny, n_dt) + (mode == 2 ? 2 * Ny * LD : 0);
 }
 
 // smem load/store of a possibly-dual value at logical index i of an array with Dual2 capacity
@@ -1040,6 +1056,107 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         for (int i = lane; i < Ny; i += 32) { J[i + Ns * LD] = fb[3 * i + 1]; J[i + (Ns + 1) * LD] = fb[3 * i + 2]; }
         __syncwarp();
     }
+}
+
+// getkfs (src/PhaseState.jl:165-171): forward rate coefficients of every reaction BEFORE diffusion limitation, vector
+// forms for the vectorised block -- what the constant-k constructors store in p[Ns+1:end] (kfsnondiff for the liquid
+// phase, src/Domain.jl:549-551).  State in w.ybuf, result in w.kf.
+__device__ __noinline__ void kfs_intrinsic(DomainArgs d, Ws w, int lane) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr;
+    const double* ns = w.ybuf();
+    double T, P, V;
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V) { T = ns[Ns]; P = ns[Ns + 1]; V = d.cond[0]; }
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { T = d.cond[0]; P = d.cond[1]; V = ns[Ns]; }
+    else { T = d.cond[0]; P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
+    double N = 0.0;
+    for (int s = 0; s < Ns; ++s) N += ns[s];
+    const double C = (d.kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (d.kind == RMSB_DOMAIN_CONSTANT_TAPHI ? 0.0 : N / V);
+    KinEnv<double> e;
+    e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+    double* kfb = w.kf();
+    for (int j = lane; j < Nr; j += 32) kfb[j] = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), false);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// jacobianp! for one reactor (src/Domain.jl:3095-3485): d(dy/dt)/dp, Ny x (Ns+Nr).  Columns 0..Ns-1: dG_i (through
+// krev = kf/Kc); column Ns+j: k_j (constant-k domains: the rate coefficient itself -- the multiplier for efficiency
+// reactions; variable-k domains: the multiplier f_j).  One lane per column: a call produces the 32 columns
+// c0 .. c0+31 into w.jp() laid out [row][lane] (JP_CHUNK doubles per row; lanes past Ns+Nr write zeros).
+// Needs cs/kf/kr/us/aux of the state in w.ybuf: `fresh` evaluates them first (rhs_warp with store_k).
+// ------------------------------------------------------------------------------------------------
+constexpr int JP_CHUNK = 32;
+__device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int c0, bool fresh) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, Np = Ns + Nr;
+    if (fresh) rhs_warp(d, w, lane, true);
+    double* col = w.jp() + lane;
+    const double* cs = w.cs();
+    const double* kfb = w.kf();
+    const double* krb = w.kr();
+    const double* ax = w.aux();
+    const double aT = ax[0], aP = ax[1], aV = ax[2], aN = ax[3], aCv = ax[5];
+    const double RTinv = 1.0 / (RMSB_R * aT);
+    const bool constk = (d.kind != RMSB_DOMAIN_CONSTANT_V);
+    const int c = c0 + lane;
+    for (int i = 0; i < Ny; ++i) col[i * JP_CHUNK] = 0.0;
+    if (c < Np) {
+        double raw = 0.0;       // dn_c/dt / V before constant-species zeroing (G columns of ConstantV)
+        if (c >= Ns) {
+            // reaction column: flux = fderiv - rderiv scattered with the stoichiometry (Domain.jl:3140-3142)
+            const int j = c - Ns;
+            double pr = 1.0, pp = 1.0;
+            for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pr *= cs[sp]; }
+            for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pp *= cs[sp]; }
+            const bool eff = G(m.eff_ptr, j + 1) > G(m.eff_ptr, j);
+            double fderiv, rderiv;
+            if (d.kind == RMSB_DOMAIN_CONSTANT_TV) {            // Domain.jl:3290-3317: chain rule through the diffusion limit
+                double pk = d.p[Ns + j];
+                fderiv = kfb[j] * kfb[j] / (pk * pk) * pr;
+                rderiv = kfb[j] * krb[j] / (pk * pk) * pp;
+            } else if (constk && !eff) { fderiv = pr; rderiv = krb[j] / kfb[j] * pp; }
+            else { fderiv = kfb[j] * pr; rderiv = krb[j] * pp; }
+            const double flux = (fderiv - rderiv) * aV;
+            for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] -= flux; }
+            for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] += flux; }
+        } else {
+            // dG column of species c: every slot occurrence of the species contributes -/+ gderiv_j (Domain.jl:3144-3199)
+            for (int q = G(m.sr_ptr, c); q < G(m.sr_ptr, c + 1); ++q) {
+                const int jr = G(m.sr_rxn, q);
+                const int j = jr & 0x7fffffff;
+                double pr = 1.0, pp = 1.0;
+                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pr *= cs[sp]; }
+                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pp *= cs[sp]; }
+                const double net = kfb[j] * pr - krb[j] * pp;
+                raw = (jr < 0) ? raw - net : raw + net;
+                // gderiv = d(reverse flux)/dG = krev*prod(c_products)/RT (the reference reaches it through rderiv*kfs*RTinv in
+                // the constant-k domains, whose rderiv carries 1/kfs -- except for efficiency reactions, Domain.jl:3144)
+                const bool eff = G(m.eff_ptr, j + 1) > G(m.eff_ptr, j);
+                double gderiv = krb[j] * pp * RTinv;
+                if (constk && eff && d.kind != RMSB_DOMAIN_CONSTANT_TV) gderiv *= kfb[j];
+                gderiv *= aV;
+                const double sg = (jr < 0) ? gderiv : -gderiv;      // reactant slot: reactant rows -= g, product rows += g
+                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] -= sg; }
+                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] += sg; }
+            }
+        }
+        // thermodynamic-variable rows
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {                 // Domain.jl:3386-3388
+            double a = 0.0;
+            for (int i = 0; i < Ns; ++i) a += col[i * JP_CHUNK];
+            col[Ns * JP_CHUNK] = a * RMSB_R * aT / aP;
+        } else if (d.kind == RMSB_DOMAIN_CONSTANT_V) {           // Domain.jl:3406-3414
+            const double* us = w.us();
+            double a = 0.0, sm = 0.0;
+            for (int i = 0; i < Ns; ++i) { a += us[i] * col[i * JP_CHUNK]; sm += col[i * JP_CHUNK]; }
+            double jt = (c < Ns) ? -(a + raw * aV) / (aN * aCv) : -a / (aN * aCv);
+            col[Ns * JP_CHUNK] = jt;
+            col[(Ns + 1) * JP_CHUNK] = sm * RMSB_R * aT / aV + aP / aT * jt;
+        }
+        for (int k = 0; k < d.nconst; ++k) col[(d.constspc[k] - 1) * JP_CHUNK] = 0.0;
+    }
+    __syncwarp();
 }
 
 }  // namespace rmsb

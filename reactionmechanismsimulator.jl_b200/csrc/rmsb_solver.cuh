@@ -24,6 +24,7 @@ constexpr int BDF_MAX_ORDER = 5;
 constexpr int NEWTON_MAXITER = 4;
 constexpr double BDF_MIN_FACTOR = 0.2;
 constexpr double BDF_MAX_FACTOR = 10.0;
+constexpr double JAC_REFRESH_RATIO = 100.0;
 
 // NDF constants (Shampine-Reichelt kappa; gamma_k = sum_{j<=k} 1/j accumulated left to right)
 #define RMSB_G1 (1.0)
@@ -70,6 +71,10 @@ struct SolveArgs {
     unsigned long long* counter;
     int domain_kind;
     int Ny;
+    double* ssave;      // sensitivities only: [n][nsave][Np][Ny]
+    double* send;       // sensitivities only: [n][Np][Ny]
+    double* sens_hist;  // sensitivities only: per resident warp [8][Ny][Npp] backward differences of S
+    int Npp;            // Ns+Nr rounded up to a multiple of 32
     int flags;      // bit 0: scipy-style Newton test (every step >= 2 iterations, tolerance min(0.03, sqrt(rtol)));
                     // bit 1: no step-size hysteresis.  0 = production defaults (CVODE-style test, hysteresis)
 };
@@ -295,8 +300,129 @@ __device__ __forceinline__ void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int 
     __syncwarp();
 }
 
-// ---- the integrator ---------------------------------------------------------------------------
+// ---- forward sensitivities: staggered direct corrector --------------------------------------------------
+// S = dy/dp obeys dS/dt = J(y) S + Jp(y), S(0) = 0 (what ODEForwardSensitivityProblem appends to the state in the
+// reference, src/Reactor.jl:63-75; per-parameter form in src/ThreadedSensitivities.jl:59-67).  Its BDF corrector is
+// linear: with S_new = S_pred + dS,  (I - c J(y_new)) dS = c (J(y_new) S_pred + Jp(y_new)) - psi_S, solved exactly
+// with a fresh Jacobian/LU after every accepted state step.  One lane per parameter column; the backward-difference
+// history of S (same step/order sequence as the state) lives in global scratch [j][row][par], L2-resident.
+struct SensHist {
+    double* D;
+    int Ny, Np, Npp;
+    size_t plane;       // Ny*Npp
+    __device__ __forceinline__ double* at(int j, int i, int p) const { return D + (size_t)j * plane + (size_t)i * Npp + p; }
+};
+
+__device__ __noinline__ void sens_init(DomainArgs d, Ws w, SensHist sh, double h, int lane) {
+    for (size_t e = lane; e < (size_t)(BDF_MAX_ORDER + 3) * sh.plane; e += 32) sh.D[e] = 0.0;
+    __syncwarp();
+    for (int c0 = 0; c0 < sh.Np; c0 += JP_CHUNK) {
+        jacp_warp(d, w, lane, c0, c0 == 0);
+        const double* b = w.jp() + lane;
+        for (int i = 0; i < sh.Ny; ++i) *sh.at(1, i, c0 + lane) = h * b[i * JP_CHUNK];     // D1 = h * dS/dt(0) = h * Jp(y0)
+        __syncwarp();
+    }
+}
+
+// the state's change_D applied to S: the 6x6 matrix R(factor) U is still in w.ru
+__device__ __noinline__ void sens_change_D(Ws w, SensHist sh, int order, int lane) {
+    const double* ru = w.ru();
+    for (size_t e = lane; e < sh.plane; e += 32) {
+        double dv[BDF_MAX_ORDER + 1], dn[BDF_MAX_ORDER + 1];
+#pragma unroll
+        for (int i = 0; i <= BDF_MAX_ORDER; ++i) dv[i] = (i <= order) ? sh.D[(size_t)i * sh.plane + e] : 0.0;
+#pragma unroll
+        for (int j = 1; j <= BDF_MAX_ORDER; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i <= BDF_MAX_ORDER; ++i) if (i <= order) acc += ru[i * 6 + j] * dv[i];
+            dn[j] = acc;
+        }
+#pragma unroll
+        for (int j = 1; j <= BDF_MAX_ORDER; ++j) if (j <= order) sh.D[(size_t)j * sh.plane + e] = dn[j];
+    }
+    __syncwarp();
+}
+
+// one accepted step of the state at order `order`, c = h/alpha: w.ybuf holds y_new.  Leaves J(y_new) and the LU of
+// I - c J(y_new) in the workspace (valid for the state's next step if h and the order stay).
 template <int R>
+__device__ __noinline__ bool sens_step(DomainArgs d, Ws w, SensHist sh, int order, double c, int lane) {
+    jac_warp(d, w, lane);
+    const int Ny = w.Ny, LD = w.LD;
+    const bool ok = lu_factor_warp<R>(w, c, lane);
+    const double* J = w.J();
+    const double* A = w.LU();
+    const double* dinv = w.dinv();
+    const int* perm = w.perm();
+    const double inv_alpha = 1.0 / c_alpha[order];
+    for (int c0 = 0; c0 < sh.Np; c0 += JP_CHUNK) {
+        jacp_warp(d, w, lane, c0, c0 == 0);
+        double* b = w.jp() + lane;
+        double* x = w.xm() + lane;
+        const int pc = c0 + lane;
+        // predictor S_pred = sum_j D_j, psi_S = sum_j gamma_j D_j / alpha;  b = c*Jp - psi_S
+        for (int i = 0; i < Ny; ++i) {
+            double sp = 0.0, ps = 0.0;
+#pragma unroll
+            for (int j = 0; j <= BDF_MAX_ORDER; ++j)
+                if (j <= order) { double v = *sh.at(j, i, pc); sp += v; ps += c_gamma[j] * v; }
+            x[i * JP_CHUNK] = sp;
+            b[i * JP_CHUNK] = c * b[i * JP_CHUNK] - ps * inv_alpha;
+        }
+        // b += c * J * S_pred
+        for (int i = 0; i < Ny; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < Ny; ++k) acc += J[i + k * LD] * x[k * JP_CHUNK];
+            b[i * JP_CHUNK] += c * acc;
+        }
+        // x = (I - cJ)^-1 b with the pivoted LU factors: every lane substitutes its own column
+        for (int i = 0; i < Ny; ++i) x[i * JP_CHUNK] = b[perm[i] * JP_CHUNK];
+        for (int i = 1; i < Ny; ++i) {
+            double acc = x[i * JP_CHUNK];
+            for (int k = 0; k < i; ++k) acc -= A[i + k * LD] * x[k * JP_CHUNK];
+            x[i * JP_CHUNK] = acc;
+        }
+        for (int i = Ny - 1; i >= 0; --i) {
+            double acc = x[i * JP_CHUNK];
+            for (int k = i + 1; k < Ny; ++k) acc -= A[i + k * LD] * x[k * JP_CHUNK];
+            x[i * JP_CHUNK] = acc * dinv[i];
+        }
+        // history update, as for the state: D[o+2] = dS - D[o+1]; D[o+1] = dS; D[j] += D[j+1], j = o..0
+        for (int i = 0; i < Ny; ++i) {
+            const double ds = x[i * JP_CHUNK];
+            double dv[BDF_MAX_ORDER + 3];
+#pragma unroll
+            for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) dv[j] = (j <= order + 1) ? *sh.at(j, i, pc) : 0.0;
+#pragma unroll
+            for (int j = 2; j < BDF_MAX_ORDER + 3; ++j) if (j == order + 2) dv[j] = ds - dv[j - 1];
+#pragma unroll
+            for (int j = 1; j < BDF_MAX_ORDER + 3; ++j) if (j == order + 1) dv[j] = ds;
+#pragma unroll
+            for (int j = BDF_MAX_ORDER; j >= 0; --j) if (j <= order) dv[j] += dv[j + 1];
+#pragma unroll
+            for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) if (j <= order + 2) *sh.at(j, i, pc) = dv[j];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// dense output of S at ts inside the last step (t - h, t]; out is [Np][Ny]
+__device__ __noinline__ void sens_interp(SensHist sh, int order, double t, double h, double ts, double* out, int lane) {
+    const int tot = sh.Ny * sh.Np;
+    for (int o = lane; o < tot; o += 32) {
+        const int p = o / sh.Ny, i = o - p * sh.Ny;
+        double pj = 1.0, acc = *sh.at(0, i, p);
+#pragma unroll
+        for (int j = 1; j <= BDF_MAX_ORDER; ++j)
+            if (j <= order) { pj *= (ts - (t - (double)(j - 1) * h)) / (h * (double)j); acc += *sh.at(j, i, p) * pj; }
+        out[o] = acc;
+    }
+}
+
+// ---- the integrator ---------------------------------------------------------------------------
+template <int R, bool SENS = false>
 __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int lane) {
     const int Ny = a.Ny;
     DomainArgs d;
@@ -312,6 +438,10 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     for (int j = 0; j < BDF_MAX_ORDER + 3; ++j)
 #pragma unroll
         for (int r = 0; r < R; ++r) D[j][r] = 0.0;
+    SensHist sh;
+    sh.Ny = Ny; sh.Np = w.Ns + w.Nr; sh.Npp = a.Npp; sh.plane = (size_t)Ny * a.Npp;
+    sh.D = SENS ? a.sens_hist + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (BDF_MAX_ORDER + 3) * sh.plane : nullptr;
+#define CHANGE_D(factor_) do { change_D<R>(D, order, (factor_), w, lane); if (SENS) sens_change_D(w, sh, order, lane); } while (0)
     double y[R], f[R], scale[R];   // scale holds the RECIPROCAL weights 1/(atol + rtol*|y_i|)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -320,6 +450,19 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     }
     int n_rhs = 0, n_jac = 0, n_lu = 0, n_steps = 0, n_nfail = 0, n_efail = 0;
     int status = RMSB_SOLVE_OK;
+    // Unit rows of I - c*J: species no reaction changes (colliders written on both sides, absent species) and the
+    // constant species have dy_i/dt == 0 and a zero Jacobian row, so row i of every Newton system reads x_i = b_i.  Partial
+    // pivoting may still eliminate through such a row (c*dR/dn_i > 1 during ignition) and return x_i = b_i + rounding noise,
+    // which an absolute tolerance of 1e-20 (the reference's habit, src/TestReactors.jl:305) turns into Newton failures.
+    // The exact row equation is imposed after each solve instead.
+    bool unit_row[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = r * 32 + lane;
+        unit_row[r] = (i < w.Ns) && G(mech().inert, i) != 0;
+        for (int k = 0; k < a.nconst; ++k) if (a.constspc[k] - 1 == i) unit_row[r] = true;
+        if (a.flags & 4) unit_row[r] = false;
+    }
 
     rhs_prepare(d, w, lane);
     // constant-k domains: rate coefficients once per reactor
@@ -333,7 +476,9 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     const int idt_index = a.idt_index;
     double idt_best = -INFINITY, idt_time = NAN;
     double* ysave = a.ysave ? a.ysave + (size_t)ir * a.nsave * Ny : nullptr;
+    double* ssave = (SENS && a.ssave) ? a.ssave + (size_t)ir * a.nsave * Ny * sh.Np : nullptr;
     while (isave < a.nsave && a.tsave[isave] <= 0.0) {
+        if (ssave) for (int o = lane; o < Ny * sh.Np; o += 32) ssave[(size_t)isave * Ny * sh.Np + o] = 0.0;
         if (ysave) {
 #pragma unroll
             for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) ysave[(size_t)isave * Ny + i] = y[r]; }
@@ -366,6 +511,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     }
     to_smem<R>(w.ybuf(), y, Ny, lane);
     jac_warp(d, w, lane); ++n_jac;
+    if (SENS) sens_init(d, w, sh, h_abs, lane);
     bool lu_valid = false;
 #pragma unroll
     for (int r = 0; r < R; ++r) { D[0][r] = y[r]; D[1][r] = f[r] * h_abs; }
@@ -373,6 +519,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     const int max_order = a.max_order;
     const double newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
     const bool scipy_newton = (a.flags & 1) != 0, hysteresis = (a.flags & 2) == 0;
+    double c_jac = 0.0;     // c = h/alpha the current Jacobian was first factorised with
     double crate = 1.0;     // Newton convergence-rate estimate carried across steps (CVODE), reset with every new LU
     // Newton tolerance coefficient: CVODE's nlscoef = 0.1 made this NDF error estimator fail 4.6x more often
     // (profiles/r01_newton_sweep.txt); 0.1/8 gives the fewest RHS evaluations at unchanged accuracy.
@@ -384,7 +531,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
         if (n_steps >= a.max_steps) { status = RMSB_SOLVE_MAX_STEPS; break; }
         const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);   // 10*(nextafter(t,inf)-t)
         if (h_abs < min_step) {
-            change_D<R>(D, order, min_step / h_abs, w, lane);
+            CHANGE_D(min_step / h_abs);
             h_abs = min_step; n_equal = 0; lu_valid = false;
         }
         bool accepted = false, current_jac = false;
@@ -393,12 +540,18 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
         while (!accepted) {
             if (h_abs < min_step) { status = RMSB_SOLVE_STEP_TOO_SMALL; break; }
             t_new = t + h_abs;
+            // The differences D are scaled for the step h_abs itself.  Recomputing it as fl(t + h_abs) - t (as scipy does)
+            // makes the formula inconsistent by ulp(t)*|dy/dt| -- an error floor that rtol = 1e-12 hits during ignition; the
+            // RHS is autonomous, so the rounding of t itself is harmless.
             if (t_new - t_end > 0.0) {
                 t_new = t_end;
-                change_D<R>(D, order, fabs(t_new - t) / h_abs, w, lane);
+                const double hc = t_end - t;
+                CHANGE_D(hc / h_abs);
                 n_equal = 0; lu_valid = false;
+                h_abs = hc;
             }
-            h = t_new - t; h_abs = fabs(h);
+            h = h_abs;
+            if (a.flags & 8) { h = t_new - t; h_abs = fabs(h); }
             double ypred[R], psi[R];
             const double alpha_o = c_alpha[order];
 #pragma unroll
@@ -417,7 +570,19 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
             int n_iter = 0;
             while (!converged) {
                 bool lu_ok = true;
-                if (!lu_valid) { lu_ok = lu_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; crate = 1.0; }
+                if (!lu_valid) {
+                    // A Jacobian evaluated at a step size 100x smaller (or larger) is refreshed before it is factorised again:
+                    // with a stale J and c -> large the modified Newton iteration looks converged in the weighted norm while
+                    // the state coasts along the equilibrium manifold (the energy-conservation null vector of I - cJ is the
+                    // stale one) -- a temperature drift of 1e-4 in the post-ignition tail of 2.6 % of the C2 sweep.
+                    if (c_jac == 0.0) c_jac = c;
+                    else if (!current_jac && (c > JAC_REFRESH_RATIO * c_jac || c * JAC_REFRESH_RATIO < c_jac)) {
+                        to_smem<R>(w.ybuf(), ypred, Ny, lane);
+                        jac_warp(d, w, lane); ++n_jac;
+                        current_jac = true; c_jac = c;
+                    }
+                    lu_ok = lu_factor_warp<R>(w, c, lane); lu_valid = true; ++n_lu; crate = 1.0;
+                }
                 // CVODE's nonlinear tolerance: the Newton error may contribute 0.1 to the (<= 1) local error test
                 const double nl_tol = scipy_newton ? newton_tol : fmax(newton_tol, nls_coef / c_ec[order]);
                 // ---- solve_bdf_system: simplified Newton on y = ypred + d, c*f(y) - psi - d = 0
@@ -434,7 +599,8 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
                         for (int r = 0; r < R; ++r) dy[r] = c * f[r] - psi[r] - dvec[r];
                         to_smem<R>(w.xs(), dy, Ny, lane);
                         lu_solve_warp<R>(w, lane);
-                        from_smem<R>(dy, w.xs(), Ny, lane);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { int i = r * 32 + lane; double v = (i < Ny) ? w.xs()[i] : 0.0; dy[r] = unit_row[r] ? dy[r] : v; }
                         double dy_norm = rms_norm_w<R>(dy, scale, Ny, lane);
                         double rate = (dy_norm_old < 0.0) ? -1.0 : dy_norm / dy_norm_old;
                         if (!(dy_norm == dy_norm)) break;   // NaN
@@ -455,14 +621,14 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
                 if (!converged) {
                     if (current_jac) break;
                     to_smem<R>(w.ybuf(), ypred, Ny, lane);
-                    jac_warp(d, w, lane); ++n_jac;
+                    jac_warp(d, w, lane); ++n_jac; c_jac = c;
                     lu_valid = false; current_jac = true;
                 }
             }
             if (!converged) {
                 ++n_nfail;
                 h_abs *= 0.5;
-                change_D<R>(D, order, 0.5, w, lane);
+                CHANGE_D(0.5);
                 n_equal = 0; lu_valid = false;
                 continue;
             }
@@ -476,7 +642,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
                 ++n_efail;
                 double factor = fmax(BDF_MIN_FACTOR, safety * fast_pow(error_norm, -1.0f / (float)(order + 1)));
                 h_abs *= factor;
-                change_D<R>(D, order, factor, w, lane);
+                CHANGE_D(factor);
                 n_equal = 0; lu_valid = false;
             } else accepted = true;
         }
@@ -494,9 +660,16 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
 #pragma unroll
             for (int j = BDF_MAX_ORDER; j >= 0; --j) if (j <= order) D[j][r] += D[j + 1][r];
         }
+        if (SENS) {
+            // sensitivities of the accepted step: fresh J, Jp and LU at y_new; the state's next step inherits them
+            to_smem<R>(w.ybuf(), D[0], Ny, lane);
+            if (!sens_step<R>(d, w, sh, order, h / c_alpha[order], lane)) status = RMSB_SOLVE_NAN;
+            ++n_jac; ++n_lu; lu_valid = true; crate = 1.0; c_jac = h / c_alpha[order];
+        }
         // ---- dense output on (t_old, t]: y(ts) = D0 + sum_j D_j prod_{m<j} (ts - (t - m h))/(h (1+m))
         while (isave < a.nsave && a.tsave[isave] <= t) {
             double ts = a.tsave[isave];
+            if (ssave) sens_interp(sh, order, t, h, ts, ssave + (size_t)isave * Ny * sh.Np, lane);
             if (ysave) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -587,7 +760,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
         if (hysteresis && delta == 0 && factor >= 1.0 && factor < 1.2) continue;
         order += delta;
         h_abs *= factor;
-        change_D<R>(D, order, factor, w, lane);
+        CHANGE_D(factor);
         n_equal = 0; lu_valid = false;
     }
 
@@ -596,10 +769,15 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
 #pragma unroll
         for (int r = 0; r < R; ++r) { int i = r * 32 + lane; if (i < Ny) a.yend[ir * Ny + i] = y[r]; }
     }
-    if (ysave) {
-        for (; isave < a.nsave; ++isave)
-            for (int i = lane; i < Ny; i += 32) ysave[(size_t)isave * Ny + i] = NAN;
+    if (SENS && a.send) {
+        double* se = a.send + (size_t)ir * Ny * sh.Np;
+        for (int o = lane; o < Ny * sh.Np; o += 32) { int p = o / Ny, i = o - p * Ny; se[o] = (status == RMSB_SOLVE_OK) ? *sh.at(0, i, p) : NAN; }
     }
+    for (; isave < a.nsave; ++isave) {
+        if (ysave) for (int i = lane; i < Ny; i += 32) ysave[(size_t)isave * Ny + i] = NAN;
+        if (ssave) for (int o = lane; o < Ny * sh.Np; o += 32) ssave[(size_t)isave * Ny * sh.Np + o] = NAN;
+    }
+#undef CHANGE_D
     if (lane == 0) {
         if (a.idt) a.idt[ir] = (idt_index >= 0) ? idt_time : NAN;
         a.status[ir] = status;

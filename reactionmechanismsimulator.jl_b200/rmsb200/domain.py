@@ -96,6 +96,28 @@ class Domain:
                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], self.Ny, self.Ny).transpose(0, 2, 1)   # column-major -> [eqn, var]
 
+    def jacobianp(self, y=None, p=None):
+        """jacobianp! for every reactor -> [n][Ny][Ns+Nr] with Jp[r, eqn, par] (src/Domain.jl:3095-3485)."""
+        y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
+        pp, ps = self._p_for_sens(p)
+        Np = self.phase.Ns + self.phase.Nr
+        out = np.empty((y.shape[0], Np * self.Ny))
+        cs = self.constantspeciesinds
+        L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
+        return out.reshape(y.shape[0], Np, self.Ny).transpose(0, 2, 1)      # column-major -> [eqn, par]
+
+    def _p_for_sens(self, p):
+        """Parameter Jacobians of ConstantTV need p itself on the device (chain rule through the diffusion limit,
+        src/Domain.jl:3290-3317), also when it is the constructor default."""
+        if self.kind != L.DOMAIN_CONSTANT_TV:
+            return self._p_for_device(p)
+        p = self.p if p is None else p
+        if p is None:
+            raise ValueError("ConstantTV parameter Jacobian needs the parameter vector p")
+        p = np.ascontiguousarray(p, dtype=float)
+        return (p, 0) if p.ndim == 1 else (p, self.phase.Ns + self.phase.Nr)
+
     def rates(self, y=None, p=None):
         """(kfs, krevs) as calcthermo returns them -> two [n][Nr] arrays."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
@@ -130,6 +152,11 @@ def _finish_constk(dom: Domain, efficiency_to_one: bool):
     kf, kr = dom.rates()
     dom.kfs, dom.krevs, dom.Gs = kf, kr, Gs
     kfp = kf.copy()
+    if ph.diffusionlimited:
+        # liquid phases store the rate coefficients BEFORE diffusion limitation (kfsnondiff, src/Domain.jl:549-551)
+        kfp = np.empty_like(kf)
+        L.check(L.lib().rmsb_kfs_batch(ph.handle, dom.kind, dom.n, L.ptr(dom.y0), L.ptr(dom.cond), L.ptr(kfp)))
+        dom.kfsnondiff = kfp.copy()
     if efficiency_to_one:
         for ind in ph.efficiencyinds:
             kfp[:, ind - 1] = 1.0

@@ -48,8 +48,8 @@ class Reactor:
                  forwardsensitivities: bool = False):
         if interfaces:
             raise NotImplementedError("interfaces are outside the accelerated hot path in this round (DESIGN.md)")
-        if forwardsensitivities:
-            raise NotImplementedError("forward sensitivities: SURVEY section 8 row a19, not built in this round")
+        if forwardsensitivities and domain.kind == L.DOMAIN_COUPLED_TP_TAPHI:
+            raise NotImplementedError("forward sensitivities of coupled gas-surface systems (DESIGN.md, 'next')")
         self.domain = domain
         self.y0 = domain.y0 if y0 is None else np.ascontiguousarray(np.atleast_2d(y0), dtype=float)
         assert tspan[0] == 0.0, "integration starts at t = 0"
@@ -57,7 +57,7 @@ class Reactor:
         self.p = domain.p if p is None else p
         self.interfaces = list(interfaces)
         self.recommendedsolver = RMSB200()
-        self.forwardsensitivities = False
+        self.forwardsensitivities = bool(forwardsensitivities)
 
     @property
     def ode(self):          # `solve(react.ode, ...)` reads naturally
@@ -70,10 +70,24 @@ class Solution:
     integrator statistics; `sol(t)` interpolates (cubic Hermite on the saved points, like the
     Sundials.jl solution object, when derivatives were requested; linear otherwise)."""
 
-    def __init__(self, reactor, t, u, yend, idt, status, stats, t_end):
+    def __init__(self, reactor, t, u, yend, idt, status, stats, t_end, sens=None, sens_end=None):
         self.reactor, self.t, self.u, self.yend = reactor, t, u, yend
         self.idt, self.status, self.stats, self.t_end = idt, status, stats, t_end
+        self.sens, self.sens_end = sens, sens_end          # [n][nsave][Np][Ny], [n][Np][Ny] (forward sensitivities only)
         self._du = None
+
+    def extract_local_sensitivities(self, t=None, r: int = 0):
+        """(x, dp) as SciMLSensitivity's extract_local_sensitivities(sol, t) returns them for reactor r
+        (call site src/TestReactors.jl:239): x = y(t), dp[j] = dy/dp_j (t).  t = None -> t_end; otherwise t must be one
+        of the saved times."""
+        if self.sens_end is None:
+            raise ValueError("solution was computed without forwardsensitivities=True")
+        if t is None:
+            return self.yend[r].copy(), [v.copy() for v in self.sens_end[r]]
+        k = int(np.argmin(np.abs(self.t - t)))
+        if abs(self.t[k] - t) > 1e-12 * max(1.0, abs(t)):
+            raise ValueError("sensitivities are available at the saved times (saveat=...) and at t_end")
+        return self.u[r, k].copy(), [v.copy() for v in self.sens[r, k]]
 
     @property
     def retcode(self):
@@ -131,9 +145,19 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
     idt = np.empty(n)
     status = np.empty(n, dtype=np.int32)
     stats = np.zeros(n, dtype=L.STATS_DTYPE)
-    pp, ps = dom._p_for_device(react.p)
+    pp, ps = dom._p_for_sens(react.p) if react.forwardsensitivities else dom._p_for_device(react.p)
     cs = dom.constantspeciesinds
     opts = L.SolveOpts(C.sizeof(L.SolveOpts), alg.max_steps, alg.max_order, idt_index, alg.first_step, alg.warps_per_block, alg.flags)
+    if react.forwardsensitivities:
+        # ODEForwardSensitivityProblem path (src/Reactor.jl:63-75): state + all Ns+Nr sensitivities in one call
+        Np = dom.phase.Ns + dom.phase.Nr
+        ssave = np.empty((n, nsave, Np, Ny)) if nsave else None
+        send = np.empty((n, Np, Ny))
+        L.check(L.lib().rmsb_sens_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                        L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats), C.byref(opts)))
+        idt[:] = np.nan
+        return Solution(react, tsave, ysave, yend, idt, status, stats, te, ssave, send)
     L.check(L.lib().rmsb_solve_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
                                      L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
                                      L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))

@@ -88,10 +88,12 @@ def test_c2_ignition_delay_golden():
     """C2: IDT = 0.038384723436228063 s with the reference's own grid definition (src/TestReactors.jl:301-310)."""
     gdom, y0, p = cases.product_domain("superminimal_V")
     ts = np.exp(np.linspace(np.log(1e-15), np.log(0.1), 10000))
-    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.101), p=p), abstol=1e-20, reltol=1e-10, saveat=ts)
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.101), p=p), abstol=1e-20, reltol=1e-12, saveat=ts)   # the reference's tolerances
     assert sol.retcode == ["Success"]
     assert rb.idt_grid(sol) == pytest.approx(0.038384723436228063, rel=1e-5)
     assert float(G["superminimal_V/idt_grid"]) == rb.idt_grid(sol)
+    sol10 = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.101), p=p), abstol=1e-20, reltol=1e-10, saveat=ts)
+    assert rb.idt_grid(sol10) == rb.idt_grid(sol)
     # continuous definition agrees with the grid one to within a grid cell (0.32 %)
     assert sol.idt[0] == pytest.approx(rb.idt_grid(sol), rel=4e-3)
 
@@ -166,16 +168,20 @@ def test_ensemble_loose_tolerance_vs_tight_cpu_oracle():
     ign = (ref["yend"][:, ig.Ns] - ens.y0[:, ig.Ns]) > 400.0
     assert ign.sum() > 1000
     np.testing.assert_allclose(sol.idt[ign], ref["idt"][ign], rtol=1e-3)
-    np.testing.assert_allclose(sol.yend[:, ig.Ns], ref["yend"][:, ig.Ns], rtol=5e-4)
+    np.testing.assert_allclose(sol.yend[:, ig.Ns], ref["yend"][:, ig.Ns], rtol=1e-4)
     # the CPU port of the same algorithm at the same loose tolerance is no more accurate than the CUDA path
     ref6 = co.CpuMech(odom.phase).solve("ConstantV", ens.y0, ens.cond, 0.1, 1e-6, 1e-16)
     e_gpu = np.max(np.abs(sol.yend[:, ig.Ns] / ref["yend"][:, ig.Ns] - 1))
     e_cpu = np.max(np.abs(ref6["yend"][:, ig.Ns] / ref["yend"][:, ig.Ns] - 1))
-    assert e_cpu < 2e-4 and e_gpu < 2e-4      # both are tolerance-limited (rtol 1e-6 over ~400 steps through ignition)
-    # with the scipy-compatible integrator flags the step counts track the CPU implementation of the same algorithm
+    assert e_cpu < 5e-5 and e_gpu < 5e-5      # both are tolerance-limited (rtol 1e-6 over ~400 steps through ignition)
+    # the step counts track the CPU implementation of the same algorithm, with the production defaults (flags 0) and with
+    # the scipy-compatible Newton test / step logic (flags 3)
+    assert abs(sol.stats["n_steps"].mean() / ref6["stats"]["n_steps"].mean() - 1.0) < 0.05
+    assert abs(sol.stats["n_rhs"].mean() / ref6["stats"]["n_rhs"].mean() - 1.0) < 0.05
+    ref3 = co.CpuMech(odom.phase).solve("ConstantV", ens.y0, ens.cond, 0.1, 1e-6, 1e-16, flags=3)
     sol3 = rb.solve(rb.Reactor(ens, None, (0.0, 0.1)), rb.RMSB200(flags=3), abstol=1e-16, reltol=1e-6)
-    assert abs(sol3.stats["n_steps"].mean() / ref6["stats"]["n_steps"].mean() - 1.0) < 0.05
-    assert abs(sol3.stats["n_rhs"].mean() / ref6["stats"]["n_rhs"].mean() - 1.0) < 0.05
+    assert abs(sol3.stats["n_steps"].mean() / ref3["stats"]["n_steps"].mean() - 1.0) < 0.05
+    assert abs(sol3.stats["n_rhs"].mean() / ref3["stats"]["n_rhs"].mean() - 1.0) < 0.05
     # the production defaults (looser Newton tolerance, step hysteresis) need fewer RHS evaluations
     assert sol.stats["n_rhs"].mean() < 0.8 * sol3.stats["n_rhs"].mean()
 
@@ -205,7 +211,6 @@ def test_ensemble_properties_at_scale():
     assert np.array_equal(sol2.yend[::-1], sol.yend) and np.array_equal(sol2.idt[::-1], sol.idt, equal_nan=True)
     # the ideal-gas law is an invariant of the ConstantV equations (dP/dt is derived from it, Domain.jl:1903):
     # P*V/(R*T) must track sum(ns) to integration accuracy (the CPU port drifts by 6e-7 at these tolerances).
-    # This is the check that exposed false Newton convergence of an explicit-inverse linear solve in round 1.
     Ni = sol.yend[:, ig.Ns + 1] * ens.cond[:, 0] / (8.314 * sol.yend[:, ig.Ns])
     np.testing.assert_allclose(Ni, sol.yend[:, :ig.Ns].sum(axis=1), rtol=1e-5)
 

@@ -1,0 +1,135 @@
+"""Config C5 parity: the CUDA parameter Jacobian (jacobianp!, src/Domain.jl:3095-3485) against the oracle, and the
+staggered-direct forward sensitivities (rmsb_sens_batch) against the oracle's augmented ODEForwardSensitivityProblem
+system (oracle/sensitivity.py) and against the reference's own C5 check (forward sensitivities of H2 normalised as in
+src/TestReactors.jl:231-255).  Tolerances: jacobianp 1e-12 relative (FP64 kernel), sensitivities 1e-4 relative to the
+column scale at integrator tolerance 1e-8 (the reference only requires 10 % agreement between its three methods)."""
+import numpy as np
+import pytest
+
+import cases
+import rmsb200 as rb
+from rmsb200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+class _Golden:
+    """tests/golden/sens_vectors.npz (made by tests/golden/make_golden_sens.py), opened on first use."""
+    _z = None
+
+    def __getitem__(self, k):
+        if _Golden._z is None:
+            _Golden._z = np.load(cases.ROOT / "tests" / "golden" / "sens_vectors.npz")
+        return _Golden._z[k]
+
+    def __contains__(self, k):
+        self["superminimal_V/y"]
+        return k in _Golden._z.files
+
+
+G = _Golden()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+
+
+def ensemble_of(gdom, ys):
+    ens = rb.Domain(gdom.kind, gdom.phase, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    ens.constantspeciesinds = gdom.constantspeciesinds
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    return ens
+
+
+@pytest.mark.parametrize("case", list(cases.CASES))
+def test_jacobianp_parity(case):
+    gdom, y0, p = cases.product_domain(case)
+    ys = G[f"{case}/y"]
+    ens = ensemble_of(gdom, ys)
+    Jp = ens.jacobianp(ys, p)
+    for k in range(len(ys)):
+        assert cases.err_jac(Jp[k], G[f"{case}/Jp"][k]) < 1e-12
+    ref = G[f"{case}/Jp"][0]
+    assert np.all(Jp[0][ref == 0.0] == 0.0)                       # structural zeros stay exact zeros
+    if f"{case}/p" in G:                                          # non-default parameters (variable-k domain)
+        Jpp = ens.jacobianp(ys, G[f"{case}/p"])
+        for k in range(len(ys)):
+            assert cases.err_jac(Jpp[k], G[f"{case}/Jp_p"][k]) < 1e-12
+
+
+def sens_err(S, Sref):
+    """max over parameters of |S - Sref| / max_i |Sref[:, par]| (column scale)."""
+    sc = np.max(np.abs(Sref), axis=-1, keepdims=True) + 1e-300
+    return float(np.max(np.abs(S - Sref) / sc))
+
+
+@pytest.mark.parametrize("case,tend", [("superminimal_TP", 150.11094), ("superminimal_V", 0.05)])
+def test_forward_sensitivities_vs_oracle(case, tend):
+    gdom, y0, p = cases.product_domain(case)
+    tq = G[f"{case}/tq"]
+    react = rb.Reactor(gdom, y0, (0.0, tend), p=p, forwardsensitivities=True)
+    sol = rb.solve(react.ode, abstol=1e-20, reltol=1e-8, saveat=tq)
+    assert sol.retcode[0] == "Success"
+    yq, Sq = G[f"{case}/yq"], G[f"{case}/Sq"]
+    big = np.abs(yq) > 1e-10 * np.max(np.abs(yq), axis=1, keepdims=True)
+    assert np.max(np.abs(sol.u[0] - yq)[big] / np.abs(yq)[big]) < 1e-5
+    for k in range(len(tq)):
+        assert sens_err(sol.sens[0, k], Sq[k]) < 1e-4, (k, sens_err(sol.sens[0, k], Sq[k]))
+    x, dp = sol.extract_local_sensitivities(float(tq[-1]))
+    assert np.allclose(np.array(dp), sol.sens[0, -1])
+    xe, dpe = sol.extract_local_sensitivities()
+    assert sens_err(np.array(dpe), Sq[-1]) < 1e-4
+    # the state computed alongside the sensitivities is the plain solve's state
+    plain = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p).ode, abstol=1e-20, reltol=1e-8, saveat=tq)
+    assert np.max(np.abs(plain.u[0] - sol.u[0])[big] / np.abs(yq)[big]) < 1e-5
+
+
+def test_c5_reference_check_normalised_h2_sensitivities():
+    """src/TestReactors.jl:231-255: d ln(n_H2) / d ln(k_j) and d ln(n_H2)/dG_i at t = 150.11094 at the reference's own
+    tolerances (abstol 1e-21, reltol 1e-7), here against the oracle instead of the adjoint solution; bar 1e-1 there."""
+    gdom, y0, p = cases.product_domain("superminimal_TP")
+    react = rb.Reactor(gdom, y0, (0.0, 150.11094), p=p, forwardsensitivities=True)
+    sol = rb.solve(react.ode, abstol=1e-21, reltol=1e-7)
+    x, dp = sol.extract_local_sensitivities()
+    Ns = gdom.phase.Ns
+    ind = gdom.phase.names.index("H2")
+    dpvs = np.array([v[ind] for v in dp])
+    dpvs[Ns:] *= np.asarray(p)[Ns:]
+    dpvs /= x[ind]
+    ref = G["superminimal_TP/Sq"][-1][:, ind].copy()
+    ref[Ns:] *= np.asarray(p)[Ns:]
+    ref /= G["superminimal_TP/yq"][-1][ind]
+    sig = np.abs(ref) > 1e-6 * np.max(np.abs(ref))
+    assert np.max(np.abs(dpvs - ref)[sig] / np.abs(ref)[sig]) < 1e-3
+
+
+def test_sensitivity_ensemble_matches_single_and_finite_difference():
+    """An ensemble of ConstantTP conditions: every reactor's sensitivities equal the one-reactor call, and a central
+    finite difference of the (GPU) state solution in one rate coefficient reproduces the matching column."""
+    gdom, y0, p = cases.product_domain("superminimal_TP")
+    ph = gdom.phase
+    n = 37
+    rng = np.random.default_rng(5)
+    T = rng.uniform(950.0, 1150.0, n)
+    P = rng.uniform(0.5e5, 3e5, n)
+    ns = np.zeros((n, ph.Ns))
+    ns[:, ph.names.index("H2")] = rng.uniform(0.4, 0.7, n)
+    ns[:, ph.names.index("O2")] = rng.uniform(0.2, 0.4, n)
+    ens = rb.ConstantTPEnsemble(ph, T, P, ns)
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 1.0), forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-8)
+    assert all(rc == "Success" for rc in sol.retcode)
+    assert np.isfinite(sol.sens_end).all()
+    for r in (0, 17, 36):
+        ic = {"T": T[r], "P": P[r], "H2": ns[r, ph.names.index("H2")], "O2": ns[r, ph.names.index("O2")]}
+        d1, y1, p1 = rb.ConstantTPDomain(phase=ph, initialconds=ic)
+        s1 = rb.solve(rb.Reactor(d1, y1, (0.0, 1.0), p=p1, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-8)
+        assert np.array_equal(s1.sens_end[0], sol.sens_end[r])            # bitwise: same kernel, same reactor
+        j = ph.Ns + 2
+        fd = []
+        for sgn in (1.0, -1.0):
+            q = np.array(p1, dtype=float)
+            q[j] *= 1.0 + sgn * 1e-4
+            fd.append(rb.solve(rb.Reactor(d1, y1, (0.0, 1.0), p=q).ode, abstol=1e-22, reltol=1e-10).yend[0])
+        fd = (fd[0] - fd[1]) / (2e-4 * p1[j])
+        assert sens_err(sol.sens_end[r][j][None], fd[None]) < 2e-3
