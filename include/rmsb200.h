@@ -271,6 +271,17 @@ int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
                          double* d_yend, double* d_idt, int32_t* d_status, rmsb_stats* d_stats,
                          const rmsb_solve_opts* opts, void* d_work, void* stream);
 
+/* ---- large mechanisms (more than 128 state variables; config C3) ---------------------------
+ * rmsb_mech_create analyses the Jacobian pattern of mechanisms with more than 128 species once (minimum-degree ordering,
+ * fill pattern, dependency levels); dydt / jac / rates / solve then run one thread block per reactor with a sparse LU of
+ * I - c*J on that fixed pattern -- the role of the GMRES + ILU path of the reference (src/Reactor.jl:342-382).
+ * ConstantTV and ConstantTAPhi domains.  info: [0] n, [1] nnz(L+U), [2] forward levels, [3] backward levels,
+ * [4] longest row, [5] multiply-adds per factorisation, [6] first row of the dense core, [7] scratch doubles per resident reactor. */
+int rmsb_large_info(const rmsb_mech* mech, int64_t info[8]);
+/* cycle counters of the block-per-reactor solver summed over blocks: [0] rhs, [1] Jacobian, [2] factorisation,
+ * [3] triangular solves, [4] whole solves; reset != 0 clears them after reading. */
+int rmsb_large_profile(const rmsb_mech* mech, int reset, double cycles[8]);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
 int64_t rmsb_kernel_launch_count(void);

@@ -39,7 +39,14 @@ def solve_forward(domain, tspan, p, rtol=1e-9, atol=1e-20, t_eval=None, method="
     """-> (t, y[t][Ny], S[t][Np][Ny])."""
     f, Ny, Np = augmented_rhs(domain, p, exact_jac)
     u0 = np.concatenate([domain.y0, np.zeros(Ny * Np)])
-    sol = solve_ivp(f, tspan, u0, method=method, rtol=rtol, atol=atol, t_eval=t_eval)
+    # Newton matrix of the implicit method: block diagonal, one Jy(y) per block (the sub-diagonal coupling d(Jy*S)/dy is
+    # left out -- it only slows the iteration down, the converged solution does not depend on it)
+    from scipy.sparse import block_diag
+
+    def jac(t, u):
+        J = ro.jacobiany(domain, u[:Ny], t, p)
+        return block_diag([J] * (Np + 1), format="csc")
+    sol = solve_ivp(f, tspan, u0, method=method, rtol=rtol, atol=atol, t_eval=t_eval, jac=jac)
     assert sol.success, sol.message
     return sol.t, sol.y[:Ny].T, sol.y[Ny:].T.reshape(-1, Np, Ny)
 

@@ -13,6 +13,8 @@
 #include "../../include/rmsb200.h"
 #include "rmsb_device.cuh"
 #include "rmsb_solver.cuh"
+#include "rmsb_large.cuh"
+#include "rmsb_sparse.h"
 
 using namespace rmsb;
 
@@ -49,6 +51,11 @@ struct rmsb_mech {
     DevMech dm{};
     std::vector<void*> allocs;
     int n_dt = 0, n_je = 0;
+    // large-mechanism path (one block per reactor, sparse LU on a fixed pattern): built when Ns > 128
+    bool large = false;
+    LargeTables lt{};
+    int large_max_row = 0;
+    long long large_factor_flops = 0;
 };
 
 template <class T>
@@ -286,6 +293,28 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     UP(dtrxn, dt_rxn); UP(dtmult, dt_mult); UP(dtoth, dt_oth); UP(dtspc, dt_spc);
     UP(jeptr, je_ptr); UP(jerow, je_row); UP(jecol, je_col); UP(jtidx, jt_idx);
     UP(rxdom, rx_dom); UP(nrp2, nrp2); UP(srmid, sr_mid); UP(inert, inert);
+    if (Ns > 128 && !dm.coupled) {
+        SparsePattern sp = analyse_pattern(Ns, jerow, jecol);
+        std::vector<int> ldiag(sp.col.size()), lnk(sp.col.size()), amap(jerow.size());
+        for (size_t p = 0; p < sp.col.size(); ++p) {
+            const int k = sp.col[p];
+            ldiag[p] = sp.diag[k];
+            lnk[p] = sp.row_ptr[k + 1] - sp.diag[k] - 1;
+        }
+        for (size_t e = 0; e < jerow.size(); ++e) {
+            amap[e] = find_entry(sp, sp.iperm[jerow[e]], sp.iperm[jecol[e]]);
+            if (amap[e] < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain a Jacobian entry");
+        }
+        LargeTables& lt = h->lt;
+        lt.n = Ns; lt.nnz = (int)sp.col.size();
+        lt.n_lvl_l = (int)sp.lvl_l_ptr.size() - 1; lt.n_lvl_u = (int)sp.lvl_u_ptr.size() - 1; lt.core = sp.core_start;
+#define UPL(vec, field) if ((rc = upload(h, vec, &lt.field)) != RMSB_OK) return rc
+        UPL(sp.perm, perm); UPL(sp.row_ptr, row_ptr); UPL(sp.col, col); UPL(sp.diag, diag); UPL(ldiag, ldiag); UPL(lnk, lnk);
+        UPL(sp.lvl_l_ptr, lvl_l_ptr); UPL(sp.lvl_l_rows, lvl_l_rows); UPL(sp.lvl_u_ptr, lvl_u_ptr); UPL(sp.lvl_u_rows, lvl_u_rows);
+        UPL(amap, amap);
+#undef UPL
+        h->large = true; h->large_max_row = sp.max_row; h->large_factor_flops = sp.factor_flops;
+    }
 #undef UP
     if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
     if (!diffr.empty()) { if ((rc = upload(h, diffr, &dm.diff_r)) != RMSB_OK) return rc; } else dm.diff_r = nullptr;
@@ -430,6 +459,73 @@ __global__ void __launch_bounds__(128, 1) sens_kernel(const __grid_constant__ De
     }
 }
 
+// ---- large-mechanism path: one block per reactor (rmsb_large.cuh) -------------------------------------------------------
+__device__ __forceinline__ LargeCtx make_large_ctx(const LargeTables& lt, double* scratch, size_t per_block, const DevMech& m) {
+    LargeCtx c;
+    c.t = lt;
+    c.s.base = scratch + (size_t)blockIdx.x * per_block;
+    c.s.n = lt.n; c.s.Nr = m.Nr; c.s.n_dt = m.n_dt; c.s.n_je = m.n_je; c.s.nnz = lt.nnz;
+    c.red = smem_ws + MECH_DOUBLES;
+    c.ru = c.red + 64;
+    c.x = c.ru + 36;
+    c.map = reinterpret_cast<int*>(c.x + lt.n) + (size_t)(threadIdx.x >> 5) * lt.n;
+    return c;
+}
+
+__global__ void __launch_bounds__(LARGE_THREADS, 1) large_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a,
+                                                                        const __grid_constant__ LargeTables lt, double* scratch, size_t per_block) {
+    stage_mech(mp);
+    LargeCtx c = make_large_ctx(lt, scratch, per_block, mech());
+    __shared__ unsigned long long next;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) next = atomicAdd(a.counter, 1ULL);
+        __syncthreads();
+        const unsigned long long ir = next;
+        if (ir >= (unsigned long long)a.n) break;
+        c.d.kind = a.domain_kind;
+        c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
+        c.d.constspc = a.constspc; c.d.nconst = a.nconst;
+        c.d.cond = a.cond + ir * a.ncond;
+        c.T = c.d.cond[0]; c.V = c.d.cond[1];
+        large_bdf_solve(a, c, (int64_t)ir);
+    }
+}
+
+// mode 0: dydt, 1: dense column-major Jacobian (zero-filled, entries scattered), 2: kf / krev
+template <int MODE>
+__global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a,
+                                                                       const __grid_constant__ LargeTables lt, double* scratch, size_t per_block) {
+    stage_mech(mp);
+    LargeCtx c = make_large_ctx(lt, scratch, per_block, mech());
+    const DevMech& m = mech();
+    const int n = lt.n, tid = threadIdx.x;
+    for (int64_t ir = blockIdx.x; ir < a.n; ir += gridDim.x) {
+        c.d.kind = a.domain_kind;
+        c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
+        c.d.constspc = a.constspc; c.d.nconst = a.nconst;
+        c.d.cond = a.cond + ir * a.ncond;
+        c.T = c.d.cond[0]; c.V = c.d.cond[1];
+        double* y = c.s.vec(8);
+        for (int i = tid; i < n; i += LARGE_THREADS) y[i] = a.y[ir * n + i];
+        __syncthreads();
+        large_setup(c, y);
+        if (MODE == 0) {
+            large_rhs(c, y, c.s.vec(14));
+            for (int i = tid; i < n; i += LARGE_THREADS) a.out[ir * n + i] = c.s.vec(14)[i];
+        } else if (MODE == 1) {
+            large_jac(c, y);
+            double* J = a.out + (size_t)ir * n * n;
+            for (size_t i = tid; i < (size_t)n * n; i += LARGE_THREADS) J[i] = 0.0;
+            __syncthreads();
+            for (int e = tid; e < m.n_je; e += LARGE_THREADS) J[G(m.je_row, e) + (size_t)G(m.je_col, e) * n] = c.s.jv()[e];
+        } else {
+            for (int j = tid; j < m.Nr; j += LARGE_THREADS) { a.out[ir * m.Nr + j] = c.s.kf()[j]; a.out2[ir * m.Nr + j] = c.s.kr()[j]; }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void gibbs_kernel(const __grid_constant__ DevMech mp, int64_t n, const double* T, int scalar_path, double* G) {
     stage_mech(mp);
     const int Ns = mech().Ns;
@@ -487,8 +583,62 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int wan
     return RMSB_OK;
 }
 
+struct LargeCfg { int grid; size_t per_block; size_t smem; };
+template <class K>
+static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, LargeCfg* cfg) {
+    if (!h->large) return fail(RMSB_ERR_UNSUPPORTED, "more than 128 state variables need the large-mechanism path, which this mechanism was not analysed for");
+    if (kind != RMSB_DOMAIN_CONSTANT_TV && kind != RMSB_DOMAIN_CONSTANT_TAPHI)
+        return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): ConstantTV / ConstantTAPhi domains only (DESIGN.md)");
+    if (h->dm.n_effrxn > 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: third-body efficiencies are not built");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    cfg->smem = large_smem_bytes(h->lt.n);
+    if (cfg->smem > prop.sharedMemPerBlockOptin) return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the block-per-reactor kernels (shared memory)");
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+    int bps = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, LARGE_THREADS, cfg->smem));
+    if (bps < 1) bps = 1;
+    if (bps > 16) bps = 16;
+    int64_t resident = (int64_t)prop.multiProcessorCount * bps;
+    cfg->grid = (int)(n < resident ? (n < 1 ? 1 : n) : resident);
+    cfg->per_block = (large_scratch_doubles(h->lt.n, h->dm.Nr, h->n_dt, h->n_je, h->lt.nnz) + 1) & ~(size_t)1;
+    return RMSB_OK;
+}
+
+template <int MODE>
+static int launch_eval_large(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+    LargeCfg cfg;
+    int rc = large_config(large_eval_kernel<MODE>, h, a.domain_kind, a.n, &cfg);
+    if (rc != RMSB_OK) return rc;
+    double* scratch = nullptr;
+    CU(cudaMallocAsync((void**)&scratch, sizeof(double) * cfg.per_block * cfg.grid, st));
+    large_eval_kernel<MODE><<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, h->lt, scratch, cfg.per_block);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(RMSB_ERR_CUDA, std::string("large_eval_kernel: ") + cudaGetErrorString(e));
+    return RMSB_OK;
+}
+
+static int launch_solve_large(const rmsb_mech* h, const SolveArgs& a, cudaStream_t st, size_t* work_bytes) {
+    LargeCfg cfg;
+    int rc = large_config(large_solve_kernel, h, a.domain_kind, a.n, &cfg);
+    if (rc != RMSB_OK) return rc;
+    if (work_bytes) { *work_bytes = 256 + sizeof(double) * cfg.per_block * cfg.grid; return RMSB_OK; }
+    CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+    double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(a.counter) + 256);
+    large_solve_kernel<<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, h->lt, scratch, cfg.per_block);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return RMSB_OK;
+}
+
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+    if (a.Ny > 128) {
+        if (MODE <= 2) return launch_eval_large<(MODE <= 2 ? MODE : 0)>(h, a, st);
+        return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
+    }
     LaunchCfg cfg;
     int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
@@ -558,7 +708,7 @@ static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cu
     case 3: return launch_solve_R<3>(h, a, want_wpb, st);
     case 4: return launch_solve_R<4>(h, a, want_wpb, st);
     }
-    return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
+    return launch_solve_large(h, a, st, nullptr);
 }
 
 static int check_common(const rmsb_mech* h, int kind, int64_t n, const void* y, const void* cond, int64_t p_stride, const void* p) {
@@ -619,7 +769,16 @@ extern "C" int rmsb_jacp_batch_dev(const rmsb_mech* h, int kind, int64_t n, cons
     return launch_eval<3>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr), (cudaStream_t)stream);
 }
 
-extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech*, int, int64_t) { return 256; }
+extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech* h, int kind, int64_t n) {
+    if (!h || domain_ny(h, kind) < 0) { fail(RMSB_ERR_ARG, "bad mechanism / domain kind"); return -1; }
+    if (domain_ny(h, kind) <= 128) return 256;
+    DeviceGuard g(h->device);
+    SolveArgs a{};
+    a.domain_kind = kind; a.n = n > 0 ? n : 1;
+    size_t bytes = 0;
+    if (launch_solve_large(h, a, nullptr, &bytes) != RMSB_OK) return -1;
+    return (int64_t)bytes;
+}
 
 static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
     o->struct_size = sizeof(rmsb_solve_opts);
@@ -828,7 +987,9 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
     if (idt) CU(didt.alloc(sizeof(double) * n));
     CU(dst.alloc(sizeof(int32_t) * n));
     if (stats) CU(dstats.alloc(sizeof(rmsb_stats) * n));
-    CU(dwork.alloc(256));
+    int64_t wbytes = rmsb_solve_work_bytes(h, kind, n);
+    if (wbytes < 0) return RMSB_ERR_UNSUPPORTED;
+    CU(dwork.alloc((size_t)wbytes));
     rc = rmsb_solve_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                               (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
                               nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr,
@@ -893,6 +1054,25 @@ extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const do
     D2H(status, dst.p, sizeof(int32_t) * n);
     if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
     CU(cudaStreamSynchronize(sg.st));
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_large_info(const rmsb_mech* h, int64_t* out) {
+    if (!h || !out) return fail(RMSB_ERR_ARG, "null argument");
+    if (!h->large) { for (int k = 0; k < 8; ++k) out[k] = 0; return RMSB_OK; }
+    out[0] = h->lt.n; out[1] = h->lt.nnz; out[2] = h->lt.n_lvl_l; out[3] = h->lt.n_lvl_u; out[4] = h->large_max_row;
+    out[5] = h->large_factor_flops; out[6] = h->lt.core; out[7] = (int64_t)large_scratch_doubles(h->lt.n, h->dm.Nr, h->n_dt, h->n_je, h->lt.nnz);
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_large_profile(const rmsb_mech* h, int reset, double* out) {
+    if (!h || !out) return fail(RMSB_ERR_ARG, "null argument");
+    DeviceGuard g(h->device);
+    unsigned long long v[8];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(v, g_large_prof, sizeof(v)));
+    for (int k = 0; k < 8; ++k) out[k] = (double)v[k];
+    if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(g_large_prof, z, sizeof(z))); }
     return RMSB_OK;
 }
 

@@ -527,6 +527,54 @@ struct DomainArgs {
     const double* cond;   // per-reactor constants
 };
 
+// kf / krev of reaction j for the constant-k domains (getkfkrevs, src/PhaseState.jl:184-257): vector path without diffusion
+// limits, per-reaction scalar path with them.  G = absolute Gibbs energies, diffs = Stokes diffusivities (liquid only).
+__device__ __forceinline__ void constk_rates(int j, const double* p, bool is_eff_dom, const double* G, const double* diffs,
+                                             const KinEnv<double>& e, double C0, double logC0, double C, const double* ns,
+                                             double V, double T, double& kf_out, double& kr_out) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr;
+    double kf, kr;
+    bool eff = (G(m.eff_ptr, j + 1) > G(m.eff_ptr, j));
+    if (!m.difflim) {
+        // getkfkrevs vector path: getkfs + getKcs (src/PhaseState.jl:226-233)
+        if (p && !(is_eff_dom && eff)) kf = p[Ns + j];
+        else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), false);
+        double ex = 0.0;
+        for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex += G(m.kc_coef, k) * (G[G(m.kc_spc, k)] / (RMSB_R * T));
+        ex += G(m.nrp, j) * logC0;
+        kr = kf / exp(ex);
+    } else {
+        // getkfkrev per reaction (src/PhaseState.jl:184-223): scalar forms, scalar Kc, diffusion limits
+        if (p) kf = p[Ns + j];
+        else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), true);
+        double Kc = kc_scalar(j, G, T, C0);
+        kr = kf / Kc;
+        int nre = 0, npr = 0;
+        for (int k = 0; k < 4; ++k) { if (G(m.rx, k * Nr + j) >= 0) ++nre; if (G(m.rx, (k + 4) * Nr + j) >= 0) ++npr; }
+        if (nre == 1) {
+            if (npr > 1) {
+                double krd = diffusive_rate(j, 1, diffs);
+                kr = kr * krd / (kr + krd);
+                kf = Kc * kr;
+            }
+        } else if (npr == 1) {
+            double kfd = diffusive_rate(j, 0, diffs);
+            kf = kf * kfd / (kf + kfd);
+            kr = kf / Kc;
+        } else if (npr == nre) {
+            double kfd = diffusive_rate(j, 0, diffs);
+            double krd = diffusive_rate(j, 1, diffs);
+            double kff = kf * kfd / (kf + kfd);
+            double krevr = kr * krd / (kr + krd);
+            double kfr = Kc * krevr;
+            if (kff > kfr) { kf = kfr; kr = krevr; }
+            else { kf = kff; kr = kf / Kc; }
+        }
+    }
+    kf_out = kf; kr_out = kr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Constant-k domain setup (TP / TV / TAPhi ctors, src/Domain.jl:42-102,500-560,660-711):
 // Gs via the scalar thermo path, kfs/krevs once per reactor.  w.g <- absolute G, w.kf/w.kr <- k's.
@@ -567,43 +615,7 @@ __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
     bool is_eff_dom = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
     for (int j = lane; j < Nr; j += 32) {
         double kf, kr;
-        bool eff = (G(m.eff_ptr, j + 1) > G(m.eff_ptr, j));
-        if (!m.difflim) {
-            // getkfkrevs vector path: getkfs + getKcs (src/PhaseState.jl:226-233)
-            if (p && !(is_eff_dom && eff)) kf = p[Ns + j];
-            else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), false);
-            double ex = 0.0;
-            for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex += G(m.kc_coef, k) * (G[G(m.kc_spc, k)] / (RMSB_R * T));
-            ex += G(m.nrp, j) * logC0;
-            kr = kf / exp(ex);
-        } else {
-            // getkfkrev per reaction (src/PhaseState.jl:184-223): scalar forms, scalar Kc, diffusion limits
-            if (p) kf = p[Ns + j];
-            else kf = eval_kin<double>(j, &e, ceff_of(j, C, ns, V), true);
-            double Kc = kc_scalar(j, G, T, C0);
-            kr = kf / Kc;
-            int nre = 0, npr = 0;
-            for (int k = 0; k < 4; ++k) { if (G(m.rx, k * Nr + j) >= 0) ++nre; if (G(m.rx, (k + 4) * Nr + j) >= 0) ++npr; }
-            if (nre == 1) {
-                if (npr > 1) {
-                    double krd = diffusive_rate(j, 1, diffs);
-                    kr = kr * krd / (kr + krd);
-                    kf = Kc * kr;
-                }
-            } else if (npr == 1) {
-                double kfd = diffusive_rate(j, 0, diffs);
-                kf = kf * kfd / (kf + kfd);
-                kr = kf / Kc;
-            } else if (npr == nre) {
-                double kfd = diffusive_rate(j, 0, diffs);
-                double krd = diffusive_rate(j, 1, diffs);
-                double kff = kf * kfd / (kf + kfd);
-                double krevr = kr * krd / (kr + krd);
-                double kfr = Kc * krevr;
-                if (kff > kfr) { kf = kfr; kr = krevr; }
-                else { kf = kff; kr = kf / Kc; }
-            }
-        }
+        constk_rates(j, p, is_eff_dom, G, diffs, e, C0, logC0, C, ns, V, T, kf, kr);
         w.kf()[j] = kf * G(m.fwd, j);          // forwardability / reversibility masks (:220-221, :254-255)
         w.kr()[j] = kr * G(m.rev, j);
     }

@@ -65,7 +65,7 @@ EXPORTS = [
     "rmsb_mech_ncond", "rmsb_mech_device", "rmsb_dydt_batch", "rmsb_jac_batch", "rmsb_rates_batch", "rmsb_gibbs_batch",
     "rmsb_solve_batch", "rmsb_dydt_batch_dev", "rmsb_jac_batch_dev", "rmsb_solve_work_bytes", "rmsb_solve_batch_dev",
     "rmsb_kernel_launch_count", "rmsb_fp64_peak_tflops", "rmsb_jacp_batch", "rmsb_jacp_batch_dev", "rmsb_sens_batch",
-    "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch",
+    "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch", "rmsb_large_info", "rmsb_large_profile",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
     L.rmsb_solve_work_bytes.argtypes = [vp, C.c_int, i64]
     L.rmsb_solve_work_bytes.restype = i64
     L.rmsb_solve_batch_dev.argtypes = common + [vp, i32, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), vp, vp]
+    L.rmsb_large_info.argtypes = [vp, vp]
+    L.rmsb_large_profile.argtypes = [vp, C.c_int, vp]
     L.rmsb_kfs_batch.argtypes = [vp, C.c_int, i64, vp, vp, vp]
     L.rmsb_jacp_batch.argtypes = common + [vp, i32, vp]
     L.rmsb_jacp_batch_dev.argtypes = common + [vp, i32, vp, vp]

@@ -1,0 +1,122 @@
+"""Synthetic large mechanisms for config C3 (~1000+ species, sparse Jacobian).  The reference ships no mechanism of that
+size (the octane fixture has 35 species), so the parity and throughput cases use a seeded generator
+with the structure of a hydrocarbon oxidation mechanism: a small pool of 'hub' species (radicals / small molecules that
+take part in most reactions) and a long tail of large molecules that only react with the hubs and with their neighbours.
+The file written is an ordinary `.rms` YAML mechanism, read by both the product (`rmsb200.readinput`) and the oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+N_HUB = 16
+
+
+def write_synthetic_mechanism(path: str, ns: int = 1000, rxn_per_species: float = 4.0, seed: int = 7) -> dict:
+    rng = np.random.default_rng(seed)
+    names = [f"S{i:04d}" for i in range(ns)]
+    lines = ["Phases:", "- Species:"]
+    # generations (carbon number) of geometrically growing size; each generation adds a CH2-like increment to cp, H and S
+    n_gen, fam = 10, 8
+    w = 1.45 ** np.arange(n_gen)
+    bounds = N_HUB + np.concatenate([[0], np.cumsum(np.round((ns - N_HUB) * w / w.sum()).astype(int))])
+    bounds[-1] = ns
+    gen_of = np.zeros(ns, dtype=int)
+    for g in range(n_gen):
+        gen_of[bounds[g]:bounds[g + 1]] = g
+    for i, nm in enumerate(names):
+        if i < N_HUB:    # small radicals / molecules: high enthalpy, low entropy (additions to them are exothermic)
+            a0, a1, a2 = rng.uniform(3.5, 4.5), 5e-4, -5e-8
+            a5, a6 = rng.uniform(1.0e4, 2.0e4), rng.uniform(3.0, 8.0)
+        else:
+            g = gen_of[i]
+            a0, a1, a2 = 4.0 + 1.5 * g + rng.uniform(-0.2, 0.2), 1e-3 * (1 + g), -1e-7 * (1 + g)
+            a5, a6 = -2.5e3 * g + rng.uniform(-1.0e3, 1.0e3), 10.0 + 1.0 * g + rng.uniform(-1.0, 1.0)
+        coefs = "[" + ", ".join(repr(float(v)) for v in (a0, a1, a2, 0.0, 0.0, a5, a6)) + "]"
+        lines += [f"  - name: {nm}", "    radicalelectrons: 0", "    thermo:", "      polys:",
+                  f"      - {{Tmax: 1000.0, Tmin: 100.0, coefs: {coefs}, type: NASApolynomial}}",
+                  f"      - {{Tmax: 5000.0, Tmin: 1000.0, coefs: {coefs}, type: NASApolynomial}}",
+                  "      type: NASA", "    type: Species"]
+    lines += ["  name: phase", "Reactions:"]
+    nr = int(rxn_per_species * ns)
+    seen = set()
+    count = 0
+    # generations (carbon number) of geometrically growing size, split into families of isomers; a family reacts within
+    # itself, with the hubs, and with two parent families of the previous generation (decomposition / recombination)
+    families = []                      # (generation, [species])
+    for g in range(n_gen):
+        idx = np.arange(bounds[g], bounds[g + 1])
+        for k in range(0, len(idx), fam):
+            families.append((g, idx[k:k + fam]))
+    by_gen = [[k for k, (g, _) in enumerate(families) if g == gg] for gg in range(n_gen)]
+    parents = []
+    for k, (g, _) in enumerate(families):
+        parents.append([] if g == 0 or not by_gen[g - 1] else list(rng.choice(by_gen[g - 1], size=min(2, len(by_gen[g - 1])), replace=False)))
+    fam_of = np.zeros(ns, dtype=int)
+    for k, (_, idx) in enumerate(families):
+        fam_of[idx] = k
+
+    def same(i):
+        return int(rng.choice(families[fam_of[i]][1]))
+
+    def parent(i):
+        ps = parents[fam_of[i]]
+        if not ps:
+            return int(rng.integers(0, N_HUB))
+        return int(rng.choice(families[int(rng.choice(ps))][1]))
+
+    def hub():
+        return int(rng.integers(0, N_HUB))
+
+    # every reaction conserves 'mass' (hubs weigh 1, generation g weighs g + 2), so the total amount stays bounded
+    while count < nr:
+        kind = rng.integers(0, 10)
+        i = int(rng.integers(N_HUB, ns))
+        if kind < 4:        # abstraction within the family: X_i + hub_a <=> X_j + hub_b
+            re, pr = [i, hub()], [same(i), hub()]
+            bimol = True
+        elif kind < 7:      # decomposition to the parent generation: X_i <=> X_parent + hub   (generation 0: two hubs)
+            re, pr = [i], [parent(i), hub()]
+            bimol = False
+        elif kind < 9:      # hub-assisted decomposition: X_i + hub <=> X_parent + hub + hub
+            re, pr = [i, hub()], [parent(i), hub(), hub()]
+            bimol = True
+        else:               # isomerisation within the family
+            re, pr = [i], [same(i)]
+            bimol = False
+        if sorted(re) == sorted(pr) or i in pr:
+            continue
+        key = (tuple(sorted(re)), tuple(sorted(pr)))
+        if key in seen:
+            continue
+        seen.add(key)
+        A = 10.0 ** (rng.uniform(0.0, 4.0) if bimol else rng.uniform(5.0, 10.0))
+        n = float(rng.uniform(0.0, 0.5))
+        Ea = float(rng.uniform(2.0e4, 1.2e5))
+        lines += [f"- kinetics: {{A: {A!r}, Ea: {Ea!r}, n: {n!r}, type: Arrhenius}}",
+                  f"  products: [{', '.join(names[k] for k in pr)}]", "  radicalchange: 0",
+                  f"  reactants: [{', '.join(names[k] for k in re)}]", "  type: ElementaryReaction"]
+        count += 1
+    lines += ["Solvents:", "- mu: {mu: 0.0005, type: ConstantViscosity}", "  name: solvent", "  type: Solvent", "Units: {}"]
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return {"names": names, "n_hub": N_HUB, "nr": nr}
+
+
+def initial_moles(ns: int, seed: int = 3) -> dict:
+    """A 'fuel' (a heavy species), an 'oxidiser' hub and a trace of everything else left at zero."""
+    rng = np.random.default_rng(seed)
+    ic = {f"S{ns - 1:04d}": 6000.0, f"S{ns // 2:04d}": 500.0, "S0000": 5.0, "S0001": 50.0}
+    for k in rng.integers(N_HUB, ns, 20):
+        ic[f"S{int(k):04d}"] = float(rng.uniform(0.1, 10.0))
+    return ic
+
+
+def species_weights(ns: int) -> np.ndarray:
+    """The 'mass' every generated reaction conserves: hubs weigh 1, generation g weighs g + 2."""
+    n_gen = 10
+    w = 1.45 ** np.arange(n_gen)
+    bounds = N_HUB + np.concatenate([[0], np.cumsum(np.round((ns - N_HUB) * w / w.sum()).astype(int))])
+    bounds[-1] = ns
+    out = np.ones(ns)
+    for g in range(n_gen):
+        out[bounds[g]:bounds[g + 1]] = g + 2.0
+    return out

@@ -1,0 +1,107 @@
+"""Config C3 (large mechanisms, more than 128 state variables): the block-per-reactor path with the fixed-pattern sparse LU
+(csrc/rmsb_large.cuh, rmsb_sparse.h) against the oracle on a seeded synthetic mechanism (tests/synth.py; the reference ships
+no mechanism of this size).  dydt / Jacobian / rate coefficients against the NumPy oracle (1e-12), trajectories against the
+C++ CPU port of the same integrator with a DENSE pivoted LU (so the sparse no-pivot factorisation is checked end to end)."""
+import numpy as np
+import pytest
+
+import cases
+import rmsb200 as rb
+import synth
+from oracle import cpu_oracle as co
+from oracle import rms_oracle as ro
+from rmsb200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+NS = 300
+
+
+@pytest.fixture(scope="module")
+def mech(tmp_path_factory):
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    path = str(tmp_path_factory.mktemp("synth") / f"synth{NS}.rms")
+    synth.write_synthetic_mechanism(path, ns=NS, seed=7)
+    d = rb.readinput(path)
+    ph = rb.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0], name="phase", diffusionlimited=False)
+    od = ro.readinput(path)
+    oph = ro.IdealDiluteSolution(od["phase"]["Species"], od["phase"]["Reactions"], od["Solvents"][0], diffusionlimited=False)
+    ic = {"T": 650.0, "V": 1.0, **synth.initial_moles(NS)}
+    gdom, y0, p = rb.ConstantTVDomain(phase=ph, initialconds=ic)
+    odom = ro.ConstantTVDomain(oph, ic)
+    return ph, oph, gdom, odom, y0, p
+
+
+def test_large_pattern_analysis(mech):
+    ph = mech[0]
+    info = np.zeros(8, dtype=np.int64)
+    L.check(L.lib().rmsb_large_info(ph.handle, L.ptr(info)))
+    n, nnz, lvl_l, lvl_u, max_row, fma, core, scratch = (int(v) for v in info)
+    assert n == NS and NS <= nnz <= NS * NS and 0 < core < NS
+    assert lvl_l >= NS - core and lvl_u >= NS - core          # the dense core is a chain
+    assert max_row <= NS and fma > 0 and scratch > 19 * NS
+
+
+def test_large_dydt_jacobian_rates_parity(mech):
+    ph, oph, gdom, odom, y0, p = mech
+    rng = np.random.default_rng(1)
+    ys = np.stack([odom.y0, np.abs(odom.y0 + 10.0 ** rng.uniform(-3, 1, NS)), np.abs(odom.y0 * rng.uniform(0.5, 1.5, NS) + 1e-6)])
+    ens = rb.Domain(gdom.kind, ph, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    f = ens.dydt(ys)
+    J = ens.jacobiany(ys)
+    for k in range(len(ys)):
+        assert cases.err_dydt(f[k], ro.dydtreactor(odom, ys[k], 0.0, None)) < 1e-12
+        Jo = ro.jacobiany(odom, ys[k], 0.0, None)
+        assert cases.err_jac(J[k], Jo) < 1e-12
+        assert np.all(J[k][Jo == 0.0] == 0.0)
+    np.testing.assert_allclose(gdom.kfs[0], odom.kfs, rtol=1e-12)
+    np.testing.assert_allclose(gdom.krevs[0], odom.krevs, rtol=1e-12)
+    np.testing.assert_allclose(p, odom.p, rtol=1e-12)
+    # explicit parameters p = [G; k] give the same answer as the device's own tables
+    q = np.array(p, dtype=float)
+    q[NS + 3] *= 1.5
+    f2 = ens.dydt(ys, q)
+    assert cases.err_dydt(f2[0], ro.dydtreactor(odom, ys[0], 0.0, q)) < 1e-12
+
+
+@pytest.mark.parametrize("tend,rtol,tol", [(1e-3, 1e-9, 1e-6), (1.0, 1e-8, 1e-5)])
+def test_large_trajectory_vs_cpu_port(mech, tend, rtol, tol):
+    ph, oph, gdom, odom, y0, p = mech
+    tq = np.array([0.1 * tend, 0.5 * tend, tend])
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p).ode, abstol=1e-14, reltol=rtol, saveat=tq)
+    assert sol.retcode == ["Success"]
+    ref = co.CpuMech(oph).solve("ConstantTV", odom.y0[None], np.array([[650.0, 1.0]]), tend, rtol, 1e-14, tsave=tq, nthreads=1)
+    assert ref["status"][0] == 0
+    for k in range(len(tq)):
+        yr = ref["ysave"][0, k]
+        big = np.abs(yr) > 1e-8 * np.abs(yr).max()
+        assert np.max(np.abs(sol.u[0, k] - yr)[big] / np.abs(yr)[big]) < tol
+    # same algorithm, sparse vs dense linear algebra: the step counts agree
+    assert abs(int(sol.stats["n_steps"][0]) - int(ref["stats"]["n_steps"][0])) <= 0.05 * ref["stats"]["n_steps"][0]
+
+
+def test_large_ensemble_properties(mech):
+    """Size-independent properties on an ensemble: all converge, 'mass' (the generator's conserved weights) is conserved,
+    results do not depend on the position in the batch, constant species stay put."""
+    ph, oph, gdom, odom, y0, p = mech
+    n = 300
+    T = np.random.default_rng(2).uniform(600.0, 700.0, n)
+    y0s = np.repeat(gdom.y0, n, axis=0) * np.random.default_rng(3).uniform(0.8, 1.2, (n, 1))
+    T[-1], y0s[-1] = T[0], y0s[0]
+    ens = rb.Domain(gdom.kind, ph, y0s, np.stack([T, np.ones(n)], axis=1))
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 1.0)).ode, abstol=1e-12, reltol=1e-6)
+    assert np.all(sol.status == 0)
+    assert np.array_equal(sol.yend[0], sol.yend[-1])
+    w = synth.species_weights(NS)
+    np.testing.assert_allclose(sol.yend @ w, y0s @ w, rtol=1e-9)
+    rev = rb.Domain(gdom.kind, ph, y0s[::-1].copy(), np.stack([T[::-1], np.ones(n)], axis=1))
+    sol2 = rb.solve(rb.Reactor(rev, None, (0.0, 1.0)).ode, abstol=1e-12, reltol=1e-6)
+    assert np.array_equal(sol2.yend[::-1], sol.yend)
+    cs = rb.Domain(gdom.kind, ph, y0s[:4], np.stack([T[:4], np.ones(4)], axis=1), constantspecies=[f"S{NS - 1:04d}"])
+    sol3 = rb.solve(rb.Reactor(cs, None, (0.0, 1e-2)).ode, abstol=1e-12, reltol=1e-6)
+    assert np.all(sol3.status == 0) and np.array_equal(sol3.yend[:, NS - 1], y0s[:4, NS - 1])
+
+
+def test_large_path_limits_are_reported(mech):
+    ph = mech[0]
+    with pytest.raises(rb.RMSBError, match="ConstantTV / ConstantTAPhi"):
+        rb.ConstantTPEnsemble(ph, [650.0], [1e5], mech[2].y0).dydt()
