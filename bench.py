@@ -57,6 +57,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one solve-kernel launch from the committed `ncu --set full` capture
+    (profiles/r01_solve_kernel_traffic.json); only valid for the launch size it was captured at, otherwise None."""
+    p = ROOT / "profiles" / "r01_solve_kernel_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        if int(d["conditions_per_launch"]) == int(n):
+            return int(d["dram__bytes_read.sum"]) + int(d["dram__bytes_write.sum"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -323,7 +336,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "kernel": "solve_kernel<1>", "algorithmic_bytes_per_solve": bytes_per_solve,
+                         "traffic": _ncu_traffic(n), "kernel": "solve_kernel<1>", "algorithmic_bytes_per_solve": bytes_per_solve,
                          "peak_source": peak_src,
                          "note": "state lives in registers/shared memory for the whole integration: the solve is FP64-pipe/latency bound, "
                                  "not HBM bound (SURVEY 8d); see roofline_fp64 and evals"},
