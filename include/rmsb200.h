@@ -60,6 +60,8 @@ extern "C" {
 #define RMSB_DOMAIN_CONSTANT_TV     2
 #define RMSB_DOMAIN_CONSTANT_TAPHI  3
 #define RMSB_DOMAIN_COUPLED_TP_TAPHI 4
+/*  CONSTANT_P      [ns; T; V] Ns+2   [P]            src/Domain.jl:173-239,1141-1192,1950-1953 (adiabatic, constant pressure) */
+#define RMSB_DOMAIN_CONSTANT_P      5
 
 /* ---- kinetics type tags (src/Calculators/Rate.jl, Ratevec.jl) -----------------------------
  * kin_params[kin_offset[j] .. kin_offset[j+1]) holds, as doubles:

@@ -335,9 +335,12 @@ template <class N>
 void rhs(const Mech& m, const Dom& d, Work& w, const N* y, N* dy, bool keep, Aux* ax) {
     const int Ns = m.Ns, Nr = m.Nr;
     for (int i = 0; i < d.Ny; ++i) dy[i] = N(0.0);
-    if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
-        N T = y[Ns], P = y[Ns + 1];
-        double V = d.cond[0];
+    if (d.kind == RMSB_DOMAIN_CONSTANT_V || d.kind == RMSB_DOMAIN_CONSTANT_P) {
+        // ConstantV: y = [ns; T; P], cond = [V].  ConstantP: y = [ns; T; V], cond = [P] (Domain.jl:1141-1192,1950-1953):
+        // enthalpies instead of internal energies, Cp instead of Cv, dV/dt instead of dP/dt; V carries no derivative seed
+        const bool isP = d.kind == RMSB_DOMAIN_CONSTANT_P;
+        N T = y[Ns], P = isP ? N(d.cond[0]) : y[Ns + 1];
+        double V = isP ? val(y[Ns + 1]) : d.cond[0];
         N Nt = P * N(V) / (N(R) * T), C = Nt / N(V);           // Domain.jl:1068-1070
         N* g = w.buf<N>(); N* us = g + Ns; N* kf = us + Ns; N* kr = kf + Nr;
         double* ns = w.tmpns.data();
@@ -347,7 +350,7 @@ void rhs(const Mech& m, const Dom& d, Work& w, const N* y, N* dy, bool keep, Aux
             hscp(m, s, T, cp, h, sr);
             if (d.p) h = h + N(d.p[s]) / (N(R) * T);
             N G = (h - sr) * (N(R) * T);
-            us[s] = (h - N(1.0)) * (N(R) * T);
+            us[s] = isP ? h * (N(R) * T) : (h - N(1.0)) * (N(R) * T);
             g[s] = G / (N(R) * T);
             ns[s] = val(y[s]);
             w.cs[s] = ns[s] / V;
@@ -371,8 +374,13 @@ void rhs(const Mech& m, const Dom& d, Work& w, const N* y, N* dy, bool keep, Aux
         add_rates<N>(m, w.cs.data(), kf, kr, dy);
         N dotU = 0.0, sumn = 0.0;
         for (int s = 0; s < Ns; ++s) { dy[s] = dy[s] * N(V); dotU = dotU + us[s] * dy[s]; sumn = sumn + dy[s]; }
-        dy[Ns] = -dotU / (Nt * Cv);                              // Domain.jl:1902
-        dy[Ns + 1] = sumn * N(R) * T / N(V) + P / T * dy[Ns];    // :1903
+        if (isP) {
+            dy[Ns] = -dotU / (Nt * (Cv + N(R)));                 // Domain.jl:1951-1952
+            dy[Ns + 1] = sumn * N(R) * T / P + dy[Ns] * N(V) / T;  // :1953
+        } else {
+            dy[Ns] = -dotU / (Nt * Cv);                          // Domain.jl:1902
+            dy[Ns + 1] = sumn * N(R) * T / N(V) + P / T * dy[Ns];  // :1903
+        }
         if (ax) *ax = {val(T), val(P), V, val(Nt), val(C), val(Cv), val(dotU)};
     } else {
         double T = d.cond[0], P, V;
@@ -447,8 +455,8 @@ void jacobian(const Mech& m, const Dom& d, Work& w, const double* y) {
     rhs<double>(m, d, w, y, dy.data(), true, &ax);
     std::fill(w.jac.begin(), w.jac.end(), 0.0);
     double* J = w.jac.data();
-    const bool hasV = d.kind == RMSB_DOMAIN_CONSTANT_TP;
-    const int Vind = Ns;
+    const bool hasV = d.kind == RMSB_DOMAIN_CONSTANT_TP || d.kind == RMSB_DOMAIN_CONSTANT_P;
+    const int Vind = d.kind == RMSB_DOMAIN_CONSTANT_P ? Ns + 1 : Ns;
     for (int i = 0; i < m.Nr; ++i) {
         jac_side(m, i, 0, w.kf[i], w.cs.data(), J, Ny, Vind, ax.V, true, false, 0.0, -1);
         jac_side(m, i, 1, w.kr[i], w.cs.data(), J, Ny, Vind, ax.V, true, false, 0.0, -1);
@@ -489,7 +497,25 @@ void jacobian(const Mech& m, const Dom& d, Work& w, const double* y) {
             J[Ns + 1 + (size_t)c * Ny] = sm * R * ax.T / ax.V + ax.P / ax.T * jt;
         }
     }
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_P) {                 // Domain.jl:2480-2490 (w.us holds the enthalpies)
+        const double Cp = ax.Cv + R, dTdt = -ax.dotU / (ax.N * Cp);
+        for (int c = 0; c < Ns + 2; ++c) {
+            if (c == Ns) continue;
+            double a = 0.0, sm = 0.0;
+            for (int i = 0; i < Ns; ++i) { a += w.us[i] * J[i + (size_t)c * Ny]; sm += J[i + (size_t)c * Ny]; }
+            double jt = -a / (ax.N * Cp);
+            if (c < Ns) jt -= dTdt * ((w.cp[c] * R / ax.N) / Cp);
+            J[Ns + (size_t)c * Ny] = jt;
+            J[Ns + 1 + (size_t)c * Ny] = sm * R * ax.T / ax.P + ax.V / ax.T * jt + (c == Ns + 1 ? dTdt / ax.T : 0.0);
+        }
+    }
     for (int k = 0; k < d.nconst; ++k) for (int c = 0; c < Ny; ++c) J[d.constspc[k] - 1 + (size_t)c * Ny] = 0.0;
+    if (d.kind == RMSB_DOMAIN_CONSTANT_P) {   // T column: derivative of the full RHS (Domain.jl:2630)
+        std::vector<D2> yd(Ny), dyd(Ny);
+        for (int i = 0; i < Ny; ++i) yd[i] = D2(y[i], i == Ns ? 1.0 : 0.0, 0.0);
+        rhs<D2>(m, d, w, yd.data(), dyd.data(), false, nullptr);
+        for (int i = 0; i < Ny; ++i) J[i + (size_t)Ns * Ny] = dyd[i].a;
+    }
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) {   // T and P columns: derivative of the full RHS (Reactor.jl:1469-1477)
         std::vector<D2> yd(Ny), dyd(Ny);
         for (int i = 0; i < Ny; ++i) yd[i] = D2(y[i], i == Ns ? 1.0 : 0.0, i == Ns + 1 ? 1.0 : 0.0);
@@ -562,7 +588,7 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
     SolveOut out{};
     rmsb_stats& st = out.st;
     std::vector<double> D((size_t)(MAXO + 3) * n, 0.0), y(y0, y0 + n), f(n), scale(n), ypred(n), psi(n), dvec(n), ynew(n), dy(n), err(n);
-    if (d.kind != RMSB_DOMAIN_CONSTANT_V) {
+    if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P) {
         double T = d.cond[0], P, V;
         if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = y[m.Ns]; } else { P = d.kind == RMSB_DOMAIN_CONSTANT_TV ? 1.0e8 : 0.0; V = d.cond[1]; }
         setup_constk(m, d, w, y.data(), T, P, V);
@@ -762,13 +788,14 @@ SolveOut bdf_solve(const Mech& m, const Dom& d, Work& w, const double* y0, doubl
 
 int domain_ny(const Mech& m, int kind) {
     switch (kind) {
-    case RMSB_DOMAIN_CONSTANT_V: return m.Ns + 2;
+    case RMSB_DOMAIN_CONSTANT_V:
+    case RMSB_DOMAIN_CONSTANT_P: return m.Ns + 2;
     case RMSB_DOMAIN_CONSTANT_TP: return m.Ns + 1;
     case RMSB_DOMAIN_CONSTANT_TV: case RMSB_DOMAIN_CONSTANT_TAPHI: return m.Ns;
     }
     return -1;
 }
-int domain_ncond(int kind) { return kind == RMSB_DOMAIN_CONSTANT_V ? 1 : 2; }
+int domain_ncond(int kind) { return (kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) ? 1 : 2; }
 
 }  // namespace
 
@@ -842,7 +869,7 @@ int rmso_eval(void* h, int mode, int kind, int64_t n, const double* y, const dou
         for (int64_t r = 0; r < n; ++r) {
             Dom d = make_dom(m, kind, r, cond, p, p_stride, cs, ncs);
             const double* yr = y + r * Ny;
-            if (kind != RMSB_DOMAIN_CONSTANT_V) {
+            if (kind != RMSB_DOMAIN_CONSTANT_V && kind != RMSB_DOMAIN_CONSTANT_P) {
                 double T = d.cond[0], P, V;
                 if (kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = yr[m.Ns]; } else { P = kind == RMSB_DOMAIN_CONSTANT_TV ? 1.0e8 : 0.0; V = d.cond[1]; }
                 setup_constk(m, d, w, yr, T, P, V);
@@ -863,7 +890,7 @@ int rmso_solve(void* h, int kind, int64_t n, const double* y0, const double* con
     const Mech& m = *static_cast<Mech*>(h);
     const int Ny = domain_ny(m, kind);
     if (Ny < 0) return -1;
-    if (idt_index < 0) idt_index = kind == RMSB_DOMAIN_CONSTANT_V ? m.Ns : -1;
+    if (idt_index < 0) idt_index = (kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) ? m.Ns : -1;
     if (max_steps <= 0) max_steps = 500000;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);

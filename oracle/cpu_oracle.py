@@ -17,7 +17,7 @@ LIB = HERE / "cpu" / "librms_cpu_oracle.so"
 SRC = HERE / "cpu" / "rms_cpu.cpp"
 
 KIN = dict(ARRHENIUS_VEC=0, ARRHENIUS=1, MULTIARRHENIUS=2, PLOG_VEC=3, PLOG=4, MULTIPLOG=5, THIRDBODY=6, LINDEMANN=7, TROE=8, CHEBYSHEV_VEC=9)
-DOMAIN = {"ConstantV": 0, "ConstantTP": 1, "ConstantTV": 2, "ConstantTAPhi": 3}
+DOMAIN = {"ConstantV": 0, "ConstantTP": 1, "ConstantTV": 2, "ConstantTAPhi": 3, "ConstantP": 5}
 PHASE = {"gas": 0, "liquid": 1, "surface": 2}
 
 _pd, _pi, _pu8 = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)

@@ -892,6 +892,61 @@ class ConstantVDomain(_Domain):
             dydt[i] = 0.0
 
 
+class ConstantPDomain(_Domain):
+    """src/Domain.jl:173-239 (ctor), :1141-1192 (calcthermo), :1950-1953 (derivatives). y = [ns; T; V], adiabatic at constant P."""
+    kind = "ConstantP"
+
+    def __init__(self, phase: Phase, initialconds: dict, constantspecies=()):
+        assert phase.kind == "gas"
+        vals, ns = _initial(phase, initialconds, ("T", "P", "V"))
+        T, P, V = vals["T"], vals["P"], vals["V"]
+        assert P != 0.0 or (T != 0.0 and V != 0.0)
+        N = ns.sum()
+        if P == 0.0:
+            P = N * R * T / V
+        elif T == 0.0:
+            T = P * V / (R * N)
+        elif V == 0.0:
+            V = N * R * T / P
+        else:
+            raise ValueError("ConstantPDomain overspecified with T,P and V")
+        self.phase, self.P = phase, P
+        self.y0 = np.concatenate([ns, [T, V]])
+        self.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+        self.constantspeciesinds = self._constspc(constantspecies)
+        self.Ny = phase.Ns + 2
+        self.cond = np.array([P])
+
+    def calcthermo(self, y, t=0.0, p=None) -> Thermo:
+        ph, Ns = self.phase, self.phase.Ns
+        ns, T, V = y[:Ns], y[Ns], y[Ns + 1]
+        P = self.P
+        N = P * V / (R * T)
+        cs = ns / V
+        C = N / V
+        cp, h, s = ph.calcHSCpdless(T)
+        if p is not None:
+            h = h + p[:Ns] / (R * T)
+        Gs = (h - s) * (R * T)
+        Hs = h * (R * T)
+        Cv = np.dot(cp, ns)
+        Cv = Cv * (R / N)
+        Cv = Cv - R
+        kfs, krevs = ph.getkfkrevs(T, P, C, N, ns, Gs, _EMPTY, V)
+        if p is not None:
+            kfs = kfs * p[Ns:Ns + ph.Nr]
+            krevs = krevs * p[Ns:Ns + ph.Nr]
+        return Thermo(ns, cs, T, P, V, C, N, 0.0, kfs, krevs, Hs, _EMPTY, Gs, _EMPTY, Cv, cp)
+
+    def derivatives(self, dydt, th: Thermo):
+        Ns = self.phase.Ns
+        Cp = th.Cvave + R
+        dydt[Ns] = -np.dot(th.Hs, dydt[:Ns]) / (th.N * Cp)
+        dydt[Ns + 1] = np.sum(dydt[:Ns]) * R * th.T / th.P + dydt[Ns] * th.V / th.T
+        for i in self.constantspeciesinds:
+            dydt[i] = 0.0
+
+
 class _ConstantKDomain(_Domain):
     def _setup_k(self, T, P, C, N, ns, V):
         ph = self.phase
@@ -1158,6 +1213,24 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30):
             yc = y.astype(complex)
             yc[col] += 1j * cstep
             jac[:, col] = dydtreactor(domain, yc, t, p).imag / cstep
+    elif domain.kind == "ConstantP":      # src/Domain.jl:2456-2632: V column analytic, T column = derivative of the full RHS
+        jacobianynsderiv(jac, domain, th, Ns + 1)
+        dydt = np.zeros(Ny)
+        addreactionratecontributions(dydt, domain.phase.rxnarray, th.cs, th.kfs, th.krevs)
+        dydt *= th.V
+        Cp = th.Cvave + R
+        dTdt = -np.dot(th.Hs, dydt[:Ns]) / (th.N * Cp)
+        for i in range(Ns):
+            dCpdni = th.cpdivR[i] * R / th.N
+            jac[Ns, i] = -np.dot(th.Hs, jac[:Ns, i]) / (th.N * Cp) - dTdt * (dCpdni / Cp)
+            jac[Ns + 1, i] = np.sum(jac[:Ns, i]) * R * th.T / th.P + th.V / th.T * jac[Ns, i]
+        jac[Ns, Ns + 1] = -np.dot(th.Hs, jac[:Ns, Ns + 1]) / (th.N * Cp)
+        jac[Ns + 1, Ns + 1] = np.sum(jac[:Ns, Ns + 1]) * R * th.T / th.P + dTdt / th.T + th.V / th.T * jac[Ns, Ns + 1]
+        for ind in domain.constantspeciesinds:
+            jac[ind, :] = 0.0
+        yc = y.astype(complex)
+        yc[Ns] += 1j * cstep
+        jac[:, Ns] = dydtreactor(domain, yc, t, p).imag / cstep
     else:  # ConstantTV / ConstantTAPhi
         jacobianynsderiv(jac, domain, th, None)
         for ind in domain.constantspeciesinds:
@@ -1243,6 +1316,17 @@ def jacobianp(domain, y, t=0.0, p=None):
         for i in range(Ns, Ns + Nr):
             jacp[Ns, i] = -np.dot(th.Us, jacp[:Ns, i]) / (th.N * th.Cvave)
             jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.V + th.P / th.T * jacp[Ns, i]
+    elif domain.kind == "ConstantP":          # src/Domain.jl:3433-3460
+        dydt = np.zeros(Ny)
+        addreactionratecontributions(dydt, ra, th.cs, th.kfs, th.krevs)
+        dydt *= th.V
+        Cp = th.Cvave + R
+        for i in range(Ns):
+            jacp[Ns, i] = -(np.dot(th.Hs, jacp[:Ns, i]) + dydt[i]) / (th.N * Cp)
+            jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.P + jacp[Ns, i] * th.V / th.T
+        for i in range(Ns, Ns + Nr):
+            jacp[Ns, i] = -np.dot(th.Hs, jacp[:Ns, i]) / (th.N * Cp)
+            jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.P + jacp[Ns, i] * th.V / th.T
     for ind in domain.constantspeciesinds:
         jacp[ind, :] = 0.0
     return jacp

@@ -80,7 +80,8 @@ extern "C" int64_t rmsb_kernel_launch_count(void) { return g_launches.load(); }
 
 static int domain_ny(const rmsb_mech* m, int kind) {
     switch (kind) {
-    case RMSB_DOMAIN_CONSTANT_V: return m->dm.Ns + 2;
+    case RMSB_DOMAIN_CONSTANT_V:
+    case RMSB_DOMAIN_CONSTANT_P: return m->dm.Ns + 2;
     case RMSB_DOMAIN_CONSTANT_TP:
     case RMSB_DOMAIN_COUPLED_TP_TAPHI: return m->dm.Ns + 1;
     case RMSB_DOMAIN_CONSTANT_TV:
@@ -90,7 +91,8 @@ static int domain_ny(const rmsb_mech* m, int kind) {
 }
 static int domain_ncond(int kind) {
     switch (kind) {
-    case RMSB_DOMAIN_CONSTANT_V: return 1;
+    case RMSB_DOMAIN_CONSTANT_V:
+    case RMSB_DOMAIN_CONSTANT_P: return 1;
     case RMSB_DOMAIN_CONSTANT_TP:
     case RMSB_DOMAIN_CONSTANT_TV:
     case RMSB_DOMAIN_CONSTANT_TAPHI: return 2;
@@ -720,7 +722,8 @@ static int check_common(const rmsb_mech* h, int kind, int64_t n, const void* y, 
     if (n < 0) return fail(RMSB_ERR_ARG, "negative batch size");
     if (n > 0 && (!y || !cond)) return fail(RMSB_ERR_ARG, "null state/condition buffer");
     if (p && p_stride != 0 && p_stride != h->dm.Ns + h->dm.Nr) return fail(RMSB_ERR_ARG, "p_stride must be 0 or Ns+Nr");
-    if (kind == RMSB_DOMAIN_CONSTANT_V && h->dm.phase_kind != RMSB_PHASE_GAS) return fail(RMSB_ERR_ARG, "ConstantV domain needs an IdealGas phase");
+    if ((kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) && h->dm.phase_kind != RMSB_PHASE_GAS)
+        return fail(RMSB_ERR_ARG, "ConstantV / ConstantP domains need an IdealGas phase");
     if (kind == RMSB_DOMAIN_CONSTANT_TAPHI && h->dm.phase_kind != RMSB_PHASE_SURFACE) return fail(RMSB_ERR_ARG, "ConstantTAPhi domain needs an IdealSurface phase");
     if ((kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) != (h->dm.coupled != 0)) return fail(RMSB_ERR_ARG, "the coupled gas-surface domain and two-phase mechanisms go together");
     return RMSB_OK;
@@ -816,7 +819,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
     a.nsave = nsave; a.tsave = tsave; a.ysave = ysave; a.yend = yend; a.idt = idt; a.status = status; a.stats = stats;
     a.max_steps = o.max_steps; a.max_order = o.max_order; a.first_step = o.first_step;
     a.domain_kind = kind; a.Ny = domain_ny(h, kind); a.flags = o.reserved;
-    a.idt_index = o.idt_index >= 0 ? o.idt_index : (kind == RMSB_DOMAIN_CONSTANT_V ? h->dm.Ns : -1);
+    a.idt_index = o.idt_index >= 0 ? o.idt_index : ((kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) ? h->dm.Ns : -1);
     if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
     a.counter = reinterpret_cast<unsigned long long*>(work);
     a.ssave = ssave; a.send = send; a.sens_hist = nullptr; a.Npp = sens_npp(h);

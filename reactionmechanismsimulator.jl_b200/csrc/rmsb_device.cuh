@@ -636,7 +636,10 @@ __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
 #define RMSB_INV_R (1.0 / 8.314)
 #define RMSB_LOG_1E5_OVER_R 9.394984624139783   /* log(1.0e5/8.314) */
 
-template <class N>
+// ISP = false: ConstantV  y = [ns; T; P], cond = [V]   (src/Domain.jl:1064-1113,1901-1906)
+// ISP = true : ConstantP  y = [ns; T; V], cond = [P]   (src/Domain.jl:1141-1192,1950-1953): enthalpies instead of internal
+//              energies, dT/dt = -dot(Hs,dn)/(N*Cp), dV/dt = sum(dn)*R*T/P + dT/dt*V/T; only T carries a derivative seed
+template <class N, bool ISP = false>
 __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
@@ -648,9 +651,9 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     double* qb = w.q();
     double* gb = w.g();
     double* ub = w.un();
-    const double V = d.cond[0];
-    const double invV = w.aux()[7];
-    N T = seed<N>(yb[Ns], 0), P = seed<N>(yb[Ns + 1], 1);
+    const double V = ISP ? yb[Ns + 1] : d.cond[0];
+    const double invV = ISP ? 1.0 / V : w.aux()[7];
+    N T = seed<N>(yb[Ns], 0), P = ISP ? N(d.cond[0]) : seed<N>(yb[Ns + 1], 1);
     TPow<N> tp(T);                       // T4 = 1/T, T6 = log(T)
     N RT = RMSB_R * T;
     N invRT = tp.T4 * RMSB_INV_R;        // 1/(R*T)
@@ -661,7 +664,7 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
         N cp, h, sr;
         nasa_hscp(s, tp, val(T), cp, h, sr);
         if (p) h = h + p[s] * invRT;                    // Domain.jl:1100
-        N U = (h - 1.0) * RT;                           // :1102
+        N U = ISP ? h * RT : (h - 1.0) * RT;            // :1102 (internal energy) / :1152 (enthalpy)
         SM::st(gb, s, h - sr);                          // G/(R*T) with G = (h-s)*R*T (:1101, PhaseState.jl:166)
         SM::st(ub, s, U);
         double nsv = yb[s];
@@ -703,8 +706,9 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     }
     N dotU = warp_sum(usum), sumn = warp_sum(nsum);
     // dT/dt = -dot(Us,dn)/(N*Cv) with N*Cv = R*(dot(cp/R,ns) - N)     (Domain.jl:1103-1105,1902)
-    N dT = -dotU / (RMSB_R * (cpsum - Nt));
-    N dP = sumn * RT * invV + P * tp.T4 * dT;            // :1903
+    // ConstantP: N*Cp = N*(Cv + R) = R*dot(cp/R,ns)                                    (Domain.jl:1951-1953)
+    N dT = ISP ? -dotU / (RMSB_R * cpsum) : -dotU / (RMSB_R * (cpsum - Nt));
+    N dP = ISP ? sumn * RT / P + dT * V * tp.T4 : sumn * RT * invV + P * tp.T4 * dT;   // :1903 / :1953 (dV/dt for ConstantP)
     if (lane == 0) {
         SM::st(fb, Ns, dT);
         SM::st(fb, Ns + 1, dP);
@@ -936,6 +940,7 @@ __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, in
 
 __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int lane, bool store_k) {
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(d, w, lane, store_k);
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_P) rhs_v<double, true>(d, w, lane, store_k);
     else if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) rhs_coupled(d, w, lane);
     else rhs_ck(d, w, lane);
 }
@@ -943,7 +948,7 @@ __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int l
 // once per reactor for every domain whose rate coefficients are constants of the reactor
 __device__ __forceinline__ void setup_domain(const DomainArgs& d, const Ws& w, int lane) {
     if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) setup_coupled(d, w, lane);
-    else if (d.kind != RMSB_DOMAIN_CONSTANT_V) setup_constk(d, w, lane);
+    else if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P) setup_constk(d, w, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,7 +987,8 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         J[G(m.je_row, e) + G(m.je_col, e) * LD] = acc;
     }
     __syncwarp();
-    const bool hasV = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
+    const bool hasV = (d.kind == RMSB_DOMAIN_CONSTANT_TP || d.kind == RMSB_DOMAIN_CONSTANT_P);
+    const int Vcol = (d.kind == RMSB_DOMAIN_CONSTANT_P) ? Ns + 1 : Ns;      // column of the volume in y
     // (3) V column of the ns block (src/Reactor.jl:1368-1413) -- lanes over species rows
     if (hasV) {
         for (int s = lane; s < Ns; s += 32) {
@@ -999,7 +1005,7 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
                 if (npr > 1) dr = -(double)(npr - 1) * pr;
                 if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
             }
-            J[s + Ns * LD] = acc;
+            J[s + Vcol * LD] = acc;
         }
         __syncwarp();
     }
@@ -1024,7 +1030,7 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
             for (int c = lane; c < ncol; c += 32) {
                 int col; double dkf;
                 if (c < ne) { col = G(m.eff_spc, G(m.eff_ptr, j) + c); dkf = dkdC * (G(m.eff_val, G(m.eff_ptr, j) + c) / aV); }
-                else { col = Ns; dkf = dkdC * (aC - Ceff) / aV; }
+                else { col = Vcol; dkf = dkdC * (aC - Ceff) / aV; }
                 double dkr = dkf / Kc;
                 double dvf = dkf * pf, dvr = dkr * pr;
                 for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * LD] -= dvf; }
@@ -1053,6 +1059,22 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
             J[Ns + c * LD] = jt;
             J[Ns + 1 + c * LD] = sm * RMSB_R * aT / aV + aP / aT * jt;
         }
+    } else if (d.kind == RMSB_DOMAIN_CONSTANT_P) {       // Domain.jl:2480-2490 (us holds the enthalpies, adotU = dot(Hs,dn))
+        const double* hs = w.us();
+        const double* cpb = w.cp();
+        const double aCp = aCv + RMSB_R;
+        const double dTdt = -adotU / (aN * aCp);
+        for (int c = lane; c < Ns + 2; c += 32) {
+            if (c == Ns) continue;                       // the T column is the derivative of the whole RHS, step (7)
+            double a = 0.0, sm = 0.0;
+            for (int i = 0; i < Ns; ++i) { double v = J[i + c * LD]; a += hs[i] * v; sm += v; }
+            double jt = -a / (aN * aCp);
+            if (c < Ns) jt -= dTdt * ((cpb[c] * RMSB_R / aN) / aCp);
+            J[Ns + c * LD] = jt;
+            double jv = sm * RMSB_R * aT / aP + aV / aT * jt;
+            if (c == Ns + 1) jv += dTdt / aT;
+            J[Ns + 1 + c * LD] = jv;
+        }
     }
     __syncwarp();
     // (6) constant species rows (Domain.jl:2216-2218,2318-2320,3053-3055)
@@ -1067,6 +1089,11 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         const double* fb = w.fbuf();
         for (int i = lane; i < Ny; i += 32) { J[i + Ns * LD] = fb[3 * i + 1]; J[i + (Ns + 1) * LD] = fb[3 * i + 2]; }
         __syncwarp();
+    } else if (d.kind == RMSB_DOMAIN_CONSTANT_P) {      // T column only; the V column above is analytic (Domain.jl:2630)
+        rhs_v<Dual2, true>(d, w, lane, false);
+        const double* fb = w.fbuf();
+        for (int i = lane; i < Ny; i += 32) J[i + Ns * LD] = fb[3 * i + 1];
+        __syncwarp();
     }
 }
 
@@ -1079,6 +1106,7 @@ __device__ __noinline__ void kfs_intrinsic(DomainArgs d, Ws w, int lane) {
     const double* ns = w.ybuf();
     double T, P, V;
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) { T = ns[Ns]; P = ns[Ns + 1]; V = d.cond[0]; }
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_P) { T = ns[Ns]; P = d.cond[0]; V = ns[Ns + 1]; }
     else if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { T = d.cond[0]; P = d.cond[1]; V = ns[Ns]; }
     else { T = d.cond[0]; P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
     double N = 0.0;
@@ -1110,7 +1138,7 @@ __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int c0, boo
     const double* ax = w.aux();
     const double aT = ax[0], aP = ax[1], aV = ax[2], aN = ax[3], aCv = ax[5];
     const double RTinv = 1.0 / (RMSB_R * aT);
-    const bool constk = (d.kind != RMSB_DOMAIN_CONSTANT_V);
+    const bool constk = (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P);
     const int c = c0 + lane;
     for (int i = 0; i < Ny; ++i) col[i * JP_CHUNK] = 0.0;
     if (c < Np) {
@@ -1165,6 +1193,15 @@ __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int c0, boo
             double jt = (c < Ns) ? -(a + raw * aV) / (aN * aCv) : -a / (aN * aCv);
             col[Ns * JP_CHUNK] = jt;
             col[(Ns + 1) * JP_CHUNK] = sm * RMSB_R * aT / aV + aP / aT * jt;
+        }
+        if (d.kind == RMSB_DOMAIN_CONSTANT_P) {                  // Domain.jl:3447-3456 (us holds the enthalpies)
+            const double* hs = w.us();
+            const double aCp = aCv + RMSB_R;
+            double a = 0.0, sm = 0.0;
+            for (int i = 0; i < Ns; ++i) { a += hs[i] * col[i * JP_CHUNK]; sm += col[i * JP_CHUNK]; }
+            double jt = (c < Ns) ? -(a + raw * aV) / (aN * aCp) : -a / (aN * aCp);
+            col[Ns * JP_CHUNK] = jt;
+            col[(Ns + 1) * JP_CHUNK] = sm * RMSB_R * aT / aP + jt * aV / aT;
         }
         for (int k = 0; k < d.nconst; ++k) col[(d.constspc[k] - 1) * JP_CHUNK] = 0.0;
     }

@@ -6,11 +6,11 @@ executable host side (same names, argument meaning and error behaviour), and `ju
 holds the `ccall` shim a Julia user would load.  There is no CPU fallback: every compute call goes
 to the CUDA library and raises if it is missing.
 """
-from ._lib import (DOMAIN_CONSTANT_TAPHI, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_V, LIB_PATH, RMSBError,
+from ._lib import (DOMAIN_CONSTANT_P, DOMAIN_CONSTANT_TAPHI, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_V, LIB_PATH, RMSBError,
                    lib)
 from .coupled import CoupledEnsemble, CoupledPhase, SystemSimulation, coupled_domain
 from .coupled import make_interface as ReactiveInternalInterfaceConstantTPhi
-from .domain import (ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
+from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
                      ConstantVDomain, ConstantVEnsemble, Domain)
 from .ensemble import shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)

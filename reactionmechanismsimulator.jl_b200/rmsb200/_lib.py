@@ -15,6 +15,7 @@ LIB_PATH = Path(os.environ.get("RMSB200_LIB", _HERE.parent / "csrc" / "librmsb20
 RMSB_OK = 0
 PHASE_GAS, PHASE_LIQUID, PHASE_SURFACE = 0, 1, 2
 DOMAIN_CONSTANT_V, DOMAIN_CONSTANT_TP, DOMAIN_CONSTANT_TV, DOMAIN_CONSTANT_TAPHI, DOMAIN_COUPLED_TP_TAPHI = 0, 1, 2, 3, 4
+DOMAIN_CONSTANT_P = 5
 (KIN_ARRHENIUS_VEC, KIN_ARRHENIUS, KIN_MULTIARRHENIUS, KIN_PLOG_VEC, KIN_PLOG, KIN_MULTIPLOG,
  KIN_THIRDBODY, KIN_LINDEMANN, KIN_TROE, KIN_CHEBYSHEV_VEC) = range(10)
 VISC_NONE, VISC_CONSTANT, VISC_RIEDEL = 0, 1, 2

@@ -30,6 +30,9 @@ class Domain:
         if kind == L.DOMAIN_CONSTANT_V:
             self.indexes = [1, Ns, Ns + 1, Ns + 2]
             self.thermovariabledict = {"T": Ns + 1, "P": Ns + 2}
+        elif kind == L.DOMAIN_CONSTANT_P:
+            self.indexes = [1, Ns, Ns + 1, Ns + 2]
+            self.thermovariabledict = {"T": Ns + 1, "V": Ns + 2}
         elif kind == L.DOMAIN_CONSTANT_TP:
             self.indexes = [1, Ns, Ns + 1]
             self.thermovariabledict = {"V": Ns + 1}
@@ -42,10 +45,12 @@ class Domain:
     # -- names mirrored from the reference structs ---------------------------------------------
     @property
     def T(self):
-        return None if self.kind == L.DOMAIN_CONSTANT_V else _scalar(self.cond[:, 0])
+        return None if self.kind in (L.DOMAIN_CONSTANT_V, L.DOMAIN_CONSTANT_P) else _scalar(self.cond[:, 0])
 
     @property
     def P(self):
+        if self.kind == L.DOMAIN_CONSTANT_P:
+            return _scalar(self.cond[:, 0])
         return _scalar(self.cond[:, 1]) if self.kind == L.DOMAIN_CONSTANT_TP else None
 
     @property
@@ -187,6 +192,27 @@ def ConstantVDomain(*, phase: Phase, initialconds: Dict[str, float], constantspe
     return dom, dom.y0[0].copy(), dom.p
 
 
+def ConstantPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """src/Domain.jl:188-239 -> (domain, y0, p); adiabatic at constant pressure, y0 = [ns; T; V], p = [zeros(Ns); ones(Nr)]."""
+    assert phase.kind == L.PHASE_GAS
+    v, ns = _parse(phase, initialconds, ("T", "P", "V"))
+    T, P, V = v["T"], v["P"], v["V"]
+    assert P != 0.0 or (T != 0.0 and V != 0.0)
+    N = ns.sum()
+    if P == 0.0:
+        P = N * R * T / V
+    elif T == 0.0:
+        T = P * V / (R * N)
+    elif V == 0.0:
+        V = N * R * T / P
+    else:
+        raise ValueError("ConstantPDomain overspecified with T,P and V")
+    dom = Domain(L.DOMAIN_CONSTANT_P, phase, np.concatenate([ns, [T, V]]), np.array([P]), constantspecies)
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, dom.y0[0].copy(), dom.p
+
+
 def ConstantTPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
     """src/Domain.jl:42-102 -> (domain, y0, p); y0 = [ns; V], p = [Gs; kfs (efficiency reactions -> 1.0)]."""
     v, ns = _parse(phase, initialconds, ("T", "P"))
@@ -225,6 +251,17 @@ def ConstantVEnsemble(phase: Phase, T, P, ns, constantspecies: Sequence[str] = (
     ns = np.atleast_2d(np.asarray(ns, dtype=float))
     V = ns.sum(axis=1) * R * T / P
     dom = Domain(L.DOMAIN_CONSTANT_V, phase, np.concatenate([ns, T[:, None], P[:, None]], axis=1), V[:, None], constantspecies)
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom
+
+
+def ConstantPEnsemble(phase: Phase, T, P, ns, constantspecies: Sequence[str] = ()) -> Domain:
+    """n adiabatic constant-pressure reactors: T[n] initial temperature, P[n] pressure, ns[n][Ns]; V0 = N*R*T/P."""
+    T, P = np.asarray(T, dtype=float), np.asarray(P, dtype=float)
+    ns = np.atleast_2d(np.asarray(ns, dtype=float))
+    V = ns.sum(axis=1) * R * T / P
+    dom = Domain(L.DOMAIN_CONSTANT_P, phase, np.concatenate([ns, T[:, None], V[:, None]], axis=1), P[:, None], constantspecies)
     dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
     dom._p_default = dom.p.copy()
     return dom

@@ -31,6 +31,8 @@ class Simulation:
         c = d.cond[self.r]
         if d.kind == L.DOMAIN_CONSTANT_V:
             return y[Ns], y[Ns + 1], c[0]
+        if d.kind == L.DOMAIN_CONSTANT_P:
+            return y[Ns], c[0], y[Ns + 1]
         if d.kind == L.DOMAIN_CONSTANT_TP:
             return c[0], c[1], y[Ns]
         if d.kind == L.DOMAIN_CONSTANT_TV:
@@ -50,7 +52,7 @@ class Simulation:
         """Total moles: P*V/(R*T) for gas domains, sum(ns) otherwise (src/Domain.jl:919,1068,1516)."""
         y = self.y(t)
         T, P, V = self._TPV(y)
-        if self.domain.kind in (L.DOMAIN_CONSTANT_V, L.DOMAIN_CONSTANT_TP):
+        if self.domain.kind in (L.DOMAIN_CONSTANT_V, L.DOMAIN_CONSTANT_TP, L.DOMAIN_CONSTANT_P):
             return P * V / (R * T)
         return float(np.sum(y[:self.domain.phase.Ns]))
 
@@ -118,7 +120,7 @@ def ignition_delay(sol: Solution, min_rise: float = 400.0) -> np.ndarray:
     ts[argmax(diff(T.(ts)))], src/TestReactors.jl:307-308); NaN for reactors whose temperature rose less
     than `min_rise` K by t_end (no ignition)."""
     dom = sol.reactor.domain
-    assert dom.kind == L.DOMAIN_CONSTANT_V
+    assert dom.kind in (L.DOMAIN_CONSTANT_V, L.DOMAIN_CONSTANT_P)
     Ti = dom.phase.Ns
     out = sol.idt.copy()
     out[(sol.yend[:, Ti] - sol.reactor.y0[:, Ti]) < min_rise] = np.nan

@@ -1,0 +1,57 @@
+"""Oracle pins for the ConstantPDomain (adiabatic, constant pressure): the reference's own golden ignition delay of the
+ethane mechanism (falloff / third-body kinetics), IDT = 0.07324954954380769 s at abstol 1e-16 / reltol 1e-6
+(src/TestReactors.jl:344-361), and its analytic-vs-AD Jacobian criteria (:363-371)."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import cpu_oracle as co
+from oracle import rms_oracle as ro
+
+IC = {"T": 1000.0, "P": 2.0e5, "ethane": 1.0, "Ar": 1.0, "O2": 3.5}
+G = np.load(cases.ROOT / "tests" / "golden" / "constp_vectors.npz")
+
+
+@pytest.fixture(scope="module")
+def dom():
+    d = ro.readinput(cases.fixture("ethane"))
+    return ro.ConstantPDomain(ro.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"]), IC)
+
+
+def test_reference_ignition_delay_golden(dom):
+    ig = dom.phase
+    ts = np.exp(np.linspace(np.log(1e-15), np.log(0.2), 10000))
+    r = co.CpuMech(ig).solve("ConstantP", dom.y0[None], dom.cond[None], 1.0, 1e-6, 1e-16, p=dom.p, tsave=ts, nthreads=1)
+    assert r["status"][0] == 0
+    idt = ts[np.argmax(np.diff(r["ysave"][0][:, ig.Ns]))]
+    assert idt == pytest.approx(0.07324954954380769, rel=1e-5)
+    # the same grid point at tight tolerance: the golden is not an artefact of the loose one
+    r2 = co.CpuMech(ig).solve("ConstantP", dom.y0[None], dom.cond[None], 1.0, 1e-10, 1e-20, p=dom.p, tsave=ts, nthreads=1)
+    assert ts[np.argmax(np.diff(r2["ysave"][0][:, ig.Ns]))] == idt
+
+
+def test_analytic_jacobians_against_derivative_of_the_rhs(dom):
+    """jacobiany vs the derivative of the complete RHS, jacobianp vs the derivative w.r.t. p: the reference's criterion
+    |a - b| <= 1e-4 |b| + 1e-16 (src/TestReactors.jl:366,370), here met to 1e-10."""
+    y = G["y"][0]
+    J = ro.jacobiany(dom, y, 0.0, dom.p)
+    Jc = ro.jacobiany_complexstep(dom, y, 0.0, dom.p)
+    assert np.all(np.abs(J - Jc) <= 1e-10 * np.abs(Jc) + 1e-10 * np.abs(Jc).max(axis=0, keepdims=True))
+    Jp = ro.jacobianp(dom, y, 0.0, dom.p)
+    Jpc = np.zeros_like(Jp)
+    for k in range(Jp.shape[1]):
+        pc = dom.p.astype(complex)
+        pc[k] += 1e-30j
+        Jpc[:, k] = ro.dydtreactor(dom, y.astype(complex), 0.0, pc).imag / 1e-30
+    assert np.all(np.abs(Jp - Jpc) <= 1e-4 * np.abs(Jpc) + 1e-16)
+
+
+def test_cpp_port_matches_numpy_oracle(dom):
+    cm = co.CpuMech(dom.phase)
+    ys = G["y"]
+    cond = np.repeat(dom.cond[None], len(ys), axis=0)
+    f = cm.dydt("ConstantP", ys, cond, dom.p)
+    J = cm.jac("ConstantP", ys, cond, dom.p)
+    for k in range(len(ys)):
+        assert cases.err_dydt(f[k], G["f"][k]) < 1e-12
+        assert cases.err_jac(J[k], G["J"][k]) < 1e-12
