@@ -92,3 +92,21 @@ def test_constp_trajectory_and_ensemble(dom, odom):
     assert np.all(s2.yend[:, Ns] > T0 + 1500.0)
     # ideal gas at constant pressure: V_end = N_end*R*T_end/P
     np.testing.assert_allclose(s2.yend[:, Ns + 1], s2.yend[:, :Ns].sum(axis=1) * 8.314 * s2.yend[:, Ns] / P, rtol=1e-5)
+
+
+def test_constp_reference_transitory_sensitivity_golden(dom):
+    """The reference's 160 transitory-sensitivity goldens (src/TestReactors.jl:373-382) recomputed from the CUDA path's
+    state y(0.01), jacobiany and jacobianp (the matrix exponential and the normalisation are host post-processing, as in the
+    reference)."""
+    from oracle import transitory as tr
+    gold = np.loadtxt(cases.ROOT / "tests" / "golden" / "transitory_ethane_reference.txt")
+    gdom, y0, p = dom
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.01), p=p), abstol=1e-16, reltol=1e-6)
+    y = sol.yend[0]
+    one = rb.Domain(gdom.kind, gdom.phase, y[None], gdom.cond)
+    one.p, one._p_default = gdom.p, gdom._p_default
+    Jy, Jp = one.jacobiany(y[None], p)[0], one.jacobianp(y[None], p)[0]
+    dSdt, tau = tr.transitorysensitivitiesfulltrapezoidal(Jy, Jp, y, p, gdom.phase.Ns)
+    row = dSdt[gdom.phase.names.index("ethane"), :]
+    ok = np.abs(row - gold) <= 1e-4 * np.abs(gold) + 1e-16
+    assert ok.sum() >= 159 and np.all(np.abs(row - gold) <= 2e-4 * np.abs(gold) + 1e-16)
