@@ -57,6 +57,23 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _issue_roofline(mean_steps, n, t_kernel, clocks, device):
+    """The bound that actually limits the solve kernel: warp-instruction issue.  Warp instructions per accepted step come from the
+    committed ncu capture (smsp__inst_executed.sum / reactors / steps, profiles/r01_solve_kernel_by_function_e.txt); the peak is
+    SMs x 4 schedulers x one instruction per cycle at the SM clock sampled during the timed region."""
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+        per_step = 5612.0
+        ach = per_step * mean_steps * n / t_kernel
+        peak = sms * 4 * float(mhz) * 1e6
+        return {"achieved_ginst_s": ach / 1e9, "peak_ginst_s": peak / 1e9, "frac": ach / peak, "warp_instructions_per_step": per_step,
+                "source": "profiles/r01_solve_kernel_by_function_e.txt (ncu source page)"}
+    except Exception as exc:
+        return {"achieved_ginst_s": None, "peak_ginst_s": None, "frac": None, "source": f"unavailable: {exc}"}
+
+
 def _ncu_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of one solve-kernel launch from the committed `ncu --set full` capture
     (profiles/r01_solve_kernel_traffic.json); only valid for the launch size it was captured at, otherwise None."""
@@ -342,6 +359,7 @@ def run_ours(args):
                                  "not HBM bound (SURVEY 8d); see roofline_fp64 and evals"},
             "roofline_fp64": {"achieved_tflops": ach_tf, "peak_tflops": fp64_peak, "frac": ach_tf / fp64_peak if fp64_peak > 0 else None,
                               "flops_per_solve": flops, "peak_source": "rmsb_fp64_peak_tflops (DFMA microbenchmark, this run)"},
+            "roofline_issue": _issue_roofline(mean["n_steps"], n, t_kernel, clocks, local),
             "evals": {"n": ne,
                       "dydt": {"evals_per_s": ne / t_dydt, "GBps": b_dydt * ne / t_dydt / 1e9, "frac_hbm": b_dydt * ne / t_dydt / 1e9 / hbm_peak,
                                "bytes_per_eval": b_dydt},

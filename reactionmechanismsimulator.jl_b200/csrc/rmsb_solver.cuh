@@ -205,6 +205,51 @@ __device__ __noinline__ bool lu_factor_warp(Ws w, double c, int lane) {
     return ok;
 }
 
+// One row per lane (Ny <= 32): same algorithm, same arithmetic, with the row / column pointers bumped instead of recomputed.
+template <>
+__device__ __noinline__ bool lu_factor_warp<1>(Ws w, double c, int lane) {
+    const int LD = w.LD, Ny = w.Ny;
+    double* A = w.LU();
+    const double* J = w.J();
+    int* perm = w.perm();
+    double* dinv = w.dinv();
+    for (int idx = lane; idx < Ny * LD; idx += 32) {
+        int col = idx / LD, row = idx - col * LD;
+        if (row < Ny) A[idx] = ((row == col) ? 1.0 : 0.0) - c * J[idx];
+    }
+    const bool act = lane < Ny;
+    if (act) perm[lane] = lane;
+    bool ok = true;
+    double* ck = A + lane;                       // my row's entry in column k
+    for (int k = 0; k < Ny; ++k, ck += LD) {
+        __syncwarp();
+        const unsigned key = (act && lane >= k) ? (unsigned)__double2hiint(fabs(*ck)) + 1u : 0u;
+        const unsigned mx = __reduce_max_sync(FULL, key);
+        const unsigned vote = __ballot_sync(FULL, key == mx && key != 0u);
+        const int pr = __ffs(vote) - 1;
+        if (pr != k) {
+            if (act) { double* pa = A + k + lane * LD; double* pb = A + pr + lane * LD; double t = *pa; *pa = *pb; *pb = t; }
+            if (lane == 0) { int t = perm[k]; perm[k] = perm[pr]; perm[pr] = t; }
+            __syncwarp();
+        }
+        double piv = A[k + k * LD];
+        if (piv == 0.0 || !isfinite(piv)) { ok = false; piv = 1.0; }
+        const double inv = 1.0 / piv;
+        if (lane == 0) dinv[k] = inv;
+        const bool below = act && lane > k;
+        double l = 0.0;
+        if (below) { l = *ck * inv; *ck = l; }
+        const double* pk = A + k + (k + 1) * LD;  // a_kj
+        double* pi = ck + LD;                     // a_ij
+        for (int j = k + 1; j < Ny; ++j, pk += LD, pi += LD) {
+            const double akj = *pk;
+            if (below) *pi -= l * akj;
+        }
+    }
+    __syncwarp();
+    return ok;
+}
+
 // Solve (I - cJ) x = b with the factors above; b in w.xs on entry (synchronised), x returned in registers.
 template <int R>
 __device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
@@ -251,25 +296,59 @@ __device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
     __syncwarp();
 }
 
+// One row per lane (Ny <= 32): the same substitution with the column pointer bumped instead of recomputed and no slot loops --
+// half the instructions of the generic version on the 14-variable headline case.
+template <>
+__device__ __noinline__ void lu_solve_warp<1>(Ws w, int lane) {
+    const int LD = w.LD, Ny = w.Ny;
+    const double* col = w.LU() + lane;         // row `lane`, column 0
+    double* xs = w.xs();
+    const bool act = lane < Ny;
+    double b = act ? xs[w.perm()[lane]] : 0.0;
+    const double di = act ? w.dinv()[lane] : 1.0;
+    for (int k = 0; k < Ny - 1; ++k, col += LD) {                 // forward, unit lower triangle
+        const double xk = __shfl_sync(FULL, b, k);
+        if (act && lane > k) b -= *col * xk;
+    }
+    for (int k = Ny - 1; k >= 0; --k, col -= LD) {                 // backward (col starts at column Ny-1)
+        if (lane == k) b *= di;
+        const double xk = __shfl_sync(FULL, b, k);
+        if (lane < k) b -= *col * xk;
+    }
+    __syncwarp();
+    if (act) xs[lane] = b;
+    __syncwarp();
+}
+
 // ---- change_D: rescale the backward differences for a step-size ratio `factor` -------------------
 // D_new[j] = sum_i (R(factor) U)[i][j] D[i], R[i][k] = prod_{l=1..i} (l-1-factor*k)/l, U = R(1).
 // The 6x6 product is formed cooperatively (one entry per lane) in w.ru.
 __device__ __noinline__ void compute_ru(Ws w, double factor, int lane) {
     double* ru = w.ru();
-    for (int e = lane; e < 36; e += 32) {
-        int i = e / 6, j = e - 6 * i;
-        double acc = 0.0;
-        for (int k = 0; k <= j; ++k) {
-            double rik;
-            if (k == 0) rik = (i == 0) ? 1.0 : 0.0;
-            else {
-                rik = 1.0;
-                for (int l = 1; l <= i; ++l) rik *= ((double)(l - 1) - factor * (double)k) * c_invl[l];
-            }
-            acc += rik * c_U[k * 6 + j];
-        }
-        ru[e] = acc;
+    // lanes 0..5 build column k of R(factor) incrementally, R[i][k] = R[i-1][k] * (i-1-factor*k)/i, into ru; every lane
+    // then reads its row of R and forms its entry (i, j) of R*U = sum_{k<=j} R[i][k] * U[k][j]
+    if (lane < 6) {
+        const double fk = factor * (double)lane;
+        double r = 1.0;
+        ru[lane] = r;
+#pragma unroll
+        for (int i = 1; i < 6; ++i) { r *= ((double)(i - 1) - fk) * c_invl[i]; ru[i * 6 + lane] = r; }
     }
+    __syncwarp();
+    double acc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int e = lane + 32 * pass;
+        if (e < 36) {
+            const int i = e / 6, j = e - 6 * i;
+            double a = 0.0;
+            for (int k = 0; k <= j; ++k) a += ru[i * 6 + k] * c_U[k * 6 + j];
+            acc[pass] = a;
+        }
+    }
+    __syncwarp();
+    ru[lane] = acc[0];
+    if (lane < 4) ru[lane + 32] = acc[1];
     __syncwarp();
 }
 
