@@ -429,11 +429,14 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
     }
 }
 
+// Resident blocks per SM the register allocation is sized for.  The kernel is latency bound (instruction fetch, dependent
+// shared-memory chains): for one row per lane (Ny <= 32) 4 blocks of 4 warps at 128 registers run 26 % faster than 2 blocks at
+// 255 (profiles/r01_configs.txt); the wider kernels are limited to one block by their shared-memory Jacobians anyway.
 #ifndef RMSB_SOLVE_MINBLOCKS
-#define RMSB_SOLVE_MINBLOCKS 1
+#define RMSB_SOLVE_MINBLOCKS 4
 #endif
 template <int R>
-__global__ void __launch_bounds__(128, RMSB_SOLVE_MINBLOCKS) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
+__global__ void __launch_bounds__(128, (R == 1 ? RMSB_SOLVE_MINBLOCKS : 1)) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Ws w = make_ws(warp, ws_per_warp, a.Ny);
@@ -447,8 +450,11 @@ __global__ void __launch_bounds__(128, RMSB_SOLVE_MINBLOCKS) solve_kernel(const 
 }
 
 // forward sensitivities ride on the same integrator (bdf_solve_warp<R, true>)
+#ifndef RMSB_SENS_MINBLOCKS
+#define RMSB_SENS_MINBLOCKS 1
+#endif
 template <int R>
-__global__ void __launch_bounds__(128, 1) sens_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
+__global__ void __launch_bounds__(128, (R == 1 ? RMSB_SENS_MINBLOCKS : 1)) sens_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Ws w = make_ws(warp, ws_per_warp, a.Ny, 2);
