@@ -151,7 +151,9 @@ typedef struct rmsb_solve_opts {
     int32_t idt_index;       /* 0-based y index whose max d/dt defines idt; -1 = domain default (T) */
     double  first_step;      /* 0 = automatic                                                      */
     int32_t warps_per_block; /* 0 = automatic                                                      */
-    int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis */
+    int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis;
+                              * bit 2 / bit 3 (diagnostics): do not impose the unit rows of inert species / recompute the step as
+                              * fl(t+h)-t like SciPy; bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
 } rmsb_solve_opts;
 
 /* ---- library ----------------------------------------------------------------------------- */

@@ -28,6 +28,7 @@ struct MechDesc
     eff_ptr::Ptr{Int32}; eff_species::Ptr{Int32}; eff_value::Ptr{Float64}
     reversible::Ptr{UInt8}; forwardable::Ptr{UInt8}; radius::Ptr{Float64}; diff_radius::Ptr{Float64}
     viscosity_kind::Int32; viscosity_params::NTuple{5,Float64}
+    species_phase::Ptr{Int32}; rxn_domain::Ptr{Int32}      # two-phase (gas + surface + interface) systems only, else C_NULL
 end
 
 struct Stats
@@ -41,7 +42,7 @@ struct SolveOpts
 end
 
 const PHASE_GAS, PHASE_LIQUID, PHASE_SURFACE = Int32(0), Int32(1), Int32(2)
-const DOMAIN_V, DOMAIN_TP, DOMAIN_TV, DOMAIN_TAPHI = Int32(0), Int32(1), Int32(2), Int32(3)
+const DOMAIN_V, DOMAIN_TP, DOMAIN_TV, DOMAIN_TAPHI, DOMAIN_COUPLED_TP_TAPHI, DOMAIN_P = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4), Int32(5)
 const KIN = (ARRHENIUS_VEC=0, ARRHENIUS=1, MULTIARRHENIUS=2, PLOG_VEC=3, PLOG=4, MULTIPLOG=5, THIRDBODY=6, LINDEMANN=7, TROE=8, CHEBYSHEV_VEC=9)
 
 lasterror() = unsafe_string(ccall((:rmsb_last_error, LIB), Cstring, ()))
@@ -109,7 +110,7 @@ function Mech(phase; device::Integer=0)
     desc = Ref(MechDesc(sizeof(MechDesc), kind, Ns, Nr, hasproperty(phase, :sitedensity) ? phase.sitedensity : 0.0,
         Int32(phase.diffusionlimited), maxr, pointer(nr), pointer(nc), pointer(tmax), pointer(coefs), pointer(rx), pointer(ktype),
         pointer(koff), pointer(kpar), pointer(effptr), pointer(effspc), pointer(effval), pointer(rev), pointer(fwd),
-        pointer(radius), pointer(diffr), visc, vp))
+        pointer(radius), pointer(diffr), visc, vp, Ptr{Int32}(C_NULL), Ptr{Int32}(C_NULL)))   # single-phase mechanism
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep check(ccall((:rmsb_mech_create, LIB), Cint, (Ref{MechDesc}, Cint, Ref{Ptr{Cvoid}}), desc, device, h))   # rmsb_mech_create
     m = Mech(h[], keep, Ns, Nr)
@@ -119,6 +120,7 @@ end
 
 # ---- domain -> (kind, cond, constant species) -----------------------------------------------------------
 domainkind(d::ConstantVDomain) = (DOMAIN_V, Float64[d.V])
+domainkind(d::ConstantPDomain) = (DOMAIN_P, Float64[d.P])
 domainkind(d::ConstantTPDomain) = (DOMAIN_TP, Float64[d.T, d.P])
 domainkind(d::ConstantTVDomain) = (DOMAIN_TV, Float64[d.T, d.V])
 domainkind(d::ConstantTAPhiDomain) = (DOMAIN_TAPHI, Float64[d.T, d.A])
@@ -147,6 +149,46 @@ function jac_batch(mech::Mech, domain, Y::Matrix{Float64}, cond::Matrix{Float64}
         (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}),
         mech.handle, kind, n, Y, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), out))
     out
+end
+
+"parameter Jacobians, Ny x (Ns+Nr) x n, Jp[eqn, par, r] (== jacobianp!'s layout, src/Domain.jl:3095-3485)"
+function jacp_batch(mech::Mech, domain, Y::Matrix{Float64}, cond::Matrix{Float64}; p=domain.p)
+    kind, _ = domainkind(domain)
+    Ny, n = size(Y); Np = length(domain.phase.species) + length(domain.phase.reactions); out = zeros(Ny, Np, n)
+    cs = Int32.(domain.constantspeciesinds)
+    pp, ps = domain isa ConstantTVDomain ? (pointer(p), 0) : devicep(domain, p)      # ConstantTV needs p itself (diffusion-limit chain rule)
+    GC.@preserve p check(ccall((:rmsb_jacp_batch, LIB), Cint,                                                                 # rmsb_jacp_batch
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}),
+        mech.handle, kind, n, Y, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), out))
+    out
+end
+
+"""
+Forward sensitivities of many reactors in ONE call (rmsb_sens_batch): what `Reactor(...; forwardsensitivities=true)` + `solve`
++ `extract_local_sensitivities(sol, t)` (src/Reactor.jl:63-75, src/TestReactors.jl:239) or `threadedsensitivities(react)`
+(src/ThreadedSensitivities.jl:15-79) compute one reactor / one parameter at a time.  Returns (yend[Ny,n], S[Ny,Np,n]) at the
+end time and, with `saveat`, (ysave[Ny,k,n], ssave[Ny,Np,k,n]).
+"""
+function sens_batch(reactors::Vector{<:RMS.Reactor}; device=0, abstol=1e-6, reltol=1e-3, saveat=Float64[], max_steps=500000)
+    r1 = reactors[1]; dom = r1.domain; mech = mechfor(dom.phase, device)
+    kind, _ = domainkind(dom)
+    n, Ny = length(reactors), length(r1.y0); Np = length(dom.phase.species) + length(dom.phase.reactions)
+    Y0 = hcat((r.y0 for r in reactors)...)
+    cond = hcat((domainkind(r.domain)[2] for r in reactors)...)
+    tend = Float64[r.tspan[2] for r in reactors]
+    ts = collect(Float64, saveat); nsave = length(ts)
+    ysave = zeros(Ny, nsave, n); ssave = zeros(Ny, Np, nsave, n); yend = zeros(Ny, n); send = zeros(Ny, Np, n)
+    status = zeros(Int32, n); stats = Vector{Stats}(undef, n)
+    opts = Ref(SolveOpts(sizeof(SolveOpts), max_steps, 5, -1, 0.0, 0, 0))
+    cs = Int32.(dom.constantspeciesinds)
+    pp, ps = dom isa ConstantTVDomain ? (pointer(r1.p), 0) : devicep(dom, r1.p)
+    GC.@preserve r1 check(ccall((:rmsb_sens_batch, LIB), Cint,                                                                  # rmsb_sens_batch
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Int32, Ptr{Float64}, Float64, Float64,
+         Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Stats}, Ref{SolveOpts}),
+        mech.handle, kind, n, Y0, cond, pp, ps, isempty(cs) ? C_NULL : cs, length(cs), tend, reltol, abstol,
+        nsave, nsave > 0 ? ts : C_NULL, nsave > 0 ? ysave : C_NULL, nsave > 0 ? ssave : C_NULL, yend, send, status, stats, opts))
+    all(status .== 0) || @warn "rmsb_sens_batch: $(count(!=(0), status)) reactors did not reach t_end"
+    (yend, send, ysave, ssave, status)
 end
 
 # ---- solve ------------------------------------------------------------------------------------------------------
