@@ -1,0 +1,78 @@
+"""C-ABI edge cases through ctypes on a GPU box: empty batches, bad arguments, per-reactor failure codes instead of global
+aborts, NaN inputs, shared / per-reactor parameter strides -- the error behaviour the header promises (include/rmsb200.h)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import rmsb200 as rb
+from rmsb200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dom():
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return cases.product_domain("superminimal_V")
+
+
+def test_empty_batch_is_a_no_op(dom):
+    gdom, y0, p = dom
+    lib = L.lib()
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, gdom.kind, 0, None, None, None, 0, None, 0, None) == 0
+    assert lib.rmsb_solve_batch(gdom.phase.handle, gdom.kind, 0, None, None, None, 0, None, 0, None, 1e-6, 1e-16, 0, None, None,
+                                None, None, None, None, None) == 0
+
+
+def test_bad_arguments_return_codes_and_messages(dom):
+    gdom, y0, p = dom
+    lib = L.lib()
+    y = np.ascontiguousarray(gdom.y0)
+    out = np.empty_like(y)
+    assert lib.rmsb_dydt_batch(None, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(out)) == -1
+    assert b"null mechanism" in lib.rmsb_last_error()
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, 77, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(out)) == -1
+    assert b"domain kind" in lib.rmsb_last_error()
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, gdom.kind, 1, None, L.ptr(gdom.cond), None, 0, None, 0, L.ptr(out)) == -1
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), L.ptr(np.ones(29)), 7, None, 0, L.ptr(out)) == -1
+    assert b"p_stride" in lib.rmsb_last_error()
+    # a gas mechanism cannot be a surface domain, and the coupled domain needs a two-phase descriptor
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, L.DOMAIN_CONSTANT_TAPHI, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(out)) == -1
+    assert lib.rmsb_dydt_batch(gdom.phase.handle, L.DOMAIN_COUPLED_TP_TAPHI, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(out)) == -1
+    te, st = np.array([0.1]), np.zeros(1, dtype=np.int32)
+    assert lib.rmsb_solve_batch(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(te), -1.0, 1e-16,
+                                0, None, None, None, None, L.ptr(st), None, None) == -1            # rtol must be positive
+    with pytest.raises(rb.RMSBError):
+        L.check(-3)
+
+
+def test_failures_are_per_reactor(dom):
+    """One reactor with a NaN state and one that runs out of steps do not disturb their neighbours."""
+    gdom, y0, p = dom
+    ys = np.repeat(gdom.y0, 4, axis=0)
+    ys[1, 4] = np.nan
+    ens = rb.Domain(gdom.kind, gdom.phase, ys, np.repeat(gdom.cond, 4, axis=0))
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 0.05)), abstol=1e-16, reltol=1e-6)
+    assert list(sol.status) == [L.SOLVE_OK, 3, L.SOLVE_OK, L.SOLVE_OK] and sol.retcode[1] == "Unstable"
+    assert np.array_equal(sol.yend[0], sol.yend[2]) and np.isfinite(sol.yend[[0, 2, 3]]).all()
+    few = rb.solve(rb.Reactor(ens, None, (0.0, 0.05)), rb.RMSB200(max_steps=20), abstol=1e-16, reltol=1e-6)
+    assert list(few.status) == [1, 3, 1, 1] and few.retcode[0] == "MaxIters" and np.all(few.stats["n_steps"][[0, 2, 3]] == 20)
+
+
+def test_parameter_strides(dom):
+    gdom, y0, p = dom
+    ys = cases.states("superminimal_V", gdom.y0[0], gdom.phase.Ns, "ConstantV")
+    ens = rb.Domain(gdom.kind, gdom.phase, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    pp = cases.parameter_vector("superminimal_V", gdom.phase.Ns, gdom.phase.Nr)
+    per = np.repeat(pp[None], len(ys), axis=0)
+    per[3, gdom.phase.Ns + 2] *= 3.0
+    f_shared, f_per = ens.dydt(ys, pp), ens.dydt(ys, per)
+    assert np.array_equal(f_shared[[0, 1, 2, 4, 5]], f_per[[0, 1, 2, 4, 5]]) and not np.array_equal(f_shared[3], f_per[3])
+    s1 = rb.solve(rb.Reactor(ens, None, (0.0, 1e-3), p=per), abstol=1e-16, reltol=1e-8)
+    one = rb.Domain(gdom.kind, gdom.phase, ys[3:4], gdom.cond)
+    s2 = rb.solve(rb.Reactor(one, None, (0.0, 1e-3), p=per[3]), abstol=1e-16, reltol=1e-8)
+    assert np.array_equal(s1.yend[3], s2.yend[0])
