@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -537,6 +538,230 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
     }
 }
 
+// ---- dydt with ONE THREAD PER REACTOR for small variable-k mechanisms (ConstantV / ConstantP, Ns <= 32, Nr <= 64) ----------------
+// The warp-per-reactor evaluation spends ~1000 warp instructions per state on a 12-species mechanism with 14 of 32 lanes busy; here
+// every lane evaluates its own state with the same scalar routines (thermo, rate coefficients, Kc, mass action) in the reference's
+// own summation order, ~100 warp instructions per state.  States are staged through shared memory so that global loads / stores
+// stay coalesced; the per-thread species / reaction arrays live in (lane-interleaved) local memory.
+constexpr int TPR_MAXNS = 32, TPR_MAXNR = 64, TPR_THREADS = 128;
+constexpr int TPR_J_MAXNY = 16, TPR_MAXDT = 160;       // Jacobian variant: the dense Ny x Ny block lives in local memory
+
+struct TprKeep {        // what the Jacobian needs from the value pass
+    double kf[TPR_MAXNR], kr[TPR_MAXNR], us[TPR_MAXNS], cp[TPR_MAXNS], cs[TPR_MAXNS];
+    double T, P, V, Nt, C, Cv, dotU;
+};
+
+// dy/dt of one reactor by one thread.  y: [ns; T; P] (ConstantV, cond = V) or [ns; T; V] (ConstantP, cond = P).
+// N = Dual2 seeds d/dT (and d/dP for ConstantV) exactly as rhs_v<Dual2> does.
+template <class N, bool ISP>
+__device__ __forceinline__ void rhs_thread(const double* y, double cond, const double* p, const int* constspc, int nconst, N* f, TprKeep* keep) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr;
+    N g[TPR_MAXNS], u[TPR_MAXNS], q[TPR_MAXNR];
+    double cs[TPR_MAXNS];
+    const double V = ISP ? y[Ns + 1] : cond;
+    const double invV = 1.0 / V;
+    N T = seed<N>(y[Ns], 0), P = ISP ? N(cond) : seed<N>(y[Ns + 1], 1);
+    TPow<N> tp(T);
+    N RT = RMSB_R * T;
+    N invRT = tp.T4 * RMSB_INV_R;
+    N Nt = P * V * invRT, C = P * invRT;
+    N cpsum = 0.0;
+    for (int s = 0; s < Ns; ++s) {
+        N cp, h, sr;
+        nasa_hscp(s, tp, val(T), cp, h, sr);
+        if (p) h = h + p[s] * invRT;
+        u[s] = ISP ? h * RT : (h - 1.0) * RT;
+        g[s] = h - sr;
+        cs[s] = y[s] * invV;
+        cpsum = cpsum + cp * y[s];
+        if (keep) { keep->us[s] = val(u[s]); keep->cp[s] = val(cp); keep->cs[s] = cs[s]; }
+    }
+    KinEnv<N> e;
+    e.T = T; e.logT = tp.T6; e.RT = RT; e.invRT = invRT; e.P = P;
+    N logC0 = RMSB_LOG_1E5_OVER_R - tp.T6;
+    for (int j = 0; j < Nr; ++j) {
+        N kf;
+        if (G(m.ktype, j) == RMSB_KIN_ARRHENIUS_VEC) kf = arr_vec(m.kpar + G(m.koff, j), e);
+        else kf = eval_kin<N>(j, &e, ceff_of(j, C, y, V), false);
+        N ex = 0.0;
+        for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex = ex + G(m.kc_coef, k) * g[G(m.kc_spc, k)];
+        ex = ex + G(m.nrp, j) * logC0;
+        N kr = kf * dexp(-ex);
+        kf = kf * G(m.fwd, j); kr = kr * G(m.rev, j);
+        if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }
+        if (keep) { keep->kf[j] = val(kf); keep->kr[j] = val(kr); }
+        q[j] = net_rate<N>(j, kf, kr, cs);
+    }
+    N usum = 0.0, nsum = 0.0;
+    for (int s = 0; s < Ns; ++s) {
+        N acc = 0.0;
+        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+            int jr = G(m.sr_rxn, k);
+            N qv = q[jr & 0x7fffffff];
+            acc = (jr < 0) ? acc - qv : acc + qv;
+        }
+        N dn = acc * V;
+        f[s] = dn;
+        usum = usum + u[s] * dn;
+        nsum = nsum + dn;
+    }
+    N dT = ISP ? -usum / (RMSB_R * cpsum) : -usum / (RMSB_R * (cpsum - Nt));
+    f[Ns] = dT;
+    f[Ns + 1] = ISP ? nsum * RT / P + dT * V * tp.T4 : nsum * RT * invV + P * tp.T4 * dT;
+    for (int k = 0; k < nconst; ++k) f[constspc[k] - 1] = N(0.0);
+    if (keep) {
+        keep->T = val(T); keep->P = val(P); keep->V = V; keep->Nt = val(Nt); keep->C = val(C);
+        keep->Cv = val(cpsum) * (RMSB_R / val(Nt)) - RMSB_R; keep->dotU = val(usum);
+    }
+}
+
+template <bool ISP>
+__global__ void __launch_bounds__(TPR_THREADS) dydt_tpr_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a) {
+    stage_mech(mp);
+    const int Ny = a.Ny, LDt = Ny | 1, tid = threadIdx.x;
+    double* tile = smem_ws + MECH_DOUBLES;                       // [TPR_THREADS][LDt]
+    for (int64_t base = (int64_t)blockIdx.x * TPR_THREADS; base < a.n; base += (int64_t)gridDim.x * TPR_THREADS) {
+        const int cnt = (int)((a.n - base < TPR_THREADS) ? a.n - base : TPR_THREADS);
+        for (int idx = tid; idx < cnt * Ny; idx += TPR_THREADS) { int r = idx / Ny; tile[r * LDt + (idx - r * Ny)] = a.y[base * Ny + idx]; }
+        __syncthreads();
+        if (tid < cnt) {
+            const int64_t ir = base + tid;
+            double* row = tile + tid * LDt;
+            double y[TPR_MAXNS + 2], f[TPR_MAXNS + 2];
+            for (int i = 0; i < Ny; ++i) y[i] = row[i];
+            rhs_thread<double, ISP>(y, a.cond[ir], a.p ? a.p + ir * a.p_stride : nullptr, a.constspc, a.nconst, f, nullptr);
+            for (int i = 0; i < Ny; ++i) row[i] = f[i];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < cnt * Ny; idx += TPR_THREADS) { int r = idx / Ny; a.out[base * Ny + idx] = tile[r * LDt + (idx - r * Ny)]; }
+        __syncthreads();
+    }
+}
+
+// jacobiany! of one reactor by one thread (Ny <= 16): the steps of jac_warp in the same order, dense block in local memory.
+template <bool ISP>
+__global__ void __launch_bounds__(TPR_THREADS) jac_tpr_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a) {
+    stage_mech(mp);
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr, Ny = a.Ny, LDt = Ny | 1, tid = threadIdx.x;
+    double* tile = smem_ws + MECH_DOUBLES;
+    for (int64_t base = (int64_t)blockIdx.x * TPR_THREADS; base < a.n; base += (int64_t)gridDim.x * TPR_THREADS) {
+        const int cnt = (int)((a.n - base < TPR_THREADS) ? a.n - base : TPR_THREADS);
+        for (int idx = tid; idx < cnt * Ny; idx += TPR_THREADS) { int r = idx / Ny; tile[r * LDt + (idx - r * Ny)] = a.y[base * Ny + idx]; }
+        __syncthreads();
+        if (tid < cnt) {
+            const int64_t ir = base + tid;
+            const double* row = tile + tid * LDt;
+            const double* p = a.p ? a.p + ir * a.p_stride : nullptr;
+            double y[TPR_J_MAXNY], f[TPR_J_MAXNY], J[TPR_J_MAXNY * TPR_J_MAXNY], dterm[TPR_MAXDT];
+            TprKeep kp;
+            for (int i = 0; i < Ny; ++i) y[i] = row[i];
+            rhs_thread<double, ISP>(y, a.cond[ir], p, a.constspc, a.nconst, f, &kp);
+            for (int i = 0; i < Ny * Ny; ++i) J[i] = 0.0;
+            // (1) derivative terms, (2) entries in the reference's accumulation order (src/Reactor.jl:899-1366)
+            for (int t = 0; t < m.n_dt; ++t) {
+                int jr = G(m.dt_rxn, t);
+                int j = jr & 0x3fffffff;
+                double v = (double)G(m.dt_mult, t) * ((jr >> 30) ? kp.kr[j] : kp.kf[j]);
+                for (int k = 0; k < 3; ++k) { int s = G(m.dt_oth, 3 * t + k); if (s < 0) break; v *= kp.cs[s]; }
+                dterm[t] = v;
+            }
+            for (int e = 0; e < m.n_je; ++e) {
+                double acc = 0.0;
+                for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
+                    int ti = G(m.jt_idx, k);
+                    double v = dterm[ti & 0x7fffffff];
+                    acc = (ti < 0) ? acc - v : acc + v;
+                }
+                J[G(m.je_row, e) + G(m.je_col, e) * Ny] = acc;
+            }
+            const int Vcol = Ns + 1;
+            if (ISP) {      // (3) V column of the species block (src/Reactor.jl:1368-1413)
+                for (int s = 0; s < Ns; ++s) {
+                    double acc = 0.0;
+                    for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+                        int jr = G(m.sr_rxn, k);
+                        int j = jr & 0x7fffffff;
+                        double df = 0.0, dr = 0.0;
+                        int nre = 0, npr = 0;
+                        double pf = kp.kf[j], pr = kp.kr[j];
+                        for (int qq = 0; qq < 4; ++qq) { int sp = G(m.rx, qq * Nr + j); if (sp < 0) break; pf *= kp.cs[sp]; ++nre; }
+                        for (int qq = 4; qq < 8; ++qq) { int sp = G(m.rx, qq * Nr + j); if (sp < 0) break; pr *= kp.cs[sp]; ++npr; }
+                        if (nre > 1) df = -(double)(nre - 1) * pf;
+                        if (npr > 1) dr = -(double)(npr - 1) * pr;
+                        if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
+                    }
+                    J[s + Vcol * Ny] = acc;
+                }
+            }
+            if (m.n_effrxn > 0) {   // (4) efficiency reactions (src/Domain.jl:2151-2167)
+                KinEnv<double> e;
+                e.T = kp.T; e.logT = log(kp.T); e.RT = RMSB_R * kp.T; e.invRT = 1.0 / (RMSB_R * kp.T); e.P = kp.P;
+                for (int qn = 0; qn < m.n_effrxn; ++qn) {
+                    int j = G(m.effrxn, qn);
+                    double Kc = kp.kf[j] / kp.kr[j];
+                    double acc = 0.0;
+                    for (int k = G(m.eff_ptr, j); k < G(m.eff_ptr, j + 1); ++k) acc += kp.cs[G(m.eff_spc, k)] * G(m.eff_val, k);
+                    double Ceff = kp.C + acc;
+                    double dkdC = dk_dCeff(j, &e, Ceff);
+                    double pa = 1.0, pb = 1.0;
+                    for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pa *= kp.cs[sp]; }
+                    for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pb *= kp.cs[sp]; }
+                    double pf = pa * kp.V, pr = pb * kp.V;
+                    int ne = G(m.eff_ptr, j + 1) - G(m.eff_ptr, j);
+                    int ncol = ne + (ISP ? 1 : 0);
+                    for (int c = 0; c < ncol; ++c) {
+                        int col; double dkf;
+                        if (c < ne) { col = G(m.eff_spc, G(m.eff_ptr, j) + c); dkf = dkdC * (G(m.eff_val, G(m.eff_ptr, j) + c) / kp.V); }
+                        else { col = Vcol; dkf = dkdC * (kp.C - Ceff) / kp.V; }
+                        double dkr = dkf / Kc;
+                        double dvf = dkf * pf, dvr = dkr * pr;
+                        for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * Ny] -= dvf; }
+                        for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * Ny] += dvf; }
+                        for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * Ny] -= dvr; }
+                        for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; J[sp + col * Ny] += dvr; }
+                    }
+                }
+            }
+            // (5) thermodynamic-variable rows
+            if (!ISP) {
+                for (int c = 0; c < Ns; ++c) {          // Domain.jl:2312-2316
+                    double dCv = kp.cp[c] * RMSB_R / kp.Nt, sa = 0.0, sm = 0.0;
+                    for (int i = 0; i < Ns; ++i) { double v = J[i + c * Ny]; sa += kp.us[i] * v; sm += v; }
+                    double jt = -sa / (kp.Nt * kp.Cv) + kp.dotU / (kp.Nt * kp.Cv * kp.Cv) * dCv;
+                    J[Ns + c * Ny] = jt;
+                    J[Ns + 1 + c * Ny] = sm * RMSB_R * kp.T / kp.V + kp.P / kp.T * jt;
+                }
+            } else {
+                const double aCp = kp.Cv + RMSB_R, dTdt = -kp.dotU / (kp.Nt * aCp);      // Domain.jl:2480-2490
+                for (int c = 0; c < Ns + 2; ++c) {
+                    if (c == Ns) continue;
+                    double sa = 0.0, sm = 0.0;
+                    for (int i = 0; i < Ns; ++i) { double v = J[i + c * Ny]; sa += kp.us[i] * v; sm += v; }
+                    double jt = -sa / (kp.Nt * aCp);
+                    if (c < Ns) jt -= dTdt * ((kp.cp[c] * RMSB_R / kp.Nt) / aCp);
+                    J[Ns + c * Ny] = jt;
+                    double jv = sm * RMSB_R * kp.T / kp.P + kp.V / kp.T * jt;
+                    if (c == Ns + 1) jv += dTdt / kp.T;
+                    J[Ns + 1 + c * Ny] = jv;
+                }
+            }
+            // (6) constant species rows
+            for (int k = 0; k < a.nconst; ++k) { int s = a.constspc[k] - 1; for (int c = 0; c < Ny; ++c) J[s + c * Ny] = 0.0; }
+            // (7) T (and P) columns: derivative of the complete RHS
+            {
+                Dual2 fd[TPR_J_MAXNY];
+                rhs_thread<Dual2, ISP>(y, a.cond[ir], p, a.constspc, a.nconst, fd, nullptr);
+                for (int i = 0; i < Ny; ++i) { J[i + Ns * Ny] = fd[i].a; if (!ISP) J[i + (Ns + 1) * Ny] = fd[i].b; }
+            }
+            double* out = a.out + (size_t)ir * Ny * Ny;
+            for (int i = 0; i < Ny * Ny; ++i) out[i] = J[i];
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void gibbs_kernel(const __grid_constant__ DevMech mp, int64_t n, const double* T, int scalar_path, double* G) {
     stage_mech(mp);
     const int Ns = mech().Ns;
@@ -570,12 +795,28 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 // ------------------------------------------------------------------------------------------------
 static int rows_per_lane(int Ny) { return (Ny + 31) / 32; }
 
+// cudaGetDeviceProperties takes milliseconds: query each device once
+static cudaError_t cached_props(int device, cudaDeviceProp* out) {
+    static std::mutex mu;
+    static std::map<int, cudaDeviceProp> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(device);
+    if (it == cache.end()) {
+        cudaDeviceProp p;
+        cudaError_t e = cudaGetDeviceProperties(&p, device);
+        if (e != cudaSuccess) return e;
+        it = cache.emplace(device, p).first;
+    }
+    *out = it->second;
+    return cudaSuccess;
+}
+
 struct LaunchCfg { int wpb; int ws; size_t smem; int blocks_per_sm; int sms; };
 
 template <class K>
 static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int want_wpb, LaunchCfg* cfg) {
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
+    CU(cached_props(h->device, &prop));
     int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, mode);
     size_t per_warp = (size_t)ws * sizeof(double);
     const size_t mech_bytes = (size_t)MECH_DOUBLES * sizeof(double);
@@ -602,7 +843,7 @@ static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, Large
         return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): ConstantTV / ConstantTAPhi domains only (DESIGN.md)");
     if (h->dm.n_effrxn > 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: third-body efficiencies are not built");
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
+    CU(cached_props(h->device, &prop));
     cfg->smem = large_smem_bytes(h->lt.n);
     if (cfg->smem > prop.sharedMemPerBlockOptin) return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the block-per-reactor kernels (shared memory)");
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
@@ -649,6 +890,33 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
     if (a.Ny > 128) {
         if (MODE <= 2) return launch_eval_large<(MODE <= 2 ? MODE : 0)>(h, a, st);
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
+    }
+    if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
+        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096) {
+        // small variable-k mechanisms, large batches: one thread per reactor
+        cudaDeviceProp prop;
+        CU(cached_props(h->device, &prop));
+        const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
+        int64_t blocks = (a.n + TPR_THREADS - 1) / TPR_THREADS, cap = (int64_t)prop.multiProcessorCount * 16;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+        if (a.domain_kind == RMSB_DOMAIN_CONSTANT_P) dydt_tpr_kernel<true><<<grid, TPR_THREADS, smem, st>>>(h->dm, a);
+        else dydt_tpr_kernel<false><<<grid, TPR_THREADS, smem, st>>>(h->dm, a);
+        ++g_launches;
+        CU(cudaGetLastError());
+        return RMSB_OK;
+    }
+    if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
+        h->dm.Nr <= TPR_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096) {
+        cudaDeviceProp prop;
+        CU(cached_props(h->device, &prop));
+        const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
+        int64_t blocks = (a.n + TPR_THREADS - 1) / TPR_THREADS, cap = (int64_t)prop.multiProcessorCount * 16;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+        if (a.domain_kind == RMSB_DOMAIN_CONSTANT_P) jac_tpr_kernel<true><<<grid, TPR_THREADS, smem, st>>>(h->dm, a);
+        else jac_tpr_kernel<false><<<grid, TPR_THREADS, smem, st>>>(h->dm, a);
+        ++g_launches;
+        CU(cudaGetLastError());
+        return RMSB_OK;
     }
     LaunchCfg cfg;
     int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
