@@ -57,6 +57,15 @@ def test_thread_per_reactor_dydt(which):
             assert cases.err_jac(J_big[k], ro.jacobiany(odom, ys[k], 0.0, par)) < 1e-12
 
 
+    # per-reactor parameter rows: only the reactor whose row differs changes
+    per = np.repeat(pp[None], n, axis=0)
+    per[7, ig.Ns + 2] *= 3.0
+    f_shared, f_per = ens.dydt(ys, pp), ens.dydt(ys, per)
+    keep = np.arange(n) != 7
+    assert np.array_equal(f_shared[keep], f_per[keep]) and not np.array_equal(f_shared[7], f_per[7])
+    assert cases.err_dydt(f_per[7], ro.dydtreactor(odom, ys[7], 0.0, per[7])) < 1e-12
+
+
 def ens_chunk(ens, ys):
     sub = rb.Domain(ens.kind, ens.phase, ys, np.repeat(ens.cond[:1], len(ys), axis=0))
     sub.constantspeciesinds = ens.constantspeciesinds
