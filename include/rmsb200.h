@@ -153,7 +153,8 @@ typedef struct rmsb_solve_opts {
     int32_t warps_per_block; /* 0 = automatic                                                      */
     int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis;
                               * bit 2 / bit 3 (diagnostics): do not impose the unit rows of inert species / recompute the step as
-                              * fl(t+h)-t like SciPy; bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
+                              * fl(t+h)-t like SciPy; bit 4 (large-mechanism path): refactorise on every change of h instead of
+                              * keeping the factors while c = h/alpha stays within 30 % (CVODE's dgmax); bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
 } rmsb_solve_opts;
 
 /* ---- library ----------------------------------------------------------------------------- */

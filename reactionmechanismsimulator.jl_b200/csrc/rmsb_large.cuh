@@ -454,6 +454,11 @@ __device__ void large_bdf_solve(const SolveArgs& a, const LargeCtx& c, int64_t i
     const int nls_v = (a.flags >> 8) & 0xff;
     const double nls_coef = ldexp(0.1, -(nls_v == 0 ? 3 : nls_v - 1));
     double crate = 1.0, c_jac = 0.0;
+    // A factorisation costs ~20 triangular solves here, so the factors are kept while c = h/alpha stays within 30 % of the c they
+    // were computed for (CVODE's dgmax rule); the Newton update is scaled by 2/(1 + c/c_lu) as in CVODE to centre the iteration.
+    double c_lu = 0.0;
+    bool jac_new = true;
+    const double dgmax = (a.flags & 16) ? 0.0 : 0.3;           // flags bit 4: refactorise on every change of c (diagnostic)
 
     while (status == RMSB_SOLVE_OK && t < t_end) {
         if (n_steps >= a.max_steps) { status = RMSB_SOLVE_MAX_STEPS; break; }
@@ -483,13 +488,15 @@ __device__ void large_bdf_solve(const SolveArgs& a, const LargeCtx& c, int64_t i
             int n_iter = 0;
             while (!converged) {
                 bool lu_ok = true;
+                if (!lu_valid && !jac_new && c_lu != 0.0 && fabs(cc / c_lu - 1.0) <= dgmax) lu_valid = true;   // keep the factors
                 if (!lu_valid) {
                     if (c_jac == 0.0) c_jac = cc;
                     else if (!current_jac && (cc > JAC_REFRESH_RATIO * c_jac || cc * JAC_REFRESH_RATIO < c_jac)) {
                         large_jac(c, ypred); ++n_jac; current_jac = true; c_jac = cc;
                     }
-                    lu_ok = large_factor(c, cc); lu_valid = true; ++n_lu; crate = 1.0;
+                    lu_ok = large_factor(c, cc); lu_valid = true; ++n_lu; crate = 1.0; c_lu = cc; jac_new = false;
                 }
+                const double gscale = (cc == c_lu) ? 1.0 : 2.0 / (1.0 + cc / c_lu);
                 const double nl_tol = scipy_newton ? newton_tol : fmax(newton_tol, nls_coef / c_ec[order]);
                 VLOOP(i) { dvec[i] = 0.0; ynew[i] = ypred[i]; }
                 __syncthreads();
@@ -509,7 +516,7 @@ __device__ void large_bdf_solve(const SolveArgs& a, const LargeCtx& c, int64_t i
                         VLOOP(i) {
                             bool unit = G(m.inert, i) != 0;
                             for (int q = 0; q < c.d.nconst; ++q) if (c.d.constspc[q] - 1 == i) unit = true;
-                            if (!unit) dy[i] = f[i];
+                            if (!unit) dy[i] = f[i] * gscale;
                         }
                         __syncthreads();
                         double dy_norm = large_norm(c, dy, iw, 1.0);
@@ -532,7 +539,7 @@ __device__ void large_bdf_solve(const SolveArgs& a, const LargeCtx& c, int64_t i
                 if (!converged) {
                     if (current_jac) break;
                     large_jac(c, ypred); ++n_jac; c_jac = cc;
-                    lu_valid = false; current_jac = true;
+                    lu_valid = false; current_jac = true; jac_new = true;
                 }
             }
             if (!converged) {
