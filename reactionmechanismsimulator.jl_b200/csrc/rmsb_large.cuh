@@ -337,18 +337,15 @@ __device__ void large_solve(const LargeCtx& c, const double* b, double* xout) {
     }
     for (int lv = 0; lv < t.n_lvl_u; ++lv) {
         const int rb = G(t.lvl_u_ptr, lv), re = G(t.lvl_u_ptr, lv + 1);
-        bool any = false;
         for (int r = rb + wid; r < re; r += LARGE_WARPS) {
             const int i = G(t.lvl_u_rows, r);
             if (i >= core) continue;
-            any = true;
             const int pd = G(t.diag, i), pe = G(t.row_ptr, i + 1);
             double acc = 0.0;
             for (int p = pd + 1 + lane; p < pe; p += 32) acc += a[p] * x[G(t.col, p)];
             acc = warp_sum(acc);
             if (lane == 0) x[i] = (x[i] - acc) / a[pd];
         }
-        (void)any;
         __syncthreads();
     }
     for (int i = tid; i < n; i += LARGE_THREADS) xout[G(t.perm, i)] = x[i];
