@@ -110,3 +110,25 @@ def test_constp_reference_transitory_sensitivity_golden(dom):
     row = dSdt[gdom.phase.names.index("ethane"), :]
     ok = np.abs(row - gold) <= 1e-4 * np.abs(gold) + 1e-16
     assert ok.sum() >= 159 and np.all(np.abs(row - gold) <= 2e-4 * np.abs(gold) + 1e-16)
+
+
+def test_constp_forward_sensitivities_vs_finite_differences(dom):
+    """Forward sensitivities of the adiabatic constant-pressure reactor (28 states, 160 parameters, R = 1 kernel with five
+    parameter chunks) in the induction period, against central finite differences of the GPU state solution."""
+    gdom, y0, p = dom
+    Ns = gdom.phase.Ns
+    tend = 0.05
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-9)
+    assert sol.retcode == ["Success"] and np.isfinite(sol.sens_end).all()
+    S = sol.sens_end[0]
+    norms = np.abs(S[:, Ns])                                   # sensitivity of T
+    for j in (Ns + int(np.argmax(norms[Ns:])), int(np.argmax(norms[:Ns])), Ns + int(np.argsort(norms[Ns:])[-3])):
+        pj = float(np.asarray(p)[j])
+        h = 1e-4 * abs(pj) if pj != 0.0 else 1e-4 * 8.314 * 1000.0
+        fd = []
+        for sgn in (1.0, -1.0):
+            q = np.array(p, dtype=float)
+            q[j] += sgn * h
+            fd.append(rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=q).ode, abstol=1e-22, reltol=1e-11).yend[0])
+        fd = (fd[0] - fd[1]) / (2.0 * h)
+        assert np.max(np.abs(S[j] - fd)) <= 2e-3 * np.max(np.abs(fd)) + 1e-30
