@@ -280,7 +280,8 @@ int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
  * rmsb_mech_create analyses the Jacobian pattern of mechanisms with more than 128 species once (minimum-degree ordering,
  * fill pattern, dependency levels); dydt / jac / rates / solve then run one thread block per reactor with a sparse LU of
  * I - c*J on that fixed pattern -- the role of the GMRES + ILU path of the reference (src/Reactor.jl:342-382).
- * ConstantTV and ConstantTAPhi domains.  info: [0] n, [1] nnz(L+U), [2] forward levels, [3] backward levels,
+ * ConstantTV, ConstantTAPhi and ConstantTP domains (ConstantTP: the species block bordered by the dense volume row and
+ * column; info describes the y = ns pattern).  info: [0] n, [1] nnz(L+U), [2] forward levels, [3] backward levels,
  * [4] longest row, [5] multiply-adds per factorisation, [6] first row of the dense core, [7] scratch doubles per resident reactor. */
 int rmsb_large_info(const rmsb_mech* mech, int64_t info[8]);
 /* cycle counters of the block-per-reactor solver summed over blocks: [0] rhs, [1] Jacobian, [2] factorisation,

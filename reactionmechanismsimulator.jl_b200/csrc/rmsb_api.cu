@@ -54,7 +54,8 @@ struct rmsb_mech {
     int n_dt = 0, n_je = 0;
     // large-mechanism path (one block per reactor, sparse LU on a fixed pattern): built when Ns > 128
     bool large = false;
-    LargeTables lt{};
+    LargeTables lt{};        // y = ns            (ConstantTV, ConstantTAPhi)
+    LargeTables lt_tp{};     // y = [ns; V]       (ConstantTP): the same block bordered by a dense row and column
     int large_max_row = 0;
     long long large_factor_flops = 0;
 };
@@ -297,26 +298,38 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     UP(jeptr, je_ptr); UP(jerow, je_row); UP(jecol, je_col); UP(jtidx, jt_idx);
     UP(rxdom, rx_dom); UP(nrp2, nrp2); UP(srmid, sr_mid); UP(inert, inert);
     if (Ns > 128 && !dm.coupled) {
-        SparsePattern sp = analyse_pattern(Ns, jerow, jecol);
-        std::vector<int> ldiag(sp.col.size()), lnk(sp.col.size()), amap(jerow.size());
-        for (size_t p = 0; p < sp.col.size(); ++p) {
-            const int k = sp.col[p];
-            ldiag[p] = sp.diag[k];
-            lnk[p] = sp.row_ptr[k + 1] - sp.diag[k] - 1;
-        }
-        for (size_t e = 0; e < jerow.size(); ++e) {
-            amap[e] = find_entry(sp, sp.iperm[jerow[e]], sp.iperm[jecol[e]]);
-            if (amap[e] < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain a Jacobian entry");
-        }
-        LargeTables& lt = h->lt;
-        lt.n = Ns; lt.nnz = (int)sp.col.size();
-        lt.n_lvl_l = (int)sp.lvl_l_ptr.size() - 1; lt.n_lvl_u = (int)sp.lvl_u_ptr.size() - 1; lt.core = sp.core_start;
+        std::vector<int> colptr(Ns + 1, 0);                        // the entry list is sorted by (column, row)
+        for (size_t e = 0; e < jecol.size(); ++e) ++colptr[jecol[e] + 1];
+        for (int c = 0; c < Ns; ++c) colptr[c + 1] += colptr[c];
+        for (int with_v = 0; with_v < 2; ++with_v) {
+            const int n = Ns + with_v;
+            std::vector<int> er(jerow), ec(jecol);
+            if (with_v) for (int i = 0; i <= Ns; ++i) { er.push_back(i); ec.push_back(Ns); er.push_back(Ns); ec.push_back(i); }
+            SparsePattern sp = analyse_pattern(n, er, ec);
+            std::vector<int> ldiag(sp.col.size()), lnk(sp.col.size()), amap(jerow.size()), vcolpos, vrowpos;
+            for (size_t p = 0; p < sp.col.size(); ++p) {
+                const int k = sp.col[p];
+                ldiag[p] = sp.diag[k];
+                lnk[p] = sp.row_ptr[k + 1] - sp.diag[k] - 1;
+            }
+            for (size_t e = 0; e < jerow.size(); ++e) {
+                amap[e] = find_entry(sp, sp.iperm[jerow[e]], sp.iperm[jecol[e]]);
+                if (amap[e] < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain a Jacobian entry");
+            }
+            if (with_v) {
+                for (int s = 0; s < Ns; ++s) vcolpos.push_back(find_entry(sp, sp.iperm[s], sp.iperm[Ns]));
+                for (int c = 0; c <= Ns; ++c) vrowpos.push_back(find_entry(sp, sp.iperm[Ns], sp.iperm[c]));
+            }
+            LargeTables& lt = with_v ? h->lt_tp : h->lt;
+            lt.n = n; lt.ns = Ns; lt.has_v = with_v; lt.nnz = (int)sp.col.size();
+            lt.n_lvl_l = (int)sp.lvl_l_ptr.size() - 1; lt.n_lvl_u = (int)sp.lvl_u_ptr.size() - 1; lt.core = sp.core_start;
 #define UPL(vec, field) if ((rc = upload(h, vec, &lt.field)) != RMSB_OK) return rc
-        UPL(sp.perm, perm); UPL(sp.row_ptr, row_ptr); UPL(sp.col, col); UPL(sp.diag, diag); UPL(ldiag, ldiag); UPL(lnk, lnk);
-        UPL(sp.lvl_l_ptr, lvl_l_ptr); UPL(sp.lvl_l_rows, lvl_l_rows); UPL(sp.lvl_u_ptr, lvl_u_ptr); UPL(sp.lvl_u_rows, lvl_u_rows);
-        UPL(amap, amap);
+            UPL(sp.perm, perm); UPL(sp.row_ptr, row_ptr); UPL(sp.col, col); UPL(sp.diag, diag); UPL(ldiag, ldiag); UPL(lnk, lnk);
+            UPL(sp.lvl_l_ptr, lvl_l_ptr); UPL(sp.lvl_l_rows, lvl_l_rows); UPL(sp.lvl_u_ptr, lvl_u_ptr); UPL(sp.lvl_u_rows, lvl_u_rows);
+            UPL(amap, amap); UPL(vcolpos, vcol_pos); UPL(vrowpos, vrow_pos); UPL(colptr, je_colptr);
 #undef UPL
-        h->large = true; h->large_max_row = sp.max_row; h->large_factor_flops = sp.factor_flops;
+            if (!with_v) { h->large = true; h->large_max_row = sp.max_row; h->large_factor_flops = sp.factor_flops; }
+        }
     }
 #undef UP
     if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
@@ -473,7 +486,7 @@ __device__ __forceinline__ LargeCtx make_large_ctx(const LargeTables& lt, double
     LargeCtx c;
     c.t = lt;
     c.s.base = scratch + (size_t)blockIdx.x * per_block;
-    c.s.n = lt.n; c.s.Nr = m.Nr; c.s.n_dt = m.n_dt; c.s.n_je = m.n_je; c.s.nnz = lt.nnz;
+    c.s.n = lt.n; c.s.Ns = m.Ns; c.s.Nr = m.Nr; c.s.n_dt = m.n_dt; c.s.n_je = m.n_je; c.s.nnz = lt.nnz;
     c.red = smem_ws + MECH_DOUBLES;
     c.ru = c.red + 64;
     c.x = c.ru + 36;
@@ -499,7 +512,7 @@ __global__ void __launch_bounds__(LARGE_THREADS, RMSB_LARGE_MINBLOCKS) large_sol
         c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
         c.d.constspc = a.constspc; c.d.nconst = a.nconst;
         c.d.cond = a.cond + ir * a.ncond;
-        c.T = c.d.cond[0]; c.V = c.d.cond[1];
+        c.T = c.d.cond[0]; c.V = c.d.cond[1]; c.P = c.d.cond[1];
         large_bdf_solve(a, c, (int64_t)ir);
     }
 }
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
         c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
         c.d.constspc = a.constspc; c.d.nconst = a.nconst;
         c.d.cond = a.cond + ir * a.ncond;
-        c.T = c.d.cond[0]; c.V = c.d.cond[1];
+        c.T = c.d.cond[0]; c.V = c.d.cond[1]; c.P = c.d.cond[1];
         double* y = c.s.vec(8);
         for (int i = tid; i < n; i += LARGE_THREADS) y[i] = a.y[ir * n + i];
         __syncthreads();
@@ -531,6 +544,10 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
             for (size_t i = tid; i < (size_t)n * n; i += LARGE_THREADS) J[i] = 0.0;
             __syncthreads();
             for (int e = tid; e < m.n_je; e += LARGE_THREADS) J[G(m.je_row, e) + (size_t)G(m.je_col, e) * n] = c.s.jv()[e];
+            if (lt.has_v) {
+                for (int s = tid; s < lt.ns; s += LARGE_THREADS) J[s + (size_t)lt.ns * n] = c.s.vcol()[s];
+                for (int col = tid; col <= lt.ns; col += LARGE_THREADS) J[lt.ns + (size_t)col * n] = c.s.vrow()[col];
+            }
         } else {
             for (int j = tid; j < m.Nr; j += LARGE_THREADS) { a.out[ir * m.Nr + j] = c.s.kf()[j]; a.out2[ir * m.Nr + j] = c.s.kr()[j]; }
         }
@@ -839,12 +856,13 @@ struct LargeCfg { int grid; size_t per_block; size_t smem; };
 template <class K>
 static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, LargeCfg* cfg) {
     if (!h->large) return fail(RMSB_ERR_UNSUPPORTED, "more than 128 state variables need the large-mechanism path, which this mechanism was not analysed for");
-    if (kind != RMSB_DOMAIN_CONSTANT_TV && kind != RMSB_DOMAIN_CONSTANT_TAPHI)
-        return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): ConstantTV / ConstantTAPhi domains only (DESIGN.md)");
+    if (kind != RMSB_DOMAIN_CONSTANT_TV && kind != RMSB_DOMAIN_CONSTANT_TAPHI && kind != RMSB_DOMAIN_CONSTANT_TP)
+        return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): ConstantTV / ConstantTAPhi / ConstantTP domains only (DESIGN.md)");
+    const LargeTables& lt = (kind == RMSB_DOMAIN_CONSTANT_TP) ? h->lt_tp : h->lt;
     if (h->dm.n_effrxn > 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: third-body efficiencies are not built");
     cudaDeviceProp prop;
     CU(cached_props(h->device, &prop));
-    cfg->smem = large_smem_bytes(h->lt.n);
+    cfg->smem = large_smem_bytes(lt.n);
     if (cfg->smem > prop.sharedMemPerBlockOptin) return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the block-per-reactor kernels (shared memory)");
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
     int bps = 0;
@@ -853,7 +871,7 @@ static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, Large
     if (bps > 16) bps = 16;
     int64_t resident = (int64_t)prop.multiProcessorCount * bps;
     cfg->grid = (int)(n < resident ? (n < 1 ? 1 : n) : resident);
-    cfg->per_block = (large_scratch_doubles(h->lt.n, h->dm.Nr, h->n_dt, h->n_je, h->lt.nnz) + 1) & ~(size_t)1;
+    cfg->per_block = (large_scratch_doubles(lt.n, h->dm.Nr, h->n_dt, h->n_je, lt.nnz) + 1) & ~(size_t)1;
     return RMSB_OK;
 }
 
@@ -864,7 +882,7 @@ static int launch_eval_large(const rmsb_mech* h, const BatchArgs& a, cudaStream_
     if (rc != RMSB_OK) return rc;
     double* scratch = nullptr;
     CU(cudaMallocAsync((void**)&scratch, sizeof(double) * cfg.per_block * cfg.grid, st));
-    large_eval_kernel<MODE><<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, h->lt, scratch, cfg.per_block);
+    large_eval_kernel<MODE><<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? h->lt_tp : h->lt, scratch, cfg.per_block);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
@@ -879,7 +897,7 @@ static int launch_solve_large(const rmsb_mech* h, const SolveArgs& a, cudaStream
     if (work_bytes) { *work_bytes = 256 + sizeof(double) * cfg.per_block * cfg.grid; return RMSB_OK; }
     CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
     double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(a.counter) + 256);
-    large_solve_kernel<<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, h->lt, scratch, cfg.per_block);
+    large_solve_kernel<<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? h->lt_tp : h->lt, scratch, cfg.per_block);
     ++g_launches;
     CU(cudaGetLastError());
     return RMSB_OK;

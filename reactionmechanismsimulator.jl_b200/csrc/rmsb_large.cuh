@@ -37,24 +37,31 @@ struct LargeTables {
     const int* lvl_l_ptr; const int* lvl_l_rows;
     const int* lvl_u_ptr; const int* lvl_u_rows;
     const int* amap;        // [n_je] Jacobian entry -> position in the factor's value array
+    // ConstantTP (y = [ns; V], n = Ns + 1): the volume adds a dense last column and row to the species block
+    int has_v, ns;
+    const int* vcol_pos;    // [Ns]   position of entry (s, V)
+    const int* vrow_pos;    // [Ns+1] position of entry (V, c), c = Ns is the diagonal
+    const int* je_colptr;   // [Ns+1] Jacobian entries of column c are je_colptr[c] .. je_colptr[c+1] (the entry list is sorted by column)
 };
 
 // per-block scratch layout (doubles)
 struct LargeScratch {
     double* base;
-    int n, Nr, n_dt, n_je, nnz;
+    int n, Ns, Nr, n_dt, n_je, nnz;
     __device__ __forceinline__ double* kf() const { return base; }
     __device__ __forceinline__ double* kr() const { return kf() + Nr; }
     __device__ __forceinline__ double* q() const { return kr() + Nr; }
     __device__ __forceinline__ double* dterm() const { return q() + Nr; }
     __device__ __forceinline__ double* jv() const { return dterm() + n_dt; }
-    __device__ __forceinline__ double* a() const { return jv() + n_je; }
+    __device__ __forceinline__ double* vcol() const { return jv() + n_je; }     // [Ns]   d(dn_s/dt)/dV   (ConstantTP)
+    __device__ __forceinline__ double* vrow() const { return vcol() + Ns; }     // [Ns+1] d(dV/dt)/dy_c   (ConstantTP)
+    __device__ __forceinline__ double* a() const { return vrow() + Ns + 1; }
     __device__ __forceinline__ double* vec(int k) const { return a() + nnz + (size_t)k * n; }
     // vec: 0..7 D, 8 y, 9 ypred, 10 psi, 11 inverse weights, 12 dvec, 13 ynew, 14 f, 15 dy, 16 cs, 17 G, 18 diffusivities
 };
 constexpr int LARGE_NVEC = 19;
 __host__ __device__ inline size_t large_scratch_doubles(int n, int Nr, int n_dt, int n_je, int nnz) {
-    return (size_t)3 * Nr + n_dt + n_je + nnz + (size_t)LARGE_NVEC * n + 8;
+    return (size_t)3 * Nr + n_dt + n_je + nnz + (size_t)(LARGE_NVEC + 2) * n + 8;
 }
 // shared memory: [DevMech][64 reduction doubles][36 RU][n x (linear-solve vector)][LARGE_WARPS * n int column map]
 __host__ __device__ inline size_t large_smem_bytes(int n) {
@@ -81,7 +88,8 @@ struct LargeCtx {
     double* ru;      // [36]
     double* x;       // [n] linear-solve vector (permuted order)
     int* map;        // this warp's column map [n]
-    double T, V;
+    double T, V, P;   // V: volume (ConstantTV) or area (ConstantTAPhi); ConstantTP reads the volume from the state, P from cond
+    __device__ __forceinline__ double vol(const double* y) const { return t.has_v ? y[t.ns] : V; }
 };
 
 // ---- constant-k set-up: G, diffusivities, kf, krev (setup_constk with block-strided loops) -----------------------------
@@ -90,7 +98,7 @@ __device__ void large_setup(const LargeCtx& c, const double* y0) {
     const int Ns = m.Ns, Nr = m.Nr, tid = threadIdx.x;
     double* Gs = c.s.vec(17);
     double* diffs = c.s.vec(18);
-    const double T = c.T, V = c.V;
+    const double T = c.T, V = c.vol(y0);
     const double* p = c.d.p;
     for (int s = tid; s < Ns; s += LARGE_THREADS) Gs[s] = p ? p[s] : gibbs_scalar(s, T);
     if (m.difflim) {
@@ -107,11 +115,11 @@ __device__ void large_setup(const LargeCtx& c, const double* y0) {
     const double N = block_sum(a, c.red);
     __syncthreads();
     KinEnv<double> e;
-    const double P = (c.d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0;
+    const double P = (c.d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : (c.d.kind == RMSB_DOMAIN_CONSTANT_TP ? c.P : 0.0);
     e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
     const double C0 = (m.phase_kind == RMSB_PHASE_SURFACE) ? m.sitedensity : 1.0e5 / (RMSB_R * T);
     const double logC0 = log(C0);
-    const double C = (c.d.kind == RMSB_DOMAIN_CONSTANT_TV) ? N / V : 0.0;
+    const double C = (c.d.kind == RMSB_DOMAIN_CONSTANT_TV) ? N / V : (c.d.kind == RMSB_DOMAIN_CONSTANT_TP ? P / (RMSB_R * T) : 0.0);
     for (int j = tid; j < Nr; j += LARGE_THREADS) {
         double kf, kr;
         constk_rates(j, p, false, Gs, diffs, e, C0, logC0, C, y0, V, T, kf, kr);
@@ -130,7 +138,7 @@ __device__ void large_rhs(const LargeCtx& c, const double* y, double* f) {
     double* qb = c.s.q();
     const double* kfb = c.s.kf();
     const double* krb = c.s.kr();
-    const double invV = 1.0 / c.V;
+    const double V = c.vol(y), invV = 1.0 / V;
     for (int s = tid; s < Ns; s += LARGE_THREADS) cs[s] = y[s] * invV;
     __syncthreads();
     for (int j = tid; j < Nr; j += LARGE_THREADS) qb[j] = net_rate<double>(j, kfb[j], krb[j], cs);
@@ -142,9 +150,16 @@ __device__ void large_rhs(const LargeCtx& c, const double* y, double* f) {
             double qv = qb[jr & 0x7fffffff];
             acc = (jr < 0) ? acc - qv : acc + qv;
         }
-        f[s] = acc * c.V;
+        f[s] = acc * V;
     }
     __syncthreads();
+    if (c.t.has_v) {                                            // dV/dt = sum(dn/dt)*R*T/P   (Domain.jl:1864), before the zeroing below
+        double a = 0.0;
+        for (int s = tid; s < Ns; s += LARGE_THREADS) a += f[s];
+        const double tot = block_sum(a, c.red);
+        if (tid == 0) f[Ns] = tot * RMSB_R * c.T / c.P;
+        __syncthreads();
+    }
     for (int k = tid; k < c.d.nconst; k += LARGE_THREADS) f[c.d.constspc[k] - 1] = 0.0;
     LPROF_END(0);
 }
@@ -159,7 +174,7 @@ __device__ void large_jac(const LargeCtx& c, const double* y) {
     double* jv = c.s.jv();
     const double* kfb = c.s.kf();
     const double* krb = c.s.kr();
-    const double invV = 1.0 / c.V;
+    const double invV = 1.0 / c.vol(y);
     for (int s = tid; s < Ns; s += LARGE_THREADS) cs[s] = y[s] * invV;
     __syncthreads();
     for (int t = tid; t < m.n_dt; t += LARGE_THREADS) {
@@ -180,6 +195,41 @@ __device__ void large_jac(const LargeCtx& c, const double* y) {
         jv[e] = acc;
     }
     __syncthreads();
+    if (c.t.has_v) {
+        // V column of the species block (src/Reactor.jl:1368-1413) and the V row = column sums * R*T/P (Domain.jl:2211-2214)
+        const int Nr = m.Nr;
+        double* vcol = c.s.vcol();
+        double* vrow = c.s.vrow();
+        double a = 0.0;
+        for (int s = tid; s < Ns; s += LARGE_THREADS) {
+            double acc = 0.0;
+            for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+                int jr = G(m.sr_rxn, k);
+                int j = jr & 0x7fffffff;
+                double df = 0.0, dr = 0.0;
+                int nre = 0, npr = 0;
+                double pf = kfb[j], pr = krb[j];
+                for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; ++nre; }
+                for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; ++npr; }
+                if (nre > 1) df = -(double)(nre - 1) * pf;
+                if (npr > 1) dr = -(double)(npr - 1) * pr;
+                if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
+            }
+            vcol[s] = acc;
+            a += acc;
+        }
+        const double rtp = RMSB_R * c.T / c.P;
+        const double tot = block_sum(a, c.red);
+        if (tid == 0) vrow[Ns] = tot * rtp;
+        for (int col = tid; col < Ns; col += LARGE_THREADS) {
+            double acc = 0.0;
+            for (int e = G(c.t.je_colptr, col); e < G(c.t.je_colptr, col + 1); ++e) acc += jv[e];
+            vrow[col] = acc * rtp;
+        }
+        __syncthreads();
+        for (int k = tid; k < c.d.nconst; k += LARGE_THREADS) vcol[c.d.constspc[k] - 1] = 0.0;
+        __syncthreads();
+    }
     // constant-species rows are zero (src/Domain.jl:3053-3055)
     if (c.d.nconst > 0) {
         for (int e = tid; e < m.n_je; e += LARGE_THREADS) {
@@ -205,6 +255,10 @@ __device__ bool large_factor(const LargeCtx& c, double cc) {
     for (int i = tid; i < n; i += LARGE_THREADS) a[G(t.diag, i)] = 1.0;
     __syncthreads();
     for (int e = tid; e < m.n_je; e += LARGE_THREADS) a[G(t.amap, e)] -= cc * jv[e];     // one entry per (row, col): no races
+    if (t.has_v) {
+        for (int s = tid; s < t.ns; s += LARGE_THREADS) a[G(t.vcol_pos, s)] -= cc * c.s.vcol()[s];
+        for (int col = tid; col <= t.ns; col += LARGE_THREADS) a[G(t.vrow_pos, col)] -= cc * c.s.vrow()[col];
+    }
     __syncthreads();
     // (a) sparse rows (i < core), up-looking, level by level: row i -= l_ik * (U part of row k) for its L entries k ascending;
     // (b) the same for the L entries k < core of the core rows (all core rows are independent here);
@@ -511,7 +565,7 @@ __device__ void large_bdf_solve(const SolveArgs& a, const LargeCtx& c, int64_t i
                         __syncthreads();
                         large_solve(c, dy, f);          // f <- solution; unit rows keep their right-hand side (x_i = b_i exactly)
                         VLOOP(i) {
-                            bool unit = G(m.inert, i) != 0;
+                            bool unit = i < m.Ns && G(m.inert, i) != 0;
                             for (int q = 0; q < c.d.nconst; ++q) if (c.d.constspc[q] - 1 == i) unit = true;
                             if (!unit) dy[i] = f[i] * gscale;
                         }

@@ -101,7 +101,42 @@ def test_large_ensemble_properties(mech):
     assert np.all(sol3.status == 0) and np.array_equal(sol3.yend[:, NS - 1], y0s[:4, NS - 1])
 
 
+def test_large_constant_tp(mech):
+    """ConstantTP on the large path (y = [ns; V]: the species block bordered by a dense volume row and column)."""
+    ph, oph, gdom, odom, y0, p = mech
+    ic = {"T": 650.0, "P": 5.0e7, **synth.initial_moles(NS)}
+    tdom, ty0, tp = rb.ConstantTPDomain(phase=ph, initialconds=ic)
+    todom = ro.ConstantTPDomain(oph, ic)
+    np.testing.assert_allclose(ty0, todom.y0, rtol=1e-14)
+    np.testing.assert_allclose(tp, todom.p, rtol=1e-12)
+    rng = np.random.default_rng(4)
+    ys = np.stack([todom.y0, np.abs(todom.y0 * rng.uniform(0.5, 1.5, NS + 1) + 1e-6)])
+    ens = rb.Domain(tdom.kind, ph, ys, np.repeat(tdom.cond, 2, axis=0))
+    f, J = ens.dydt(ys), ens.jacobiany(ys)
+    for k in range(2):
+        assert cases.err_dydt(f[k], ro.dydtreactor(todom, ys[k], 0.0, None)) < 1e-12
+        assert cases.err_jac(J[k], ro.jacobiany(todom, ys[k], 0.0, None)) < 1e-12
+    tq = np.array([1e-4, 1e-3])
+    sol = rb.solve(rb.Reactor(tdom, ty0, (0.0, 1e-3), p=tp).ode, abstol=1e-14, reltol=1e-9, saveat=tq)
+    assert sol.retcode == ["Success"]
+    ref = co.CpuMech(oph).solve("ConstantTP", todom.y0[None], np.array([[650.0, 5.0e7]]), 1e-3, 1e-9, 1e-14, tsave=tq, nthreads=1)
+    assert ref["status"][0] == 0
+    for k in range(len(tq)):
+        yr = ref["ysave"][0, k]
+        big = np.abs(yr) > 1e-8 * np.abs(yr[:NS]).max()
+        assert np.max(np.abs(sol.u[0, k] - yr)[big] / np.abs(yr)[big]) < 1e-6
+    assert sol.yend[0, NS] != ty0[NS]                                   # the volume moves
+
+
 def test_large_path_limits_are_reported(mech):
     ph = mech[0]
-    with pytest.raises(rb.RMSBError, match="ConstantTV / ConstantTAPhi"):
-        rb.ConstantTPEnsemble(ph, [650.0], [1e5], mech[2].y0).dydt()
+    with pytest.raises(rb.RMSBError):
+        _variable_k_domain_on_large_mechanism(ph, mech[2].y0)
+
+
+def _variable_k_domain_on_large_mechanism(ph, y0):
+    # a variable-k domain on more than 128 species is outside the large path; build the call through the C ABI directly
+    y = np.concatenate([y0[0], [650.0, 1e5]])[None]
+    out = np.empty_like(y)
+    rc = L.lib().rmsb_dydt_batch(ph.handle, L.DOMAIN_CONSTANT_P, 1, L.ptr(np.ascontiguousarray(y)), L.ptr(np.array([[1e5]])), None, 0, None, 0, L.ptr(out))
+    L.check(rc)
