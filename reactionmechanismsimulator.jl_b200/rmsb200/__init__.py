@@ -15,7 +15,7 @@ from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, Co
 from .ensemble import shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)
 from .phase import IdealDiluteSolution, IdealGas, IdealSurface, Phase
-from .reactor import RMSB200, Reactor, Solution, solve
+from .reactor import RMSB200, Reactor, Solution, solve, threadedsensitivities
 from .simulation import Simulation, idt_grid, ignition_delay
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -129,6 +129,25 @@ class Solution:
         return h00 * y0 + h10 * h * d0 + h01 * y1 + h11 * h * d1
 
 
+def threadedsensitivities(react: Reactor, paramindices=None, odesolver: Optional[RMSB200] = None, senssolver=None,
+                          odekwargs: Optional[dict] = None, senskwargs: Optional[dict] = None) -> "Solution":
+    """threadedsensitivities(react; paramindices, odesolver, senssolver, odekwargs, senskwargs)
+    (src/ThreadedSensitivities.jl:15-79).  The reference solves the state once and then one linear sensitivity ODE per
+    parameter on a thread each; here the state and ALL parameter columns advance together in one rmsb_sens_batch call, so
+    the result is the same object `solve` returns for a reactor built with forwardsensitivities=True.  `paramindices`
+    (1-based, as in the reference) selects which columns are kept; tolerances are taken from `odekwargs`."""
+    kw = dict(odekwargs or {})
+    kw.update({k: v for k, v in (senskwargs or {}).items() if k not in kw})
+    r2 = Reactor(react.domain, react.y0, react.tspan, p=react.p, forwardsensitivities=True)
+    sol = solve(r2, odesolver, abstol=kw.get("abstol", 1e-6), reltol=kw.get("reltol", 1e-3), saveat=kw.get("saveat"))
+    if paramindices is not None:
+        idx = np.asarray(paramindices, dtype=int) - 1
+        sol.sens_end = sol.sens_end[:, idx]
+        if sol.sens is not None:
+            sol.sens = sol.sens[:, :, idx]
+    return sol
+
+
 def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6, reltol: float = 1e-3,
           saveat: Optional[Sequence[float]] = None, idt_index: int = -1, t_end=None) -> Solution:
     """solve(react.ode, alg; abstol, reltol[, saveat]) -- default tolerances are SciML's (1e-6, 1e-3)."""

@@ -177,3 +177,15 @@ def test_constant_v_sensitivities_through_ignition():
     assert peak > 10.0                                            # K per unit multiplier, just before ignition
     assert np.all(np.abs(ST - fd[:, Ns]) <= 0.03 * np.abs(fd[:, Ns]) + 2e-4 * peak)
     assert abs(ST[-1]) < 1e-4 * peak
+
+
+def test_threadedsensitivities_entry_point():
+    """threadedsensitivities(react; odekwargs, senskwargs) of the reference's C5 check (src/TestReactors.jl:234-236) gives the
+    forward-sensitivity result (the reference compares the two at 10 %), and `paramindices` selects columns."""
+    gdom, y0, p = cases.product_domain("superminimal_TP")
+    react = rb.Reactor(gdom, y0, (0.0, 150.11094), p=p)
+    th = rb.threadedsensitivities(react, odekwargs={"abstol": 1e-21, "reltol": 1e-7}, senskwargs={"abstol": 1e-21, "reltol": 1e-7})
+    fw = rb.solve(rb.Reactor(gdom, y0, (0.0, 150.11094), p=p, forwardsensitivities=True).ode, abstol=1e-21, reltol=1e-7)
+    assert np.array_equal(th.sens_end, fw.sens_end)
+    sub = rb.threadedsensitivities(react, paramindices=[3, 20], odekwargs={"abstol": 1e-21, "reltol": 1e-7})
+    assert sub.sens_end.shape == (1, 2, gdom.Ny) and np.array_equal(sub.sens_end[0, 1], fw.sens_end[0, 19])
