@@ -561,21 +561,22 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
 // own summation order, ~100 warp instructions per state.  States are staged through shared memory so that global loads / stores
 // stay coalesced; the per-thread species / reaction arrays live in (lane-interleaved) local memory.
 constexpr int TPR_MAXNS = 32, TPR_MAXNR = 64, TPR_THREADS = 128;
-constexpr int TPR_J_MAXNY = 16, TPR_MAXDT = 160;       // Jacobian variant: the dense Ny x Ny block lives in local memory
+constexpr int TPR_J_MAXNY = 16, TPR_J_MAXNR = 32, TPR_MAXDT = 96;   // Jacobian variant: the dense Ny x Ny block lives in local memory
 
+template <int MS, int MR>
 struct TprKeep {        // what the Jacobian needs from the value pass
-    double kf[TPR_MAXNR], kr[TPR_MAXNR], us[TPR_MAXNS], cp[TPR_MAXNS], cs[TPR_MAXNS];
+    double kf[MR], kr[MR], us[MS], cp[MS], cs[MS];
     double T, P, V, Nt, C, Cv, dotU;
 };
 
 // dy/dt of one reactor by one thread.  y: [ns; T; P] (ConstantV, cond = V) or [ns; T; V] (ConstantP, cond = P).
 // N = Dual2 seeds d/dT (and d/dP for ConstantV) exactly as rhs_v<Dual2> does.
-template <class N, bool ISP>
-__device__ __forceinline__ void rhs_thread(const double* y, double cond, const double* p, const int* constspc, int nconst, N* f, TprKeep* keep) {
+template <class N, bool ISP, int MS, int MR>
+__device__ __forceinline__ void rhs_thread(const double* y, double cond, const double* p, const int* constspc, int nconst, N* f, TprKeep<MS, MR>* keep) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
-    N g[TPR_MAXNS], u[TPR_MAXNS], q[TPR_MAXNR];
-    double cs[TPR_MAXNS];
+    N g[MS], u[MS], q[MR];
+    double cs[MS];
     const double V = ISP ? y[Ns + 1] : cond;
     const double invV = 1.0 / V;
     N T = seed<N>(y[Ns], 0), P = ISP ? N(cond) : seed<N>(y[Ns + 1], 1);
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(TPR_THREADS) dydt_tpr_kernel(const __grid_cons
             double* row = tile + tid * LDt;
             double y[TPR_MAXNS + 2], f[TPR_MAXNS + 2];
             for (int i = 0; i < Ny; ++i) y[i] = row[i];
-            rhs_thread<double, ISP>(y, a.cond[ir], a.p ? a.p + ir * a.p_stride : nullptr, a.constspc, a.nconst, f, nullptr);
+            rhs_thread<double, ISP, TPR_MAXNS, TPR_MAXNR>(y, a.cond[ir], a.p ? a.p + ir * a.p_stride : nullptr, a.constspc, a.nconst, f, nullptr);
             for (int i = 0; i < Ny; ++i) row[i] = f[i];
         }
         __syncthreads();
@@ -672,9 +673,9 @@ __global__ void __launch_bounds__(TPR_THREADS) jac_tpr_kernel(const __grid_const
             const double* row = tile + tid * LDt;
             const double* p = a.p ? a.p + ir * a.p_stride : nullptr;
             double y[TPR_J_MAXNY], f[TPR_J_MAXNY], J[TPR_J_MAXNY * TPR_J_MAXNY], dterm[TPR_MAXDT];
-            TprKeep kp;
+            TprKeep<TPR_J_MAXNY, TPR_J_MAXNR> kp;
             for (int i = 0; i < Ny; ++i) y[i] = row[i];
-            rhs_thread<double, ISP>(y, a.cond[ir], p, a.constspc, a.nconst, f, &kp);
+            rhs_thread<double, ISP, TPR_J_MAXNY, TPR_J_MAXNR>(y, a.cond[ir], p, a.constspc, a.nconst, f, &kp);
             for (int i = 0; i < Ny * Ny; ++i) J[i] = 0.0;
             // (1) derivative terms, (2) entries in the reference's accumulation order (src/Reactor.jl:899-1366)
             for (int t = 0; t < m.n_dt; ++t) {
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(TPR_THREADS) jac_tpr_kernel(const __grid_const
             // (7) T (and P) columns: derivative of the complete RHS
             {
                 Dual2 fd[TPR_J_MAXNY];
-                rhs_thread<Dual2, ISP>(y, a.cond[ir], p, a.constspc, a.nconst, fd, nullptr);
+                rhs_thread<Dual2, ISP, TPR_J_MAXNY, TPR_J_MAXNR>(y, a.cond[ir], p, a.constspc, a.nconst, fd, nullptr);
                 for (int i = 0; i < Ny; ++i) { J[i + Ns * Ny] = fd[i].a; if (!ISP) J[i + (Ns + 1) * Ny] = fd[i].b; }
             }
             double* out = a.out + (size_t)ir * Ny * Ny;
@@ -924,7 +925,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         return RMSB_OK;
     }
     if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
-        h->dm.Nr <= TPR_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096) {
+        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096) {
         cudaDeviceProp prop;
         CU(cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
