@@ -189,3 +189,27 @@ def test_threadedsensitivities_entry_point():
     assert np.array_equal(th.sens_end, fw.sens_end)
     sub = rb.threadedsensitivities(react, paramindices=[3, 20], odekwargs={"abstol": 1e-21, "reltol": 1e-7})
     assert sub.sens_end.shape == (1, 2, gdom.Ny) and np.array_equal(sub.sens_end[0, 1], fw.sens_end[0, 19])
+
+
+@pytest.mark.parametrize("case,tend", [("liquid_TV", 1.0e4), ("surface_TAPhi", 1.0e-6), ("ethane_V", 1.0e-3)])
+def test_forward_sensitivities_wider_systems_vs_finite_differences(case, tend):
+    """Sensitivities on the wider kernels and the other domains: liquid ConstantTV (35 states, two rows per lane, 415
+    parameters, diffusion-limit chain rule, a constant species), surface ConstantTAPhi, ethane ConstantV (falloff kinetics):
+    central finite differences of the GPU state solution in the three most influential parameters."""
+    gdom, y0, p = cases.product_domain(case)
+    Ns = gdom.phase.Ns
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-9)
+    assert sol.retcode == ["Success"] and np.isfinite(sol.sens_end).all()
+    S = sol.sens_end[0]
+    pv = np.asarray(p, dtype=float)
+    infl = np.abs(S).max(axis=1) * np.where(pv != 0.0, np.abs(pv), 8.314 * 1000.0)     # |dy/dln p| (dG columns: per RT)
+    picks = [int(np.argmax(infl[Ns:])) + Ns, int(np.argsort(infl[Ns:])[-2]) + Ns, int(np.argmax(infl[:Ns]))]
+    for j in picks:
+        h = 1e-4 * abs(pv[j]) if pv[j] != 0.0 else 1e-4 * 8.314 * 1000.0
+        fd = []
+        for sgn in (1.0, -1.0):
+            q = pv.copy()
+            q[j] += sgn * h
+            fd.append(rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=q).ode, abstol=1e-22, reltol=1e-11).yend[0])
+        fd = (fd[0] - fd[1]) / (2.0 * h)
+        assert np.max(np.abs(S[j] - fd)) <= 5e-3 * np.max(np.abs(fd)) + 1e-30, (case, j)
