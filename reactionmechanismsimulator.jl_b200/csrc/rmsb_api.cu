@@ -844,11 +844,20 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int wan
     int wpb = want_wpb > 0 ? want_wpb : 4;
     if (wpb > 4) wpb = 4;
     while (wpb > 1 && per_warp * wpb > max_smem) --wpb;
-    size_t smem = per_warp * wpb + mech_bytes;
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb + mech_bytes)));
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, wpb * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, wpb * 32, per_warp * wpb + mech_bytes));
     if (bps < 1) bps = 1;
+    if (want_wpb <= 0) {
+        // the per-warp workspace of a 33..128-variable mechanism is tens of KB: fewer warps per block can pack more warps
+        // into the SM's shared memory (e.g. 2 x 3 warps instead of 1 x 4), and these kernels are latency bound
+        for (int cand = wpb - 1; cand >= 1; --cand) {
+            int b = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, cand * 32, per_warp * cand + mech_bytes));
+            if (b * cand > bps * wpb) { bps = b; wpb = cand; }
+        }
+    }
+    size_t smem = per_warp * wpb + mech_bytes;
     cfg->wpb = wpb; cfg->ws = ws; cfg->smem = smem; cfg->blocks_per_sm = bps; cfg->sms = prop.multiProcessorCount;
     return RMSB_OK;
 }

@@ -188,6 +188,7 @@ struct Ws {
 
 // The mechanism descriptor lives at the start of the block's dynamic shared memory: every routine reads it
 // through a pointer of known address space (LDS with immediate offsets), never through a generic reference.
+constexpr int COOP_ROW = 48;   // species rows with more reaction entries than this are summed by the whole warp (rhs_coupled)
 constexpr int MECH_DOUBLES = (int)((sizeof(DevMech) + 15) / 16 * 2);
 __device__ __forceinline__ const DevMech& mech() { return *reinterpret_cast<const DevMech*>(smem_ws); }
 #define G(ptr, idx) __ldg((ptr) + (idx))   /* mechanism tables are immutable global memory: read-only path */
@@ -826,6 +827,43 @@ __device__ __noinline__ void setup_coupled(DomainArgs d, Ws w, int lane) {
     __syncwarp();
 }
 
+// out[s] = sum over the reactions of species s of +-q_j.  RHS: the entries before sr_mid (reactions of the species' own domain)
+// are multiplied by the domain size V or A (dydt[block] .*= V, src/Reactor.jl:662-725), interface reactions (already * A) are
+// not; returns this lane's part of sum_{bulk} out[s].  A species that takes part in most reactions (the vacant site) would
+// serialise the warp behind one lane: rows longer than COOP_ROW are summed by the whole warp.
+template <bool RHS>
+__device__ __forceinline__ double coupled_rows(const double* qb, double* out, int Ns, int Nb, double V, double A, int lane) {
+    const DevMech& m = mech();
+    double nsum = 0.0;
+    for (int s0 = 0; s0 < Ns; s0 += 32) {
+        const int s = s0 + lane;
+        int k0 = 0, k1 = 0, k2 = 0;
+        if (s < Ns) { k0 = G(m.sr_ptr, s); k1 = RHS ? G(m.sr_mid, s) : k0; k2 = G(m.sr_ptr, s + 1); }
+        const bool heavy = (k2 - k0) > COOP_ROW;
+        if (s < Ns && !heavy) {
+            double acc = 0.0;
+            for (int k = k0; k < k1; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
+            acc *= (s < Nb ? V : A);
+            for (int k = k1; k < k2; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
+            out[s] = acc;
+            if (s < Nb) nsum += acc;
+        }
+        unsigned hv = __ballot_sync(FULL, heavy);
+        while (hv) {
+            const int src = __ffs(hv) - 1;
+            hv &= hv - 1;
+            const int sh = s0 + src;
+            const int h0 = __shfl_sync(FULL, k0, src), h1 = __shfl_sync(FULL, k1, src), h2 = __shfl_sync(FULL, k2, src);
+            double a1 = 0.0, a2 = 0.0;
+            for (int k = h0 + lane; k < h1; k += 32) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; a1 = (jr < 0) ? a1 - qv : a1 + qv; }
+            for (int k = h1 + lane; k < h2; k += 32) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; a2 = (jr < 0) ? a2 - qv : a2 + qv; }
+            const double acc = warp_sum(a1) * (sh < Nb ? V : A) + warp_sum(a2);
+            if (lane == 0) { out[sh] = acc; if (sh < Nb) nsum += acc; }
+        }
+    }
+    return nsum;
+}
+
 __device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Nb = m.n_bulk;
@@ -845,16 +883,7 @@ __device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
         qb[j] = q;
     }
     __syncwarp();
-    double nsum = 0.0;
-    for (int s = lane; s < Ns; s += 32) {
-        double acc = 0.0;
-        const int k0 = G(m.sr_ptr, s), k1 = G(m.sr_mid, s), k2 = G(m.sr_ptr, s + 1);
-        for (int k = k0; k < k1; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
-        acc *= (s < Nb ? V : A);                                           // dydt[block] .*= V (or A)
-        for (int k = k1; k < k2; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; acc = (jr < 0) ? acc - qv : acc + qv; }
-        fb[s] = acc;
-        if (s < Nb) nsum += acc;
-    }
+    double nsum = coupled_rows<true>(qb, fb, Ns, Nb, V, A, lane);
     double dV = warp_sum(nsum) * RMSB_R * T / P;                           // Domain.jl:1864 on the gas block
     if (lane == 0) {
         fb[Ns] = dV;
@@ -889,35 +918,43 @@ __device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
         dterm[t] = v * scale / size;
     }
     __syncwarp();
-    for (int e = lane; e < m.n_je; e += 32) {
-        double acc = 0.0;
-        for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
-            int ti = G(m.jt_idx, k);
-            double v = dterm[ti & 0x7fffffff];
-            acc = (ti < 0) ? acc - v : acc + v;
+    for (int e0 = 0; e0 < m.n_je; e0 += 32) {
+        const int e = e0 + lane;
+        int k0 = 0, k1 = 0, pos = 0;
+        if (e < m.n_je) { k0 = G(m.je_ptr, e); k1 = G(m.je_ptr, e + 1); pos = G(m.je_row, e) + G(m.je_col, e) * LD; }
+        const bool heavy = (k1 - k0) > COOP_ROW;
+        if (e < m.n_je && !heavy) {
+            double acc = 0.0;
+            for (int k = k0; k < k1; ++k) { int ti = G(m.jt_idx, k); double v = dterm[ti & 0x7fffffff]; acc = (ti < 0) ? acc - v : acc + v; }
+            J[pos] = acc;
         }
-        J[G(m.je_row, e) + G(m.je_col, e) * LD] = acc;
+        unsigned hv = __ballot_sync(FULL, heavy);
+        while (hv) {                                                        // (vacant site, vacant site) and the like
+            const int src = __ffs(hv) - 1;
+            hv &= hv - 1;
+            const int h0 = __shfl_sync(FULL, k0, src), h1 = __shfl_sync(FULL, k1, src), hp = __shfl_sync(FULL, pos, src);
+            double acc = 0.0;
+            for (int k = h0 + lane; k < h1; k += 32) { int ti = G(m.jt_idx, k); double v = dterm[ti & 0x7fffffff]; acc = (ti < 0) ? acc - v : acc + v; }
+            acc = warp_sum(acc);
+            if (lane == 0) J[hp] = acc;
+        }
     }
     __syncwarp();
     // V column: d(scale_j * k prod c)/dV = (k prod c) * ([bulk reaction] - scale_j * (#bulk species in the side)/V)
-    for (int s = lane; s < Ns; s += 32) {
-        double acc = 0.0;
-        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
-            int jr = G(m.sr_rxn, k);
-            int j = jr & 0x7fffffff;
-            const int dom = G(m.rx_dom, j);
-            const double scale = (dom == 0) ? V : A;
-            double pf = kfb[j], pr = krb[j];
-            int gf = 0, gr = 0;
-            for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; if (sp < Nb) ++gf; }
-            for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; if (sp < Nb) ++gr; }
-            double df = pf * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gf / V);
-            double dr = pr * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gr / V);
-            double dq = df - dr;
-            acc = (jr < 0) ? acc - dq : acc + dq;
-        }
-        J[s + Ns * LD] = acc;
+    double* qb = w.q();                                                     // the rates of rhs_coupled are not needed any more
+    for (int j = lane; j < Nr; j += 32) {
+        const int dom = G(m.rx_dom, j);
+        const double scale = (dom == 0) ? V : A;
+        double pf = kfb[j], pr = krb[j];
+        int gf = 0, gr = 0;
+        for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; if (sp < Nb) ++gf; }
+        for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; if (sp < Nb) ++gr; }
+        double df = pf * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gf / V);
+        double dr = pr * ((dom == 0 ? 1.0 : 0.0) - scale * (double)gr / V);
+        qb[j] = df - dr;
     }
+    __syncwarp();
+    coupled_rows<false>(qb, J + Ns * LD, Ns, Nb, V, A, lane);
     __syncwarp();
     for (int c = lane; c <= Ns; c += 32) {                                   // V row from the gas block
         double a = 0.0;
