@@ -290,6 +290,7 @@ __device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
             double xk = __shfl_sync(FULL, b[kr], kl);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                if (r < kr) continue;                        // rows of earlier slots are all above row k
                 int i = r * 32 + lane;
                 if (i > k && i < Ny) b[r] -= A[i + k * LD] * xk;
             }
@@ -305,6 +306,7 @@ __device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
             double xk = __shfl_sync(FULL, b[kr], kl);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+                if (r > kr) continue;                        // rows of later slots are all below row k
                 int i = r * 32 + lane;
                 if (i < k) b[r] -= A[i + k * LD] * xk;
             }
