@@ -76,3 +76,26 @@ def test_parameter_strides(dom):
     one = rb.Domain(gdom.kind, gdom.phase, ys[3:4], gdom.cond)
     s2 = rb.solve(rb.Reactor(one, None, (0.0, 1e-3), p=per[3]), abstol=1e-16, reltol=1e-8)
     assert np.array_equal(s1.yend[3], s2.yend[0])
+
+
+def test_result_does_not_depend_on_launch_geometry(dom):
+    """warps_per_block = 1, 2, 4 or the library's own choice (most resident warps per SM): bit-identical trajectories and
+    integrator statistics -- a reactor's arithmetic never depends on which warp or block picks it up from the work queue."""
+    gdom, y0, p = dom
+    rng = np.random.default_rng(5)
+    n = 300
+    ys = np.repeat(gdom.y0, n, axis=0)
+    cond = np.repeat(gdom.cond, n, axis=0)
+    ys[:, -2] = rng.uniform(1000.0, 1400.0, n)            # T0; P0 follows from the fixed volume
+    ys[:, -1] = ys[:, :-2].sum(axis=1) * rb.R * ys[:, -2] / cond[:, 0]
+    ens = rb.Domain(gdom.kind, gdom.phase, ys, cond)
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    ref = None
+    for wpb in (0, 1, 2, 4):
+        sol = rb.solve(rb.Reactor(ens, None, (0.0, 0.02)), rb.RMSB200(warps_per_block=wpb), abstol=1e-16, reltol=1e-6, saveat=[0.01])
+        assert (sol.status == L.SOLVE_OK).all()
+        if ref is None:
+            ref = sol
+            continue
+        assert np.array_equal(sol.yend, ref.yend) and np.array_equal(sol.u, ref.u)
+        assert np.array_equal(sol.stats["n_steps"], ref.stats["n_steps"]) and np.array_equal(sol.stats["n_rhs"], ref.stats["n_rhs"])
