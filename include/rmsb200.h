@@ -150,7 +150,8 @@ typedef struct rmsb_solve_opts {
     int32_t max_order;       /* 1..5, default 5                                                    */
     int32_t idt_index;       /* 0-based y index whose max d/dt defines idt; -1 = domain default (T) */
     double  first_step;      /* 0 = automatic                                                      */
-    int32_t warps_per_block; /* 0 = automatic                                                      */
+    int32_t warps_per_block; /* 0 = automatic (most resident warps per SM); 1..4 fixed; results
+                                are bit-identical for every value                                   */
     int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis;
                               * bit 2 / bit 3 (diagnostics): do not impose the unit rows of inert species / recompute the step as
                               * fl(t+h)-t like SciPy; bit 4 (large-mechanism path): refactorise on every change of h instead of
