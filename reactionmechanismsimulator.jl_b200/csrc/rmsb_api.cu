@@ -19,57 +19,13 @@
 
 using namespace rmsb;
 
-// ------------------------------------------------------------------------------------------------
-// error plumbing
-// ------------------------------------------------------------------------------------------------
-static thread_local std::string g_err;
-static std::atomic<long long> g_launches{0};
+#include "rmsb_internal.h"
 
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+thread_local std::string rmsb_g_err;
+std::atomic<long long> rmsb_g_launches{0};
+int rmsb_fail(int code, const std::string& msg) { rmsb_g_err = msg; return code; }
 
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t _e = (call);                                                                   \
-        if (_e != cudaSuccess)                                                                     \
-            return fail(RMSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));        \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = (cudaSetDevice(dev) == cudaSuccess);
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-// ------------------------------------------------------------------------------------------------
-// mechanism handle
-// ------------------------------------------------------------------------------------------------
-struct rmsb_mech {
-    int device = 0;
-    DevMech dm{};
-    std::vector<void*> allocs;
-    int n_dt = 0, n_je = 0;
-    // large-mechanism path (one block per reactor, sparse LU on a fixed pattern): built when Ns > 128
-    bool large = false;
-    LargeTables lt{};        // y = ns            (ConstantTV, ConstantTAPhi)
-    LargeTables lt_tp{};     // y = [ns; V]       (ConstantTP): the same block bordered by a dense row and column
-    int large_max_row = 0;
-    long long large_factor_flops = 0;
-};
-
-template <class T>
-static int upload(rmsb_mech* h, const std::vector<T>& v, const T** out) {
-    void* p = nullptr;
-    size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
-    CU(cudaMalloc(&p, bytes));
-    h->allocs.push_back(p);
-    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = reinterpret_cast<const T*>(p);
-    return RMSB_OK;
-}
+#define upload rmsb_upload
 
 extern "C" int rmsb_version(void) { return RMSB_VERSION; }
 extern "C" const char* rmsb_last_error(void) { return g_err.c_str(); }
@@ -332,6 +288,7 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
         }
     }
 #undef UP
+    if ((rc = rmsb_small_build(h, rx, srptr, srrxn, kcptr, kcspc, kccoef, nrp, ktype, koff, kpar, fwd, rev, nr, nc, tmax, coef, maxr)) != RMSB_OK) return rc;
     if (!radius.empty()) { if ((rc = upload(h, radius, &dm.radius)) != RMSB_OK) return rc; } else dm.radius = nullptr;
     if (!diffr.empty()) { if ((rc = upload(h, diffr, &dm.diff_r)) != RMSB_OK) return rc; } else dm.diff_r = nullptr;
     return RMSB_OK;
@@ -358,20 +315,6 @@ extern "C" int rmsb_mech_create(const rmsb_mech_desc* desc, int device, rmsb_mec
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-struct BatchArgs {
-    int64_t n;
-    const double* y;
-    const double* cond;
-    int ncond;
-    const double* p;
-    int64_t p_stride;
-    const int* constspc;
-    int nconst;
-    double* out;     // dydt or J
-    double* out2;    // krev (rates kernel)
-    int domain_kind;
-    int Ny;
-};
 
 // Stage the mechanism descriptor at the start of the block's dynamic shared memory (see mech()).
 __device__ __forceinline__ void stage_mech(const DevMech& mp) {
@@ -814,7 +757,7 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 static int rows_per_lane(int Ny) { return (Ny + 31) / 32; }
 
 // cudaGetDeviceProperties takes milliseconds: query each device once
-static cudaError_t cached_props(int device, cudaDeviceProp* out) {
+cudaError_t rmsb_cached_props(int device, cudaDeviceProp* out) {
     static std::mutex mu;
     static std::map<int, cudaDeviceProp> cache;
     std::lock_guard<std::mutex> lock(mu);
@@ -834,7 +777,7 @@ struct LaunchCfg { int wpb; int ws; size_t smem; int blocks_per_sm; int sms; };
 template <class K>
 static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int want_wpb, LaunchCfg* cfg) {
     cudaDeviceProp prop;
-    CU(cached_props(h->device, &prop));
+    CU(rmsb_cached_props(h->device, &prop));
     int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, mode);
     size_t per_warp = (size_t)ws * sizeof(double);
     const size_t mech_bytes = (size_t)MECH_DOUBLES * sizeof(double);
@@ -871,7 +814,7 @@ static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, Large
     const LargeTables& lt = (kind == RMSB_DOMAIN_CONSTANT_TP) ? h->lt_tp : h->lt;
     if (h->dm.n_effrxn > 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: third-body efficiencies are not built");
     cudaDeviceProp prop;
-    CU(cached_props(h->device, &prop));
+    CU(rmsb_cached_props(h->device, &prop));
     cfg->smem = large_smem_bytes(lt.n);
     if (cfg->smem > prop.sharedMemPerBlockOptin) return fail(RMSB_ERR_UNSUPPORTED, "mechanism too large for the block-per-reactor kernels (shared memory)");
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
@@ -923,7 +866,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096) {
         // small variable-k mechanisms, large batches: one thread per reactor
         cudaDeviceProp prop;
-        CU(cached_props(h->device, &prop));
+        CU(rmsb_cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
         int64_t blocks = (a.n + TPR_THREADS - 1) / TPR_THREADS, cap = (int64_t)prop.multiProcessorCount * 16;
         const int grid = (int)(blocks < cap ? blocks : cap);
@@ -936,7 +879,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
     if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
         h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096) {
         cudaDeviceProp prop;
-        CU(cached_props(h->device, &prop));
+        CU(rmsb_cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
         int64_t blocks = (a.n + TPR_THREADS - 1) / TPR_THREADS, cap = (int64_t)prop.multiProcessorCount * 16;
         const int grid = (int)(blocks < cap ? blocks : cap);
@@ -946,6 +889,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         CU(cudaGetLastError());
         return RMSB_OK;
     }
+    if ((MODE == 0 || MODE == 1) && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
     LaunchCfg cfg;
     int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
@@ -1009,6 +953,7 @@ static int sens_dispatch(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, si
 }
 
 static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
+    if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
     switch (rows_per_lane(a.Ny)) {
     case 1: return launch_solve_R<1>(h, a, want_wpb, st);
     case 2: return launch_solve_R<2>(h, a, want_wpb, st);
@@ -1144,8 +1089,14 @@ extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, con
 extern "C" int64_t rmsb_sens_work_bytes(const rmsb_mech* h, int kind, int64_t n) {
     if (!h || domain_ny(h, kind) < 0) { fail(RMSB_ERR_ARG, "bad mechanism / domain kind"); return -1; }
     DeviceGuard g(h->device);
+    // the history buffer is indexed by resident warp (blockIdx.x * warps_per_block + warp): size it for the launch geometry that
+    // needs the most warps over every warps_per_block the caller may pass in rmsb_solve_opts (0 = automatic, 1..4 fixed)
     size_t bytes = 0;
-    if (sens_dispatch(h, domain_ny(h, kind), n > 0 ? n : 1, 0, &bytes, nullptr, nullptr) != RMSB_OK) return -1;
+    for (int wpb = 0; wpb <= 4; ++wpb) {
+        size_t b = 0;
+        if (sens_dispatch(h, domain_ny(h, kind), n > 0 ? n : 1, wpb, &b, nullptr, nullptr) != RMSB_OK) return -1;
+        if (b > bytes) bytes = b;
+    }
     return (int64_t)bytes;
 }
 

@@ -268,7 +268,7 @@ __device__ __forceinline__ void nasa_hscp(int s, const TPow<N>& t, double Tv, N&
 
 // getGibbs through the scalar path: evalpoly Horner (src/Tools.jl:13-22) with exact c_k/k
 // (src/Calculators/Thermo.jl:6-8,75-93).  Used by the constant-T domains at setup.
-__device__ __noinline__ double gibbs_scalar(int s, double T) {
+static __device__ __noinline__ double gibbs_scalar(int s, double T) {
     const DevMech& m = mech();
     int r = select_poly(s, T);
     const double* c = m.nasa_c + (size_t)(r * 9) * m.Ns + s;
@@ -449,7 +449,7 @@ __device__ __noinline__ N eval_kin(int j, const KinEnv<N>* ep, N Ceff, bool scal
 }
 
 // _calcdkdCeff, src/Calculators/Rate.jl:232-262
-__device__ __noinline__ double dk_dCeff(int j, const KinEnv<double>* ep, double Ceff) {
+static __device__ __noinline__ double dk_dCeff(int j, const KinEnv<double>* ep, double Ceff) {
     const DevMech& m = mech();
     const KinEnv<double>& e = *ep;
     const double* a = m.kpar + G(m.koff, j);
@@ -497,7 +497,7 @@ __device__ __forceinline__ N net_rate(int j, N kf, N kr, const double* cs) {
 }
 
 // scalar getKc (src/PhaseState.jl:106-129, phi = 0) from absolute Gibbs energies G[]
-__device__ __noinline__ double kc_scalar(int j, const double* G, double T, double C0) {
+static __device__ __noinline__ double kc_scalar(int j, const double* G, double T, double C0) {
     const DevMech& m = mech();
     const int Nr = m.Nr;
     double acc = G[G(m.rx, j)];
@@ -582,7 +582,7 @@ __device__ __forceinline__ void constk_rates(int j, const double* p, bool is_eff
 // The initial amounts are read from w.ybuf (only efficiency reactions look at them, and those are
 // re-evaluated on every RHS call for TP).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
@@ -723,7 +723,7 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
 }
 
 // constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns).  setup_constk() must have filled w.g / w.kf / w.kr.
-__device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* p = d.p;
@@ -791,7 +791,7 @@ __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
 // construction src/Interface.jl:89-108; two-phase getKc src/PhaseState.jl:131-162.  All rate coefficients are
 // constants of the reactor (T fixed) and are computed once by setup_coupled.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void setup_coupled(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void setup_coupled(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     double* Gb = w.g();
@@ -864,7 +864,7 @@ __device__ __forceinline__ double coupled_rows(const double* qb, double* out, in
     return nsum;
 }
 
-__device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Nb = m.n_bulk;
     const double* yb = w.ybuf();
@@ -896,7 +896,7 @@ __device__ __noinline__ void rhs_coupled(DomainArgs d, Ws w, int lane) {
 }
 
 // Analytic Jacobian of the coupled system (the reference differentiates the whole RHS with ForwardDiff, src/Reactor.jl:203).
-__device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Nb = m.n_bulk, Ny = w.Ny, LD = w.LD;
     rhs_coupled(d, w, lane);
@@ -991,7 +991,7 @@ __device__ __forceinline__ void setup_domain(const DomainArgs& d, const Ws& w, i
 // ------------------------------------------------------------------------------------------------
 // jacobiany! for one reactor: in w.ybuf, out dense column-major Ny x LD matrix in w.J.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, LD = w.LD;
     if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) { jac_coupled(d, w, lane); return; }
@@ -1137,7 +1137,7 @@ __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
 // getkfs (src/PhaseState.jl:165-171): forward rate coefficients of every reaction BEFORE diffusion limitation, vector
 // forms for the vectorised block -- what the constant-k constructors store in p[Ns+1:end] (kfsnondiff for the liquid
 // phase, src/Domain.jl:549-551).  State in w.ybuf, result in w.kf.
-__device__ __noinline__ void kfs_intrinsic(DomainArgs d, Ws w, int lane) {
+static __device__ __noinline__ void kfs_intrinsic(DomainArgs d, Ws w, int lane) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr;
     const double* ns = w.ybuf();
@@ -1164,7 +1164,7 @@ __device__ __noinline__ void kfs_intrinsic(DomainArgs d, Ws w, int lane) {
 // Needs cs/kf/kr/us/aux of the state in w.ybuf: `fresh` evaluates them first (rhs_warp with store_k).
 // ------------------------------------------------------------------------------------------------
 constexpr int JP_CHUNK = 32;
-__device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int c0, bool fresh) {
+static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int c0, bool fresh) {
     const DevMech& m = mech();
     const int Ns = m.Ns, Nr = m.Nr, Ny = w.Ny, Np = Ns + Nr;
     if (fresh) rhs_warp(d, w, lane, true);

@@ -10,6 +10,7 @@
 // Jacobian refresh), written with block-strided loops instead of warp-distributed registers.
 #pragma once
 #include "rmsb_solver.cuh"
+#include "rmsb_tables.h"
 
 namespace rmsb {
 
@@ -26,23 +27,6 @@ __device__ unsigned long long g_large_prof[8];
 constexpr int LARGE_THREADS = RMSB_LARGE_THREADS;
 constexpr int LARGE_WARPS = LARGE_THREADS / 32;
 
-struct LargeTables {
-    int n, nnz, n_lvl_l, n_lvl_u, core;   // core: first row / column of the dense trailing block
-    const int* perm;        // new -> old
-    const int* row_ptr;
-    const int* col;
-    const int* diag;
-    const int* ldiag;       // [nnz] for an entry in column k: position of the diagonal of row k
-    const int* lnk;         // [nnz] ... and the number of U entries of row k right of its diagonal
-    const int* lvl_l_ptr; const int* lvl_l_rows;
-    const int* lvl_u_ptr; const int* lvl_u_rows;
-    const int* amap;        // [n_je] Jacobian entry -> position in the factor's value array
-    // ConstantTP (y = [ns; V], n = Ns + 1): the volume adds a dense last column and row to the species block
-    int has_v, ns;
-    const int* vcol_pos;    // [Ns]   position of entry (s, V)
-    const int* vrow_pos;    // [Ns+1] position of entry (V, c), c = Ns is the diagonal
-    const int* je_colptr;   // [Ns+1] Jacobian entries of column c are je_colptr[c] .. je_colptr[c+1] (the entry list is sorted by column)
-};
 
 // per-block scratch layout (doubles)
 struct LargeScratch {

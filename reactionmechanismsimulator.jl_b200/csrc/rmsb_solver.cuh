@@ -36,15 +36,15 @@ constexpr double JAC_REFRESH_RATIO = 100.0;
 #define RMSB_K2 (-1.0 / 9.0)
 #define RMSB_K3 (-0.0823)
 #define RMSB_K4 (-0.0415)
-__constant__ double c_gamma[6] = {0.0, RMSB_G1, RMSB_G2, RMSB_G3, RMSB_G4, RMSB_G5};
-__constant__ double c_alpha[6] = {0.0, (1.0 - RMSB_K1) * RMSB_G1, (1.0 - RMSB_K2) * RMSB_G2, (1.0 - RMSB_K3) * RMSB_G3,
+static __constant__ double c_gamma[6] = {0.0, RMSB_G1, RMSB_G2, RMSB_G3, RMSB_G4, RMSB_G5};
+static __constant__ double c_alpha[6] = {0.0, (1.0 - RMSB_K1) * RMSB_G1, (1.0 - RMSB_K2) * RMSB_G2, (1.0 - RMSB_K3) * RMSB_G3,
                                   (1.0 - RMSB_K4) * RMSB_G4, (1.0 - 0.0) * RMSB_G5};
-__constant__ double c_ec[6] = {1.0, RMSB_K1 * RMSB_G1 + 1.0 / 2.0, RMSB_K2 * RMSB_G2 + 1.0 / 3.0, RMSB_K3 * RMSB_G3 + 1.0 / 4.0,
+static __constant__ double c_ec[6] = {1.0, RMSB_K1 * RMSB_G1 + 1.0 / 2.0, RMSB_K2 * RMSB_G2 + 1.0 / 3.0, RMSB_K3 * RMSB_G3 + 1.0 / 4.0,
                                RMSB_K4 * RMSB_G4 + 1.0 / 5.0, 0.0 * RMSB_G5 + 1.0 / 6.0};
 // U = R(factor = 1): U[k][j] = prod_{l=1..k} (l-1-j)/l = (-1)^k C(j,k)
-__constant__ double c_U[36] = {1, 1, 1, 1, 1, 1,   0, -1, -2, -3, -4, -5,   0, 0, 1, 3, 6, 10,
+static __constant__ double c_U[36] = {1, 1, 1, 1, 1, 1,   0, -1, -2, -3, -4, -5,   0, 0, 1, 3, 6, 10,
                                0, 0, 0, -1, -4, -10,   0, 0, 0, 0, 1, 5,   0, 0, 0, 0, 0, -1};
-__constant__ double c_invl[6] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0};
+static __constant__ double c_invl[6] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0};
 
 struct SolveArgs {
     int64_t n;
@@ -77,6 +77,21 @@ struct SolveArgs {
     int Npp;            // Ns+Nr rounded up to a multiple of 32
     int flags;      // bit 0: scipy-style Newton test (every step >= 2 iterations, tolerance min(0.03, sqrt(rtol)));
                     // bit 1: no step-size hysteresis.  0 = production defaults (CVODE-style test, hysteresis)
+};
+
+struct BatchArgs {
+    int64_t n;
+    const double* y;
+    const double* cond;
+    int ncond;
+    const double* p;
+    int64_t p_stride;
+    const int* constspc;
+    int nconst;
+    double* out;     // dydt or J
+    double* out2;    // krev (rates kernel)
+    int domain_kind;
+    int Ny;
 };
 
 // ---- distributed vector helpers -----------------------------------------------------------------
@@ -227,7 +242,7 @@ __device__ __noinline__ bool lu_factor_warp(Ws w, double c, int lane) {
 
 // One row per lane (Ny <= 32): same algorithm, same arithmetic, with the row / column pointers bumped instead of recomputed.
 template <>
-__device__ __noinline__ bool lu_factor_warp<1>(Ws w, double c, int lane) {
+inline __device__ __noinline__ bool lu_factor_warp<1>(Ws w, double c, int lane) {
     const int LD = w.LD, Ny = w.Ny;
     double* A = w.LU();
     const double* J = w.J();
@@ -321,7 +336,7 @@ __device__ __noinline__ void lu_solve_warp(Ws w, int lane) {
 // One row per lane (Ny <= 32): the same substitution with the column pointer bumped instead of recomputed and no slot loops --
 // half the instructions of the generic version on the 14-variable headline case.
 template <>
-__device__ __noinline__ void lu_solve_warp<1>(Ws w, int lane) {
+inline __device__ __noinline__ void lu_solve_warp<1>(Ws w, int lane) {
     const int LD = w.LD, Ny = w.Ny;
     const double* col = w.LU() + lane;         // row `lane`, column 0
     double* xs = w.xs();
@@ -345,7 +360,7 @@ __device__ __noinline__ void lu_solve_warp<1>(Ws w, int lane) {
 // ---- change_D: rescale the backward differences for a step-size ratio `factor` -------------------
 // D_new[j] = sum_i (R(factor) U)[i][j] D[i], R[i][k] = prod_{l=1..i} (l-1-factor*k)/l, U = R(1).
 // The 6x6 product is formed cooperatively (one entry per lane) in w.ru.
-__device__ __noinline__ void compute_ru(Ws w, double factor, int lane) {
+static __device__ __noinline__ void compute_ru(Ws w, double factor, int lane) {
     double* ru = w.ru();
     // lanes 0..5 build column k of R(factor) incrementally, R[i][k] = R[i-1][k] * (i-1-factor*k)/i, into ru; every lane
     // then reads its row of R and forms its entry (i, j) of R*U = sum_{k<=j} R[i][k] * U[k][j]
@@ -414,7 +429,7 @@ struct SensHist {
     __device__ __forceinline__ double* at(int j, int i, int p) const { return D + (size_t)j * plane + (size_t)i * Npp + p; }
 };
 
-__device__ __noinline__ void sens_init(DomainArgs d, Ws w, SensHist sh, double h, int lane) {
+static __device__ __noinline__ void sens_init(DomainArgs d, Ws w, SensHist sh, double h, int lane) {
     for (size_t e = lane; e < (size_t)(BDF_MAX_ORDER + 3) * sh.plane; e += 32) sh.D[e] = 0.0;
     __syncwarp();
     for (int c0 = 0; c0 < sh.Np; c0 += JP_CHUNK) {
@@ -426,7 +441,7 @@ __device__ __noinline__ void sens_init(DomainArgs d, Ws w, SensHist sh, double h
 }
 
 // the state's change_D applied to S: the 6x6 matrix R(factor) U is still in w.ru
-__device__ __noinline__ void sens_change_D(Ws w, SensHist sh, int order, int lane) {
+static __device__ __noinline__ void sens_change_D(Ws w, SensHist sh, int order, int lane) {
     const double* ru = w.ru();
     for (size_t e = lane; e < sh.plane; e += 32) {
         double dv[BDF_MAX_ORDER + 1], dn[BDF_MAX_ORDER + 1];
@@ -510,7 +525,7 @@ __device__ __noinline__ bool sens_step(DomainArgs d, Ws w, SensHist sh, int orde
 }
 
 // dense output of S at ts inside the last step (t - h, t]; out is [Np][Ny]
-__device__ __noinline__ void sens_interp(SensHist sh, int order, double t, double h, double ts, double* out, int lane) {
+static __device__ __noinline__ void sens_interp(SensHist sh, int order, double t, double h, double ts, double* out, int lane) {
     const int tot = sh.Ny * sh.Np;
     for (int o = lane; o < tot; o += 32) {
         const int p = o / sh.Ny, i = o - p * sh.Ny;

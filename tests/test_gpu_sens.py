@@ -213,3 +213,22 @@ def test_forward_sensitivities_wider_systems_vs_finite_differences(case, tend):
             fd.append(rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=q).ode, abstol=1e-22, reltol=1e-11).yend[0])
         fd = (fd[0] - fd[1]) / (2.0 * h)
         assert np.max(np.abs(S[j] - fd)) <= 5e-3 * np.max(np.abs(fd)) + 1e-30, (case, j)
+
+
+def test_sensitivity_launch_geometry_small_batches():
+    """Small batches with every warps_per_block: the per-warp sensitivity history is indexed by resident warp, so the work
+    buffer must cover the launch geometry actually used (rmsb_sens_work_bytes sizes it for the worst case over 0..4), and the
+    results never depend on which warp integrates a reactor."""
+    gdom, y0, p = cases.product_domain("superminimal_TP")
+    for n in (1, 5):
+        ens = rb.Domain(gdom.kind, gdom.phase, np.repeat(gdom.y0, n, axis=0), np.repeat(gdom.cond, n, axis=0))
+        ens.p, ens._p_default = gdom.p, gdom._p_default
+        ref = None
+        for wpb in (0, 1, 2, 3, 4):
+            sol = rb.solve(rb.Reactor(ens, None, (0.0, 1.0), p=p, forwardsensitivities=True).ode, rb.RMSB200(warps_per_block=wpb),
+                           abstol=1e-20, reltol=1e-8)
+            assert all(rc == "Success" for rc in sol.retcode) and np.isfinite(sol.sens_end).all()
+            if ref is None:
+                ref = sol
+            assert np.array_equal(sol.sens_end, ref.sens_end) and np.array_equal(sol.yend, ref.yend)
+        assert np.array_equal(ref.sens_end[0], ref.sens_end[-1])
