@@ -5,6 +5,7 @@ not the product's, into the descriptor layout of include/rmsb200.h.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -37,11 +38,40 @@ STATS = np.dtype([("n_steps", "i4"), ("n_rhs", "i4"), ("n_jac", "i4"), ("n_lu", 
                   ("n_err_fail", "i4"), ("last_order", "i4"), ("reserved", "i4"), ("last_h", "f8")])
 
 
-def build(force=False):
-    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-fno-fast-math", "-ffp-contract=off",
-                        "-o", str(LIB), str(SRC)], check=True)
-    return LIB
+STRICT_FLAGS = ["-O2", "-fno-fast-math", "-ffp-contract=off"]                       # the checker: no FMA contraction, portable code
+# the CPU BASELINE build (bench.py only): what a tuned native build of the same source gives on this host -- the reference runs its
+# hot path under @fastmath with native code generation.  -ffinite-math-only is left out: the integrator tests isfinite().
+FAST_FLAGS = ["-O3", "-march=native", "-ffast-math", "-fno-finite-math-only", "-funroll-loops"]
+_build_kind = "strict"
+
+
+def _fast_lib_path():
+    """-march=native code must not travel between hosts: one file per CPU model."""
+    import hashlib
+    try:
+        model = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        model = ["unknown"]
+    return HERE / "cpu" / f"librms_cpu_fast_{hashlib.sha1(''.join(model).encode()).hexdigest()[:10]}.so"
+
+
+def build(force=False, kind=None):
+    kind = kind or _build_kind
+    out = LIB if kind == "strict" else _fast_lib_path()
+    if force or not out.exists() or out.stat().st_mtime < SRC.stat().st_mtime:
+        flags = STRICT_FLAGS if kind == "strict" else FAST_FLAGS
+        tmp = out.with_suffix(f".so.{os.getpid()}.tmp")
+        subprocess.run(["g++", *flags, "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-o", str(tmp), str(SRC)], check=True)
+        os.replace(tmp, out)
+    return out
+
+
+def select_build(kind: str):
+    """"strict" (default: the checker) or "fast" (CPU baseline timing, bench.py).  Handles made before the switch keep their library."""
+    global _build_kind, _lib
+    assert kind in ("strict", "fast")
+    if kind != _build_kind:
+        _build_kind, _lib = kind, None
 
 
 _lib = None
@@ -50,8 +80,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(str(LIB))
+        L = C.CDLL(str(build()))
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.rmso_create.argtypes = [C.POINTER(Desc)]
         L.rmso_create.restype = vp
@@ -150,11 +179,12 @@ class CpuMech:
             else:
                 d.viscosity_kind, d.viscosity_params[0] = 1, mu["mu"]
         self.desc = d
-        self.h = lib().rmso_create(C.byref(d))
+        self.L = lib()
+        self.h = self.L.rmso_create(C.byref(d))
 
     def __del__(self):
         try:
-            lib().rmso_destroy(self.h)
+            self.L.rmso_destroy(self.h)
         except Exception:
             pass
 
@@ -177,7 +207,7 @@ class CpuMech:
     def dydt(self, kind, y, cond, p=None, constspc=(), nthreads=0):
         y, cond, p, ps, cs = self._common(kind, y, cond, p, constspc)
         out = np.empty_like(y)
-        rc = lib().rmso_eval(self.h, 0, DOMAIN[kind], y.shape[0], self._p(y), self._p(cond), self._p(p), ps, self._p(cs),
+        rc = self.L.rmso_eval(self.h, 0, DOMAIN[kind], y.shape[0], self._p(y), self._p(cond), self._p(p), ps, self._p(cs),
                              0 if cs is None else cs.size, self._p(out), nthreads)
         assert rc == 0
         return out
@@ -186,13 +216,13 @@ class CpuMech:
         y, cond, p, ps, cs = self._common(kind, y, cond, p, constspc)
         n, Ny = y.shape
         out = np.empty((n, Ny * Ny))
-        rc = lib().rmso_eval(self.h, 1, DOMAIN[kind], n, self._p(y), self._p(cond), self._p(p), ps, self._p(cs),
+        rc = self.L.rmso_eval(self.h, 1, DOMAIN[kind], n, self._p(y), self._p(cond), self._p(p), ps, self._p(cs),
                              0 if cs is None else cs.size, self._p(out), nthreads)
         assert rc == 0
         return out.reshape(n, Ny, Ny).transpose(0, 2, 1)
 
     def solve(self, kind, y0, cond, t_end, rtol, atol, p=None, constspc=(), tsave=None, max_steps=500000, idt_index=-1, nthreads=0, flags=0):
-        lib().rmso_set_flags(int(flags))     # same meaning as RMSB200(flags=...): 0 = the CUDA path's defaults, 3 = scipy.integrate.BDF's step logic
+        self.L.rmso_set_flags(int(flags))     # same meaning as RMSB200(flags=...): 0 = the CUDA path's defaults, 3 = scipy.integrate.BDF's step logic
         y0, cond, p, ps, cs = self._common(kind, y0, cond, p, constspc)
         n, Ny = y0.shape
         te = np.ascontiguousarray(np.broadcast_to(np.asarray(t_end, dtype=float), (n,)))
@@ -201,7 +231,7 @@ class CpuMech:
         ysave = np.empty((n, ns, Ny)) if ns else None
         yend, idt = np.empty((n, Ny)), np.empty(n)
         status, stats = np.empty(n, dtype=np.int32), np.zeros(n, dtype=STATS)
-        rc = lib().rmso_solve(self.h, DOMAIN[kind], n, self._p(y0), self._p(cond), self._p(p), ps, self._p(cs),
+        rc = self.L.rmso_solve(self.h, DOMAIN[kind], n, self._p(y0), self._p(cond), self._p(p), ps, self._p(cs),
                               0 if cs is None else cs.size, self._p(te), rtol, atol, ns, self._p(ts), self._p(ysave), self._p(yend),
                               self._p(idt), self._p(status), self._p(stats), max_steps, idt_index, nthreads)
         assert rc == 0

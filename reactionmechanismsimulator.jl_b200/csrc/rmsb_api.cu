@@ -111,7 +111,26 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
         rev[j] = d->reversible[j] ? 1.0 : 0.0;
         fwd[j] = d->forwardable[j] ? 1.0 : 0.0;
     }
+    if (maxr < 1) return fail(RMSB_ERR_ARG, "nasa_max_ranges must be >= 1");
     for (int j = 0; j <= Nr; ++j) { koff[j] = d->kin_offset[j]; effptr[j] = d->eff_ptr ? d->eff_ptr[j] : 0; }
+    if (koff[0] < 0 || effptr[0] != 0) return fail(RMSB_ERR_ARG, "kin_offset[0] must be >= 0 and eff_ptr[0] must be 0");
+    for (int j = 0; j < Nr; ++j) {
+        if (koff[j + 1] < koff[j] || effptr[j + 1] < effptr[j]) return fail(RMSB_ERR_ARG, "kin_offset / eff_ptr must be non-decreasing");
+        // parameter block sizes the kernels read for each kinetics type (rmsb200.h, RMSB_KIN_*)
+        const int len = koff[j + 1] - koff[j];
+        const double* a = d->kin_params + koff[j];
+        int need = 3;
+        switch (ktype[j]) {
+        case RMSB_KIN_ARRHENIUS_VEC: case RMSB_KIN_ARRHENIUS: case RMSB_KIN_THIRDBODY: need = 3; break;
+        case RMSB_KIN_LINDEMANN: need = 6; break;
+        case RMSB_KIN_TROE: need = 10; break;
+        case RMSB_KIN_MULTIARRHENIUS: need = len >= 1 ? 1 + 3 * (int)a[0] : 1; break;
+        case RMSB_KIN_PLOG_VEC: need = len >= 1 ? 1 + 4 * (int)a[0] : 1; break;
+        case RMSB_KIN_CHEBYSHEV_VEC: need = len >= 6 ? 6 + (int)a[4] * (int)a[5] : 6; break;
+        default: need = 1; break;       // PLOG / MULTIPLOG: nested blocks, walked by their own counts
+        }
+        if (len < need) return fail(RMSB_ERR_ARG, "kin_params block shorter than its kinetics type needs");
+    }
     std::vector<double> kpar(d->kin_params, d->kin_params + koff[Nr]);
     for (int k = 0; k < effptr[Nr]; ++k) {
         int s = d->eff_species[k];
@@ -976,6 +995,15 @@ static int check_common(const rmsb_mech* h, int kind, int64_t n, const void* y, 
     return RMSB_OK;
 }
 
+// const_species of the host-buffer entry points: 1-based species indices (the *_dev variants take a device array and document the
+// requirement instead)
+static int check_const_species(const rmsb_mech* h, const int32_t* cs, int32_t ncs) {
+    if (!cs || ncs <= 0) return RMSB_OK;
+    for (int k = 0; k < ncs; ++k)
+        if (cs[k] < 1 || cs[k] > h->dm.Ns) return fail(RMSB_ERR_ARG, "const_species entries are 1-based species indices in 1..Ns");
+    return RMSB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ------------------------------------------------------------------------------------------------
@@ -1144,6 +1172,7 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     int rc = check_common(h, kind, n, y, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
+    if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!out || (mode == 2 && !out2)) return fail(RMSB_ERR_ARG, "null output buffer");
     DeviceGuard g(h->device);
