@@ -59,25 +59,25 @@ def measured_peaks():
 
 def _issue_roofline(mean_steps, n, t_kernel, clocks, device):
     """The bound that actually limits the solve kernel: warp-instruction issue.  Warp instructions per accepted step come from the
-    committed ncu capture (smsp__inst_executed.sum / reactors / steps, profiles/r01_solve_kernel_by_function_f.txt); the peak is
+    committed ncu capture (smsp__inst_executed.sum / reactors / steps, profiles/r02_small_solve_kernel_by_line_c.txt); the peak is
     SMs x 4 schedulers x one instruction per cycle at the SM clock sampled during the timed region."""
     try:
         import torch
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
-        per_step = 5593.0
+        per_step = 3316.0
         ach = per_step * mean_steps * n / t_kernel
         peak = sms * 4 * float(mhz) * 1e6
         return {"achieved_ginst_s": ach / 1e9, "peak_ginst_s": peak / 1e9, "frac": ach / peak, "warp_instructions_per_step": per_step,
-                "source": "profiles/r01_solve_kernel_by_function_f.txt (ncu source page)"}
+                "source": "profiles/r02_small_solve_kernel_by_line_c.txt (ncu source page)"}
     except Exception as exc:
         return {"achieved_ginst_s": None, "peak_ginst_s": None, "frac": None, "source": f"unavailable: {exc}"}
 
 
 def _ncu_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of one solve-kernel launch from the committed `ncu --set full` capture
-    (profiles/r01_solve_kernel_traffic.json); only valid for the launch size it was captured at, otherwise None."""
-    p = ROOT / "profiles" / "r01_solve_kernel_traffic.json"
+    (profiles/r02_solve_kernel_traffic.json); only valid for the launch size it was captured at, otherwise None."""
+    p = ROOT / "profiles" / "r02_solve_kernel_traffic.json"
     try:
         d = json.loads(p.read_text())
         if int(d["conditions_per_launch"]) == int(n):
@@ -126,9 +126,15 @@ class ClockSampler:
 # reference arm: the reference's CPU implementation of the path.  RMS is a Julia package (no julia in this
 # image, nothing to compile into oracle/_ref), so this is the C++ port oracle/cpu/rms_cpu.cpp on all host cores.
 # ------------------------------------------------------------------------------------------------------
-def cpu_port(nthreads=0):
+CPU_BUILD_NOTE = ("C++/OpenMP port of the RMS CPU path (oracle/cpu/rms_cpu.cpp) built for timing with g++ -O3 -march=native -ffast-math "
+                  "-fno-finite-math-only on this host (the strict -O2 -ffp-contract=off build is the checker only); RMS itself is Julia "
+                  "and cannot run in this image")
+
+
+def cpu_port(fast=True):
     from oracle import cpu_oracle as co
     from oracle import rms_oracle as ro
+    co.select_build("fast" if fast else "strict")
     d = ro.readinput(FIXTURE)
     ph = ro.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"])
     return co, co.CpuMech(ph), ph
@@ -165,8 +171,7 @@ def run_reference(args):
             "config": {"workload": "H2/O2 (superminimal) ConstantVDomain IDT ensemble, configs[1]", "conditions_per_step": sample,
                        "full_workload_conditions": args.n_per_gpu, "t_end": T_END, "rtol": RTOL, "atol": ATOL},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} of {args.n_per_gpu} conditions per step (same seeded sweep), C++/OpenMP port "
-                                       "oracle/cpu/rms_cpu.cpp of the RMS CPU path; RMS itself is Julia and cannot run here"},
+                             "sample": f"{sample} of {args.n_per_gpu} conditions per step (same seeded sweep); " + CPU_BUILD_NOTE},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -334,10 +339,65 @@ def run_ours(args):
             sample = int(max(256, min(n, rate * 10.0)))
             val, dt = cpu_solve_rate(cm, ph.names, sample, SEED, cores)
             cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {sample} of the {n} conditions, {dt:.1f} s on {cores} threads, C++/OpenMP port of the RMS CPU path "
-                             "(oracle/cpu/rms_cpu.cpp); RMS itself is Julia and cannot run in this image"}
+                   "sample": f"first {sample} of the {n} conditions, {dt:.1f} s on {cores} threads; " + CPU_BUILD_NOTE}
+            try:       # the strict (checker) build of the same source on a smaller sample, for the record
+                _, cm_s, _ = cpu_port(fast=False)
+                s_n = int(max(256, sample // 8))
+                cpu["strict_build_value"], _ = cpu_solve_rate(cm_s, ph.names, s_n, SEED, cores)
+            except Exception:
+                pass
         except Exception as exc:   # the checker failing must not take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+    # ---- strong scaling: the SAME 100k-condition set split over the ranks (BASELINE quotes 100k conditions in total).  Reactors are
+    #      sorted by the work the warm-up solve measured for them (n_rhs, a pilot pass) and dealt round-robin in sorted chunks, so every
+    #      rank gets the same mix; the limiter that shows is per-reactor serial latency (the tail), not a collective.
+    strong = None
+    if world > 1:
+        n_tot = n
+        y0g, Vg = conditions(ig.names, n_tot, SEED)                # identical on every rank
+        # pilot: rank r measures the work of its contiguous block, all-gathered
+        lo, hi = n_tot * rank // world, n_tot * (rank + 1) // world
+        m = hi - lo
+        ty, tv, tte = torch.from_numpy(y0g[lo:hi]).to(dev), torch.from_numpy(Vg[lo:hi]).to(dev), torch.full((m,), T_END, dtype=torch.float64, device=dev)
+        L.check(lib.rmsb_solve_batch_dev(h, KIND, m, ty.data_ptr(), tv.data_ptr(), None, 0, None, 0, tte.data_ptr(), RTOL, ATOL, 0, None, None,
+                                         t_yend.data_ptr(), t_idt.data_ptr(), t_status.data_ptr(), t_stats.data_ptr(), C.byref(opts), t_work.data_ptr(), sp))
+        torch.cuda.synchronize()
+        mx = max(n_tot * (r + 1) // world - n_tot * r // world for r in range(world))
+        work_local = torch.zeros(mx, dtype=torch.int32, device=dev)
+        work_local[:m] = t_stats[:m, 1]
+        parts = [torch.empty(mx, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(parts, work_local)
+        work_all = np.concatenate([parts[r][:n_tot * (r + 1) // world - n_tot * r // world].cpu().numpy() for r in range(world)])
+        from rmsb200.ensemble import balanced_shards
+        mine = balanced_shards(work_all, world, 64)[rank]           # heaviest first, round-robin of sorted chunks
+        ms_by = {}
+        for name, sel in (("sorted_round_robin", mine), ("contiguous", np.arange(lo, hi))):
+            ty, tv = torch.from_numpy(np.ascontiguousarray(y0g[sel])).to(dev), torch.from_numpy(np.ascontiguousarray(Vg[sel])).to(dev)
+            mm = len(sel)
+            tte = torch.full((mm,), T_END, dtype=torch.float64, device=dev)
+
+            def step_strong():
+                L.check(lib.rmsb_solve_batch_dev(h, KIND, mm, ty.data_ptr(), tv.data_ptr(), None, 0, None, 0, tte.data_ptr(), RTOL, ATOL, 0, None, None,
+                                                 t_yend.data_ptr(), t_idt.data_ptr(), t_status.data_ptr(), t_stats.data_ptr(), C.byref(opts),
+                                                 t_work.data_ptr(), sp))
+            k_strong = max(3, args.steps)
+            ms_s, _, _ = timed(step_strong, k_strong, 2)
+            ms_by[name] = (ms_s / k_strong, k_strong)
+        strong = {"conditions_total": n_tot, "split": "stiffness sort (n_rhs of a pilot solve, heaviest first) + round-robin of 64-reactor chunks",
+                  "value": n_tot / (ms_by["sorted_round_robin"][0] * 1e-3), "ms_per_step": ms_by["sorted_round_robin"][0],
+                  "contiguous_split_value": n_tot / (ms_by["contiguous"][0] * 1e-3), "unit": UNIT, "timing": "CUDA events, max over ranks",
+                  "limiter": "per-reactor serial latency: 12.5k reactors per GPU at N=8 are ~2.6 waves of the 4736 resident lane groups, "
+                             "the last wave runs partly empty; no collective on the data path"}
+
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        try:
+            sys.path.insert(0, str(ROOT / "scripts"))
+            import bench_configs
+            others = bench_configs.run_all()
+        except Exception as exc:
+            others = {"error": repr(exc)}
 
     if rank == 0:
         line = {
@@ -346,14 +406,14 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "H2/O2 (superminimal) ConstantVDomain IDT ensemble, configs[1]", "conditions_per_gpu": n,
                        "Ny": Ny, "n_species": Ns, "n_reactions": Nr, "t_end": T_END, "rtol": RTOL, "atol": ATOL,
-                       "integrator": "variable-order NDF/BDF 1-5, one warp per reactor", "l2": "flushed between timed steps (256 MiB fill)",
+                       "integrator": "variable-order NDF/BDF 1-5, one 16-lane group per reactor (two reactors per warp), mechanism tables in shared memory", "l2": "flushed between timed steps (256 MiB fill)",
                        "all_converged": st_ok, "mean_per_solve": mean, "wall_s_timed_region": wall},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "rmsb_solve_batch (host buffers, pinned)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": _ncu_traffic(n), "kernel": "solve_kernel<1>", "algorithmic_bytes_per_solve": bytes_per_solve,
+                         "traffic": _ncu_traffic(n), "kernel": "small_solve_kernel<16>", "algorithmic_bytes_per_solve": bytes_per_solve,
                          "peak_source": peak_src,
                          "note": "state lives in registers/shared memory for the whole integration: the solve is FP64-pipe/latency bound, "
                                  "not HBM bound (SURVEY 8d); see roofline_fp64 and evals"},
@@ -366,6 +426,8 @@ def run_ours(args):
                       "jac": {"evals_per_s": ne / t_jac, "GBps": b_jac * ne / t_jac / 1e9, "frac_hbm": b_jac * ne / t_jac / 1e9 / hbm_peak,
                               "bytes_per_eval": b_jac}},
             "cpu_baseline": cpu,
+            "others": others,
+            "scaling_strong": strong,
         }
         print(json.dumps(line))
     if world > 1:
@@ -382,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--warps-per-block", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the `others` block (the BASELINE configs besides the headline one)")
     ap.add_argument("--flags", type=int, default=0, help="integrator flags (rmsb_solve_opts.reserved); 0 = defaults")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

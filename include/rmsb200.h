@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMSB_VERSION 100
+#define RMSB_VERSION 200
 
 /* ---- error codes -------------------------------------------------------------------------- */
 #define RMSB_OK             0
@@ -156,6 +156,10 @@ typedef struct rmsb_solve_opts {
                               * bit 2 / bit 3 (diagnostics): do not impose the unit rows of inert species / recompute the step as
                               * fl(t+h)-t like SciPy; bit 4 (large-mechanism path): refactorise on every change of h instead of
                               * keeping the factors while c = h/alpha stays within 30 % (CVODE's dgmax); bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
+    /* ---- version 2 (struct_size >= 40; version-1 callers with struct_size 32 are still accepted) ---- */
+    double* dysave;          /* rmsb_solve_batch only (host buffer, may be NULL): [n][nsave][Ny], dy/dt = dydtreactor!(u) at every
+                              * saved state -- the `du` of sol.interp (src/Simulation.jl:27-34), so the caller's Hermite interpolation
+                              * needs no host RHS.  NaN where ysave is NaN. */
 } rmsb_solve_opts;
 
 /* ---- library ----------------------------------------------------------------------------- */
@@ -277,6 +281,20 @@ int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
                          double* d_yend, double* d_idt, int32_t* d_status, rmsb_stats* d_stats,
                          const rmsb_solve_opts* opts, void* d_work, void* stream);
 
+/* ---- one host process, several GPUs -------------------------------------------------------------
+ * rmsb_solve_batch over n_mech handles of the SAME mechanism created on different devices: the reactors are split into
+ * contiguous blocks by index (block g = reactors [g*n/n_mech, (g+1)*n/n_mech)), each block runs rmsb_solve_batch on its
+ * handle's device from its own host thread, the outputs land in the caller's buffers at the reactor's index.  No exchange
+ * between devices (reactors are independent); a one-process Julia caller reaches every GPU of the node through
+ * this call.  Returns the first non-zero status of any block. */
+int rmsb_solve_batch_multi(const rmsb_mech* const* mechs, int32_t n_mech, int domain_kind, int64_t n,
+                           const double* y0, const double* cond, const double* p, int64_t p_stride,
+                           const int32_t* const_species, int32_t n_const,
+                           const double* t_end, double rtol, double atol,
+                           int32_t nsave, const double* tsave, double* ysave,
+                           double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                           const rmsb_solve_opts* opts);
+
 /* ---- large mechanisms (more than 128 state variables; config C3) ---------------------------
  * rmsb_mech_create analyses the Jacobian pattern of mechanisms with more than 128 species once (minimum-degree ordering,
  * fill pattern, dependency levels); dydt / jac / rates / solve then run one thread block per reactor with a sparse LU of
@@ -292,6 +310,9 @@ int rmsb_large_profile(const rmsb_mech* mech, int reset, double cycles[8]);
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */
 int64_t rmsb_kernel_launch_count(void);
+/* Device time (CUDA events on the call's stream, milliseconds) of the kernels of the last rmsb_solve_batch / rmsb_sens_batch
+ * call made by this host thread, copies excluded; < 0 if none. */
+double  rmsb_last_kernel_ms(void);
 /* FP64 FMA microbenchmark on `device`: returns sustained DFMA TFLOP/s (2 flop per FMA), <0 on error.
  * Used as the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 double  rmsb_fp64_peak_tflops(int device, int iters);

@@ -225,7 +225,7 @@ def readinput(fname: str) -> dict:
     ``{phasename: {"Species": [...], "Reactions": [...]}, frozenset({p1,p2}): {"Reactions": [...]},
     "Solvents": [...]}``."""
     with open(fname) as fh:
-        D = yaml.safe_load(fh)
+        D = yaml.load(fh, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
     out: dict = {}
     if "Solvents" in D and D["Solvents"]:
         out["Solvents"] = [Solvent(name=s["name"], mu={k: (_f(v) if k != "type" else v) for k, v in s["mu"].items()})

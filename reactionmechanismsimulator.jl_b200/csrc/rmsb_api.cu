@@ -19,6 +19,7 @@
 
 using namespace rmsb;
 
+#include <thread>
 #include "rmsb_internal.h"
 
 thread_local std::string rmsb_g_err;
@@ -510,6 +511,17 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
                 for (int s = tid; s < lt.ns; s += LARGE_THREADS) J[s + (size_t)lt.ns * n] = c.s.vcol()[s];
                 for (int col = tid; col <= lt.ns; col += LARGE_THREADS) J[lt.ns + (size_t)col * n] = c.s.vrow()[col];
             }
+        } else if (MODE == 4) {
+            // getkfs (src/PhaseState.jl:165-171): forward rate coefficients BEFORE diffusion limitation (kfs_intrinsic, block-strided)
+            double acc = 0.0;
+            for (int s = tid; s < m.Ns; s += LARGE_THREADS) acc += y[s];
+            const double N = block_sum(acc, c.red);
+            const double T = c.T, V = c.vol(y);
+            const double P = (a.domain_kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? c.P : 0.0);
+            const double C = (a.domain_kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TAPHI ? 0.0 : N / V);
+            KinEnv<double> e;
+            e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
+            for (int j = tid; j < m.Nr; j += LARGE_THREADS) a.out[ir * m.Nr + j] = eval_kin<double>(j, &e, ceff_of(j, C, y, V), false);
         } else {
             for (int j = tid; j < m.Nr; j += LARGE_THREADS) { a.out[ir * m.Nr + j] = c.s.kf()[j]; a.out2[ir * m.Nr + j] = c.s.kr()[j]; }
         }
@@ -878,7 +890,7 @@ static int launch_solve_large(const rmsb_mech* h, const SolveArgs& a, cudaStream
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
     if (a.Ny > 128) {
-        if (MODE <= 2) return launch_eval_large<(MODE <= 2 ? MODE : 0)>(h, a, st);
+        if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
     }
     if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
@@ -1061,10 +1073,13 @@ extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech* h, int kind, int64_t n
     return (int64_t)bytes;
 }
 
+constexpr int32_t RMSB_SOLVE_OPTS_V1_SIZE = 32;    // rmsb_solve_opts before dysave was added
 static void default_opts(rmsb_solve_opts* o, const rmsb_solve_opts* in) {
     o->struct_size = sizeof(rmsb_solve_opts);
     o->max_steps = 500000; o->max_order = 5; o->idt_index = -1; o->first_step = 0.0; o->warps_per_block = 0; o->reserved = 0;
-    if (in && in->struct_size == (int32_t)sizeof(rmsb_solve_opts)) {
+    o->dysave = nullptr;
+    if (in && (in->struct_size == (int32_t)sizeof(rmsb_solve_opts) || in->struct_size == RMSB_SOLVE_OPTS_V1_SIZE)) {
+        if (in->struct_size == (int32_t)sizeof(rmsb_solve_opts)) o->dysave = in->dysave;
         if (in->max_steps > 0) o->max_steps = in->max_steps;
         if (in->max_order >= 1 && in->max_order <= 5) o->max_order = in->max_order;
         o->idt_index = in->idt_index;
@@ -1162,6 +1177,31 @@ static void tune_pool(int device) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     done.fetch_or(bit);
+}
+
+// device time of the kernels of the last host-buffer solve of this thread (rmsb_last_kernel_ms)
+static thread_local double g_last_kernel_ms = -1.0;
+extern "C" double rmsb_last_kernel_ms(void) { return g_last_kernel_ms; }
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    cudaError_t start(cudaStream_t st) {
+        cudaError_t e = cudaEventCreate(&a);
+        if (e == cudaSuccess) e = cudaEventCreate(&b);
+        if (e == cudaSuccess) e = cudaEventRecord(a, st);
+        return e;
+    }
+    cudaError_t stop(cudaStream_t st) { return cudaEventRecord(b, st); }
+    void read() { float ms = -1.f; if (a && b && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) g_last_kernel_ms = ms; }
+};
+
+// out[(r*rep + k)][:] = in[r][:]: per-reactor constants repeated for each of a reactor's saved states
+__global__ void expand_rows_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n, int rep, int width) {
+    const int64_t tot = n * rep * (int64_t)width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / width;
+        out[i] = in[(row / rep) * width + (i - row * width)];
+    }
 }
 
 #define H2D(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sg.st))
@@ -1278,18 +1318,84 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
     int64_t wbytes = rmsb_solve_work_bytes(h, kind, n);
     if (wbytes < 0) return RMSB_ERR_UNSUPPORTED;
     CU(dwork.alloc((size_t)wbytes));
+    EventPair ev;
+    CU(ev.start(sg.st));
     rc = rmsb_solve_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                               (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
                               nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr,
                               yend ? dye.as<double>() : nullptr, idt ? didt.as<double>() : nullptr, dst.as<int32_t>(),
                               stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st);
     if (rc != RMSB_OK) return rc;
+    // du at the saved states (opts->dysave): one dydt evaluation of the n*nsave saved states, each with its reactor's constants
+    double* dysave = (opts && opts->struct_size == (int32_t)sizeof(rmsb_solve_opts)) ? opts->dysave : nullptr;
+    DevBuf dce(sg.st), dpe(sg.st), ddy(sg.st);
+    if (dysave && nsave > 0) {
+        const int64_t ne = n * nsave;
+        CU(dce.alloc(sizeof(double) * ne * nc)); CU(ddy.alloc(sizeof(double) * ne * Ny));
+        expand_rows_kernel<<<(int)std::min<int64_t>((ne * nc + 255) / 256, 65535), 256, 0, sg.st>>>(dc.as<double>(), dce.as<double>(), n, nsave, nc);
+        ++g_launches;
+        const double* pe = p ? dp.as<double>() : nullptr;
+        if (p && p_stride) {
+            CU(dpe.alloc(sizeof(double) * ne * Np));
+            expand_rows_kernel<<<(int)std::min<int64_t>((ne * Np + 255) / 256, 65535), 256, 0, sg.st>>>(dp.as<double>(), dpe.as<double>(), n, nsave, Np);
+            ++g_launches;
+            pe = dpe.as<double>();
+        }
+        CU(cudaGetLastError());
+        rc = launch_eval<0>(h, make_batch(h, kind, ne, dys.as<double>(), dce.as<double>(), pe, p_stride, (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs,
+                                          ddy.as<double>(), nullptr), sg.st);
+        if (rc != RMSB_OK) return rc;
+    }
+    CU(ev.stop(sg.st));
+    if (dysave && nsave > 0) D2H(dysave, ddy.p, sizeof(double) * n * nsave * Ny);
     if (nsave > 0) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
     if (yend) D2H(yend, dye.p, sizeof(double) * n * Ny);
     if (idt) D2H(idt, didt.p, sizeof(double) * n);
     D2H(status, dst.p, sizeof(int32_t) * n);
     if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
     CU(cudaStreamSynchronize(sg.st));
+    ev.read();
+    return RMSB_OK;
+}
+
+extern "C" int rmsb_solve_batch_multi(const rmsb_mech* const* mechs, int32_t n_mech, int kind, int64_t n, const double* y0,
+                                      const double* cond, const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
+                                      const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave, double* ysave,
+                                      double* yend, double* idt, int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    if (!mechs || n_mech < 1) return fail(RMSB_ERR_ARG, "rmsb_solve_batch_multi: at least one mechanism handle");
+    for (int g = 0; g < n_mech; ++g) {
+        if (!mechs[g]) return fail(RMSB_ERR_ARG, "rmsb_solve_batch_multi: null mechanism handle");
+        if (mechs[g]->dm.Ns != mechs[0]->dm.Ns || mechs[g]->dm.Nr != mechs[0]->dm.Nr) return fail(RMSB_ERR_ARG, "rmsb_solve_batch_multi: handles of different mechanisms");
+    }
+    int rc = check_common(mechs[0], kind, n, y0, cond, p_stride, p);
+    if (rc != RMSB_OK) return rc;
+    if (n == 0) return RMSB_OK;
+    if (!t_end || !status) return fail(RMSB_ERR_ARG, "t_end and status are required");
+    const int Ny = domain_ny(mechs[0], kind), nc = domain_ncond(kind), Np = mechs[0]->dm.Ns + mechs[0]->dm.Nr;
+    std::vector<int> rcs(n_mech, RMSB_OK);
+    std::vector<std::string> errs(n_mech);
+    std::vector<double> kms(n_mech, -1.0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_mech; ++g) {
+        const int64_t lo = n * g / n_mech, hi = n * (g + 1) / n_mech, m = hi - lo;
+        if (m == 0) continue;
+        th.emplace_back([=, &rcs, &errs, &kms]() {
+            rmsb_solve_opts o;
+            if (opts) { std::memset(&o, 0, sizeof(o)); std::memcpy(&o, opts, std::min<size_t>(sizeof(o), (size_t)std::max(0, opts->struct_size))); }
+            if (opts && opts->struct_size == (int32_t)sizeof(rmsb_solve_opts) && o.dysave) o.dysave += (size_t)lo * nsave * Ny;
+            rcs[g] = rmsb_solve_batch(mechs[g], kind, m, y0 + lo * Ny, cond + lo * nc, (p && p_stride) ? p + lo * Np : p, p_stride, cs, ncs,
+                                      t_end + lo, rtol, atol, nsave, tsave, ysave ? ysave + (size_t)lo * nsave * Ny : nullptr,
+                                      yend ? yend + lo * Ny : nullptr, idt ? idt + lo : nullptr, status + lo, stats ? stats + lo : nullptr,
+                                      opts ? &o : nullptr);
+            if (rcs[g] != RMSB_OK) errs[g] = rmsb_g_err;     // thread-local message of the worker
+            kms[g] = g_last_kernel_ms;
+        });
+    }
+    for (auto& t : th) t.join();
+    double worst = -1.0;
+    for (int g = 0; g < n_mech; ++g) worst = std::max(worst, kms[g]);
+    g_last_kernel_ms = worst;                                 // the slowest device bounds the call
+    for (int g = 0; g < n_mech; ++g) if (rcs[g] != RMSB_OK) return fail(rcs[g], "device block " + std::to_string(g) + ": " + errs[g]);
     return RMSB_OK;
 }
 
@@ -1328,6 +1434,8 @@ extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const do
     CU(dst.alloc(sizeof(int32_t) * n));
     if (stats) CU(dstats.alloc(sizeof(rmsb_stats) * n));
     CU(dwork.alloc((size_t)wb));
+    EventPair ev;
+    CU(ev.start(sg.st));
     rc = rmsb_sens_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
                              nsave > 0 ? dts.as<double>() : nullptr, (nsave > 0 && ysave) ? dys.as<double>() : nullptr,
@@ -1335,6 +1443,7 @@ extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const do
                              send ? dse.as<double>() : nullptr, dst.as<int32_t>(), stats ? dstats.as<rmsb_stats>() : nullptr, opts,
                              dwork.p, sg.st);
     if (rc != RMSB_OK) return rc;
+    CU(ev.stop(sg.st));
     if (nsave > 0 && ysave) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
     if (nsave > 0 && ssave) D2H(ssave, dss.p, sizeof(double) * n * nsave * sper);
     if (yend) D2H(yend, dye.p, sizeof(double) * n * Ny);
@@ -1342,6 +1451,7 @@ extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const do
     D2H(status, dst.p, sizeof(int32_t) * n);
     if (stats) D2H(stats, dstats.p, sizeof(rmsb_stats) * n);
     CU(cudaStreamSynchronize(sg.st));
+    ev.read();
     return RMSB_OK;
 }
 

@@ -52,7 +52,8 @@ assert STATS_DTYPE.itemsize == C.sizeof(Stats)
 
 class SolveOpts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("max_steps", C.c_int32), ("max_order", C.c_int32), ("idt_index", C.c_int32),
-                ("first_step", C.c_double), ("warps_per_block", C.c_int32), ("reserved", C.c_int32)]
+                ("first_step", C.c_double), ("warps_per_block", C.c_int32), ("reserved", C.c_int32),
+                ("dysave", C.c_void_p)]          # version 2: host buffer [n][nsave][Ny] for du at the saved states (rmsb_solve_batch)
 
 
 class RMSBError(RuntimeError):
@@ -67,6 +68,7 @@ EXPORTS = [
     "rmsb_solve_batch", "rmsb_dydt_batch_dev", "rmsb_jac_batch_dev", "rmsb_solve_work_bytes", "rmsb_solve_batch_dev",
     "rmsb_kernel_launch_count", "rmsb_fp64_peak_tflops", "rmsb_jacp_batch", "rmsb_jacp_batch_dev", "rmsb_sens_batch",
     "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch", "rmsb_large_info", "rmsb_large_profile",
+    "rmsb_solve_batch_multi", "rmsb_last_kernel_ms",
 ]
 
 
@@ -109,6 +111,9 @@ def lib():
     L.rmsb_sens_work_bytes.restype = i64
     L.rmsb_sens_batch_dev.argtypes = common + [vp, i32, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts), vp, vp]
     L.rmsb_kernel_launch_count.restype = i64
+    L.rmsb_solve_batch_multi.argtypes = [vp, i32, C.c_int, i64, vp, vp, vp, i64, vp, i32, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp,
+                                         C.POINTER(SolveOpts)]
+    L.rmsb_last_kernel_ms.restype = dbl
     L.rmsb_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.rmsb_fp64_peak_tflops.restype = dbl
     _lib = L

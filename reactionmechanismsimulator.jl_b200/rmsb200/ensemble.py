@@ -24,6 +24,21 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def balanced_shards(work, world: int, chunk: int = 64):
+    """Strong-scaling split: reactors sorted by a work estimate (e.g. n_rhs of a pilot solve at loose tolerance, or of
+    the previous sweep), heaviest first, then dealt round-robin (in snake order) in chunks so every rank gets the same mix and starts with its
+    heaviest reactors (longest-processing-time order inside each rank's work queue).  Returns one index array per rank; together
+    they are a permutation of range(len(work))."""
+    work = np.asarray(work)
+    order = np.argsort(-work, kind="stable")
+    nchunks = (len(order) + chunk - 1) // chunk
+    parts = [[] for _ in range(world)]
+    for c in range(nchunks):                       # snake order: 0..W-1, W-1..0, ... so no rank always gets the heavier chunk of a round
+        rnd, pos = divmod(c, world)
+        parts[pos if rnd % 2 == 0 else world - 1 - pos].append(order[c * chunk:(c + 1) * chunk])
+    return [np.concatenate(p) if p else np.empty(0, dtype=order.dtype) for p in parts]
+
+
 def shard_domain(dom: Domain, world: int, rank: int) -> Domain:
     """The rank's slice of an ensemble domain (same phase handle semantics, own device tables)."""
     lo, hi = shard_bounds(dom.n, world, rank)

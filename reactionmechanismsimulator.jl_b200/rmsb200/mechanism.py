@@ -188,7 +188,7 @@ def readinput(fname: str) -> dict:
     if ext not in ("rms", "rmg", "yml", "yaml"):
         raise ValueError(f"file extension {ext} not understood, use .rms yaml mechanisms")
     with open(fname) as fh:
-        doc = yaml.safe_load(fh)
+        doc = yaml.load(fh, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
     out: dict = {}
     if doc.get("Solvents"):
         out["Solvents"] = [Solvent(s["name"], {k: (v if k == "type" else float(v)) for k, v in s["mu"].items()})

@@ -123,6 +123,7 @@ class Phase:
         self._species_phase = None      # two-phase systems only (rmsb200/coupled.py)
         self._rxn_domain = None
         self._handle = None
+        self._more_handles = {}
         self._build_desc()
 
     # -- SoA descriptor -----------------------------------------------------------------------
@@ -192,10 +193,22 @@ class Phase:
             self._handle = h
         return self._handle
 
+    def handle_on(self, device: int):
+        """Handle of this mechanism on another GPU (tables are replicated per device; rmsb_solve_batch_multi)."""
+        if device == self._device:
+            return self.handle
+        if device not in self._more_handles:
+            h = C.c_void_p()
+            L.check(L.lib().rmsb_mech_create(C.byref(self.desc), int(device), C.byref(h)))
+            self._more_handles[device] = h
+        return self._more_handles[device]
+
     def __del__(self):
         try:
-            if self._handle is not None and L._lib is not None:
-                L._lib.rmsb_mech_destroy(self._handle)
+            if L._lib is not None:
+                for h in [self._handle, *self._more_handles.values()]:
+                    if h is not None:
+                        L._lib.rmsb_mech_destroy(h)
         except Exception:
             pass
 

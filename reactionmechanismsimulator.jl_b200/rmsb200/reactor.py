@@ -94,7 +94,8 @@ class Solution:
         return ["Success" if s == L.SOLVE_OK else {1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}[int(s)] for s in self.status]
 
     def derivatives(self):
-        """du/dt at the saved points (one batched dydt call)."""
+        """du/dt at the saved points: returned by the solve call itself when it was asked to (save_derivatives=True, the
+        `dysave` buffer of rmsb_solve_opts), otherwise one batched dydt call per saved time."""
         if self._du is None:
             dom = self.reactor.domain
             n, k, Ny = self.u.shape
@@ -149,8 +150,12 @@ def threadedsensitivities(react: Reactor, paramindices=None, odesolver: Optional
 
 
 def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6, reltol: float = 1e-3,
-          saveat: Optional[Sequence[float]] = None, idt_index: int = -1, t_end=None) -> Solution:
-    """solve(react.ode, alg; abstol, reltol[, saveat]) -- default tolerances are SciML's (1e-6, 1e-3)."""
+          saveat: Optional[Sequence[float]] = None, idt_index: int = -1, t_end=None, save_derivatives: bool = False,
+          devices: Optional[Sequence[int]] = None) -> Solution:
+    """solve(react.ode, alg; abstol, reltol[, saveat]) -- default tolerances are SciML's (1e-6, 1e-3).
+    save_derivatives: also return du at the saved states (what sol.interp.du holds in the reference) from the same call.
+    devices: GPU ordinals to shard the ensemble over from this one process (rmsb_solve_batch_multi: contiguous blocks by
+    reactor index, one host thread per device); None = the device of the phase's handle."""
     alg = alg or react.recommendedsolver
     dom = react.domain
     y0 = react.y0
@@ -176,8 +181,22 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
                                         L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
                                         L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats), C.byref(opts)))
         idt[:] = np.nan
-        return Solution(react, tsave, ysave, yend, idt, status, stats, te, ssave, send)
-    L.check(L.lib().rmsb_solve_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
-                                     L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
-                                     L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
-    return Solution(react, tsave, ysave, yend, idt, status, stats, te)
+        sol = Solution(react, tsave, ysave, yend, idt, status, stats, te, ssave, send)
+        sol.kernel_ms = float(L.lib().rmsb_last_kernel_ms())
+        return sol
+    dysave = np.empty((n, nsave, Ny)) if (save_derivatives and nsave) else None
+    if dysave is not None:
+        opts.dysave = dysave.ctypes.data
+    if devices is not None and len(devices) > 0:
+        handles = (C.c_void_p * len(devices))(*[dom.phase.handle_on(int(d)) for d in devices])
+        L.check(L.lib().rmsb_solve_batch_multi(handles, len(devices), dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                               L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
+    else:
+        L.check(L.lib().rmsb_solve_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                         L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                         L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
+    sol = Solution(react, tsave, ysave, yend, idt, status, stats, te)
+    sol._du = dysave
+    sol.kernel_ms = float(L.lib().rmsb_last_kernel_ms())
+    return sol

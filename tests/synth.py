@@ -120,3 +120,92 @@ def species_weights(ns: int) -> np.ndarray:
     for g in range(n_gen):
         out[bounds[g]:bounds[g + 1]] = g + 2.0
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8(d) recipe for config C3 at its stated size: the reference's own 35-species liquid octane oxidation
+# mechanism (tests/fixtures/liquid_phase.rms, src/TestReactors.jl:7-27) replicated over K homologous "fuel families" that
+# share the small-species pool (inert gases, O2, HO2, OH).  Family species keep the template's SMILES (so radii, diffusivities
+# and thermo are the template's) under a family-prefixed name; every family reaction is the template's with a seeded rate
+# perturbation A * 10^U(-0.3, 0.3).  K = 36, keep = 0.85  ->  Ns = 7 + 36*28 = 1015 species, Nr ~ 11.6 k reactions.
+# ------------------------------------------------------------------------------------------------------------------
+SHARED = ("Ar", "He", "Ne", "N2", "oxygen", "[O]O", "OH(D)")
+
+
+def _flow(v):
+    """YAML flow scalar for a name (SMILES need quoting)."""
+    return "'" + v.replace("'", "''") + "'"
+
+
+def write_octane_families(path: str, families: int = 36, keep: float = 0.85, seed: int = 20261019, template: str | None = None) -> dict:
+    import yaml
+    from pathlib import Path
+    tpl = template or str(Path(__file__).resolve().parent / "fixtures" / "liquid_phase.rms")
+    with open(tpl) as fh:
+        doc = yaml.load(fh, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
+    rng = np.random.default_rng(seed)
+    species = doc["Phases"][0]["Species"]
+    shared = [s for s in species if s["name"] in SHARED]
+    own = [s for s in species if s["name"] not in SHARED]
+    fam_name = lambda k, nm: f"F{k:02d}_{nm}"
+    lines = ["Phases:", "- Species:"]
+
+    def emit_species(sp, name):
+        lines.append(f"  - name: {_flow(name)}")
+        lines.append(f"    radicalelectrons: {sp.get('radicalelectrons', 0)}")
+        lines.append(f"    smiles: {_flow(sp['smiles'])}")
+        lines.append("    thermo:")
+        lines.append("      polys:")
+        for pl in sp["thermo"]["polys"]:
+            coefs = "[" + ", ".join(repr(float(c)) for c in pl["coefs"]) + "]"
+            lines.append(f"      - {{Tmax: {float(pl['Tmax'])!r}, Tmin: {float(pl['Tmin'])!r}, coefs: {coefs}, type: NASApolynomial}}")
+        lines.append("      type: NASA")
+        lines.append("    type: Species")
+
+    names = []
+    for sp in shared:
+        emit_species(sp, sp["name"]); names.append(sp["name"])
+    for k in range(families):
+        for sp in own:
+            emit_species(sp, fam_name(k, sp["name"])); names.append(fam_name(k, sp["name"]))
+    lines += ["  name: phase", "Reactions:"]
+    nr = 0
+
+    def emit_reaction(r, k, scale):
+        nonlocal nr
+        ren = lambda nm: nm if (nm in SHARED or k is None) else fam_name(k, nm)
+        kin = r["kinetics"]
+        assert kin["type"] == "Arrhenius"
+        lines.append(f"- kinetics: {{A: {float(kin['A']) * scale!r}, Ea: {float(kin['Ea'])!r}, n: {float(kin['n'])!r}, type: Arrhenius}}")
+        lines.append("  products: [" + ", ".join(_flow(ren(x)) for x in r["products"]) + "]")
+        lines.append(f"  radicalchange: {r.get('radicalchange', 0)}")
+        lines.append("  reactants: [" + ", ".join(_flow(ren(x)) for x in r["reactants"]) + "]")
+        lines.append("  type: ElementaryReaction")
+        nr += 1
+
+    for r in doc["Reactions"]:
+        if all(x in SHARED for x in list(r["reactants"]) + list(r["products"])):
+            emit_reaction(r, None, 1.0)                    # pool-only chemistry: once
+    for k in range(families):
+        for r in doc["Reactions"]:
+            if all(x in SHARED for x in list(r["reactants"]) + list(r["products"])):
+                continue
+            if rng.uniform() > keep:
+                continue
+            emit_reaction(r, k, 10.0 ** rng.uniform(-0.3, 0.3))
+    mu = doc["Solvents"][0]["mu"]
+    lines += ["Solvents:", "- mu: {" + ", ".join(f"{a}: {mu[a]!r}" for a in mu) + "}", f"  name: {doc['Solvents'][0]['name']}", "  type: Solvent", "Units: {}"]
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return {"names": names, "families": families, "nr": nr, "ns": len(names)}
+
+
+def octane_family_moles(families: int = 36, seed: int = 5) -> dict:
+    """Initial amounts: the reference's C3 charge (octane 6154 mol, oxygen 4.953 mol held constant, src/TestReactors.jl:18-22) with
+    the fuel split unevenly over the families."""
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(0.5, 1.5, families)
+    w /= w.sum()
+    ic = {f"F{k:02d}_octane": 6154.0 * float(w[k]) for k in range(families)}
+    ic["oxygen"] = 4.953
+    return ic

@@ -21,6 +21,21 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_shards_are_a_balanced_permutation():
+    from rmsb200.ensemble import balanced_shards
+    rng = np.random.default_rng(0)
+    work = rng.lognormal(6.0, 0.6, 100003)
+    for world in (1, 2, 4, 8):
+        parts = balanced_shards(work, world, 64)
+        allidx = np.concatenate(parts)
+        assert np.array_equal(np.sort(allidx), np.arange(len(work)))
+        tot = np.array([work[p].sum() for p in parts])
+        assert tot.max() / tot.mean() < 1.02                       # same mix on every rank (the excess is the single heaviest chunk)
+        for p in parts:
+            assert np.all(np.diff(work[p]) <= 0)                   # each rank's queue runs heaviest first
+    assert len(balanced_shards(np.ones(3), 8, 64)) == 8             # more ranks than chunks: empty shards are fine
+
+
 def _worker(rank, world, port, n, outfile):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     for p in (str(cases.ROOT), str(cases.ROOT / "reactionmechanismsimulator.jl_b200"), str(cases.ROOT / "tests")):
