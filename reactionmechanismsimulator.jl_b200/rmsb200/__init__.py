@@ -12,10 +12,11 @@ from .coupled import CoupledEnsemble, CoupledPhase, SystemSimulation, coupled_do
 from .coupled import make_interface as ReactiveInternalInterfaceConstantTPhi
 from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
                      ConstantVDomain, ConstantVEnsemble, Domain)
-from .ensemble import shard_bounds, shard_domain, solve_sharded
+from .ensemble import balanced_shards, shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)
 from .phase import IdealDiluteSolution, IdealGas, IdealSurface, Phase
 from .reactor import RMSB200, Reactor, Solution, solve, threadedsensitivities
 from .simulation import Simulation, idt_grid, ignition_delay
+from .transitory import getdividingtimescale, transitorysensitivitiesfulltrapezoidal
 
 __all__ = [n for n in dir() if not n.startswith("_")]

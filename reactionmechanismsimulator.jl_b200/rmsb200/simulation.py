@@ -91,6 +91,12 @@ class Simulation:
             out[j] = (f - b) * V
         return out
 
+    def transitorysensitivitiesfulltrapezoidal(self, t, tau=float("nan"), normalized=True):
+        """transitorysensitivitiesfulltrapezoidal(sim, t; tau, normalized) -> (dSdt, tau)  src/TransitorySensitivities.jl:284-302"""
+        from .transitory import transitorysensitivitiesfulltrapezoidal as tsens
+        dS, taus = tsens(_single(self.domain, self.r), self.y(t)[None, :], self.p, tau, normalized)
+        return dS[0], float(taus[0])
+
     def rops(self, name, t):
         """rops(sim, name, t): (#product - #reactant occurrences) * rate * V per reaction (src/Simulation.jl:357-373)."""
         d = self.domain

@@ -101,12 +101,17 @@ def test_constp_reference_transitory_sensitivity_golden(dom):
     from oracle import transitory as tr
     gold = np.loadtxt(cases.ROOT / "tests" / "golden" / "transitory_ethane_reference.txt")
     gdom, y0, p = dom
-    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.01), p=p), abstol=1e-16, reltol=1e-6)
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.01), p=p), abstol=1e-16, reltol=1e-6, saveat=[0.01])
+    # the product's consumer (rmsb200/transitory.py through the Simulation accessor, as the reference calls it) ...
+    dSdt, tau = rb.Simulation(sol, gdom).transitorysensitivitiesfulltrapezoidal(0.01)
+    # ... and the oracle's restatement fed with the same CUDA Jacobians agree to rounding
     y = sol.yend[0]
     one = rb.Domain(gdom.kind, gdom.phase, y[None], gdom.cond)
     one.p, one._p_default = gdom.p, gdom._p_default
-    Jy, Jp = one.jacobiany(y[None], p)[0], one.jacobianp(y[None], p)[0]
-    dSdt, tau = tr.transitorysensitivitiesfulltrapezoidal(Jy, Jp, y, p, gdom.phase.Ns)
+    dS_o, tau_o = tr.transitorysensitivitiesfulltrapezoidal(one.jacobiany(y[None], p)[0], one.jacobianp(y[None], p)[0], y, p, gdom.phase.Ns)
+    assert tau == tau_o
+    fin = np.isfinite(dS_o)
+    np.testing.assert_allclose(dSdt[fin], dS_o[fin], rtol=1e-9, atol=1e-300)
     row = dSdt[gdom.phase.names.index("ethane"), :]
     ok = np.abs(row - gold) <= 1e-4 * np.abs(gold) + 1e-16
     assert ok.sum() >= 159 and np.all(np.abs(row - gold) <= 2e-4 * np.abs(gold) + 1e-16)

@@ -140,3 +140,98 @@ def _variable_k_domain_on_large_mechanism(ph, y0):
     out = np.empty_like(y)
     rc = L.lib().rmsb_dydt_batch(ph.handle, L.DOMAIN_CONSTANT_P, 1, L.ptr(np.ascontiguousarray(y)), L.ptr(np.array([[1e5]])), None, 0, None, 0, L.ptr(out))
     L.check(rc)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Config C3 AT ITS STATED SIZE (BASELINE.json configs[2], SURVEY 8d recipe): the reference's 35-species liquid octane mechanism
+# replicated over 36 fuel families sharing the O2 / HO2 / OH pool -- 1015 species, 11 593 reactions, diffusion limited, ConstantTV.
+# dydt / Jacobian / rate coefficients against the NumPy oracle (live and committed vectors), the trajectory against the committed
+# SciPy-BDF golden (tests/golden/make_c3_golden.py), a 4096-condition sweep with zero non-OK statuses.
+# ---------------------------------------------------------------------------------------------------------------------------------
+K_FAM = 36
+
+
+@pytest.fixture(scope="module")
+def octane_families(tmp_path_factory):
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    path = str(tmp_path_factory.mktemp("c3") / "octane_families.rms")
+    info = synth.write_octane_families(path, families=K_FAM)
+    d = rb.readinput(path)
+    ph = rb.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0], name="phase")
+    od = ro.readinput(path)
+    oph = ro.IdealDiluteSolution(od["phase"]["Species"], od["phase"]["Reactions"], od["Solvents"][0])
+    ic = {"T": 450.0, "V": 1.0, **synth.octane_family_moles(K_FAM)}
+    gdom, y0, p = rb.ConstantTVDomain(phase=ph, initialconds=ic, constantspecies=["oxygen"])
+    odom = ro.ConstantTVDomain(oph, ic, constantspecies=("oxygen",))
+    gold = np.load(cases.ROOT / "tests" / "golden" / "c3_octane_families.npz")
+    assert info["ns"] == int(gold["ns"]) == ph.Ns and info["nr"] == int(gold["nr"]) == ph.Nr
+    return ph, oph, gdom, odom, y0, p, gold
+
+
+def test_c3_stated_size_pattern(octane_families):
+    ph = octane_families[0]
+    assert ph.Ns >= 1000 and 10000 <= ph.Nr <= 12000
+    info = np.zeros(8, dtype=np.int64)
+    L.check(L.lib().rmsb_large_info(ph.handle, L.ptr(info)))
+    n, nnz, lvl_l, lvl_u, max_row, fma, core, scratch = (int(v) for v in info)
+    assert n == ph.Ns and 0.01 < nnz / n ** 2 < 0.04          # 1-4 % dense
+    assert lvl_l < 80 and n - core < 64                        # families eliminate in parallel; the shared pool is the dense core
+
+
+def test_c3_stated_size_dydt_jacobian_rates_parity(octane_families):
+    from oracle import floors as fl
+    ph, oph, gdom, odom, y0, p, gold = octane_families
+    ys = gold["ys"]
+    ens = rb.Domain(gdom.kind, ph, ys, np.repeat(gdom.cond, len(ys), axis=0), constantspecies=["oxygen"])
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    f, J = ens.dydt(ys, p), ens.jacobiany(ys, p)
+    np.testing.assert_allclose(gdom.kfs[0], gold["kfs"], rtol=1e-12)
+    np.testing.assert_allclose(gdom.krevs[0], gold["krevs"], rtol=1e-12)
+    for k in range(len(ys)):
+        fo, M = fl.dydt_terms(odom, ys[k], 0.0, odom.p)
+        np.testing.assert_allclose(fo, gold["f"][k], rtol=1e-12, atol=1e-30)       # the committed vectors are the live oracle's
+        rep = fl.report(f[k], fo, fl.EPS * M, 1e-12, slack=16.0)
+        assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, rep
+        Jo = ro.jacobiany(odom, ys[k], 0.0, odom.p)
+        assert cases.err_jac(J[k], Jo) < 1e-12
+        nz = Jo != 0.0
+        # species-block entries are short sums of same-signed or few terms: plain relative error on every non-zero entry
+        assert np.max(np.abs(J[k][nz] - Jo[nz]) / np.abs(Jo[nz])) < 1e-9
+        assert np.all(J[k][~nz] == 0.0)
+
+
+def test_c3_stated_size_trajectory_vs_scipy_golden(octane_families):
+    ph, oph, gdom, odom, y0, p, gold = octane_families
+    tq, yq = gold["tq"], gold["yq"]
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-18, reltol=1e-9, saveat=tq)
+    assert sol.retcode == ["Success"]
+    for k in range(len(tq)):
+        big = np.abs(yq[k]) > 1e-9 * np.abs(yq[k]).max()
+        assert np.max(np.abs(sol.u[0, k] - yq[k])[big] / np.abs(yq[k])[big]) < 1e-6, tq[k]
+    i_oct = ph.names.index("F00_octane")
+    assert sol.u[0, -1, i_oct] < 0.5 * y0[i_oct]                               # the fuel is mostly converted by t_end: not a trivial trajectory
+    # the reference's loose setting lands on the same solution
+    sol6 = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-16, reltol=1e-6, saveat=tq[-1:])
+    big = np.abs(yq[-1]) > 1e-6 * np.abs(yq[-1]).max()
+    assert np.max(np.abs(sol6.u[0, 0] - yq[-1])[big] / np.abs(yq[-1])[big]) < 2e-3
+
+
+def test_c3_stated_size_4k_sweep_all_converge(octane_families):
+    """BASELINE configs[2]: the 4k-condition sweep.  Zero non-OK statuses, O2 held, every family's carbon skeleton count conserved
+    (each family reaction maps family species to family species one to one), batch position does not matter."""
+    ph, oph, gdom, odom, y0, p, gold = octane_families
+    n = 4096
+    rng = np.random.default_rng(cases.SEED)
+    T = rng.uniform(400.0, 500.0, n)
+    y0s = np.repeat(gdom.y0, n, axis=0) * rng.uniform(0.8, 1.2, (n, 1))
+    io2 = ph.names.index("oxygen")
+    y0s[:, io2] = 4.953 * rng.uniform(0.5, 2.0, n)
+    T[-1], y0s[-1] = T[0], y0s[0]
+    ens = rb.Domain(gdom.kind, ph, y0s, np.stack([T, np.ones(n)], axis=1), constantspecies=["oxygen"])
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 140000.01)).ode, abstol=1e-16, reltol=1e-6)
+    assert np.array_equal(np.bincount(sol.status, minlength=4), [n, 0, 0, 0])
+    assert np.array_equal(sol.yend[:, io2], y0s[:, io2])
+    assert np.array_equal(sol.yend[0], sol.yend[-1])
+    fam = np.array([int(nm[1:3]) if nm.startswith("F") and nm[3] == "_" else -1 for nm in ph.names])
+    for k in (0, 17, K_FAM - 1):
+        np.testing.assert_allclose(sol.yend[:, fam == k].sum(axis=1), y0s[:, fam == k].sum(axis=1), rtol=1e-9)

@@ -22,11 +22,11 @@ def test_library_exports_every_header_symbol():
     for name in declared:
         assert hasattr(lib, name), f"librmsb200.so does not export {name}"
     assert set(L.EXPORTS) == declared
-    assert lib.rmsb_version() == 100
+    assert lib.rmsb_version() == 200
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(L.Stats) == 40 and C.sizeof(L.SolveOpts) == 32
+    assert C.sizeof(L.Stats) == 40 and C.sizeof(L.SolveOpts) == 40        # v2: + dysave (a version-1 struct of 32 bytes is still accepted)
     assert C.sizeof(L.MechDesc) == C.sizeof(co.Desc)
 
 
@@ -146,3 +146,27 @@ def test_coupled_descriptor_host_side():
     # molecular weights come from the SMILES (RDKit MolWt in the reference, src/Parse.jl:143)
     mw = {s.name: s.molecularweight for s in ig.species}
     assert mw["CH4"] == pytest.approx(0.016043, rel=1e-4) and mw["CO2"] == pytest.approx(0.044009, rel=1e-4)
+
+
+def test_transitory_time_scale_selection_matches_the_oracle_restatement():
+    """rmsb200.transitory.getdividingtimescale (host post-processing of the batched Jacobians) against the oracle's independent
+    restatement of src/TransitorySensitivities.jl:5-113 on random bimodal time-scale spectra."""
+    from oracle import transitory as tr
+    from rmsb200 import transitory as pt
+    rng = np.random.default_rng(0)
+    seen = 0
+    for _ in range(100):
+        n = int(rng.integers(20, 80))
+        d = -10.0 ** np.concatenate([rng.normal(8, 1, n // 2), rng.normal(0, 1.5, n - n // 2)])
+        J = np.diag(d)
+        try:
+            a = tr.getdividingtimescale(J)
+        except ValueError:
+            a = None
+        try:
+            b = pt.getdividingtimescale(J)
+        except ValueError:
+            b = None
+        assert a == b
+        seen += a is not None
+    assert seen > 50
