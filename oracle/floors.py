@@ -5,9 +5,12 @@ cancel to a fraction 1/kappa of their magnitude cannot be reproduced to better t
 neither by this repo's CUDA path nor by the reference (whose hot path is compiled under @fastmath and re-associates).
 This module derives that floor so the tests can report the plain relative error on every entry above it:
 
-* dydt_terms(): the magnitude sum M_i = sum_t |term_t| of every component of dydtreactor! -- for the species rows
-  V * sum_j |nu_ij| (|Rf_j| + |Rr_j|) from addreactionratecontributions! (src/Reactor.jl:465-507), for the thermodynamic-variable
-  rows the same sums pushed through calcdomainderivatives! (src/Domain.jl:1863-1953).  floor_i = eps * M_i.
+* dydt_terms(): the magnitude sum M_i = sum_t kappa_t |term_t| of every component of dydtreactor! -- for the species rows
+  V * sum_j |nu_ij| (kappa_f |Rf_j| + kappa_r |Rr_j|) from addreactionratecontributions! (src/Reactor.jl:465-507), for the
+  thermodynamic-variable rows the same sums pushed through calcdomainderivatives! (src/Domain.jl:1863-1953).  kappa is the
+  conditioning of the exponentials inside a term: k_f = A*exp(x) carries a relative error |x|*eps from the rounding of x, and
+  k_rev = k_f/K_c adds sum |nu_i G_i/RT| * eps from the exponent of K_c (50-300 for large molecules) -- any FP64 evaluation,
+  the reference's included.  floor_i = eps * M_i.
 * numeric_floor(): for the Jacobians (whose terms are the derivatives of those, src/Reactor.jl:899-1477, Domain.jl:3095-3485)
   the floor is measured instead of re-derived: the spread of the oracle's own result when every input (state, conditions,
   parameters) is perturbed by a random relative 2 ulp.  For an entry sum_t m_t(u) of monomial terms this spread is
@@ -29,6 +32,9 @@ def dydt_terms(domain, y, t=0.0, p=None):
     ra = domain.phase.rxnarray
     Ns = domain.phase.Ns
     M = np.zeros(len(y))
+    Gs = th.Gs if len(th.Gs) == Ns else np.asarray(getattr(domain, "Gs", np.zeros(Ns)))     # constant-k domains keep them on the domain
+    if p is not None and domain.kind in ("ConstantTP", "ConstantTV", "ConstantTAPhi"):
+        Gs = np.asarray(p)[:Ns]
     for i in range(ra.shape[1]):
         fR = th.kfs[i]
         for j in range(4):
@@ -40,7 +46,10 @@ def dydt_terms(domain, y, t=0.0, p=None):
             if ra[j, i] < 0:
                 break
             rR = rR * th.cs[ra[j, i]]
-        mag = abs(fR) + abs(rR)
+        with np.errstate(divide="ignore"):
+            kap_f = 2.0 + (abs(np.log(abs(th.kfs[i]))) if th.kfs[i] != 0.0 else 0.0)
+        kap_r = kap_f + sum(abs(Gs[ra[j, i]]) for j in range(8) if ra[j, i] >= 0) / (ro.R * th.T)
+        mag = kap_f * abs(fR) + kap_r * abs(rR)
         for j in range(8):
             if ra[j, i] >= 0:
                 M[ra[j, i]] += mag
@@ -59,16 +68,19 @@ def dydt_terms(domain, y, t=0.0, p=None):
     return ro.dydtreactor(domain, y, t, p), M
 
 
-def numeric_floor(fn, inputs, nsample=6, ulps=2.0, seed=0):
-    """max over `nsample` random perturbations (relative size `ulps`*eps on every entry of every array in `inputs`) of
-    |fn(*perturbed) - fn(*inputs)|, elementwise.  None entries of `inputs` are passed through."""
+def numeric_floor(fn, inputs, nsample=6, ulps=2.0, seed=0, amplify=16.0):
+    """max over `nsample` random perturbations of every entry of every array in `inputs` of |fn(*perturbed) - fn(*inputs)|,
+    elementwise, scaled to a relative input uncertainty of `ulps`*eps.  The perturbations are drawn uniformly from
+    +-amplify*ulps*eps (continuous magnitudes: with equal magnitudes and random signs the perturbations of two cancelling terms
+    coincide exactly in a third of the draws and the floor of such an entry comes out as zero) and the spread is divided by
+    `amplify` again -- the response is linear at 1e-15.  None entries of `inputs` are passed through."""
     rng = np.random.default_rng(seed)
     base = np.asarray(fn(*inputs), dtype=float)
     floor = np.zeros_like(base)
     for _ in range(nsample):
-        pert = [None if a is None else np.asarray(a, dtype=float) * (1.0 + ulps * EPS * rng.choice([-1.0, 1.0], size=np.shape(a))) for a in inputs]
+        pert = [None if a is None else np.asarray(a, dtype=float) * (1.0 + amplify * ulps * EPS * rng.uniform(-1.0, 1.0, size=np.shape(a))) for a in inputs]
         floor = np.maximum(floor, np.abs(np.asarray(fn(*pert), dtype=float) - base))
-    return base, floor
+    return base, floor / amplify
 
 
 def closure_floor(domain, y, p, Jabs, t=0.0):
@@ -97,6 +109,27 @@ def jac_floor(fn, domain, y, p, t=0.0, **kw):
     Ns = domain.phase.Ns
     if ref.shape[0] > Ns:
         floor[Ns:] += 4.0 * closure_floor(domain, y, p, ref, t)
+    # entries that are EXACTLY zero in the oracle because +d / -d pairs of one reaction cancel (a species on both sides, e.g. a
+    # collider): another summation order leaves a residue of a few eps of the column's largest term
+    zero = ref == 0.0
+    if zero.any():
+        col = np.max(np.abs(ref), axis=0, keepdims=True) * np.ones_like(ref)
+        floor[zero] += EPS * col[zero]
+    return ref, floor
+
+
+def jacp_floor(domain, y, p, t=0.0, **kw):
+    """(ref, floor) of jacobianp!: jac_floor plus the term the adiabatic domains add to the T row of the dG columns,
+    -(dot(U, Jp[:, i]) + dn_i/dt) / (N*Cv) (src/Domain.jl:3433-3460): dn_i/dt is itself a cancelling sum whose floor is eps*M_i."""
+    ref, floor = jac_floor(lambda yy, pp: ro.jacobianp(domain, yy, t, pp), domain, y, p, t, **kw)
+    if domain.kind in ("ConstantV", "ConstantP"):
+        Ns = domain.phase.Ns
+        th = domain.calcthermo(np.asarray(y, dtype=float), t, p)
+        _, M = dydt_terms(domain, y, t, p)
+        den = abs(th.N * th.Cvave) if domain.kind == "ConstantV" else abs(th.N * (th.Cvave + ro.R))
+        add = 4.0 * EPS * M[:Ns] / den
+        floor[Ns, :Ns] += add
+        floor[Ns + 1, :Ns] += add * (th.P / th.T if domain.kind == "ConstantV" else th.V / th.T)
     return ref, floor
 
 
@@ -109,5 +142,7 @@ def report(x, ref, floor, bar=1e-12, slack=8.0):
     err = np.abs(x - ref)
     above = (np.abs(ref) > 0) & (floor <= 0.1 * bar * np.abs(ref))
     rel = np.max(err[above] / np.abs(ref[above])) if above.any() else 0.0
-    excess = np.max(err / (bar * np.abs(ref) + slack * floor + 1e-300))
-    return {"n": int(x.size), "n_above": int(above.sum()), "max_rel_above": float(rel), "worst_excess": float(excess)}
+    ratio = err / (bar * np.abs(ref) + slack * floor + 1e-300)
+    worst = np.unravel_index(int(np.argmax(ratio)), ratio.shape)
+    return {"n": int(x.size), "n_above": int(above.sum()), "max_rel_above": float(rel), "worst_excess": float(ratio[worst]),
+            "worst_at": tuple(int(i) for i in worst), "worst_x": float(x[worst]), "worst_ref": float(ref[worst]), "worst_floor": float(floor[worst])}

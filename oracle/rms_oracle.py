@@ -1092,7 +1092,140 @@ class ConstantTAPhiDomain(_ConstantKDomain):
 # --------------------------------------------------------------------------------------
 # RHS: src/Reactor.jl:653-660
 # --------------------------------------------------------------------------------------
-def dydtreactor(domain, y, t=0.0, p=None):
+# --------------------------------------------------------------------------------------
+# Boundary interfaces: src/Interface.jl:234-400 (structs), consumed by calcdomainderivatives!
+# (src/Domain.jl:1839-1998) and by jacobiany! (:2220-2294, 2322-2448, 2493-2628, 3057-3088)
+# --------------------------------------------------------------------------------------
+def _flow(F, t):
+    return F(t) if callable(F) else F
+
+
+def _species_enthalpies(phase: Phase, T):
+    return np.array([getEnthalpy(selectPoly(s.polys, T), T) for s in phase.species])
+
+
+class Inlet:
+    """Inlet(domain, conddict, F): molar flow F(t) of composition y (mole fractions) and enthalpy H (src/Interface.jl:234-263)."""
+
+    def __init__(self, domain, conddict: dict, F):
+        T, P = float(conddict.get("T", 0.0)), float(conddict.get("P", 0.0))
+        y = np.zeros(domain.phase.Ns)
+        for k, v in conddict.items():
+            if k not in ("T", "P", "Hin"):
+                y[domain.phase.spcdict[k]] = float(v)
+        self.domain, self.y, self.F, self.T, self.P = domain, y / y.sum(), F, T, P
+        if "Hin" in conddict:
+            self.H = float(conddict["Hin"])
+        else:
+            assert T != 0.0 and P != 0.0, "T and P need to be provided if Hin is not provided for Inlet"
+            self.H = float(np.dot(_species_enthalpies(domain.phase, T), self.y))
+
+
+class Outlet:
+    """Outlet(domain, F): molar flow F(t) of the reactor's own composition (src/Interface.jl:265-269)."""
+
+    def __init__(self, domain, F):
+        self.domain, self.F = domain, F
+
+
+class VolumetricFlowRateInlet:
+    """VolumetricFlowRateInlet(domain, conddict, Vin): volumetric flow of concentrations cs (src/Interface.jl:320-353)."""
+
+    def __init__(self, domain, conddict: dict, Vin):
+        T, P = float(conddict.get("T", 0.0)), float(conddict.get("P", 0.0))
+        cs = np.zeros(domain.phase.Ns)
+        for k, v in conddict.items():
+            if k not in ("T", "P", "Hin"):
+                cs[domain.phase.spcdict[k]] = float(v)
+        self.domain, self.cs, self.Vin, self.T, self.P = domain, cs, Vin, T, P
+        if "Hin" in conddict:
+            self.Hpervolume = float(conddict["Hin"]) / cs.sum()
+        else:
+            assert T != 0.0 and P != 0.0
+            self.Hpervolume = float(np.dot(_species_enthalpies(domain.phase, T), cs))
+
+
+class VolumetricFlowRateOutlet:
+    """src/Interface.jl:314-318"""
+
+    def __init__(self, domain, Vout):
+        self.domain, self.Vout = domain, Vout
+
+
+class VolumeMaintainingOutlet:
+    """Outlet whose flow keeps the volume constant (src/Interface.jl:356-365); evaluated after every other interface."""
+
+    def __init__(self, domain):
+        self.domain = domain
+
+
+def apply_interfaces(domain, dydt, th: Thermo, t, interfaces):
+    """The interface loops of calcdomainderivatives! (src/Domain.jl:1843-1860 generic, 1868-1898 ConstantTP, 1907-1947 ConstantV,
+    1957-1997 ConstantP), after the constant-species zeroing."""
+    Ns = domain.phase.Ns
+    kind = domain.kind
+    T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
+    for it in interfaces:
+        if it.domain is not domain:
+            continue
+        if isinstance(it, Inlet):
+            flow = _flow(it.F, t)
+            dydt[:Ns] += it.y * flow
+            if kind == "ConstantTP":
+                dydt[Ns] += flow * R * T / P
+            elif kind == "ConstantV":
+                dTdt = flow * (it.H - np.dot(th.Us, ns) / N) / (N * th.Cvave)
+                dydt[Ns] += dTdt
+                dydt[Ns + 1] += flow * R * T / V + P / T * dTdt
+            elif kind == "ConstantP":
+                dTdt = flow * (it.H - np.dot(th.Hs, ns) / N) / (N * (th.Cvave + R))
+                dydt[Ns] += dTdt
+                dydt[Ns + 1] += flow * R * T / P + dTdt * V / T
+        elif isinstance(it, Outlet):
+            flow = _flow(it.F, t)
+            dydt[:Ns] -= flow * ns / N
+            if kind == "ConstantTP":
+                dydt[Ns] -= flow * R * T / P
+            elif kind == "ConstantV":
+                dTdt = (P * V / N * flow) / (N * th.Cvave)
+                dydt[Ns] -= dTdt
+                dydt[Ns + 1] -= flow * R * T / V + P / T * dTdt
+            elif kind == "ConstantP":
+                dydt[Ns + 1] -= flow * R * T / P
+        elif isinstance(it, VolumetricFlowRateInlet):
+            vin = _flow(it.Vin, t)
+            dydt[:Ns] += vin * it.cs
+            if kind == "ConstantTP":
+                dydt[Ns] += vin
+            elif kind == "ConstantV":
+                dTdt = vin * (it.Hpervolume - np.dot(th.Us, ns) / V) / (N * th.Cvave)
+                dydt[Ns] += dTdt
+                dydt[Ns + 1] += vin * P / V + P / T * dTdt
+            elif kind == "ConstantP":
+                dTdt = vin * (it.Hpervolume - np.dot(th.Hs, ns) / V) / (N * (th.Cvave + R))
+                dydt[Ns] += dTdt
+                dydt[Ns + 1] += vin
+        elif isinstance(it, VolumetricFlowRateOutlet):
+            vout = _flow(it.Vout, t)
+            dydt[:Ns] -= vout * ns / V
+            if kind == "ConstantTP":
+                dydt[Ns] -= vout
+            elif kind == "ConstantV":
+                dTdt = (P * vout) / (N * th.Cvave)
+                dydt[Ns] -= dTdt
+                dydt[Ns + 1] -= vout * P / V + P / T * dTdt
+            elif kind == "ConstantP":
+                dydt[Ns + 1] -= vout
+    for it in interfaces:
+        if isinstance(it, VolumeMaintainingOutlet) and it.domain is domain and kind in ("ConstantTP", "ConstantP"):
+            iv = Ns if kind == "ConstantTP" else Ns + 1
+            dVdt = dydt[iv]
+            flow = P * dVdt / (R * T)
+            dydt[:Ns] -= flow * ns / N
+            dydt[iv] -= dVdt
+
+
+def dydtreactor(domain, y, t=0.0, p=None, interfaces=()):
     y = np.asarray(y)
     th = domain.calcthermo(y, t, p)
     dt = np.result_type(y.dtype, th.kfs.dtype, np.asarray(th.V).dtype, float)
@@ -1100,6 +1233,8 @@ def dydtreactor(domain, y, t=0.0, p=None):
     addreactionratecontributions(dydt, domain.phase.rxnarray, th.cs, th.kfs, th.krevs)
     dydt *= th.V
     domain.derivatives(dydt, th)
+    if interfaces:
+        apply_interfaces(domain, dydt, th, t, interfaces)
     return dydt
 
 
@@ -1182,7 +1317,99 @@ def jacobianynsderiv(jac, domain, th: Thermo, Vind: Optional[int]):
                 _jacobianykderiv(jac, Vind, dkdV, dkdV / Kc, ph.rxnarray, i, th.cs, th.V)
 
 
-def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30):
+def _jac_interfaces(jac, domain, th: Thermo, t, interfaces):
+    """Analytic interface terms of the species columns (and of the volume column where the reference has them): src/Domain.jl:2220-2294
+    (ConstantTP), 2322-2448 (ConstantV), 2493-2628 (ConstantP), 3057-3088 (ConstantTV / ConstantTAPhi).  VolumeMaintainingOutlet has
+    no analytic terms in the reference."""
+    Ns = domain.phase.Ns
+    kind = domain.kind
+    T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
+    for it in interfaces:
+        if it.domain is not domain:
+            continue
+        if kind == "ConstantTP":
+            if isinstance(it, Outlet):
+                flow = _flow(it.F, t)
+                for i in range(Ns):
+                    jac[i, i] -= flow / N
+                jac[:Ns, Ns] -= -flow * ns / (N * V)
+            elif isinstance(it, VolumetricFlowRateOutlet):
+                vout = _flow(it.Vout, t)
+                for i in range(Ns):
+                    jac[i, i] -= vout / V
+                jac[:Ns, Ns] -= -vout * ns / (V * V)
+        elif kind == "ConstantV":
+            Cv = th.Cvave
+            if isinstance(it, (Inlet, VolumetricFlowRateInlet)):
+                if isinstance(it, Inlet):
+                    flow = _flow(it.F, t)
+                    dTdt = flow * (it.H - np.dot(th.Us, ns) / N) / (N * Cv)
+                else:
+                    flow = _flow(it.Vin, t)
+                    dTdt = (flow * (it.Hpervolume - np.dot(th.Us, ns) / V)) / (N * Cv)
+                for i in range(Ns):
+                    dC = th.cpdivR[i] * R / N
+                    dd = flow * (-th.Us[i] / N) / (N * Cv) - dTdt * (dC / Cv)
+                    jac[Ns, i] += dd
+                    jac[Ns + 1, i] += P / T * dd
+            elif isinstance(it, (Outlet, VolumetricFlowRateOutlet)):
+                if isinstance(it, Outlet):
+                    flow = _flow(it.F, t)
+                    dTdt = (P * V / N * flow) / (N * Cv)
+                    diag = flow / N
+                else:
+                    flow = _flow(it.Vout, t)
+                    dTdt = (P * flow) / (N * Cv)
+                    diag = flow / V
+                for i in range(Ns):
+                    jac[i, i] -= diag
+                    dC = th.cpdivR[i] * R / N
+                    dd = -dTdt * (dC / Cv)
+                    jac[Ns, i] -= dd
+                    jac[Ns + 1, i] -= P / T * dd
+        elif kind == "ConstantP":
+            Cp = th.Cvave + R
+            if isinstance(it, Inlet):
+                flow = _flow(it.F, t)
+                H = np.dot(th.Hs, ns) / N
+                dTdt = flow * (it.H - H) / (N * Cp)
+                for i in range(Ns):
+                    dC = th.cpdivR[i] * R / N
+                    dd = flow * (-th.Hs[i] / N) / (N * Cp) - dTdt * (dC / Cp)
+                    jac[Ns, i] += dd
+                    jac[Ns + 1, i] += V / T * dd
+                ddV = flow * H / V / (N * Cp)
+                jac[Ns, Ns + 1] += ddV
+                jac[Ns + 1, Ns + 1] += V / T * ddV
+            elif isinstance(it, Outlet):
+                flow = _flow(it.F, t)
+                for i in range(Ns):
+                    jac[i, i] -= flow / N
+                jac[:Ns, Ns + 1] -= -flow * ns / N / V
+            elif isinstance(it, VolumetricFlowRateInlet):
+                vin = _flow(it.Vin, t)
+                dTdt = vin * (it.Hpervolume - np.dot(th.Hs, ns) / V) / (N * Cp)
+                for i in range(Ns):
+                    dC = th.cpdivR[i] * R / N
+                    jac[Ns, i] += vin * (-th.Hs[i] / N) / (N * Cp) - dTdt * (dC / Cp)
+            elif isinstance(it, VolumetricFlowRateOutlet):
+                vout = _flow(it.Vout, t)
+                for i in range(Ns):
+                    jac[i, i] -= vout / V
+                jac[:Ns, Ns + 1] -= -vout / (V * V) * ns
+        else:   # ConstantTV / ConstantTAPhi (N = sum(ns))
+            if isinstance(it, Outlet):
+                flow = _flow(it.F, t)
+                for i in range(Ns):
+                    jac[i, i] -= flow / N
+                    jac[i, :] += flow * ns[i] / (N * N)
+            elif isinstance(it, VolumetricFlowRateOutlet):
+                vout = _flow(it.Vout, t)
+                for i in range(Ns):
+                    jac[i, i] -= vout / V
+
+
+def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30, interfaces=()):
     """Analytic Jacobian jac[row = equation, col = variable], src/Domain.jl:2204-2454,3049-3055.
     The ConstantV T and P columns are the derivative of the complete RHS (reference: ForwardDiff,
     src/Reactor.jl:1469-1477; here: complex step with h = ``cstep``, exact to rounding)."""
@@ -1197,6 +1424,7 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30):
             jac[Ns, i] = np.sum(jac[:Ns, i]) * R * th.T / th.P
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
+        _jac_interfaces(jac, domain, th, t, interfaces)
     elif domain.kind == "ConstantV":
         jacobianynsderiv(jac, domain, th, None)
         dydt = np.zeros(Ny)
@@ -1209,10 +1437,11 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30):
             jac[Ns + 1, i] = np.sum(jac[:Ns, i]) * R * th.T / th.V + th.P / th.T * jac[Ns, i]
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
+        _jac_interfaces(jac, domain, th, t, interfaces)
         for col in (Ns, Ns + 1):
             yc = y.astype(complex)
             yc[col] += 1j * cstep
-            jac[:, col] = dydtreactor(domain, yc, t, p).imag / cstep
+            jac[:, col] = dydtreactor(domain, yc, t, p, interfaces).imag / cstep
     elif domain.kind == "ConstantP":      # src/Domain.jl:2456-2632: V column analytic, T column = derivative of the full RHS
         jacobianynsderiv(jac, domain, th, Ns + 1)
         dydt = np.zeros(Ny)
@@ -1228,24 +1457,26 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30):
         jac[Ns + 1, Ns + 1] = np.sum(jac[:Ns, Ns + 1]) * R * th.T / th.P + dTdt / th.T + th.V / th.T * jac[Ns, Ns + 1]
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
+        _jac_interfaces(jac, domain, th, t, interfaces)
         yc = y.astype(complex)
         yc[Ns] += 1j * cstep
-        jac[:, Ns] = dydtreactor(domain, yc, t, p).imag / cstep
+        jac[:, Ns] = dydtreactor(domain, yc, t, p, interfaces).imag / cstep
     else:  # ConstantTV / ConstantTAPhi
         jacobianynsderiv(jac, domain, th, None)
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
+        _jac_interfaces(jac, domain, th, t, interfaces)
     return jac
 
 
-def jacobiany_complexstep(domain, y, t=0.0, p=None, h=1e-30):
+def jacobiany_complexstep(domain, y, t=0.0, p=None, h=1e-30, interfaces=()):
     """Stand-in for jacobianyforwarddiff (src/Reactor.jl:771-782): derivative of the full RHS."""
     y = np.asarray(y, dtype=float)
     J = np.zeros((len(y), len(y)))
     for k in range(len(y)):
         yc = y.astype(complex)
         yc[k] += 1j * h
-        J[:, k] = dydtreactor(domain, yc, t, p).imag / h
+        J[:, k] = dydtreactor(domain, yc, t, p, interfaces).imag / h
     return J
 
 

@@ -277,12 +277,43 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
         std::vector<int> colptr(Ns + 1, 0);                        // the entry list is sorted by (column, row)
         for (size_t e = 0; e < jecol.size(); ++e) ++colptr[jecol[e] + 1];
         for (int c = 0; c < Ns; ++c) colptr[c + 1] += colptr[c];
-        for (int with_v = 0; with_v < 2; ++with_v) {
-            const int n = Ns + with_v;
+        // third-body efficiency entries (row = a species of the reaction, col = a species with a listed efficiency): distinct pairs,
+        // per-reaction index blocks [listed species][8 slots] and the same entries grouped by column
+        std::vector<int> eerow, eecol, eeptr(1, 0), eeidx;
+        {
+            std::map<std::pair<int, int>, int> ids;
+            for (int j : effrxn) {
+                for (int k = effptr[j]; k < effptr[j + 1]; ++k) {
+                    const int col = effspc[k];
+                    for (int q = 0; q < 8; ++q) {
+                        const int sp = rx[(size_t)q * Nr + j];
+                        if (sp < 0) { eeidx.push_back(-1); continue; }
+                        auto it = ids.find({sp, col});
+                        if (it == ids.end()) { it = ids.emplace(std::make_pair(sp, col), (int)eerow.size()).first; eerow.push_back(sp); eecol.push_back(col); }
+                        eeidx.push_back(it->second);
+                    }
+                }
+                eeptr.push_back((int)eeidx.size());
+            }
+        }
+        const int n_ee = (int)eerow.size();
+        std::vector<int> eecolptr(Ns + 1, 0), eebycol(n_ee);
+        for (int e = 0; e < n_ee; ++e) ++eecolptr[eecol[e] + 1];
+        for (int c = 0; c < Ns; ++c) eecolptr[c + 1] += eecolptr[c];
+        {
+            std::vector<int> fill(eecolptr.begin(), eecolptr.end() - 1);
+            for (int e = 0; e < n_ee; ++e) eebycol[fill[eecol[e]]++] = e;
+        }
+        if (eeidx.empty()) eeidx.push_back(-1);
+        for (int nb = 0; nb < 3; ++nb) {
+            if (nb == 2 && dm.phase_kind != RMSB_PHASE_GAS) continue;   // ConstantV / ConstantP need an ideal gas
+            const int n = Ns + nb;
             std::vector<int> er(jerow), ec(jecol);
-            if (with_v) for (int i = 0; i <= Ns; ++i) { er.push_back(i); ec.push_back(Ns); er.push_back(Ns); ec.push_back(i); }
+            if (nb > 0) { er.insert(er.end(), eerow.begin(), eerow.end()); ec.insert(ec.end(), eecol.begin(), eecol.end()); }
+            for (int b2 = 0; b2 < nb; ++b2)
+                for (int i = 0; i < n; ++i) { er.push_back(i); ec.push_back(Ns + b2); er.push_back(Ns + b2); ec.push_back(i); }
             SparsePattern sp = analyse_pattern(n, er, ec);
-            std::vector<int> ldiag(sp.col.size()), lnk(sp.col.size()), amap(jerow.size()), vcolpos, vrowpos;
+            std::vector<int> ldiag(sp.col.size()), lnk(sp.col.size()), amap(jerow.size()), bcolpos, browpos, eepos;
             for (size_t p = 0; p < sp.col.size(); ++p) {
                 const int k = sp.col[p];
                 ldiag[p] = sp.diag[k];
@@ -292,19 +323,25 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
                 amap[e] = find_entry(sp, sp.iperm[jerow[e]], sp.iperm[jecol[e]]);
                 if (amap[e] < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain a Jacobian entry");
             }
-            if (with_v) {
-                for (int s = 0; s < Ns; ++s) vcolpos.push_back(find_entry(sp, sp.iperm[s], sp.iperm[Ns]));
-                for (int c = 0; c <= Ns; ++c) vrowpos.push_back(find_entry(sp, sp.iperm[Ns], sp.iperm[c]));
+            for (int b2 = 0; b2 < nb; ++b2) {
+                for (int i = 0; i < n; ++i) bcolpos.push_back(find_entry(sp, sp.iperm[i], sp.iperm[Ns + b2]));
+                for (int c = 0; c < Ns; ++c) browpos.push_back(find_entry(sp, sp.iperm[Ns + b2], sp.iperm[c]));
             }
-            LargeTables& lt = with_v ? h->lt_tp : h->lt;
-            lt.n = n; lt.ns = Ns; lt.has_v = with_v; lt.nnz = (int)sp.col.size();
+            if (nb > 0) for (int e = 0; e < n_ee; ++e) eepos.push_back(find_entry(sp, sp.iperm[eerow[e]], sp.iperm[eecol[e]]));
+            for (int v : bcolpos) if (v < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain a border entry");
+            for (int v : eepos) if (v < 0) return fail(RMSB_ERR_ARG, "internal: sparse pattern does not contain an efficiency entry");
+            LargeTables& lt = nb == 0 ? h->lt : (nb == 1 ? h->lt_tp : h->lt_vk);
+            lt.n = n; lt.ns = Ns; lt.nb = nb; lt.has_v = (nb == 1) ? 1 : 0; lt.bv = 0; lt.nnz = (int)sp.col.size();
+            lt.n_ee = nb > 0 ? n_ee : 0;
             lt.n_lvl_l = (int)sp.lvl_l_ptr.size() - 1; lt.n_lvl_u = (int)sp.lvl_u_ptr.size() - 1; lt.core = sp.core_start;
 #define UPL(vec, field) if ((rc = upload(h, vec, &lt.field)) != RMSB_OK) return rc
             UPL(sp.perm, perm); UPL(sp.row_ptr, row_ptr); UPL(sp.col, col); UPL(sp.diag, diag); UPL(ldiag, ldiag); UPL(lnk, lnk);
             UPL(sp.lvl_l_ptr, lvl_l_ptr); UPL(sp.lvl_l_rows, lvl_l_rows); UPL(sp.lvl_u_ptr, lvl_u_ptr); UPL(sp.lvl_u_rows, lvl_u_rows);
-            UPL(amap, amap); UPL(vcolpos, vcol_pos); UPL(vrowpos, vrow_pos); UPL(colptr, je_colptr);
+            UPL(amap, amap); UPL(bcolpos, bcol_pos); UPL(browpos, brow_pos); UPL(colptr, je_colptr);
+            UPL(eepos, ee_pos); UPL(eerow, ee_row); UPL(eecol, ee_col); UPL(eeptr, ee_ptr); UPL(eeidx, ee_idx);
+            UPL(eecolptr, ee_colptr); UPL(eebycol, ee_bycol);
 #undef UPL
-            if (!with_v) { h->large = true; h->large_max_row = sp.max_row; h->large_factor_flops = sp.factor_flops; }
+            if (nb == 0) { h->large = true; h->large_max_row = sp.max_row; h->large_factor_flops = sp.factor_flops; }
         }
     }
 #undef UP
@@ -450,6 +487,7 @@ __device__ __forceinline__ LargeCtx make_large_ctx(const LargeTables& lt, double
     c.t = lt;
     c.s.base = scratch + (size_t)blockIdx.x * per_block;
     c.s.n = lt.n; c.s.Ns = m.Ns; c.s.Nr = m.Nr; c.s.n_dt = m.n_dt; c.s.n_je = m.n_je; c.s.nnz = lt.nnz;
+    c.s.nb = lt.nb; c.s.n_ee = lt.n_ee; c.s.vk = (lt.nb == 2) ? 1 : 0;
     c.red = smem_ws + MECH_DOUBLES;
     c.ru = c.red + 64;
     c.x = c.ru + 36;
@@ -475,7 +513,8 @@ __global__ void __launch_bounds__(LARGE_THREADS, RMSB_LARGE_MINBLOCKS) large_sol
         c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
         c.d.constspc = a.constspc; c.d.nconst = a.nconst;
         c.d.cond = a.cond + ir * a.ncond;
-        c.T = c.d.cond[0]; c.V = c.d.cond[1]; c.P = c.d.cond[1];
+        c.T = c.d.cond[0]; c.V = c.P = (a.ncond > 1) ? c.d.cond[1] : 0.0;
+        c.t.bv = (a.domain_kind == RMSB_DOMAIN_CONSTANT_P) ? 1 : 0; c.t.has_v = (a.domain_kind == RMSB_DOMAIN_CONSTANT_P || a.domain_kind == RMSB_DOMAIN_CONSTANT_TP) ? 1 : 0;
         large_bdf_solve(a, c, (int64_t)ir);
     }
 }
@@ -493,13 +532,14 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
         c.d.p = a.p ? a.p + ir * a.p_stride : nullptr;
         c.d.constspc = a.constspc; c.d.nconst = a.nconst;
         c.d.cond = a.cond + ir * a.ncond;
-        c.T = c.d.cond[0]; c.V = c.d.cond[1]; c.P = c.d.cond[1];
+        c.T = c.d.cond[0]; c.V = c.P = (a.ncond > 1) ? c.d.cond[1] : 0.0;
+        c.t.bv = (a.domain_kind == RMSB_DOMAIN_CONSTANT_P) ? 1 : 0; c.t.has_v = (a.domain_kind == RMSB_DOMAIN_CONSTANT_P || a.domain_kind == RMSB_DOMAIN_CONSTANT_TP) ? 1 : 0;
         double* y = c.s.vec(8);
         for (int i = tid; i < n; i += LARGE_THREADS) y[i] = a.y[ir * n + i];
         __syncthreads();
-        large_setup(c, y);
+        if (!c.vk()) large_setup(c, y);
         if (MODE == 0) {
-            large_rhs(c, y, c.s.vec(14));
+            large_rhs_any(c, y, c.s.vec(14));
             for (int i = tid; i < n; i += LARGE_THREADS) a.out[ir * n + i] = c.s.vec(14)[i];
         } else if (MODE == 1) {
             large_jac(c, y);
@@ -507,18 +547,27 @@ __global__ void __launch_bounds__(LARGE_THREADS, 1) large_eval_kernel(const __gr
             for (size_t i = tid; i < (size_t)n * n; i += LARGE_THREADS) J[i] = 0.0;
             __syncthreads();
             for (int e = tid; e < m.n_je; e += LARGE_THREADS) J[G(m.je_row, e) + (size_t)G(m.je_col, e) * n] = c.s.jv()[e];
-            if (lt.has_v) {
-                for (int s = tid; s < lt.ns; s += LARGE_THREADS) J[s + (size_t)lt.ns * n] = c.s.vcol()[s];
-                for (int col = tid; col <= lt.ns; col += LARGE_THREADS) J[lt.ns + (size_t)col * n] = c.s.vrow()[col];
+            __syncthreads();
+            for (int e = tid; e < lt.n_ee; e += LARGE_THREADS) J[G(lt.ee_row, e) + (size_t)G(lt.ee_col, e) * n] += c.s.effv()[e];
+            for (int b = 0; b < lt.nb; ++b) {
+                for (int i = tid; i < n; i += LARGE_THREADS) J[i + (size_t)(lt.ns + b) * n] = c.s.bcolv()[(size_t)b * n + i];
+                for (int col = tid; col < lt.ns; col += LARGE_THREADS) J[lt.ns + b + (size_t)col * n] = c.s.browv()[(size_t)b * lt.ns + col];
             }
+        } else if (MODE == 2 && c.vk()) {
+            // kf / krev as calcthermo returns them: the value pass of the variable-k RHS keeps them
+            if (a.domain_kind == RMSB_DOMAIN_CONSTANT_P) large_rhs_v<double, true>(c, y, c.s.fd(), true);
+            else large_rhs_v<double, false>(c, y, c.s.fd(), true);
+            for (int j = tid; j < m.Nr; j += LARGE_THREADS) { a.out[ir * m.Nr + j] = c.s.kf()[j]; a.out2[ir * m.Nr + j] = c.s.kr()[j]; }
         } else if (MODE == 4) {
             // getkfs (src/PhaseState.jl:165-171): forward rate coefficients BEFORE diffusion limitation (kfs_intrinsic, block-strided)
             double acc = 0.0;
             for (int s = tid; s < m.Ns; s += LARGE_THREADS) acc += y[s];
             const double N = block_sum(acc, c.red);
-            const double T = c.T, V = c.vol(y);
-            const double P = (a.domain_kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? c.P : 0.0);
-            const double C = (a.domain_kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TAPHI ? 0.0 : N / V);
+            const bool vk = c.vk(), isp = a.domain_kind == RMSB_DOMAIN_CONSTANT_P;
+            const double T = vk ? y[m.Ns] : c.T, V = vk ? (isp ? y[m.Ns + 1] : c.d.cond[0]) : c.vol(y);
+            const double P = vk ? (isp ? c.d.cond[0] : y[m.Ns + 1])
+                                : ((a.domain_kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? c.P : 0.0));
+            const double C = (vk || a.domain_kind == RMSB_DOMAIN_CONSTANT_TP) ? P / (RMSB_R * T) : (a.domain_kind == RMSB_DOMAIN_CONSTANT_TAPHI ? 0.0 : N / V);
             KinEnv<double> e;
             e.T = T; e.logT = log(T); e.RT = RMSB_R * T; e.invRT = 1.0 / (RMSB_R * T); e.P = P;
             for (int j = tid; j < m.Nr; j += LARGE_THREADS) a.out[ir * m.Nr + j] = eval_kin<double>(j, &e, ceff_of(j, C, y, V), false);
@@ -836,14 +885,18 @@ static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int wan
     return RMSB_OK;
 }
 
+static const LargeTables& large_tables(const rmsb_mech* h, int kind) {
+    if (kind == RMSB_DOMAIN_CONSTANT_TP) return h->lt_tp;
+    if (kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) return h->lt_vk;
+    return h->lt;
+}
 struct LargeCfg { int grid; size_t per_block; size_t smem; };
 template <class K>
 static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, LargeCfg* cfg) {
     if (!h->large) return fail(RMSB_ERR_UNSUPPORTED, "more than 128 state variables need the large-mechanism path, which this mechanism was not analysed for");
-    if (kind != RMSB_DOMAIN_CONSTANT_TV && kind != RMSB_DOMAIN_CONSTANT_TAPHI && kind != RMSB_DOMAIN_CONSTANT_TP)
-        return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): ConstantTV / ConstantTAPhi / ConstantTP domains only (DESIGN.md)");
-    const LargeTables& lt = (kind == RMSB_DOMAIN_CONSTANT_TP) ? h->lt_tp : h->lt;
-    if (h->dm.n_effrxn > 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: third-body efficiencies are not built");
+    if (kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path (Ny > 128): coupled gas-surface systems are not built");
+    const LargeTables& lt = large_tables(h, kind);
+    if (lt.n == 0) return fail(RMSB_ERR_UNSUPPORTED, "large-mechanism path: this domain kind was not analysed for this phase");
     cudaDeviceProp prop;
     CU(rmsb_cached_props(h->device, &prop));
     cfg->smem = large_smem_bytes(lt.n);
@@ -855,7 +908,7 @@ static int large_config(K kernel, const rmsb_mech* h, int kind, int64_t n, Large
     if (bps > 16) bps = 16;
     int64_t resident = (int64_t)prop.multiProcessorCount * bps;
     cfg->grid = (int)(n < resident ? (n < 1 ? 1 : n) : resident);
-    cfg->per_block = (large_scratch_doubles(lt.n, h->dm.Nr, h->n_dt, h->n_je, lt.nnz) + 1) & ~(size_t)1;
+    cfg->per_block = (large_scratch_doubles(lt.n, h->dm.Ns, h->dm.Nr, h->n_dt, h->n_je, lt.nnz, lt.nb, lt.n_ee, lt.nb == 2 ? 1 : 0) + 1) & ~(size_t)1;
     return RMSB_OK;
 }
 
@@ -866,7 +919,7 @@ static int launch_eval_large(const rmsb_mech* h, const BatchArgs& a, cudaStream_
     if (rc != RMSB_OK) return rc;
     double* scratch = nullptr;
     CU(cudaMallocAsync((void**)&scratch, sizeof(double) * cfg.per_block * cfg.grid, st));
-    large_eval_kernel<MODE><<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? h->lt_tp : h->lt, scratch, cfg.per_block);
+    large_eval_kernel<MODE><<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, large_tables(h, a.domain_kind), scratch, cfg.per_block);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
@@ -881,10 +934,17 @@ static int launch_solve_large(const rmsb_mech* h, const SolveArgs& a, cudaStream
     if (work_bytes) { *work_bytes = 256 + sizeof(double) * cfg.per_block * cfg.grid; return RMSB_OK; }
     CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
     double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(a.counter) + 256);
-    large_solve_kernel<<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, a.domain_kind == RMSB_DOMAIN_CONSTANT_TP ? h->lt_tp : h->lt, scratch, cfg.per_block);
+    large_solve_kernel<<<cfg.grid, LARGE_THREADS, cfg.smem, st>>>(h->dm, a, large_tables(h, a.domain_kind), scratch, cfg.per_block);
     ++g_launches;
     CU(cudaGetLastError());
     return RMSB_OK;
+}
+
+// RMSB_NO_TPR=1 in the environment routes large batches of small mechanisms to the lane-group kernels instead of the
+// thread-per-reactor ones (A/B measurements, scripts/prof_evals.py)
+static bool tpr_disabled() {
+    static const bool off = [] { const char* v = std::getenv("RMSB_NO_TPR"); return v && v[0] == '1'; }();
+    return off;
 }
 
 template <int MODE>
@@ -894,7 +954,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
     }
     if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
-        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096) {
+        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled()) {
         // small variable-k mechanisms, large batches: one thread per reactor
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
@@ -908,7 +968,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         return RMSB_OK;
     }
     if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
-        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096) {
+        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096 && !tpr_disabled()) {
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
@@ -1459,7 +1519,7 @@ extern "C" int rmsb_large_info(const rmsb_mech* h, int64_t* out) {
     if (!h || !out) return fail(RMSB_ERR_ARG, "null argument");
     if (!h->large) { for (int k = 0; k < 8; ++k) out[k] = 0; return RMSB_OK; }
     out[0] = h->lt.n; out[1] = h->lt.nnz; out[2] = h->lt.n_lvl_l; out[3] = h->lt.n_lvl_u; out[4] = h->large_max_row;
-    out[5] = h->large_factor_flops; out[6] = h->lt.core; out[7] = (int64_t)large_scratch_doubles(h->lt.n, h->dm.Nr, h->n_dt, h->n_je, h->lt.nnz);
+    out[5] = h->large_factor_flops; out[6] = h->lt.core; out[7] = (int64_t)large_scratch_doubles(h->lt.n, h->dm.Ns, h->dm.Nr, h->n_dt, h->n_je, h->lt.nnz, 0, 0, 0);
     return RMSB_OK;
 }
 

@@ -51,6 +51,7 @@ struct rmsb_mech {
     bool large = false;
     rmsb::LargeTables lt{};        // y = ns            (ConstantTV, ConstantTAPhi)
     rmsb::LargeTables lt_tp{};     // y = [ns; V]       (ConstantTP): the same block bordered by a dense row and column
+    rmsb::LargeTables lt_vk{};     // y = [ns; T; P|V]  (ConstantV, ConstantP): two dense border rows and columns
     int large_max_row = 0;
     long long large_factor_flops = 0;
     // small-mechanism path (group of 16 / 32 lanes per reactor, tables staged in shared memory): rmsb_small.cu

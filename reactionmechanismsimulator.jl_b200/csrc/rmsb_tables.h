@@ -17,11 +17,21 @@ struct LargeTables {
     const int* lvl_l_ptr; const int* lvl_l_rows;
     const int* lvl_u_ptr; const int* lvl_u_rows;
     const int* amap;        // [n_je] Jacobian entry -> position in the factor's value array
-    // ConstantTP (y = [ns; V], n = Ns + 1): the volume adds a dense last column and row to the species block
-    int has_v, ns;
-    const int* vcol_pos;    // [Ns]   position of entry (s, V)
-    const int* vrow_pos;    // [Ns+1] position of entry (V, c), c = Ns is the diagonal
+    // border: nb state variables after the species block, each a dense row and column of I - c*J
+    //   ConstantTP: nb = 1 (V);  ConstantV: nb = 2 (T, P);  ConstantP: nb = 2 (T, V)   (has_v: the volume is a state, border bv)
+    int has_v, ns, nb, bv;
+    const int* bcol_pos;    // [nb][n]  position of entry (i, ns + b) for every row i (border-border entries included)
+    const int* brow_pos;    // [nb][ns] position of entry (ns + b, c) for the species columns c
     const int* je_colptr;   // [Ns+1] Jacobian entries of column c are je_colptr[c] .. je_colptr[c+1] (the entry list is sorted by column)
+    // third-body efficiency entries d(rate)/d n_s through Ceff (src/Domain.jl:2151-2167): distinct (row, col) species pairs
+    int n_ee;
+    const int* ee_pos;      // [n_ee] position in the factor's value array
+    const int* ee_row;      // [n_ee]
+    const int* ee_col;      // [n_ee]
+    const int* ee_ptr;      // [n_effrxn+1] start of reaction q's block in ee_idx
+    const int* ee_idx;      // per efficiency reaction: [n_listed_species][8] entry id of (species of slot k, listed species), -1 = empty slot
+    const int* ee_colptr;   // [Ns+1] entries grouped by column ...
+    const int* ee_bycol;    // [n_ee] ... entry ids in that order
 };
 
 

@@ -137,7 +137,11 @@ def _flow(v):
     return "'" + v.replace("'", "''") + "'"
 
 
-def write_octane_families(path: str, families: int = 36, keep: float = 0.85, seed: int = 20261019, template: str | None = None) -> dict:
+def write_octane_families(path: str, families: int = 36, keep: float = 0.85, seed: int = 20261019, template: str | None = None,
+                          falloff: bool = False) -> dict:
+    """falloff=True (for the gas-phase variant of the same mechanism, read as an IdealGas): the association reactions R + O2 -> ROO of
+    every family (six per family in the template) become, in turn, Troe, Lindemann and ThirdBody reactions with third-body
+    efficiencies on pool species and on the family's fuel, so the large-mechanism path sees falloff kinetics and efficiencies."""
     import yaml
     from pathlib import Path
     tpl = template or str(Path(__file__).resolve().parent / "fixtures" / "liquid_phase.rms")
@@ -171,12 +175,29 @@ def write_octane_families(path: str, families: int = 36, keep: float = 0.85, see
     lines += ["  name: phase", "Reactions:"]
     nr = 0
 
+    n_assoc = [0]
+
     def emit_reaction(r, k, scale):
         nonlocal nr
         ren = lambda nm: nm if (nm in SHARED or k is None) else fam_name(k, nm)
         kin = r["kinetics"]
         assert kin["type"] == "Arrhenius"
-        lines.append(f"- kinetics: {{A: {float(kin['A']) * scale!r}, Ea: {float(kin['Ea'])!r}, n: {float(kin['n'])!r}, type: Arrhenius}}")
+        A, Ea, n = float(kin["A"]) * scale, float(kin["Ea"]), float(kin["n"])
+        if falloff and k is not None and len(r["reactants"]) == 2 and len(r["products"]) == 1:
+            form = n_assoc[0] % 3
+            n_assoc[0] += 1
+            eff = "{" + ", ".join(f"{_flow(a)}: {b!r}" for a, b in (("N2", 1.4), ("Ar", 0.7), ("oxygen", 1.2), (fam_name(k, "octane"), 3.0))) + "}"
+            hi = f"{{A: {A!r}, Ea: {Ea!r}, n: {n!r}, type: Arrhenius}}"
+            lo = f"{{A: {A * 2.0e1!r}, Ea: {Ea * 0.5!r}, n: {n - 1.0!r}, type: Arrhenius}}"
+            if form == 0:
+                lines.extend(["- kinetics:", "    T1: 1500.0", "    T2: 5000.0", "    T3: 100.0", "    a: 0.6", f"    arrhigh: {hi}", f"    arrlow: {lo}",
+                              f"    efficiencies: {eff}", "    type: Troe"])
+            elif form == 1:
+                lines.extend(["- kinetics:", f"    arrhigh: {hi}", f"    arrlow: {lo}", f"    efficiencies: {eff}", "    type: Lindemann"])
+            else:
+                lines.extend(["- kinetics:", f"    arr: {lo}", f"    efficiencies: {eff}", "    type: ThirdBody"])
+        else:
+            lines.append(f"- kinetics: {{A: {A!r}, Ea: {Ea!r}, n: {n!r}, type: Arrhenius}}")
         lines.append("  products: [" + ", ".join(_flow(ren(x)) for x in r["products"]) + "]")
         lines.append(f"  radicalchange: {r.get('radicalchange', 0)}")
         lines.append("  reactants: [" + ", ".join(_flow(ren(x)) for x in r["reactants"]) + "]")

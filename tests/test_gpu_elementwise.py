@@ -48,7 +48,10 @@ def test_elementwise_parity(case):
     def merge(what, rep):
         a = agg.setdefault(what, {"n": 0, "n_above": 0, "max_rel_above": 0.0, "worst_excess": 0.0})
         a["n"] += rep["n"]; a["n_above"] += rep["n_above"]
-        a["max_rel_above"] = max(a["max_rel_above"], rep["max_rel_above"]); a["worst_excess"] = max(a["worst_excess"], rep["worst_excess"])
+        a["max_rel_above"] = max(a["max_rel_above"], rep["max_rel_above"])
+        if rep["worst_excess"] >= a["worst_excess"]:
+            a["worst_excess"] = rep["worst_excess"]
+            a["worst"] = {k: rep[k] for k in ("worst_at", "worst_x", "worst_ref", "worst_floor")}
 
     for po in pset:
         pg = p if po is odom.p or po is None else po
@@ -57,11 +60,11 @@ def test_elementwise_parity(case):
         Jp = ens.jacobianp(ys, pg if (pg is not None or odom.kind != "ConstantTV") else p)
         for k, y in enumerate(ys):
             fo, M = fl.dydt_terms(odom, y, 0.0, po)
-            merge("dydt", fl.report(f[k], fo, fl.EPS * M, BAR, slack=16.0))
+            merge("dydt", fl.report(f[k], fo, fl.EPS * M, BAR, slack=4.0))
             Jo, Jf = fl.jac_floor(lambda yy, pp: ro.jacobiany(odom, yy, 0.0, pp), odom, y, po)
             merge("J", fl.report(J[k], Jo, Jf, BAR))
             pj = po if po is not None else odom.p
-            Po, Pf = fl.jac_floor(lambda yy, pp: ro.jacobianp(odom, yy, 0.0, pp), odom, y, pj)
+            Po, Pf = fl.jacp_floor(odom, y, pj)
             merge("Jp", fl.report(Jp[k], Po, Pf, BAR))
             th = odom.calcthermo(y, 0.0, po)
             # rate coefficients are products and exponentials, no cancellation: the floor is the conditioning of exp() only
@@ -71,9 +74,11 @@ def test_elementwise_parity(case):
             merge("krev", fl.report(kr[k], th.krevs, krf, BAR))
     for what, rep in agg.items():
         _row(case, what, rep)
+        if rep["worst_excess"] > 0.5 or rep["max_rel_above"] > 0.5 * BAR:
+            print("    worst entry:", rep.get("worst"), "Ns", Ns, "Nr", Nr)
     for what, rep in agg.items():
-        assert rep["max_rel_above"] <= BAR, (case, what, rep)
-        assert rep["worst_excess"] <= 1.0, (case, what, rep)
+        assert rep["max_rel_above"] <= BAR, (case, what, rep.get("worst"))
+        assert rep["worst_excess"] <= 1.0, (case, what, rep.get("worst"))
 
 
 def test_elementwise_parity_thread_per_reactor_and_group_kernels():
@@ -100,7 +105,7 @@ def test_elementwise_parity_thread_per_reactor_and_group_kernels():
         for k in range(48):
             fo, M = fl.dydt_terms(odom, ys[k], 0.0, odom.p)
             Jo, Jf = fl.jac_floor(lambda yy, pp: ro.jacobiany(odom, yy, 0.0, pp), odom, ys[k], odom.p, nsample=4)
-            for agg, rep in ((agg_f, fl.report(f[k], fo, fl.EPS * M, BAR, slack=16.0)), (agg_J, fl.report(J[k], Jo, Jf, BAR))):
+            for agg, rep in ((agg_f, fl.report(f[k], fo, fl.EPS * M, BAR, slack=4.0)), (agg_J, fl.report(J[k], Jo, Jf, BAR))):
                 agg["n"] += rep["n"]; agg["n_above"] += rep["n_above"]
                 agg["max_rel_above"] = max(agg["max_rel_above"], rep["max_rel_above"]); agg["worst_excess"] = max(agg["worst_excess"], rep["worst_excess"])
         _row(f"C2 {name}", "dydt", agg_f)

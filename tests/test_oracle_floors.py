@@ -20,7 +20,7 @@ def test_cpu_port_vs_numpy_oracle_elementwise(case):
         f, M = fl.dydt_terms(od, y, 0.0, po)
         assert np.all(M >= np.abs(f) * (1 - 1e-12))                  # a sum of magnitudes bounds the signed sum
         fc = cm.dydt(od.kind, y[None], od.cond[None], po, constspc=od.constantspeciesinds)[0]
-        r = fl.report(fc, f, fl.EPS * M, 1e-12, slack=16.0)
+        r = fl.report(fc, f, fl.EPS * M, 1e-12, slack=4.0)
         assert r["n_above"] >= 0.6 * r["n"] and r["max_rel_above"] < 1e-12 and r["worst_excess"] < 1.0, r
         Jo, Jf = fl.jac_floor(lambda yy, pp: ro.jacobiany(od, yy, 0.0, pp), od, y, po, nsample=4)
         Jc = cm.jac(od.kind, y[None], od.cond[None], po, constspc=od.constantspeciesinds)[0]
