@@ -281,6 +281,34 @@ int rmsb_solve_batch_dev(const rmsb_mech* mech, int domain_kind, int64_t n,
                          double* d_yend, double* d_idt, int32_t* d_status, rmsb_stats* d_stats,
                          const rmsb_solve_opts* opts, void* d_work, void* stream);
 
+/* ---- boundary interfaces (CSTR / PFR ensembles) ----------------------------------------------------
+ * Inlet, Outlet, VolumetricFlowRateInlet, VolumetricFlowRateOutlet and VolumeMaintainingOutlet of the reference
+ * (src/Interface.jl:234-365; consumed by calcdomainderivatives!, src/Domain.jl:1839-1998, and by jacobiany!, :2220-2294,
+ * 2322-2448, 2493-2628, 3057-3088) with CONSTANT flows, for the ConstantTP, ConstantV, ConstantP, ConstantTV and ConstantTAPhi
+ * domains with at most 128 state variables.  `interfaces` holds one row of 7 + 2*Ns doubles per reactor (if_stride = 7 + 2*Ns)
+ * or one row shared by all (if_stride = 0):
+ *   [0] Inlet molar flow F (mol/s)   [1] Outlet molar flow   [2] VolumetricFlowRateInlet Vin (m^3/s)   [3] VolumetricFlowRateOutlet Vout
+ *   [4] VolumeMaintainingOutlet present (0 / 1; ConstantTP and ConstantP)   [5] Inlet enthalpy H (J/mol)
+ *   [6] VolumetricFlowRateInlet enthalpy per volume (J/m^3)   [7 .. 7+Ns) Inlet mole fractions   [7+Ns .. 7+2Ns) inlet concentrations
+ * Several interfaces of one type are merged by the caller (the terms are linear in flow * composition and flow * enthalpy).
+ * Time-dependent flows F(t), the kLAkH reservoir interface, parameter Jacobians and sensitivities with interfaces: not built. */
+int rmsb_dydt_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
+                       const double* y, const double* cond, const double* p, int64_t p_stride,
+                       const int32_t* const_species, int32_t n_const,
+                       const double* interfaces, int64_t if_stride, double* dydt);
+int rmsb_jac_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
+                      const double* y, const double* cond, const double* p, int64_t p_stride,
+                      const int32_t* const_species, int32_t n_const,
+                      const double* interfaces, int64_t if_stride, double* J);
+int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
+                        const double* y0, const double* cond, const double* p, int64_t p_stride,
+                        const int32_t* const_species, int32_t n_const,
+                        const double* interfaces, int64_t if_stride,
+                        const double* t_end, double rtol, double atol,
+                        int32_t nsave, const double* tsave, double* ysave,
+                        double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                        const rmsb_solve_opts* opts);
+
 /* ---- one host process, several GPUs -------------------------------------------------------------
  * rmsb_solve_batch over n_mech handles of the SAME mechanism created on different devices: the reactors are split into
  * contiguous blocks by index (block g = reactors [g*n/n_mech, (g+1)*n/n_mech)), each block runs rmsb_solve_batch on its

@@ -102,13 +102,77 @@ def closure_floor(domain, y, p, Jabs, t=0.0):
     return np.zeros((0, A.shape[1]))
 
 
+def species_block_magnitude(domain, y, p, t=0.0):
+    """Sum of the magnitudes of the terms of every entry of the analytic species block of jacobiany! (and of its volume column):
+    jacobianynsderiv! (src/Domain.jl:2169-2202) run with every +-deriv accumulated as |deriv|.  An entry like +d - d + small (a
+    species on both sides of one reaction next to another reaction's contribution) is only reproducible to eps*d."""
+    from unittest import mock
+    yv = np.asarray(y, dtype=float)
+    th = domain.calcthermo(yv, t, p)
+    Ns = domain.phase.Ns
+    Vind = Ns if domain.kind == "ConstantTP" else (Ns + 1 if domain.kind == "ConstantP" else None)
+    Jabs = np.zeros((len(yv), len(yv)))
+
+    def abs_spread(jac, deriv, slots, col, sign):
+        for sl in slots:
+            jac[sl, col] += abs(deriv)
+
+    with mock.patch.object(ro, "_spread", abs_spread):
+        ro.jacobianynsderiv(Jabs, domain, th, Vind)
+    return Jabs
+
+
+def jacp_magnitude(domain, y, p, t=0.0):
+    """The same for the species rows of jacobianp! (src/Domain.jl:3095-3233): |flux terms| of the rate-coefficient columns and the
+    accumulated |gderiv| of the dG columns."""
+    yv = np.asarray(y, dtype=float)
+    ph = domain.phase
+    Ns, Nr = ph.Ns, ph.Nr
+    th = domain.calcthermo(yv, t, p)
+    M = np.zeros((len(yv), Ns + Nr))
+    RTinv = 1.0 / (ro.R * th.T)
+    ra = ph.rxnarray
+    constk = domain.kind in ("ConstantTP", "ConstantTAPhi", "ConstantTV")
+    for i in range(Nr):
+        rs = [ra[j, i] for j in range(4) if ra[j, i] >= 0]
+        ps = [ra[j, i] for j in range(4, 8) if ra[j, i] >= 0]
+        prodr = np.prod([th.cs[q] for q in rs])
+        prodp = np.prod([th.cs[q] for q in ps])
+        if domain.kind == "ConstantTV":
+            pk = (domain.p if p is None else p)[Ns + i]
+            fderiv = th.kfs[i] * th.kfs[i] / (pk * pk) * prodr
+            rderiv = th.kfs[i] * th.krevs[i] / (pk * pk) * prodp
+            gderiv = rderiv * (pk * pk) / th.kfs[i] * RTinv
+        elif constk:
+            if i in ph.efficiencyinds:
+                fderiv, rderiv = th.kfs[i] * prodr, th.krevs[i] * prodp
+            else:
+                fderiv, rderiv = prodr, th.krevs[i] / th.kfs[i] * prodp
+            gderiv = rderiv * th.kfs[i] * RTinv
+        else:
+            fderiv, rderiv = th.kfs[i] * prodr, th.krevs[i] * prodp
+            gderiv = rderiv * RTinv
+        for q in rs + ps:
+            M[q, Ns + i] += abs(fderiv) + abs(rderiv)
+        for sp in rs + ps:
+            for q in rs + ps:
+                M[q, sp] += abs(gderiv)
+    M *= abs(th.V)
+    return M
+
+
 def jac_floor(fn, domain, y, p, t=0.0, **kw):
     """(ref, floor) for a Jacobian-like fn(y, p) -> Ny x ncol: conditioning floor (numeric_floor) plus the accumulation floor of the
     closure rows (closure_floor, with a factor for the number of summands' roundings)."""
+    mag = kw.pop("magnitude", None)
     ref, floor = numeric_floor(fn, [y, p], **kw)
     Ns = domain.phase.Ns
+    if mag is None and ref.shape[1] == ref.shape[0]:
+        mag = species_block_magnitude(domain, y, p, t)
+    if mag is not None:
+        floor[:Ns] += 2.0 * EPS * mag[:Ns]                       # accumulation order of each entry's own terms
     if ref.shape[0] > Ns:
-        floor[Ns:] += 4.0 * closure_floor(domain, y, p, ref, t)
+        floor[Ns:] += 4.0 * closure_floor(domain, y, p, np.maximum(np.abs(ref), mag) if mag is not None else ref, t)
     # entries that are EXACTLY zero in the oracle because +d / -d pairs of one reaction cancel (a species on both sides, e.g. a
     # collider): another summation order leaves a residue of a few eps of the column's largest term
     zero = ref == 0.0
@@ -121,7 +185,7 @@ def jac_floor(fn, domain, y, p, t=0.0, **kw):
 def jacp_floor(domain, y, p, t=0.0, **kw):
     """(ref, floor) of jacobianp!: jac_floor plus the term the adiabatic domains add to the T row of the dG columns,
     -(dot(U, Jp[:, i]) + dn_i/dt) / (N*Cv) (src/Domain.jl:3433-3460): dn_i/dt is itself a cancelling sum whose floor is eps*M_i."""
-    ref, floor = jac_floor(lambda yy, pp: ro.jacobianp(domain, yy, t, pp), domain, y, p, t, **kw)
+    ref, floor = jac_floor(lambda yy, pp: ro.jacobianp(domain, yy, t, pp), domain, y, p, t, magnitude=jacp_magnitude(domain, y, p, t), **kw)
     if domain.kind in ("ConstantV", "ConstantP"):
         Ns = domain.phase.Ns
         th = domain.calcthermo(np.asarray(y, dtype=float), t, p)

@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
         d.p = a.p ? a.p + ir * a.p_stride : nullptr;
         d.constspc = a.constspc; d.nconst = a.nconst;
         d.cond = a.cond + ir * a.ncond;
+        d.flow = a.flow ? a.flow + ir * a.flow_stride : nullptr;
         double* yb = w.ybuf();
         for (int i = lane; i < Ny; i += 32) yb[i] = a.y[ir * Ny + i];
         rhs_prepare(d, w, lane);
@@ -949,12 +950,18 @@ static bool tpr_disabled() {
 
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
+    if (a.flow) {
+        // boundary interfaces are evaluated by the warp-per-reactor routines (rhs_v / rhs_ck / jac_warp)
+        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the large-mechanism path (Ny > 128) are not built");
+        if (MODE != 0 && MODE != 1) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces: dydt, Jacobian and solve only");
+        if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
+    }
     if (a.Ny > 128) {
         if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
     }
     if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
-        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled()) {
+        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled() && !a.flow) {
         // small variable-k mechanisms, large batches: one thread per reactor
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
@@ -968,7 +975,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         return RMSB_OK;
     }
     if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
-        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096 && !tpr_disabled()) {
+        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096 && !tpr_disabled() && !a.flow) {
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
@@ -980,7 +987,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         CU(cudaGetLastError());
         return RMSB_OK;
     }
-    if ((MODE == 0 || MODE == 1) && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
+    if ((MODE == 0 || MODE == 1) && !a.flow && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
     LaunchCfg cfg;
     int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
@@ -1044,7 +1051,10 @@ static int sens_dispatch(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, si
 }
 
 static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
-    if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
+    if (a.flow) {      // boundary interfaces: the warp-per-reactor integrator (rhs_v / rhs_ck / jac_warp carry the interface terms)
+        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the large-mechanism path (Ny > 128) are not built");
+        if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
+    } else if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
     switch (rows_per_lane(a.Ny)) {
     case 1: return launch_solve_R<1>(h, a, want_wpb, st);
     case 2: return launch_solve_R<2>(h, a, want_wpb, st);
@@ -1085,6 +1095,11 @@ static BatchArgs make_batch(const rmsb_mech* h, int kind, int64_t n, const doubl
     a.n = n; a.y = y; a.cond = cond; a.ncond = domain_ncond(kind); a.p = p; a.p_stride = p ? p_stride : 0;
     a.constspc = cs; a.nconst = cs ? ncs : 0; a.out = out; a.out2 = out2; a.domain_kind = kind; a.Ny = domain_ny(h, kind);
     return a;
+}
+
+static int check_interfaces(const rmsb_mech* h, const double* ifs, int64_t if_stride) {
+    if (ifs && if_stride != 0 && if_stride != 7 + 2 * (int64_t)h->dm.Ns) return fail(RMSB_ERR_ARG, "if_stride must be 0 or 7 + 2*Ns");
+    return RMSB_OK;
 }
 
 extern "C" int rmsb_dydt_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond,
@@ -1153,10 +1168,11 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
                           const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
                           const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
                           double* ysave, double* ssave, double* yend, double* send, double* idt, int32_t* status, rmsb_stats* stats,
-                          const rmsb_solve_opts* opts, void* work, void* stream) {
+                          const rmsb_solve_opts* opts, void* work, void* stream, const double* flow = nullptr, int64_t flow_stride = 0) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     if (sens && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
+    if (sens && flow) return fail(RMSB_ERR_UNSUPPORTED, "forward sensitivities with boundary interfaces are not built");
     if (n == 0) return RMSB_OK;
     if (!t_end || !status || !work) return fail(RMSB_ERR_ARG, "t_end, status and work buffers are required");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(RMSB_ERR_ARG, "rtol must be > 0 and atol >= 0");
@@ -1173,6 +1189,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
     if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
     a.counter = reinterpret_cast<unsigned long long*>(work);
     a.ssave = ssave; a.send = send; a.sens_hist = nullptr; a.Npp = sens_npp(h);
+    a.flow = flow; a.flow_stride = flow ? flow_stride : 0;
     DeviceGuard g(h->device);
     if (!sens) return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
     a.idt_index = -1; a.idt = nullptr;
@@ -1268,9 +1285,11 @@ __global__ void expand_rows_kernel(const double* __restrict__ in, double* __rest
 #define D2H(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sg.st))
 
 static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
-                     int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2) {
+                     int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2,
+                     const double* ifs = nullptr, int64_t if_stride = 0) {
     int rc = check_common(h, kind, n, y, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
+    if ((rc = check_interfaces(h, ifs, if_stride)) != RMSB_OK) return rc;
     if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
@@ -1291,6 +1310,12 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     if (mode == 2) CU(dout2.alloc(sizeof(double) * n * out_per));
     BatchArgs a = make_batch(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dout.as<double>(), dout2.as<double>());
+    DevBuf dif(sg.st);
+    if (ifs) {
+        const size_t nif = (size_t)(if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
+        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ifs, sizeof(double) * nif);
+        a.flow = dif.as<double>(); a.flow_stride = if_stride;
+    }
     if (mode == 0) rc = launch_eval<0>(h, a, sg.st);
     else if (mode == 1) rc = launch_eval<1>(h, a, sg.st);
     else if (mode == 3) rc = launch_eval<3>(h, a, sg.st);
@@ -1314,6 +1339,14 @@ extern "C" int rmsb_jac_batch(const rmsb_mech* h, int kind, int64_t n, const dou
 extern "C" int rmsb_jacp_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                int64_t p_stride, const int32_t* cs, int32_t ncs, double* Jp) {
     return eval_host(3, h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr);
+}
+extern "C" int rmsb_dydt_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride, double* dydt) {
+    return eval_host(0, h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr, ifs, if_stride);
+}
+extern "C" int rmsb_jac_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                 int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride, double* J) {
+    return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr, ifs, if_stride);
 }
 extern "C" int rmsb_rates_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                 int64_t p_stride, double* kf, double* krev) {
@@ -1345,12 +1378,15 @@ extern "C" int rmsb_gibbs_batch(const rmsb_mech* h, int64_t n, const double* T, 
     return RMSB_OK;
 }
 
-extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
-                                int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
-                                int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
-                                rmsb_stats* stats, const rmsb_solve_opts* opts) {
+static int solve_host_impl(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                           int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride,
+                           const double* t_end, double rtol, double atol,
+                           int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
+                           rmsb_stats* stats, const rmsb_solve_opts* opts) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
+    if ((rc = check_interfaces(h, ifs, if_stride)) != RMSB_OK) return rc;
+    if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!t_end || !status) return fail(RMSB_ERR_ARG, "t_end and status are required");
     if (nsave > 0 && (!tsave || !ysave)) return fail(RMSB_ERR_ARG, "tsave/ysave required when nsave > 0");
@@ -1378,16 +1414,22 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
     int64_t wbytes = rmsb_solve_work_bytes(h, kind, n);
     if (wbytes < 0) return RMSB_ERR_UNSUPPORTED;
     CU(dwork.alloc((size_t)wbytes));
+    DevBuf dif(sg.st);
+    if (ifs) {
+        const size_t nif = (size_t)(if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
+        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ifs, sizeof(double) * nif);
+    }
     EventPair ev;
     CU(ev.start(sg.st));
-    rc = rmsb_solve_batch_dev(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
-                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
-                              nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr,
-                              yend ? dye.as<double>() : nullptr, idt ? didt.as<double>() : nullptr, dst.as<int32_t>(),
-                              stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st);
+    rc = solve_dev_impl(false, h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
+                        (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
+                        nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr, nullptr,
+                        yend ? dye.as<double>() : nullptr, nullptr, idt ? didt.as<double>() : nullptr, dst.as<int32_t>(),
+                        stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st, ifs ? dif.as<double>() : nullptr, if_stride);
     if (rc != RMSB_OK) return rc;
     // du at the saved states (opts->dysave): one dydt evaluation of the n*nsave saved states, each with its reactor's constants
     double* dysave = (opts && opts->struct_size == (int32_t)sizeof(rmsb_solve_opts)) ? opts->dysave : nullptr;
+    if (dysave && ifs && if_stride != 0) return fail(RMSB_ERR_UNSUPPORTED, "dysave with per-reactor boundary interfaces is not built (use one shared row)");
     DevBuf dce(sg.st), dpe(sg.st), ddy(sg.st);
     if (dysave && nsave > 0) {
         const int64_t ne = n * nsave;
@@ -1402,8 +1444,10 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
             pe = dpe.as<double>();
         }
         CU(cudaGetLastError());
-        rc = launch_eval<0>(h, make_batch(h, kind, ne, dys.as<double>(), dce.as<double>(), pe, p_stride, (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs,
-                                          ddy.as<double>(), nullptr), sg.st);
+        BatchArgs be = make_batch(h, kind, ne, dys.as<double>(), dce.as<double>(), pe, p_stride, (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs,
+                                  ddy.as<double>(), nullptr);
+        if (ifs) { be.flow = dif.as<double>(); be.flow_stride = 0; }
+        rc = launch_eval<0>(h, be, sg.st);
         if (rc != RMSB_OK) return rc;
     }
     CU(ev.stop(sg.st));
@@ -1416,6 +1460,21 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
     CU(cudaStreamSynchronize(sg.st));
     ev.read();
     return RMSB_OK;
+}
+
+extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                                int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
+                                int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
+                                rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, nullptr, 0, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
+}
+
+extern "C" int rmsb_solve_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                                   int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride,
+                                   const double* t_end, double rtol, double atol,
+                                   int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
+                                   rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, ifs, if_stride, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
 }
 
 extern "C" int rmsb_solve_batch_multi(const rmsb_mech* const* mechs, int32_t n_mech, int kind, int64_t n, const double* y0,

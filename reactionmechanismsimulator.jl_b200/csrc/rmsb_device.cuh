@@ -526,7 +526,15 @@ struct DomainArgs {
     const double* p;      // nullptr or per-reactor parameter row
     const int* constspc;  // 1-based (reference convention)
     const double* cond;   // per-reactor constants
+    const double* flow = nullptr;   // boundary interfaces of this reactor (IF_* layout below) or nullptr
 };
+
+// Boundary interfaces with constant flows (src/Interface.jl:234-365), one row of 7 + 2*Ns doubles per reactor.  Several interfaces
+// of one type are merged by the host (the terms are linear in flow*composition and flow*enthalpy).
+//   [0] Inlet molar flow F   [1] Outlet molar flow   [2] VolumetricFlowRateInlet Vin   [3] VolumetricFlowRateOutlet Vout
+//   [4] VolumeMaintainingOutlet present (0 / 1)   [5] Inlet enthalpy H (J/mol)   [6] VolumetricFlowRateInlet Hpervolume (J/m^3)
+//   [7 .. 7+Ns) Inlet mole fractions   [7+Ns .. 7+2Ns) VolumetricFlowRateInlet concentrations
+constexpr int IF_FIN = 0, IF_FOUT = 1, IF_VIN = 2, IF_VOUT = 3, IF_VM = 4, IF_HIN = 5, IF_HPV = 6, IF_Y = 7;
 
 // kf / krev of reaction j for the constant-k domains (getkfkrevs, src/PhaseState.jl:184-257): vector path without diffusion
 // limits, per-reaction scalar path with them.  G = absolute Gibbs energies, diffs = Stokes diffusivities (liquid only).
@@ -720,6 +728,47 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     __syncwarp();
     for (int k = lane; k < d.nconst; k += 32) SM::st(fb, d.constspc[k] - 1, N(0.0));   // Domain.jl:1904-1906
     __syncwarp();
+    if (d.flow) {
+        // boundary interfaces (src/Domain.jl:1907-1947 ConstantV, 1957-1997 ConstantP), in N arithmetic: the T / P columns of the
+        // Jacobian are the derivative of the COMPLETE right-hand side (jacobianytherm!, src/Reactor.jl:1469-1477)
+        const double* fl = d.flow;
+        const double Fin = fl[IF_FIN], Fout = fl[IF_FOUT], Vin = fl[IF_VIN], Vout = fl[IF_VOUT];
+        N un = 0.0;
+        for (int s = lane; s < Ns; s += 32) un = un + SM::ld(ub, s) * yb[s];
+        N dotUn = warp_sum(un);                                   // dot(Us, ns) (ConstantP: dot(Hs, ns))
+        N NC = ISP ? RMSB_R * cpsum : RMSB_R * (cpsum - Nt);      // N*Cv (N*Cp)
+        N iNt = 1.0 / Nt;
+        N dTi = 0.0, dPi = 0.0;
+        if (!ISP) {
+            N a1 = Fin * (fl[IF_HIN] - dotUn * iNt) / NC;          dTi = dTi + a1; dPi = dPi + (Fin * RT * invV + P * tp.T4 * a1);
+            N a2 = (P * V * iNt * Fout) / NC;                      dTi = dTi - a2; dPi = dPi - (Fout * RT * invV + P * tp.T4 * a2);
+            N a3 = Vin * (fl[IF_HPV] - dotUn * invV) / NC;         dTi = dTi + a3; dPi = dPi + (Vin * P * invV + P * tp.T4 * a3);
+            N a4 = (P * Vout) / NC;                                dTi = dTi - a4; dPi = dPi - (Vout * P * invV + P * tp.T4 * a4);
+        } else {
+            N a1 = Fin * (fl[IF_HIN] - dotUn * iNt) / NC;          dTi = dTi + a1; dPi = dPi + (Fin * RT / P + a1 * V * tp.T4);
+            dPi = dPi - Fout * RT / P;
+            N a3 = Vin * (fl[IF_HPV] - dotUn * invV) / NC;         dTi = dTi + a3; dPi = dPi + Vin;
+            dPi = dPi - Vout;
+        }
+        for (int s = lane; s < Ns; s += 32) {
+            N v = SM::ld(fb, s);
+            v = v + fl[IF_Y + s] * Fin;
+            v = v - Fout * yb[s] * iNt;
+            v = v + Vin * fl[IF_Y + Ns + s];
+            v = v - Vout * yb[s] * invV;
+            SM::st(fb, s, v);
+        }
+        __syncwarp();
+        N fT = SM::ld(fb, Ns) + dTi, fP = SM::ld(fb, Ns + 1) + dPi;
+        __syncwarp();
+        if (ISP && fl[IF_VM] != 0.0) {                            // VolumeMaintainingOutlet: after everything else (:1990-1997)
+            N flowm = P * fP / RT;
+            for (int s = lane; s < Ns; s += 32) SM::st(fb, s, SM::ld(fb, s) - flowm * yb[s] * iNt);
+            fP = fP - fP;
+        }
+        if (lane == 0) { SM::st(fb, Ns, fT); SM::st(fb, Ns + 1, fP); }
+        __syncwarp();
+    }
 }
 
 // constant-k domains: TP (y = [ns; V]), TV / TAPhi (y = ns).  setup_constk() must have filled w.g / w.kf / w.kr.
@@ -783,6 +832,33 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     __syncwarp();
     for (int k = lane; k < d.nconst; k += 32) fb[d.constspc[k] - 1] = 0.0;   // Domain.jl:1840-1842,1865-1867
     __syncwarp();
+    if (d.flow) {
+        // boundary interfaces: src/Domain.jl:1843-1860 (ConstantTV / ConstantTAPhi: species only), 1868-1898 (ConstantTP)
+        const double* fl = d.flow;
+        const double Fin = fl[IF_FIN], Fout = fl[IF_FOUT], Vin = fl[IF_VIN], Vout = fl[IF_VOUT];
+        const double iNt = 1.0 / Nt;
+        for (int s = lane; s < Ns; s += 32) {
+            double v = fb[s];
+            v += fl[IF_Y + s] * Fin;
+            v -= Fout * yb[s] * iNt;
+            v += Vin * fl[IF_Y + Ns + s];
+            v -= Vout * yb[s] * invV;
+            fb[s] = v;
+        }
+        __syncwarp();
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
+            const double rtp = RMSB_R * T / P;
+            double dV = fb[Ns] + Fin * rtp - Fout * rtp + Vin - Vout;
+            __syncwarp();
+            if (fl[IF_VM] != 0.0) {                                // VolumeMaintainingOutlet (:1890-1897)
+                const double flowm = P * dV / (RMSB_R * T);
+                for (int s = lane; s < Ns; s += 32) fb[s] -= flowm * yb[s] * iNt;
+                dV -= dV;
+            }
+            if (lane == 0) fb[Ns] = dV;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1120,6 +1196,77 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         for (int c = lane; c < Ny; c += 32) J[s + c * LD] = 0.0;
     }
     __syncwarp();
+    // (6b) boundary interfaces: the analytic terms of the species (and volume) columns exactly as the reference writes them
+    //      (src/Domain.jl:2220-2294 ConstantTP, 2322-2448 ConstantV, 2493-2628 ConstantP, 3057-3088 ConstantTV / ConstantTAPhi);
+    //      the VolumeMaintainingOutlet has none there.  Lanes own columns / diagonal entries: no two lanes touch one entry.
+    if (d.flow) {
+        const double* fl = d.flow;
+        const double* yb = w.ybuf();
+        const double Fin = fl[IF_FIN], Fout = fl[IF_FOUT], Vin = fl[IF_VIN], Vout = fl[IF_VOUT];
+        if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
+            for (int i = lane; i < Ns; i += 32) {
+                J[i + i * LD] -= Fout / aN;
+                J[i + Ns * LD] -= -Fout * yb[i] / (aN * aV);
+                J[i + i * LD] -= Vout / aV;
+                J[i + Ns * LD] -= -Vout * yb[i] / (aV * aV);
+            }
+        } else if (d.kind == RMSB_DOMAIN_CONSTANT_V || d.kind == RMSB_DOMAIN_CONSTANT_P) {
+            const bool isp = d.kind == RMSB_DOMAIN_CONSTANT_P;
+            const double* us = w.us();
+            const double* cpb = w.cp();
+            double un = 0.0;
+            for (int s = lane; s < Ns; s += 32) un += us[s] * yb[s];
+            const double dotUn = warp_sum(un);
+            const double aC2 = isp ? aCv + RMSB_R : aCv;                      // Cv (ConstantV) or Cp (ConstantP)
+            const double NC = aN * aC2;
+            if (!isp) {
+                const double dT1 = Fin * (fl[IF_HIN] - dotUn / aN) / NC;
+                const double dT2 = (aP * aV / aN * Fout) / NC;
+                const double dT3 = (Vin * (fl[IF_HPV] - dotUn / aV)) / NC;
+                const double dT4 = (aP * Vout) / NC;
+                for (int i = lane; i < Ns; i += 32) {
+                    const double dC = cpb[i] * RMSB_R / aN;
+                    double dd = Fin * (-us[i] / aN) / NC - dT1 * (dC / aC2);     // Inlet
+                    J[Ns + i * LD] += dd; J[Ns + 1 + i * LD] += aP / aT * dd;
+                    J[i + i * LD] -= Fout / aN;                                   // Outlet
+                    dd = -dT2 * (dC / aC2);
+                    J[Ns + i * LD] -= dd; J[Ns + 1 + i * LD] -= aP / aT * dd;
+                    dd = Vin * (-us[i] / aN) / NC - dT3 * (dC / aC2);            // VolumetricFlowRateInlet
+                    J[Ns + i * LD] += dd; J[Ns + 1 + i * LD] += aP / aT * dd;
+                    J[i + i * LD] -= Vout / aV;                                   // VolumetricFlowRateOutlet
+                    dd = -dT4 * (dC / aC2);
+                    J[Ns + i * LD] -= dd; J[Ns + 1 + i * LD] -= aP / aT * dd;
+                }
+            } else {
+                const double H = dotUn / aN;
+                const double dT1 = Fin * (fl[IF_HIN] - H) / NC;
+                const double dT3 = Vin * (fl[IF_HPV] - dotUn / aV) / NC;
+                for (int i = lane; i < Ns; i += 32) {
+                    const double dC = cpb[i] * RMSB_R / aN;
+                    double dd = Fin * (-us[i] / aN) / NC - dT1 * (dC / aC2);     // Inlet
+                    J[Ns + i * LD] += dd; J[Ns + 1 + i * LD] += aV / aT * dd;
+                    J[i + i * LD] -= Fout / aN;                                   // Outlet
+                    J[i + (Ns + 1) * LD] -= -Fout * yb[i] / aN / aV;
+                    J[Ns + i * LD] += Vin * (-us[i] / aN) / NC - dT3 * (dC / aC2);   // VolumetricFlowRateInlet
+                    J[i + i * LD] -= Vout / aV;                                   // VolumetricFlowRateOutlet
+                    J[i + (Ns + 1) * LD] -= -Vout / (aV * aV) * yb[i];
+                }
+                if (lane == 0) {
+                    const double ddV = Fin * H / aV / NC;
+                    J[Ns + (Ns + 1) * LD] += ddV;
+                    J[Ns + 1 + (Ns + 1) * LD] += aV / aT * ddV;
+                }
+            }
+        } else {                                                              // ConstantTV / ConstantTAPhi: N = sum(ns)
+            for (int i = lane; i < Ns; i += 32) {
+                J[i + i * LD] -= Fout / aN;
+                const double r = Fout * yb[i] / (aN * aN);
+                for (int c = 0; c < Ny; ++c) J[i + c * LD] += r;
+                J[i + i * LD] -= Vout / aV;
+            }
+        }
+        __syncwarp();
+    }
     // (7) ConstantV: T and P columns = derivative of the complete RHS (src/Reactor.jl:1469-1477)
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
         rhs_v<Dual2>(d, w, lane, false);

@@ -77,6 +77,8 @@ struct SolveArgs {
     int Npp;            // Ns+Nr rounded up to a multiple of 32
     int flags;      // bit 0: scipy-style Newton test (every step >= 2 iterations, tolerance min(0.03, sqrt(rtol)));
                     // bit 1: no step-size hysteresis.  0 = production defaults (CVODE-style test, hysteresis)
+    const double* flow = nullptr;   // boundary interfaces (see BatchArgs)
+    int64_t flow_stride = 0;
 };
 
 struct BatchArgs {
@@ -92,6 +94,8 @@ struct BatchArgs {
     double* out2;    // krev (rates kernel)
     int domain_kind;
     int Ny;
+    const double* flow = nullptr;   // boundary interfaces [n][flow_stride] (flow_stride 0: one row shared), IF_* layout of rmsb_device.cuh
+    int64_t flow_stride = 0;
 };
 
 // ---- distributed vector helpers -----------------------------------------------------------------
@@ -546,6 +550,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     d.p = a.p ? a.p + ir * a.p_stride : nullptr;
     d.constspc = a.constspc; d.nconst = a.nconst;
     d.cond = a.cond + ir * a.ncond;
+    d.flow = a.flow ? a.flow + ir * a.flow_stride : nullptr;
     const double rtol = a.rtol, atol = a.atol;
     const double t_end = a.t_end[ir];
 

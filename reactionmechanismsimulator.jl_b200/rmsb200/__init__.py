@@ -12,6 +12,7 @@ from .coupled import CoupledEnsemble, CoupledPhase, SystemSimulation, coupled_do
 from .coupled import make_interface as ReactiveInternalInterfaceConstantTPhi
 from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
                      ConstantVDomain, ConstantVEnsemble, Domain)
+from .interfaces import Inlet, Outlet, VolumeMaintainingOutlet, VolumetricFlowRateInlet, VolumetricFlowRateOutlet, pack_interfaces
 from .ensemble import balanced_shards, shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)
 from .phase import IdealDiluteSolution, IdealGas, IdealSurface, Phase

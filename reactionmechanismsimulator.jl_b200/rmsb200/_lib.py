@@ -68,7 +68,7 @@ EXPORTS = [
     "rmsb_solve_batch", "rmsb_dydt_batch_dev", "rmsb_jac_batch_dev", "rmsb_solve_work_bytes", "rmsb_solve_batch_dev",
     "rmsb_kernel_launch_count", "rmsb_fp64_peak_tflops", "rmsb_jacp_batch", "rmsb_jacp_batch_dev", "rmsb_sens_batch",
     "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch", "rmsb_large_info", "rmsb_large_profile",
-    "rmsb_solve_batch_multi", "rmsb_last_kernel_ms",
+    "rmsb_solve_batch_multi", "rmsb_last_kernel_ms", "rmsb_dydt_batch_if", "rmsb_jac_batch_if", "rmsb_solve_batch_if",
 ]
 
 
@@ -114,6 +114,9 @@ def lib():
     L.rmsb_solve_batch_multi.argtypes = [vp, i32, C.c_int, i64, vp, vp, vp, i64, vp, i32, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp,
                                          C.POINTER(SolveOpts)]
     L.rmsb_last_kernel_ms.restype = dbl
+    L.rmsb_dydt_batch_if.argtypes = common + [vp, i32, vp, i64, vp]
+    L.rmsb_jac_batch_if.argtypes = common + [vp, i32, vp, i64, vp]
+    L.rmsb_solve_batch_if.argtypes = common + [vp, i32, vp, i64, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
     L.rmsb_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.rmsb_fp64_peak_tflops.restype = dbl
     _lib = L

@@ -81,24 +81,59 @@ class Domain:
         return p, Np
 
     # -- batched hot-path calls ------------------------------------------------------------------
-    def dydt(self, y=None, p=None):
-        """dydtreactor! for every reactor of the ensemble (src/Reactor.jl:653-660)."""
+    def _cond_for(self, n: int) -> np.ndarray:
+        """Per-reactor constants for n states: the domain's own rows, or its single row repeated (one condition, many states)."""
+        if self.cond.shape[0] == n:
+            return self.cond
+        if self.cond.shape[0] == 1:
+            return np.ascontiguousarray(np.repeat(self.cond, n, axis=0))
+        raise ValueError(f"{n} states for a domain of {self.cond.shape[0]} reactors")
+
+    def _interfaces_for(self, interfaces, n: int):
+        """(array, stride) of the boundary interfaces for n states: a packed row / matrix (rmsb200.interfaces.pack_interfaces) or a
+        list of interface objects attached to this domain."""
+        if interfaces is None or (isinstance(interfaces, (list, tuple)) and len(interfaces) == 0):
+            return None, 0
+        if not isinstance(interfaces, np.ndarray):
+            from .interfaces import pack_interfaces
+            interfaces = pack_interfaces(self, interfaces)
+        a = np.ascontiguousarray(interfaces, dtype=float)
+        if a.ndim == 1:
+            return a, 0
+        if a.shape[0] != n:
+            raise ValueError("one interface row per reactor")
+        return a, a.shape[1]
+
+    def dydt(self, y=None, p=None, interfaces=None):
+        """dydtreactor! for every reactor of the ensemble (src/Reactor.jl:653-660), with boundary interfaces if given."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
         pp, ps = self._p_for_device(p)
         out = np.empty_like(y)
         cs = self.constantspeciesinds
-        L.check(L.lib().rmsb_dydt_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+        cond = self._cond_for(y.shape[0])
+        fa, fs = self._interfaces_for(interfaces, y.shape[0])
+        if fa is not None:
+            L.check(L.lib().rmsb_dydt_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+            return out
+        L.check(L.lib().rmsb_dydt_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
                                         L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out
 
-    def jacobiany(self, y=None, p=None):
+    def jacobiany(self, y=None, p=None, interfaces=None):
         """jacobiany! for every reactor -> [n][Ny][Ny] with J[r, eqn, var] (src/Domain.jl:2204-3091)."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
         pp, ps = self._p_for_device(p)
         out = np.empty((y.shape[0], self.Ny * self.Ny))
         cs = self.constantspeciesinds
-        L.check(L.lib().rmsb_jac_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
-                                       L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
+        cond = self._cond_for(y.shape[0])
+        fa, fs = self._interfaces_for(interfaces, y.shape[0])
+        if fa is not None:
+            L.check(L.lib().rmsb_jac_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
+                                              L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+        else:
+            L.check(L.lib().rmsb_jac_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
+                                           L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], self.Ny, self.Ny).transpose(0, 2, 1)   # column-major -> [eqn, var]
 
     def jacobianp(self, y=None, p=None):
@@ -108,7 +143,7 @@ class Domain:
         Np = self.phase.Ns + self.phase.Nr
         out = np.empty((y.shape[0], Np * self.Ny))
         cs = self.constantspeciesinds
-        L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+        L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
                                         L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], Np, self.Ny).transpose(0, 2, 1)      # column-major -> [eqn, par]
 
@@ -129,7 +164,7 @@ class Domain:
         pp, ps = self._p_for_device(p)
         kf = np.empty((y.shape[0], self.phase.Nr))
         kr = np.empty_like(kf)
-        L.check(L.lib().rmsb_rates_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self.cond), L.ptr(pp), ps,
+        L.check(L.lib().rmsb_rates_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
                                          L.ptr(kf), L.ptr(kr)))
         return kf, kr
 

@@ -46,8 +46,8 @@ class Reactor:
 
     def __init__(self, domain: Domain, y0=None, tspan: Tuple[float, float] = (0.0, 1.0), interfaces: Sequence = (), p=None,
                  forwardsensitivities: bool = False):
-        if interfaces:
-            raise NotImplementedError("interfaces are outside the accelerated hot path in this round (DESIGN.md)")
+        if interfaces is not None and len(interfaces) > 0 and forwardsensitivities:
+            raise NotImplementedError("forward sensitivities with boundary interfaces (DESIGN.md, 'out of scope')")
         if forwardsensitivities and domain.kind == L.DOMAIN_COUPLED_TP_TAPHI:
             raise NotImplementedError("forward sensitivities of coupled gas-surface systems (DESIGN.md, 'next')")
         self.domain = domain
@@ -55,7 +55,7 @@ class Reactor:
         assert tspan[0] == 0.0, "integration starts at t = 0"
         self.tspan = (float(tspan[0]), tspan[1])
         self.p = domain.p if p is None else p
-        self.interfaces = list(interfaces)
+        self.interfaces = interfaces if isinstance(interfaces, np.ndarray) else list(interfaces)     # interface objects, or packed rows (pack_interfaces)
         self.recommendedsolver = RMSB200()
         self.forwardsensitivities = bool(forwardsensitivities)
 
@@ -187,7 +187,14 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
     dysave = np.empty((n, nsave, Ny)) if (save_derivatives and nsave) else None
     if dysave is not None:
         opts.dysave = dysave.ctypes.data
-    if devices is not None and len(devices) > 0:
+    fa, fs = (None, 0) if dom.kind == L.DOMAIN_COUPLED_TP_TAPHI else dom._interfaces_for(react.interfaces, n)   # internal interfaces live in the merged mechanism
+    if fa is not None:
+        if devices is not None and len(devices) > 1:
+            raise NotImplementedError("boundary interfaces with the multi-device call")
+        L.check(L.lib().rmsb_solve_batch_if(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                            L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
+    elif devices is not None and len(devices) > 0:
         handles = (C.c_void_p * len(devices))(*[dom.phase.handle_on(int(d)) for d in devices])
         L.check(L.lib().rmsb_solve_batch_multi(handles, len(devices), dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
                                                L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),

@@ -170,3 +170,25 @@ def test_transitory_time_scale_selection_matches_the_oracle_restatement():
         assert a == b
         seen += a is not None
     assert seen > 50
+
+
+def test_pack_interfaces_merges_by_type_and_matches_oracle_enthalpy():
+    """Host packing of boundary interfaces (rmsb200/interfaces.py): two inlets merge into one row (flow-weighted composition and
+    enthalpy), the inlet enthalpy equals the oracle's getEnthalpy sum, per-reactor flows override the row."""
+    from types import SimpleNamespace
+    d = rb.readinput(cases.fixture("superminimal"))
+    gdom = SimpleNamespace(phase=rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"], name="phase"), kind=L.DOMAIN_CONSTANT_TP)   # no device needed
+    odom = cases.oracle_domain("superminimal_TP")
+    a = rb.Inlet(gdom, {"H2": 0.67, "O2": 0.33, "T": 1000.0, "P": 1e5}, lambda t: 0.001)
+    b = rb.Inlet(gdom, {"H2": 1.0, "T": 800.0, "P": 1e5}, 0.003)
+    oa = ro.Inlet(odom, {"H2": 0.67, "O2": 0.33, "T": 1000.0, "P": 1e5}, 0.001)
+    assert a.H == pytest.approx(oa.H, rel=1e-14) and np.allclose(a.y, oa.y, rtol=1e-15)
+    row = rb.pack_interfaces(gdom, [a, b, rb.Outlet(gdom, 0.004), rb.VolumeMaintainingOutlet(gdom)])
+    Ns = gdom.phase.Ns
+    assert row.shape == (7 + 2 * Ns,) and row[0] == pytest.approx(0.004) and row[1] == 0.004 and row[4] == 1.0
+    np.testing.assert_allclose(row[7:7 + Ns] * row[0], a.y * a.F + b.y * b.F, rtol=1e-14)
+    assert row[5] * row[0] == pytest.approx(a.H * a.F + b.H * b.F, rel=1e-14)
+    rows = rb.pack_interfaces(gdom, [a], np.array([[1e-3, 2e-3, 0, 0], [5e-3, 0, 0, 0]]))
+    assert rows.shape == (2, 7 + 2 * Ns) and rows[1, 0] == 5e-3 and rows[0, 1] == 2e-3
+    with pytest.raises(NotImplementedError):
+        rb.Outlet(gdom, lambda t: 1e-3 * (1.0 + t))

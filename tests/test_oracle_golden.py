@@ -233,3 +233,22 @@ def test_c2_constant_v_idt_golden():  # src/TestReactors.jl:301-310
     assert oi.idt_grid(sol.sol) == pytest.approx(0.038384723436228063, rel=1e-5)
     g = np.load(cases.ROOT / "tests" / "golden" / "parity_vectors.npz")
     assert float(g["superminimal_V/idt_grid"]) == pytest.approx(0.038384723436228063, rel=1e-5)
+
+
+@pytest.mark.parametrize("case,ifs", [
+    ("superminimal_TP", lambda d: [ro.Inlet(d, {"H2": 0.67, "O2": 0.33, "T": 1000.0, "P": 1e5}, lambda t: 0.001), ro.Outlet(d, lambda t: 0.001)]),
+    ("superminimal_V", lambda d: [ro.Inlet(d, {"H2": 0.67, "O2": 0.33, "T": 900.0, "P": 1e5}, 0.002), ro.Outlet(d, 0.001)]),
+    ("liquid_TV", lambda d: [ro.VolumetricFlowRateInlet(d, {"octane": 6154.0, "oxygen": 4.953, "T": 450.0, "P": 1e5}, 1.0), ro.VolumetricFlowRateOutlet(d, 1.0)]),
+])
+def test_boundary_interfaces_analytic_jacobian_equals_ad(case, ifs):
+    """The reference's own criterion for reactors with interfaces (src/TestReactors.jl:271-280, 53-62): the analytic Jacobian with the
+    interface terms equals the derivative of the full RHS, |ja - j| <= 1e-4 |j| + 1e-16 -- here complex step stands in for ForwardDiff."""
+    from oracle import rms_oracle as ro2  # noqa: F401
+    od = cases.oracle_domain(case)
+    y = cases.states(case, od.y0, od.phase.Ns, od.kind)[0]
+    po = od.p if od.kind in ("ConstantV", "ConstantTP") else None
+    inter = ifs(od)
+    ja = ro.jacobiany(od, y, 0.0, po, interfaces=inter)
+    j = ro.jacobiany_complexstep(od, y, 0.0, po, interfaces=inter)
+    assert not np.any(np.abs(ja - j) > 1e-4 * np.abs(j) + 1e-16 * np.abs(j).max())
+    assert np.any(ja != ro.jacobiany(od, y, 0.0, po))
