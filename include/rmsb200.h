@@ -309,6 +309,37 @@ int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
                         double* yend, double* idt, int32_t* status, rmsb_stats* stats,
                         const rmsb_solve_opts* opts);
 
+/* ---- time profiles (ParametrizedVDomain / ParametrizedPDomain) and the general extended calls ---------
+ * The reference's rapid-compression-machine / shock-tube domains (src/Domain.jl:331-498): the ConstantV domain whose volume
+ * follows V(t), the ConstantP domain whose pressure follows P(t) -- dT/dt and dP/dt (dV/dt) gain the dV/dt (dP/dt) terms of
+ * src/Domain.jl:2003-2090, the Jacobian those of :2726-2748,2874-2896.  The profile is a natural cubic spline (the reference's
+ * getspline, src/Tools.jl:46-85) handed over as [nt, ts[nt], values[nt], gamma[nt]] (gamma = second derivatives at the knots,
+ * gamma[0] = gamma[nt-1] = 0; linear extrapolation outside the knots), one row per reactor (profile_stride = 1 + 3*nt) or one row
+ * shared by all (0).  `cond` keeps its layout (its V / P entry is ignored).  domain_kind stays RMSB_DOMAIN_CONSTANT_V / _P.
+ * t: evaluation time of every state for dydt / jac (NULL = 0); solve integrates from t = 0.
+ * ParametrizedTPDomain and ParametrizedTConstantVDomain: not built. */
+typedef struct rmsb_extras {
+    int32_t struct_size;          /* = sizeof(rmsb_extras) */
+    const double* interfaces;     /* boundary interfaces, see rmsb_dydt_batch_if; NULL = none */
+    int64_t if_stride;
+    const double* profile;        /* time profile(s); NULL = none */
+    int64_t profile_stride;
+    const double* t;              /* [n] evaluation times (dydt / jac only); NULL = 0 */
+} rmsb_extras;
+int rmsb_dydt_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n,
+                       const double* y, const double* cond, const double* p, int64_t p_stride,
+                       const int32_t* const_species, int32_t n_const, const rmsb_extras* extras, double* dydt);
+int rmsb_jac_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n,
+                      const double* y, const double* cond, const double* p, int64_t p_stride,
+                      const int32_t* const_species, int32_t n_const, const rmsb_extras* extras, double* J);
+int rmsb_solve_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n,
+                        const double* y0, const double* cond, const double* p, int64_t p_stride,
+                        const int32_t* const_species, int32_t n_const, const rmsb_extras* extras,
+                        const double* t_end, double rtol, double atol,
+                        int32_t nsave, const double* tsave, double* ysave,
+                        double* yend, double* idt, int32_t* status, rmsb_stats* stats,
+                        const rmsb_solve_opts* opts);
+
 /* ---- one host process, several GPUs -------------------------------------------------------------
  * rmsb_solve_batch over n_mech handles of the SAME mechanism created on different devices: the reactors are split into
  * contiguous blocks by index (block g = reactors [g*n/n_mech, (g+1)*n/n_mech)), each block runs rmsb_solve_batch on its

@@ -55,10 +55,10 @@ def dydt_terms(domain, y, t=0.0, p=None):
                 M[ra[j, i]] += mag
     M[:Ns] *= abs(th.V)
     R = ro.R
-    if domain.kind == "ConstantV":          # src/Domain.jl:1901-1906
+    if domain.kind in ("ConstantV", "ParametrizedV"):          # src/Domain.jl:1901-1906
         M[Ns] = np.dot(np.abs(th.Us), M[:Ns]) / abs(th.N * th.Cvave)
         M[Ns + 1] = np.sum(M[:Ns]) * R * th.T / th.V + th.P / th.T * M[Ns]
-    elif domain.kind == "ConstantP":        # :1950-1953
+    elif domain.kind in ("ConstantP", "ParametrizedP"):        # :1950-1953
         M[Ns] = np.dot(np.abs(th.Hs), M[:Ns]) / abs(th.N * (th.Cvave + R))
         M[Ns + 1] = np.sum(M[:Ns]) * R * th.T / th.P + M[Ns] * th.V / th.T
     elif domain.kind == "ConstantTP":       # :1863-1866
@@ -93,10 +93,10 @@ def closure_floor(domain, y, p, Jabs, t=0.0):
     A = np.abs(Jabs[:Ns])
     if domain.kind == "ConstantTP":
         return EPS * (A.sum(axis=0) * R * th.T / th.P)[None]
-    if domain.kind == "ConstantV":
+    if domain.kind in ("ConstantV", "ParametrizedV"):
         trow = np.abs(th.Us) @ A / abs(th.N * th.Cvave)
         return EPS * np.stack([trow, A.sum(axis=0) * R * th.T / th.V + th.P / th.T * trow])
-    if domain.kind == "ConstantP":
+    if domain.kind in ("ConstantP", "ParametrizedP"):
         trow = np.abs(th.Hs) @ A / abs(th.N * (th.Cvave + R))
         return EPS * np.stack([trow, A.sum(axis=0) * R * th.T / th.P + th.V / th.T * trow])
     return np.zeros((0, A.shape[1]))
@@ -110,7 +110,7 @@ def species_block_magnitude(domain, y, p, t=0.0):
     yv = np.asarray(y, dtype=float)
     th = domain.calcthermo(yv, t, p)
     Ns = domain.phase.Ns
-    Vind = Ns if domain.kind == "ConstantTP" else (Ns + 1 if domain.kind == "ConstantP" else None)
+    Vind = Ns if domain.kind == "ConstantTP" else (Ns + 1 if domain.kind in ("ConstantP", "ParametrizedP") else None)
     Jabs = np.zeros((len(yv), len(yv)))
 
     def abs_spread(jac, deriv, slots, col, sign):

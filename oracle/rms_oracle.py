@@ -809,6 +809,7 @@ class Thermo:
     Cvave: float
     cpdivR: np.ndarray
     phi: float = 0.0
+    t: float = 0.0          # evaluation time (only the Parametrized* domains look at it)
 
 
 _EMPTY = np.zeros(0)
@@ -943,6 +944,143 @@ class ConstantPDomain(_Domain):
         Cp = th.Cvave + R
         dydt[Ns] = -np.dot(th.Hs, dydt[:Ns]) / (th.N * Cp)
         dydt[Ns + 1] = np.sum(dydt[:Ns]) * R * th.T / th.P + dydt[Ns] * th.V / th.T
+        for i in self.constantspeciesinds:
+            dydt[i] = 0.0
+
+
+class Spline:
+    """getspline (src/Tools.jl:46-85): the reference fits a SmoothingSplines.jl smoothing spline with lambda = 1e-10 (third party, absent)
+    and evaluates it with `_predict` (:54-85, restated in __call__).  With lambda -> 0 that fit is the interpolating NATURAL cubic
+    spline, which is what is built here (gamma = second derivatives at the knots, zero at both ends); the difference to the
+    reference's fit is O(1e-10) of the data -- parity unpinned at that level.  derivative(): analytic (the reference uses
+    Calculus.derivative, a central finite difference, src/Domain.jl:2003,2047)."""
+
+    def __init__(self, xs, vals):
+        self.x = np.asarray(xs, dtype=float)
+        self.g = np.asarray(vals, dtype=float)
+        n = len(self.x)
+        assert n >= 2 and np.all(np.diff(self.x) > 0)
+        gam = np.zeros(n)
+        if n > 2:
+            h = np.diff(self.x)
+            A = np.zeros((n - 2, n - 2))
+            rhs = np.zeros(n - 2)
+            for i in range(1, n - 1):
+                A[i - 1, i - 1] = (h[i - 1] + h[i]) / 3.0
+                if i > 1:
+                    A[i - 1, i - 2] = h[i - 1] / 6.0
+                if i < n - 2:
+                    A[i - 1, i] = h[i] / 6.0
+                rhs[i - 1] = (self.g[i + 1] - self.g[i]) / h[i] - (self.g[i] - self.g[i - 1]) / h[i - 1]
+            gam[1:-1] = np.linalg.solve(A, rhs)
+        self.gamma = gam
+
+    def table(self):
+        """[nt, ts, values, gamma]: the layout of the device profile (include/rmsb200.h, rmsb_extras.profile)."""
+        return np.concatenate([[float(len(self.x))], self.x, self.g, self.gamma])
+
+    def _piece(self, x):
+        n = len(self.x)
+        if x <= self.x[0]:
+            h = self.x[1] - self.x[0]
+            gp = (self.g[1] - self.g[0]) / h - h * self.gamma[1] / 6.0
+            return self.g[0] - (self.x[0] - x) * gp, gp
+        if x >= self.x[-1]:
+            h = self.x[-1] - self.x[-2]
+            gp = (self.g[-1] - self.g[-2]) / h + h * self.gamma[-2] / 6.0
+            return self.g[-1] + (x - self.x[-1]) * gp, gp
+        i = int(np.searchsorted(self.x, x, side="right")) - 1
+        xl, xr, gl, gr, cl, cr = self.x[i], self.x[i + 1], self.g[i], self.g[i + 1], self.gamma[i], self.gamma[i + 1]
+        h = xr - xl
+        a, b = x - xl, xr - x
+        w = (1 + a / h) * cr + (1 + b / h) * cl
+        val = (a * gr + b * gl) / h - a * b * w / 6.0
+        dv = (gr - gl) / h - ((b - a) * w + a * b * (cr - cl) / h) / 6.0
+        return val, dv
+
+    def __call__(self, x):
+        return self._piece(float(x))[0]
+
+    def derivative(self, x):
+        return self._piece(float(x))[1]
+
+
+class ParametrizedVDomain(ConstantVDomain):
+    """src/Domain.jl:331-411 (ctor), :1219-1290 (calcthermo), :2002-2045 (derivatives): adiabatic reactor whose volume follows V(t).
+    y = [ns; T; P]."""
+    kind = "ParametrizedV"
+
+    def __init__(self, phase: Phase, initialconds: dict, constantspecies=()):
+        assert phase.kind == "gas"
+        ic = dict(initialconds)
+        ts, Vs = ic.pop("ts"), ic.pop("V")
+        self.Vf = Spline(ts, Vs)
+        vals, ns = _initial(phase, ic, ("T", "P"))
+        T = vals["T"]
+        N = ns.sum()
+        V0 = self.Vf(0.0)
+        P = vals["P"] if vals["P"] != 0.0 else N * R * T / V0
+        if T == 0.0:
+            T = P * V0 / (R * N)
+        self.phase, self.V = phase, V0
+        self.y0 = np.concatenate([ns, [T, P]])
+        self.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+        self.constantspeciesinds = self._constspc(constantspecies)
+        self.Ny = phase.Ns + 2
+        self.cond = np.array([V0])
+
+    def calcthermo(self, y, t=0.0, p=None) -> Thermo:
+        self.V = self.Vf(t)
+        th = ConstantVDomain.calcthermo(self, y, t, p)
+        th.t = t
+        return th
+
+    def derivatives(self, dydt, th: Thermo):
+        Ns = self.phase.Ns
+        dVdt = self.Vf.derivative(th.t)
+        dydt[Ns] = (-np.dot(th.Us, dydt[:Ns]) - th.P * dVdt) / (th.N * th.Cvave)
+        dydt[Ns + 1] = np.sum(dydt[:Ns]) * R * th.T / th.V + dydt[Ns] * th.P / th.T - th.P / th.V * dVdt
+        for i in self.constantspeciesinds:
+            dydt[i] = 0.0
+
+
+class ParametrizedPDomain(ConstantPDomain):
+    """src/Domain.jl:413-498 (ctor), :1292-1368 (calcthermo), :2046-2095 (derivatives): adiabatic reactor whose pressure follows P(t).
+    y = [ns; T; V]."""
+    kind = "ParametrizedP"
+
+    def __init__(self, phase: Phase, initialconds: dict, constantspecies=()):
+        assert phase.kind == "gas"
+        ic = dict(initialconds)
+        ts, Ps = ic.pop("ts"), ic.pop("P")
+        self.Pf = Spline(ts, Ps)
+        vals, ns = _initial(phase, ic, ("T", "V"))
+        T, V = vals["T"], vals["V"]
+        N = ns.sum()
+        P0 = self.Pf(0.0)
+        if V == 0.0:
+            V = N * R * T / P0
+        elif T == 0.0:
+            T = P0 * V / (R * N)
+        self.phase, self.P = phase, P0
+        self.y0 = np.concatenate([ns, [T, V]])
+        self.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+        self.constantspeciesinds = self._constspc(constantspecies)
+        self.Ny = phase.Ns + 2
+        self.cond = np.array([P0])
+
+    def calcthermo(self, y, t=0.0, p=None) -> Thermo:
+        self.P = self.Pf(t)
+        th = ConstantPDomain.calcthermo(self, y, t, p)
+        th.t = t
+        return th
+
+    def derivatives(self, dydt, th: Thermo):
+        Ns = self.phase.Ns
+        Cp = th.Cvave + R
+        dPdt = self.Pf.derivative(th.t)
+        dydt[Ns] = (-np.dot(th.Hs, dydt[:Ns]) + th.V * dPdt) / (th.N * Cp)
+        dydt[Ns + 1] = np.sum(dydt[:Ns]) * R * th.T / th.P + dydt[Ns] * th.V / th.T - dPdt * th.V / th.P
         for i in self.constantspeciesinds:
             dydt[i] = 0.0
 
@@ -1163,7 +1301,7 @@ def apply_interfaces(domain, dydt, th: Thermo, t, interfaces):
     """The interface loops of calcdomainderivatives! (src/Domain.jl:1843-1860 generic, 1868-1898 ConstantTP, 1907-1947 ConstantV,
     1957-1997 ConstantP), after the constant-species zeroing."""
     Ns = domain.phase.Ns
-    kind = domain.kind
+    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP"}.get(domain.kind, domain.kind)   # same interface terms (Domain.jl:2007-2044,2052-2094)
     T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
     for it in interfaces:
         if it.domain is not domain:
@@ -1322,7 +1460,7 @@ def _jac_interfaces(jac, domain, th: Thermo, t, interfaces):
     (ConstantTP), 2322-2448 (ConstantV), 2493-2628 (ConstantP), 3057-3088 (ConstantTV / ConstantTAPhi).  VolumeMaintainingOutlet has
     no analytic terms in the reference."""
     Ns = domain.phase.Ns
-    kind = domain.kind
+    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP"}.get(domain.kind, domain.kind)
     T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
     for it in interfaces:
         if it.domain is not domain:
@@ -1425,15 +1563,16 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30, interfaces=()):
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
         _jac_interfaces(jac, domain, th, t, interfaces)
-    elif domain.kind == "ConstantV":
+    elif domain.kind in ("ConstantV", "ParametrizedV"):
         jacobianynsderiv(jac, domain, th, None)
         dydt = np.zeros(Ny)
         addreactionratecontributions(dydt, domain.phase.rxnarray, th.cs, th.kfs, th.krevs)
         dydt *= th.V
+        PdVdt = th.P * domain.Vf.derivative(t) if domain.kind == "ParametrizedV" else 0.0     # src/Domain.jl:2743-2746
         for i in range(Ns):
             dCvdni = th.cpdivR[i] * R / th.N
             jac[Ns, i] = (-np.dot(th.Us, jac[:Ns, i]) / (th.N * th.Cvave)
-                          + np.dot(th.Us, dydt[:Ns]) / (th.N * th.Cvave * th.Cvave) * dCvdni)
+                          + (np.dot(th.Us, dydt[:Ns]) + PdVdt) / (th.N * th.Cvave * th.Cvave) * dCvdni)
             jac[Ns + 1, i] = np.sum(jac[:Ns, i]) * R * th.T / th.V + th.P / th.T * jac[Ns, i]
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
@@ -1442,19 +1581,20 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30, interfaces=()):
             yc = y.astype(complex)
             yc[col] += 1j * cstep
             jac[:, col] = dydtreactor(domain, yc, t, p, interfaces).imag / cstep
-    elif domain.kind == "ConstantP":      # src/Domain.jl:2456-2632: V column analytic, T column = derivative of the full RHS
+    elif domain.kind in ("ConstantP", "ParametrizedP"):      # src/Domain.jl:2456-2632 / 2874-2896: V column analytic, T column = derivative of the full RHS
         jacobianynsderiv(jac, domain, th, Ns + 1)
         dydt = np.zeros(Ny)
         addreactionratecontributions(dydt, domain.phase.rxnarray, th.cs, th.kfs, th.krevs)
         dydt *= th.V
         Cp = th.Cvave + R
-        dTdt = -np.dot(th.Hs, dydt[:Ns]) / (th.N * Cp)
+        dPdt = domain.Pf.derivative(t) if domain.kind == "ParametrizedP" else 0.0
+        dTdt = (-np.dot(th.Hs, dydt[:Ns]) + th.V * dPdt) / (th.N * Cp)
         for i in range(Ns):
             dCpdni = th.cpdivR[i] * R / th.N
             jac[Ns, i] = -np.dot(th.Hs, jac[:Ns, i]) / (th.N * Cp) - dTdt * (dCpdni / Cp)
             jac[Ns + 1, i] = np.sum(jac[:Ns, i]) * R * th.T / th.P + th.V / th.T * jac[Ns, i]
-        jac[Ns, Ns + 1] = -np.dot(th.Hs, jac[:Ns, Ns + 1]) / (th.N * Cp)
-        jac[Ns + 1, Ns + 1] = np.sum(jac[:Ns, Ns + 1]) * R * th.T / th.P + dTdt / th.T + th.V / th.T * jac[Ns, Ns + 1]
+        jac[Ns, Ns + 1] = (-np.dot(th.Hs, jac[:Ns, Ns + 1]) + dPdt) / (th.N * Cp)
+        jac[Ns + 1, Ns + 1] = np.sum(jac[:Ns, Ns + 1]) * R * th.T / th.P + dTdt / th.T + th.V / th.T * jac[Ns, Ns + 1] - dPdt / th.P
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
         _jac_interfaces(jac, domain, th, t, interfaces)

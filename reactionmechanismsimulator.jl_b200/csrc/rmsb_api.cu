@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMe
         d.constspc = a.constspc; d.nconst = a.nconst;
         d.cond = a.cond + ir * a.ncond;
         d.flow = a.flow ? a.flow + ir * a.flow_stride : nullptr;
+        d.ptab = a.ptab ? a.ptab + ir * a.ptab_stride : nullptr;
+        d.t = a.tval ? a.tval[ir] : 0.0;
         double* yb = w.ybuf();
         for (int i = lane; i < Ny; i += 32) yb[i] = a.y[ir * Ny + i];
         rhs_prepare(d, w, lane);
@@ -950,18 +952,21 @@ static bool tpr_disabled() {
 
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
-    if (a.flow) {
-        // boundary interfaces are evaluated by the warp-per-reactor routines (rhs_v / rhs_ck / jac_warp)
-        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the large-mechanism path (Ny > 128) are not built");
-        if (MODE != 0 && MODE != 1) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces: dydt, Jacobian and solve only");
+    const bool extras = a.flow || a.ptab;
+    if (extras) {
+        // boundary interfaces / time profiles are evaluated by the warp-per-reactor routines (rhs_v / rhs_ck / jac_warp)
+        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
+        if (MODE != 0 && MODE != 1) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles: dydt, Jacobian and solve only");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
+        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P)
+            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV) and ConstantP (ParametrizedP) domains only");
     }
     if (a.Ny > 128) {
         if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
     }
     if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
-        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled() && !a.flow) {
+        h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled() && !extras) {
         // small variable-k mechanisms, large batches: one thread per reactor
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
@@ -975,7 +980,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         return RMSB_OK;
     }
     if (MODE == 1 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) && a.Ny <= TPR_J_MAXNY &&
-        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096 && !tpr_disabled() && !a.flow) {
+        h->dm.Nr <= TPR_J_MAXNR && h->n_dt <= TPR_MAXDT && a.n >= 4096 && !tpr_disabled() && !extras) {
         cudaDeviceProp prop;
         CU(rmsb_cached_props(h->device, &prop));
         const size_t smem = ((size_t)MECH_DOUBLES + (size_t)TPR_THREADS * (a.Ny | 1)) * sizeof(double);
@@ -987,7 +992,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         CU(cudaGetLastError());
         return RMSB_OK;
     }
-    if ((MODE == 0 || MODE == 1) && !a.flow && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
+    if ((MODE == 0 || MODE == 1) && !extras && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
     LaunchCfg cfg;
     int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
@@ -1051,9 +1056,11 @@ static int sens_dispatch(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, si
 }
 
 static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
-    if (a.flow) {      // boundary interfaces: the warp-per-reactor integrator (rhs_v / rhs_ck / jac_warp carry the interface terms)
-        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the large-mechanism path (Ny > 128) are not built");
+    if (a.flow || a.ptab) {      // boundary interfaces / time profiles: the warp-per-reactor integrator (rhs_v / rhs_ck / jac_warp carry the terms)
+        if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
+        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P)
+            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV) and ConstantP (ParametrizedP) domains only");
     } else if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
     switch (rows_per_lane(a.Ny)) {
     case 1: return launch_solve_R<1>(h, a, want_wpb, st);
@@ -1097,8 +1104,22 @@ static BatchArgs make_batch(const rmsb_mech* h, int kind, int64_t n, const doubl
     return a;
 }
 
-static int check_interfaces(const rmsb_mech* h, const double* ifs, int64_t if_stride) {
-    if (ifs && if_stride != 0 && if_stride != 7 + 2 * (int64_t)h->dm.Ns) return fail(RMSB_ERR_ARG, "if_stride must be 0 or 7 + 2*Ns");
+// validated copy of the caller's rmsb_extras (NULL / short structs give the defaults)
+struct Extras { const double* ifs = nullptr; int64_t if_stride = 0; const double* prof = nullptr; int64_t prof_stride = 0; const double* t = nullptr; int64_t prof_len = 0; };
+static int check_extras(const rmsb_mech* h, const rmsb_extras* x, Extras* e) {
+    *e = Extras();
+    if (!x) return RMSB_OK;
+    if (x->struct_size != (int32_t)sizeof(rmsb_extras)) return fail(RMSB_ERR_ARG, "rmsb_extras size mismatch (ABI)");
+    e->ifs = x->interfaces; e->if_stride = x->interfaces ? x->if_stride : 0;
+    e->prof = x->profile; e->prof_stride = x->profile ? x->profile_stride : 0; e->t = x->t;
+    if (e->ifs && e->if_stride != 0 && e->if_stride != 7 + 2 * (int64_t)h->dm.Ns) return fail(RMSB_ERR_ARG, "if_stride must be 0 or 7 + 2*Ns");
+    if (e->prof) {
+        const int64_t nt = (int64_t)e->prof[0];
+        if (nt < 2 || (double)nt != e->prof[0]) return fail(RMSB_ERR_ARG, "profile: the first entry is the number of knots (>= 2)");
+        e->prof_len = 1 + 3 * nt;
+        if (e->prof_stride != 0 && e->prof_stride != e->prof_len) return fail(RMSB_ERR_ARG, "profile_stride must be 0 or 1 + 3*nt");
+        for (int64_t k = 1; k < nt; ++k) if (!(e->prof[1 + k] > e->prof[k])) return fail(RMSB_ERR_ARG, "profile: knot times must increase");
+    }
     return RMSB_OK;
 }
 
@@ -1168,11 +1189,12 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
                           const double* p, int64_t p_stride, const int32_t* cs, int32_t ncs,
                           const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
                           double* ysave, double* ssave, double* yend, double* send, double* idt, int32_t* status, rmsb_stats* stats,
-                          const rmsb_solve_opts* opts, void* work, void* stream, const double* flow = nullptr, int64_t flow_stride = 0) {
+                          const rmsb_solve_opts* opts, void* work, void* stream, const double* flow = nullptr, int64_t flow_stride = 0,
+                          const double* ptab = nullptr, int64_t ptab_stride = 0) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     if (sens && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
-    if (sens && flow) return fail(RMSB_ERR_UNSUPPORTED, "forward sensitivities with boundary interfaces are not built");
+    if (sens && (flow || ptab)) return fail(RMSB_ERR_UNSUPPORTED, "forward sensitivities with boundary interfaces / time profiles are not built");
     if (n == 0) return RMSB_OK;
     if (!t_end || !status || !work) return fail(RMSB_ERR_ARG, "t_end, status and work buffers are required");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(RMSB_ERR_ARG, "rtol must be > 0 and atol >= 0");
@@ -1190,6 +1212,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
     a.counter = reinterpret_cast<unsigned long long*>(work);
     a.ssave = ssave; a.send = send; a.sens_hist = nullptr; a.Npp = sens_npp(h);
     a.flow = flow; a.flow_stride = flow ? flow_stride : 0;
+    a.ptab = ptab; a.ptab_stride = ptab ? ptab_stride : 0;
     DeviceGuard g(h->device);
     if (!sens) return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
     a.idt_index = -1; a.idt = nullptr;
@@ -1286,10 +1309,11 @@ __global__ void expand_rows_kernel(const double* __restrict__ in, double* __rest
 
 static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                      int64_t p_stride, const int32_t* cs, int32_t ncs, double* out, double* out2,
-                     const double* ifs = nullptr, int64_t if_stride = 0) {
+                     const rmsb_extras* xtr = nullptr) {
     int rc = check_common(h, kind, n, y, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
-    if ((rc = check_interfaces(h, ifs, if_stride)) != RMSB_OK) return rc;
+    Extras ex;
+    if ((rc = check_extras(h, xtr, &ex)) != RMSB_OK) return rc;
     if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
@@ -1310,12 +1334,18 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     if (mode == 2) CU(dout2.alloc(sizeof(double) * n * out_per));
     BatchArgs a = make_batch(h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                              (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dout.as<double>(), dout2.as<double>());
-    DevBuf dif(sg.st);
-    if (ifs) {
-        const size_t nif = (size_t)(if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
-        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ifs, sizeof(double) * nif);
-        a.flow = dif.as<double>(); a.flow_stride = if_stride;
+    DevBuf dif(sg.st), dpr(sg.st), dtv(sg.st);
+    if (ex.ifs) {
+        const size_t nif = (size_t)(ex.if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
+        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ex.ifs, sizeof(double) * nif);
+        a.flow = dif.as<double>(); a.flow_stride = ex.if_stride;
     }
+    if (ex.prof) {
+        const size_t np = (size_t)(ex.prof_stride ? n : 1) * (size_t)ex.prof_len;
+        CU(dpr.alloc(sizeof(double) * np)); H2D(dpr.p, ex.prof, sizeof(double) * np);
+        a.ptab = dpr.as<double>(); a.ptab_stride = ex.prof_stride;
+    }
+    if (ex.t) { CU(dtv.alloc(sizeof(double) * n)); H2D(dtv.p, ex.t, sizeof(double) * n); a.tval = dtv.as<double>(); }
     if (mode == 0) rc = launch_eval<0>(h, a, sg.st);
     else if (mode == 1) rc = launch_eval<1>(h, a, sg.st);
     else if (mode == 3) rc = launch_eval<3>(h, a, sg.st);
@@ -1340,13 +1370,29 @@ extern "C" int rmsb_jacp_batch(const rmsb_mech* h, int kind, int64_t n, const do
                                int64_t p_stride, const int32_t* cs, int32_t ncs, double* Jp) {
     return eval_host(3, h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr);
 }
+static rmsb_extras extras_of_interfaces(const double* ifs, int64_t if_stride) {
+    rmsb_extras x;
+    std::memset(&x, 0, sizeof(x));
+    x.struct_size = sizeof(x); x.interfaces = ifs; x.if_stride = if_stride;
+    return x;
+}
+extern "C" int rmsb_dydt_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras, double* dydt) {
+    return eval_host(0, h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr, extras);
+}
+extern "C" int rmsb_jac_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                 int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras, double* J) {
+    return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr, extras);
+}
 extern "C" int rmsb_dydt_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                   int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride, double* dydt) {
-    return eval_host(0, h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr, ifs, if_stride);
+    rmsb_extras x = extras_of_interfaces(ifs, if_stride);
+    return eval_host(0, h, kind, n, y, cond, p, p_stride, cs, ncs, dydt, nullptr, &x);
 }
 extern "C" int rmsb_jac_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride, double* J) {
-    return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr, ifs, if_stride);
+    rmsb_extras x = extras_of_interfaces(ifs, if_stride);
+    return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr, &x);
 }
 extern "C" int rmsb_rates_batch(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                 int64_t p_stride, double* kf, double* krev) {
@@ -1379,13 +1425,16 @@ extern "C" int rmsb_gibbs_batch(const rmsb_mech* h, int64_t n, const double* T, 
 }
 
 static int solve_host_impl(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
-                           int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride,
+                           int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* xtr,
                            const double* t_end, double rtol, double atol,
                            int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
                            rmsb_stats* stats, const rmsb_solve_opts* opts) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
-    if ((rc = check_interfaces(h, ifs, if_stride)) != RMSB_OK) return rc;
+    Extras ex;
+    if ((rc = check_extras(h, xtr, &ex)) != RMSB_OK) return rc;
+    const double* ifs = ex.ifs;
+    const int64_t if_stride = ex.if_stride;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!t_end || !status) return fail(RMSB_ERR_ARG, "t_end and status are required");
@@ -1414,10 +1463,14 @@ static int solve_host_impl(const rmsb_mech* h, int kind, int64_t n, const double
     int64_t wbytes = rmsb_solve_work_bytes(h, kind, n);
     if (wbytes < 0) return RMSB_ERR_UNSUPPORTED;
     CU(dwork.alloc((size_t)wbytes));
-    DevBuf dif(sg.st);
+    DevBuf dif(sg.st), dpr(sg.st);
     if (ifs) {
         const size_t nif = (size_t)(if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
         CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ifs, sizeof(double) * nif);
+    }
+    if (ex.prof) {
+        const size_t np = (size_t)(ex.prof_stride ? n : 1) * (size_t)ex.prof_len;
+        CU(dpr.alloc(sizeof(double) * np)); H2D(dpr.p, ex.prof, sizeof(double) * np);
     }
     EventPair ev;
     CU(ev.start(sg.st));
@@ -1425,11 +1478,12 @@ static int solve_host_impl(const rmsb_mech* h, int kind, int64_t n, const double
                         (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
                         nsave > 0 ? dts.as<double>() : nullptr, nsave > 0 ? dys.as<double>() : nullptr, nullptr,
                         yend ? dye.as<double>() : nullptr, nullptr, idt ? didt.as<double>() : nullptr, dst.as<int32_t>(),
-                        stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st, ifs ? dif.as<double>() : nullptr, if_stride);
+                        stats ? dstats.as<rmsb_stats>() : nullptr, opts, dwork.p, sg.st, ifs ? dif.as<double>() : nullptr, if_stride,
+                        ex.prof ? dpr.as<double>() : nullptr, ex.prof_stride);
     if (rc != RMSB_OK) return rc;
     // du at the saved states (opts->dysave): one dydt evaluation of the n*nsave saved states, each with its reactor's constants
     double* dysave = (opts && opts->struct_size == (int32_t)sizeof(rmsb_solve_opts)) ? opts->dysave : nullptr;
-    if (dysave && ifs && if_stride != 0) return fail(RMSB_ERR_UNSUPPORTED, "dysave with per-reactor boundary interfaces is not built (use one shared row)");
+    if (dysave && ((ifs && if_stride != 0) || ex.prof)) return fail(RMSB_ERR_UNSUPPORTED, "dysave with per-reactor boundary interfaces or time profiles is not built");
     DevBuf dce(sg.st), dpe(sg.st), ddy(sg.st);
     if (dysave && nsave > 0) {
         const int64_t ne = n * nsave;
@@ -1466,7 +1520,7 @@ extern "C" int rmsb_solve_batch(const rmsb_mech* h, int kind, int64_t n, const d
                                 int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
                                 int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
                                 rmsb_stats* stats, const rmsb_solve_opts* opts) {
-    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, nullptr, 0, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
+    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, nullptr, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
 }
 
 extern "C" int rmsb_solve_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
@@ -1474,7 +1528,16 @@ extern "C" int rmsb_solve_batch_if(const rmsb_mech* h, int kind, int64_t n, cons
                                    const double* t_end, double rtol, double atol,
                                    int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
                                    rmsb_stats* stats, const rmsb_solve_opts* opts) {
-    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, ifs, if_stride, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
+    rmsb_extras x = extras_of_interfaces(ifs, if_stride);
+    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, &x, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
+}
+
+extern "C" int rmsb_solve_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                                   int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras,
+                                   const double* t_end, double rtol, double atol,
+                                   int32_t nsave, const double* tsave, double* ysave, double* yend, double* idt, int32_t* status,
+                                   rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    return solve_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, extras, t_end, rtol, atol, nsave, tsave, ysave, yend, idt, status, stats, opts);
 }
 
 extern "C" int rmsb_solve_batch_multi(const rmsb_mech* const* mechs, int32_t n_mech, int kind, int64_t n, const double* y0,

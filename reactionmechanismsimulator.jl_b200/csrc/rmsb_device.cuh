@@ -527,7 +527,40 @@ struct DomainArgs {
     const int* constspc;  // 1-based (reference convention)
     const double* cond;   // per-reactor constants
     const double* flow = nullptr;   // boundary interfaces of this reactor (IF_* layout below) or nullptr
+    const double* ptab = nullptr;   // time profile of the domain's "constant" (ParametrizedV: V(t), ParametrizedP: P(t)) or nullptr
+    double t = 0.0;                 // time of the evaluation (only the profile looks at it: the chemistry is autonomous)
 };
+
+// Time profile: a natural cubic spline through (ts, vs) -- the role of getspline (src/Tools.jl:46-85; the reference fits a
+// third-party smoothing spline with lambda = 1e-10, which is this interpolating spline to ~1e-10) -- stored as
+// [nt, ts[nt], vs[nt], gamma[nt]] with gamma the second derivatives (gamma[0] = gamma[nt-1] = 0); linear extrapolation outside.
+// Returns the value; *dv = the ANALYTIC derivative (the reference differentiates numerically, Calculus.derivative, Domain.jl:2003,2047).
+__device__ __forceinline__ double profile_eval(const double* tab, double x, double* dv) {
+    const int nt = (int)tab[0];
+    const double* ts = tab + 1;
+    const double* vs = ts + nt;
+    const double* gm = vs + nt;
+    if (x <= ts[0]) {
+        const double h = ts[1] - ts[0];
+        const double gp = (vs[1] - vs[0]) / h - h * gm[1] / 6.0;
+        *dv = gp;
+        return vs[0] - (ts[0] - x) * gp;
+    }
+    if (x >= ts[nt - 1]) {
+        const double h = ts[nt - 1] - ts[nt - 2];
+        const double gp = (vs[nt - 1] - vs[nt - 2]) / h + h * gm[nt - 2] / 6.0;
+        *dv = gp;
+        return vs[nt - 1] + (x - ts[nt - 1]) * gp;
+    }
+    int lo = 0, hi = nt - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (ts[mid] <= x) lo = mid; else hi = mid; }
+    const double xl = ts[lo], xr = ts[hi], h = xr - xl, gl = vs[lo], gr = vs[hi], cl = gm[lo], cr = gm[hi];
+    const double a = x - xl, b = xr - x;
+    // src/Tools.jl:76-83: val = ((x-xl)*gr + (xr-x)*gl)/h - 1/6*(x-xl)*(xr-x)*((1+(x-xl)/h)*gamma_r + (1+(xr-x)/h)*gamma_l)
+    const double w = (1.0 + a / h) * cr + (1.0 + b / h) * cl;
+    *dv = (gr - gl) / h - ((b - a) * w + a * b * (cr - cl) / h) / 6.0;
+    return (a * gr + b * gl) / h - a * b * w / 6.0;
+}
 
 // Boundary interfaces with constant flows (src/Interface.jl:234-365), one row of 7 + 2*Ns doubles per reactor.  Several interfaces
 // of one type are merged by the host (the terms are linear in flow*composition and flow*enthalpy).
@@ -660,9 +693,12 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     double* qb = w.q();
     double* gb = w.g();
     double* ub = w.un();
-    const double V = ISP ? yb[Ns + 1] : d.cond[0];
-    const double invV = ISP ? 1.0 / V : w.aux()[7];
-    N T = seed<N>(yb[Ns], 0), P = ISP ? N(d.cond[0]) : seed<N>(yb[Ns + 1], 1);
+    // ParametrizedVDomain / ParametrizedPDomain (src/Domain.jl:1219-1370,2003-2090): the domain's constant follows a time profile
+    double dprof = 0.0;
+    const double prof = d.ptab ? profile_eval(d.ptab, d.t, &dprof) : d.cond[0];
+    const double V = ISP ? yb[Ns + 1] : prof;
+    const double invV = (ISP || d.ptab) ? 1.0 / V : w.aux()[7];
+    N T = seed<N>(yb[Ns], 0), P = ISP ? N(prof) : seed<N>(yb[Ns + 1], 1);
     TPow<N> tp(T);                       // T4 = 1/T, T6 = log(T)
     N RT = RMSB_R * T;
     N invRT = tp.T4 * RMSB_INV_R;        // 1/(R*T)
@@ -716,13 +752,19 @@ __device__ __noinline__ void rhs_v(DomainArgs d, Ws w, int lane, bool store_k) {
     N dotU = warp_sum(usum), sumn = warp_sum(nsum);
     // dT/dt = -dot(Us,dn)/(N*Cv) with N*Cv = R*(dot(cp/R,ns) - N)     (Domain.jl:1103-1105,1902)
     // ConstantP: N*Cp = N*(Cv + R) = R*dot(cp/R,ns)                                    (Domain.jl:1951-1953)
-    N dT = ISP ? -dotU / (RMSB_R * cpsum) : -dotU / (RMSB_R * (cpsum - Nt));
+    // with a profile: dT/dt = (-dot(Us,dn) - P*dV/dt)/(N*Cv), dP/dt = ... - P/V*dV/dt   (ParametrizedV, Domain.jl:2003-2006)
+    //                 dT/dt = (-dot(Hs,dn) + V*dP/dt)/(N*Cp), dV/dt = ... - dP/dt*V/P   (ParametrizedP, Domain.jl:2047-2051)
+    N dotE = ISP ? dotU - V * dprof : dotU + P * dprof;                               // dprof = 0 without a profile: exact
+    N dT = ISP ? -dotE / (RMSB_R * cpsum) : -dotE / (RMSB_R * (cpsum - Nt));
     N dP = ISP ? sumn * RT / P + dT * V * tp.T4 : sumn * RT * invV + P * tp.T4 * dT;   // :1903 / :1953 (dV/dt for ConstantP)
+    if (d.ptab) dP = ISP ? dP - dprof * V / P : dP - P * invV * dprof;
     if (lane == 0) {
         SM::st(fb, Ns, dT);
         SM::st(fb, Ns + 1, dP);
         double* ax = w.aux();
-        ax[0] = val(T); ax[1] = val(P); ax[2] = V; ax[3] = val(Nt); ax[4] = val(C); ax[6] = val(dotU);
+        // ax[6]: the numerator of -dT/dt*(N*C) -- what the Jacobian's d/dn_i(dT/dt) rows multiply by dC/C (Domain.jl:2743-2746,2892)
+        ax[0] = val(T); ax[1] = val(P); ax[2] = V; ax[3] = val(Nt); ax[4] = val(C); ax[6] = val(dotE);
+        if (ISP) ax[7] = dprof;                                                       // dP/dt of the profile for the volume column
         if (store_k) ax[5] = val(cpsum) * (RMSB_R / val(Nt)) - RMSB_R;   // Cvave
     }
     __syncwarp();
@@ -1181,11 +1223,13 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
             if (c == Ns) continue;                       // the T column is the derivative of the whole RHS, step (7)
             double a = 0.0, sm = 0.0;
             for (int i = 0; i < Ns; ++i) { double v = J[i + c * LD]; a += hs[i] * v; sm += v; }
+            const double dPdt = d.ptab ? ax[7] : 0.0;
             double jt = -a / (aN * aCp);
             if (c < Ns) jt -= dTdt * ((cpb[c] * RMSB_R / aN) / aCp);
+            else jt += dPdt / (aN * aCp);                       // ParametrizedP: d/dV of V*dP/dt (Domain.jl:2895)
             J[Ns + c * LD] = jt;
             double jv = sm * RMSB_R * aT / aP + aV / aT * jt;
-            if (c == Ns + 1) jv += dTdt / aT;
+            if (c == Ns + 1) jv += dTdt / aT - dPdt / aP;        // :2896
             J[Ns + 1 + c * LD] = jv;
         }
     }

@@ -79,6 +79,8 @@ struct SolveArgs {
                     // bit 1: no step-size hysteresis.  0 = production defaults (CVODE-style test, hysteresis)
     const double* flow = nullptr;   // boundary interfaces (see BatchArgs)
     int64_t flow_stride = 0;
+    const double* ptab = nullptr;   // time profiles (see BatchArgs)
+    int64_t ptab_stride = 0;
 };
 
 struct BatchArgs {
@@ -96,6 +98,9 @@ struct BatchArgs {
     int Ny;
     const double* flow = nullptr;   // boundary interfaces [n][flow_stride] (flow_stride 0: one row shared), IF_* layout of rmsb_device.cuh
     int64_t flow_stride = 0;
+    const double* ptab = nullptr;   // time profiles [n][ptab_stride] (0: shared), layout of profile_eval
+    int64_t ptab_stride = 0;
+    const double* tval = nullptr;   // [n] evaluation times (nullptr: t = 0)
 };
 
 // ---- distributed vector helpers -----------------------------------------------------------------
@@ -551,6 +556,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
     d.constspc = a.constspc; d.nconst = a.nconst;
     d.cond = a.cond + ir * a.ncond;
     d.flow = a.flow ? a.flow + ir * a.flow_stride : nullptr;
+    d.ptab = a.ptab ? a.ptab + ir * a.ptab_stride : nullptr;
     const double rtol = a.rtol, atol = a.atol;
     const double t_end = a.t_end[ir];
 
@@ -623,7 +629,9 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
         double y1[R], f1[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) y1[r] = y[r] + h0 * f[r];
+        d.t = h0;
         eval_rhs<R>(d, w, y1, f1, lane); ++n_rhs;
+        d.t = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) f1[r] = f1[r] - f[r];
         double d2 = rms_norm_w<R>(f1, scale, Ny, lane) / h0;
@@ -673,6 +681,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
             }
             h = h_abs;
             if (a.flags & 8) { h = t_new - t; h_abs = fabs(h); }
+            d.t = t_new;                    // time profiles (ParametrizedV / ParametrizedP) are evaluated at the new time level
             double ypred[R], psi[R];
             const double alpha_o = c_alpha[order];
 #pragma unroll

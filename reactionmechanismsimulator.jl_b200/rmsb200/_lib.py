@@ -56,6 +56,11 @@ class SolveOpts(C.Structure):
                 ("dysave", C.c_void_p)]          # version 2: host buffer [n][nsave][Ny] for du at the saved states (rmsb_solve_batch)
 
 
+class Extras(C.Structure):       # rmsb_extras
+    _fields_ = [("struct_size", C.c_int32), ("interfaces", C.c_void_p), ("if_stride", C.c_int64), ("profile", C.c_void_p),
+                ("profile_stride", C.c_int64), ("t", C.c_void_p)]
+
+
 class RMSBError(RuntimeError):
     pass
 
@@ -69,6 +74,7 @@ EXPORTS = [
     "rmsb_kernel_launch_count", "rmsb_fp64_peak_tflops", "rmsb_jacp_batch", "rmsb_jacp_batch_dev", "rmsb_sens_batch",
     "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch", "rmsb_large_info", "rmsb_large_profile",
     "rmsb_solve_batch_multi", "rmsb_last_kernel_ms", "rmsb_dydt_batch_if", "rmsb_jac_batch_if", "rmsb_solve_batch_if",
+    "rmsb_dydt_batch_ex", "rmsb_jac_batch_ex", "rmsb_solve_batch_ex",
 ]
 
 
@@ -117,6 +123,9 @@ def lib():
     L.rmsb_dydt_batch_if.argtypes = common + [vp, i32, vp, i64, vp]
     L.rmsb_jac_batch_if.argtypes = common + [vp, i32, vp, i64, vp]
     L.rmsb_solve_batch_if.argtypes = common + [vp, i32, vp, i64, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
+    L.rmsb_dydt_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp]
+    L.rmsb_jac_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp]
+    L.rmsb_solve_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
     L.rmsb_fp64_peak_tflops.argtypes = [C.c_int, C.c_int]
     L.rmsb_fp64_peak_tflops.restype = dbl
     _lib = L

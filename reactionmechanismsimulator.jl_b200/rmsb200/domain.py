@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
@@ -104,33 +106,60 @@ class Domain:
             raise ValueError("one interface row per reactor")
         return a, a.shape[1]
 
-    def dydt(self, y=None, p=None, interfaces=None):
-        """dydtreactor! for every reactor of the ensemble (src/Reactor.jl:653-660), with boundary interfaces if given."""
+    def _extras(self, interfaces, n: int, t=None):
+        """(rmsb_extras or None, arrays to keep alive) for n states: boundary interfaces, the domain's time profile (Parametrized*
+        domains: self.profile, one table or one per reactor) and the evaluation times."""
+        fa, fs = self._interfaces_for(interfaces, n)
+        prof = getattr(self, "profile", None)
+        if fa is None and prof is None:
+            return None, ()
+        x = L.Extras()
+        x.struct_size = C.sizeof(L.Extras)
+        keep = [fa]
+        if fa is not None:
+            x.interfaces, x.if_stride = fa.ctypes.data, fs
+        if prof is not None:
+            pa = np.ascontiguousarray(prof, dtype=float)
+            if pa.ndim == 2 and pa.shape[0] == 1:
+                pa = np.ascontiguousarray(pa[0])
+            if pa.ndim == 2 and pa.shape[0] != n:
+                raise ValueError("one profile row per reactor")
+            x.profile, x.profile_stride = pa.ctypes.data, (0 if pa.ndim == 1 else pa.shape[1])
+            keep.append(pa)
+            if t is not None:
+                ta = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=float), (n,)))
+                x.t = ta.ctypes.data
+                keep.append(ta)
+        return x, keep
+
+    def dydt(self, y=None, p=None, interfaces=None, t=None):
+        """dydtreactor! for every reactor of the ensemble (src/Reactor.jl:653-660), with boundary interfaces if given; t: evaluation
+        time(s), only looked at by the Parametrized* domains."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
         pp, ps = self._p_for_device(p)
         out = np.empty_like(y)
         cs = self.constantspeciesinds
         cond = self._cond_for(y.shape[0])
-        fa, fs = self._interfaces_for(interfaces, y.shape[0])
-        if fa is not None:
-            L.check(L.lib().rmsb_dydt_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
-                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+        x, keep = self._extras(interfaces, y.shape[0], t)
+        if x is not None:
+            L.check(L.lib().rmsb_dydt_batch_ex(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, C.byref(x), L.ptr(out)))
             return out
         L.check(L.lib().rmsb_dydt_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
                                         L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out
 
-    def jacobiany(self, y=None, p=None, interfaces=None):
+    def jacobiany(self, y=None, p=None, interfaces=None, t=None):
         """jacobiany! for every reactor -> [n][Ny][Ny] with J[r, eqn, var] (src/Domain.jl:2204-3091)."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
         pp, ps = self._p_for_device(p)
         out = np.empty((y.shape[0], self.Ny * self.Ny))
         cs = self.constantspeciesinds
         cond = self._cond_for(y.shape[0])
-        fa, fs = self._interfaces_for(interfaces, y.shape[0])
-        if fa is not None:
-            L.check(L.lib().rmsb_jac_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
-                                              L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+        x, keep = self._extras(interfaces, y.shape[0], t)
+        if x is not None:
+            L.check(L.lib().rmsb_jac_batch_ex(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
+                                              L.ptr(cs) if cs.size else None, cs.size, C.byref(x), L.ptr(out)))
         else:
             L.check(L.lib().rmsb_jac_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(cond), L.ptr(pp), ps,
                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
@@ -246,6 +275,58 @@ def ConstantPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspe
     dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
     dom._p_default = dom.p.copy()
     return dom, dom.y0[0].copy(), dom.p
+
+
+def ParametrizedVDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """ParametrizedVDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:331-411: adiabatic reactor whose
+    volume follows a profile -- initialconds carries "ts" and "V" as arrays (the reference also accepts a function; here the profile
+    is always the spline table the device evaluates).  y = [ns; T; P]; on the device this is the ConstantV domain with a time
+    profile (include/rmsb200.h, rmsb_extras)."""
+    from .profile import profile_value, spline_table
+    assert phase.kind == L.PHASE_GAS, "ParametrizedVDomain needs an IdealGas phase"
+    ic = dict(initialconds)
+    tab = spline_table(ic.pop("ts"), ic.pop("V"))
+    vals, ns = _parse(phase, ic, ("T", "P"))
+    T, P = vals["T"], vals["P"]
+    N = float(ns.sum())
+    V0 = profile_value(tab, 0.0)
+    if P == 0.0:
+        P = N * R * T / V0
+    elif T == 0.0:
+        T = P * V0 / (R * N)
+    y0 = np.concatenate([ns, [T, P]])
+    dom = Domain(L.DOMAIN_CONSTANT_V, phase, y0, np.array([V0]), constantspecies)
+    dom.profile = tab
+    dom.indexes = [1, phase.Ns, phase.Ns + 1, phase.Ns + 2]
+    dom.thermovariabledict = {"T": phase.Ns + 1, "P": phase.Ns + 2}
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, y0.copy(), dom.p.copy()
+
+
+def ParametrizedPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """ParametrizedPDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:413-498: adiabatic reactor whose
+    pressure follows a profile ("ts", "P" arrays).  y = [ns; T; V]; the ConstantP domain with a time profile on the device."""
+    from .profile import profile_value, spline_table
+    assert phase.kind == L.PHASE_GAS, "ParametrizedPDomain needs an IdealGas phase"
+    ic = dict(initialconds)
+    tab = spline_table(ic.pop("ts"), ic.pop("P"))
+    vals, ns = _parse(phase, ic, ("T", "V"))
+    T, V = vals["T"], vals["V"]
+    N = float(ns.sum())
+    P0 = profile_value(tab, 0.0)
+    if V == 0.0:
+        V = N * R * T / P0
+    elif T == 0.0:
+        T = P0 * V / (R * N)
+    y0 = np.concatenate([ns, [T, V]])
+    dom = Domain(L.DOMAIN_CONSTANT_P, phase, y0, np.array([P0]), constantspecies)
+    dom.profile = tab
+    dom.indexes = [1, phase.Ns, phase.Ns + 1, phase.Ns + 2]
+    dom.thermovariabledict = {"T": phase.Ns + 1, "V": phase.Ns + 2}
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, y0.copy(), dom.p.copy()
 
 
 def ConstantTPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):

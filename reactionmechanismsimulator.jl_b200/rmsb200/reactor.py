@@ -187,12 +187,13 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
     dysave = np.empty((n, nsave, Ny)) if (save_derivatives and nsave) else None
     if dysave is not None:
         opts.dysave = dysave.ctypes.data
-    fa, fs = (None, 0) if dom.kind == L.DOMAIN_COUPLED_TP_TAPHI else dom._interfaces_for(react.interfaces, n)   # internal interfaces live in the merged mechanism
-    if fa is not None:
+    xtr, keep = (None, ()) if dom.kind == L.DOMAIN_COUPLED_TP_TAPHI else dom._extras(react.interfaces, n)   # internal interfaces live in the merged mechanism
+    if xtr is not None:
+        # boundary interfaces and / or a time profile (Parametrized* domains)
         if devices is not None and len(devices) > 1:
-            raise NotImplementedError("boundary interfaces with the multi-device call")
-        L.check(L.lib().rmsb_solve_batch_if(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
-                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+            raise NotImplementedError("boundary interfaces / time profiles with the multi-device call")
+        L.check(L.lib().rmsb_solve_batch_ex(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                            L.ptr(cs) if cs.size else None, cs.size, C.byref(xtr), L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
                                             L.ptr(ysave), L.ptr(yend), L.ptr(idt), L.ptr(status), L.ptr(stats), C.byref(opts)))
     elif devices is not None and len(devices) > 0:
         handles = (C.c_void_p * len(devices))(*[dom.phase.handle_on(int(d)) for d in devices])

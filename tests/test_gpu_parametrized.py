@@ -1,0 +1,106 @@
+"""ParametrizedVDomain / ParametrizedPDomain: adiabatic reactors whose volume / pressure follows a time profile
+(rapid-compression-machine and shock-tube traces), src/Domain.jl:331-498,1219-1368,2002-2095,2726-2748,2874-2896.  The reference's own
+tests pin only analytic-vs-AD Jacobian consistency (src/TestReactors.jl:425-467); here the CUDA path is checked against the oracle's
+restatement at 1e-12 (with the derived floors) on the reference's test inputs, and a compression trajectory against SciPy BDF."""
+import numpy as np
+import pytest
+
+import cases
+import rmsb200 as rb
+from oracle import floors as fl
+from oracle import rms_oracle as ro
+from rmsb200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+IC_V = {"T": 1000.0, "ts": [0.0, 100.0, 200.0], "V": [0.01, 0.05, 0.1], "H2": 0.67, "O2": 0.33}          # src/TestReactors.jl:427
+IC_P = {"T": 1000.0, "ts": [0.0, 100.0, 200.0], "P": [2.0e5, 3.0e5, 5.0e5], "H2": 0.67, "O2": 0.33}      # :449
+
+
+def _phases():
+    d = rb.readinput(cases.fixture("superminimal")); ig = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"], name="phase")
+    od = ro.readinput(cases.fixture("superminimal")); oig = ro.IdealGas(od["phase"]["Species"], od["phase"]["Reactions"])
+    return ig, oig
+
+
+@pytest.mark.parametrize("which", ["V", "P"])
+def test_parametrized_dydt_jacobian_parity(which):
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    ig, oig = _phases()
+    if which == "V":
+        gdom, y0, p = rb.ParametrizedVDomain(phase=ig, initialconds=IC_V)
+        odom = ro.ParametrizedVDomain(oig, IC_V)
+    else:
+        gdom, y0, p = rb.ParametrizedPDomain(phase=ig, initialconds=IC_P)
+        odom = ro.ParametrizedPDomain(oig, IC_P)
+    np.testing.assert_allclose(y0, odom.y0, rtol=1e-14)
+    ys = cases.states("superminimal_V", odom.y0, ig.Ns, "ConstantV")[:3]
+    ts = np.array([0.1, 37.0, 150.0])                           # the reference's test time, and two well inside the profile
+    par = cases.parameter_vector("superminimal_V", ig.Ns, ig.Nr)
+    ens = rb.Domain(gdom.kind, ig, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    ens.profile = gdom.profile
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    for pp in (p, par):
+        f, J = ens.dydt(ys, pp, t=ts), ens.jacobiany(ys, pp, t=ts)
+        for k, y in enumerate(ys):
+            fo, M = fl.dydt_terms(odom, y, ts[k], pp)
+            rep = fl.report(f[k], fo, fl.EPS * (M + np.abs(fo)), 1e-12, slack=4.0)
+            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, (which, k, rep)
+            Jo, Jf = fl.jac_floor(lambda yy, qq: ro.jacobiany(odom, yy, ts[k], qq), odom, y, pp, t=ts[k])
+            rep = fl.report(J[k], Jo, Jf, 1e-12)
+            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, (which, k, rep["worst_at"], rep["worst_excess"], rep["max_rel_above"])
+            # the reference's criterion: analytic == derivative of the full RHS
+            Jc = ro.jacobiany_complexstep(odom, y, ts[k], pp)
+            assert not np.any(np.abs(J[k] - Jc) > 1e-4 * np.abs(Jc) + 1e-16 * np.abs(Jc).max())
+    # the profile matters: at t = 150 the volume / pressure is far from its initial value
+    plain = rb.Domain(gdom.kind, ig, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    plain.p, plain._p_default = gdom.p, gdom._p_default
+    assert not np.allclose(plain.dydt(ys, p)[2], ens.dydt(ys, p, t=ts)[2], rtol=1e-3)
+
+
+def test_rapid_compression_trajectory_vs_scipy():
+    """A compression stroke: V(t) falls by 8x in 20 ms, H2/O2/N2 ignites near top dead centre.  Trajectory against SciPy BDF over
+    the oracle, ignition delay against the oracle's dT/dt maximum; an ensemble of compression ratios through per-reactor profiles."""
+    ig, oig = _phases()
+    ts = np.array([0.0, 0.004, 0.008, 0.012, 0.016, 0.02, 0.03, 0.06])
+    V0 = 1.0e-3
+    shape = np.array([1.0, 0.93, 0.74, 0.48, 0.24, 0.125, 0.125, 0.125])
+    ic = {"T": 420.0, "P": 1.0e5, "ts": ts, "V": V0 * shape, "H2": 2.0, "O2": 1.0, "N2": 3.76}
+    n0 = 1.0e5 * V0 / (8.314 * 420.0)
+    for k in ("H2", "O2", "N2"):
+        ic[k] = ic[k] / 6.76 * n0
+    ic.pop("P")
+    gdom, y0, p = rb.ParametrizedVDomain(phase=ig, initialconds=ic)
+    odom = ro.ParametrizedVDomain(oig, ic)
+    tq = np.array([0.01, 0.02, 0.05])
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, 0.05), p=p).ode, abstol=1e-18, reltol=1e-9, saveat=tq)
+    assert sol.retcode == ["Success"]
+    from scipy.integrate import solve_ivp
+    ref = solve_ivp(lambda t, y: ro.dydtreactor(odom, y, t, odom.p), (0.0, 0.05), odom.y0, method="BDF", rtol=1e-10, atol=1e-20,
+                    jac=lambda t, y: ro.jacobiany(odom, y, t, odom.p), t_eval=tq)
+    assert ref.status == 0
+    Ns = ig.Ns
+    assert ref.y[Ns, 1] > 800.0                                  # compression heating
+    for k in range(len(tq)):
+        yr = ref.y[:, k]
+        big = np.abs(yr) > 1e-6 * np.abs(yr[:Ns]).max()
+        assert np.max(np.abs(sol.u[0, k] - yr)[big] / np.abs(yr)[big]) < 1e-6, tq[k]
+        trace = np.abs(yr) > 1e-12 * np.abs(yr[:Ns]).max()         # the radical pool grows exponentially during the induction time
+        assert np.max(np.abs(sol.u[0, k] - yr)[trace] / np.abs(yr)[trace]) < 1e-4, tq[k]
+    # ensemble: compression ratios 6..12 through per-reactor profile rows
+    n = 32
+    cr = np.linspace(6.0, 12.0, n)
+    tabs = np.stack([rb.spline_table(ts, V0 * (1.0 - (1.0 - shape) * (1.0 - 1.0 / c) / (1.0 - 0.125))) for c in cr])
+    ens = rb.Domain(gdom.kind, ig, np.repeat(gdom.y0, n, axis=0), np.repeat(gdom.cond, n, axis=0))
+    ens.profile = tabs
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    s = rb.solve(rb.Reactor(ens, None, (0.0, 0.06), p=p).ode, abstol=1e-16, reltol=1e-6)
+    assert np.all(s.status == 0)
+    Tend = s.yend[:, Ns]
+    assert Tend[-1] > Tend[0] and np.all(np.diff(Tend) > -1.0)   # more compression, hotter end state
+    k8 = int(np.argmin(np.abs(cr - 8.0)))
+    one = rb.Domain(gdom.kind, ig, gdom.y0, gdom.cond)
+    one.profile = tabs[k8]
+    one.p, one._p_default = gdom.p, gdom._p_default
+    s1 = rb.solve(rb.Reactor(one, None, (0.0, 0.06), p=p).ode, abstol=1e-16, reltol=1e-6)
+    assert np.array_equal(s1.yend[0], s.yend[k8])

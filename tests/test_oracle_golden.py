@@ -252,3 +252,25 @@ def test_boundary_interfaces_analytic_jacobian_equals_ad(case, ifs):
     j = ro.jacobiany_complexstep(od, y, 0.0, po, interfaces=inter)
     assert not np.any(np.abs(ja - j) > 1e-4 * np.abs(j) + 1e-16 * np.abs(j).max())
     assert np.any(ja != ro.jacobiany(od, y, 0.0, po))
+
+
+@pytest.mark.parametrize("which", ["V", "P"])
+def test_parametrized_domains_analytic_jacobian_equals_ad(which):
+    """src/TestReactors.jl:425-467: ParametrizedVDomain / ParametrizedPDomain built from arrays ("ts" + "V" / "P"), analytic Jacobian
+    vs the derivative of the full RHS at t = 0.1 (|ja - j| <= 1e-4 |j| + 1e-16); and the profile is the natural cubic spline."""
+    from scipy.interpolate import CubicSpline
+    d = ro.readinput(cases.fixture("superminimal"))
+    ig = ro.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"])
+    if which == "V":
+        dom = ro.ParametrizedVDomain(ig, {"T": 1000.0, "ts": [0.0, 100.0, 200.0], "V": [0.01, 0.05, 0.1], "H2": 0.67, "O2": 0.33})
+        spl, xs, vs = dom.Vf, [0.0, 100.0, 200.0], [0.01, 0.05, 0.1]
+    else:
+        dom = ro.ParametrizedPDomain(ig, {"T": 1000.0, "ts": [0.0, 100.0, 200.0], "P": [2.0e5, 3.0e5, 5.0e5], "H2": 0.67, "O2": 0.33})
+        spl, xs, vs = dom.Pf, [0.0, 100.0, 200.0], [2.0e5, 3.0e5, 5.0e5]
+    cs = CubicSpline(xs, vs, bc_type="natural")
+    for x in (0.0, 0.1, 63.0, 199.0):
+        assert spl(x) == pytest.approx(float(cs(x)), rel=1e-13) and spl.derivative(x) == pytest.approx(float(cs(x, 1)), rel=1e-12)
+    y = cases.states("superminimal_V", dom.y0, ig.Ns, "ConstantV")[0]
+    ja = ro.jacobiany(dom, y, 0.1, dom.p)
+    j = ro.jacobiany_complexstep(dom, y, 0.1, dom.p)
+    assert not np.any(np.abs(ja - j) > 1e-4 * np.abs(j) + 1e-16 * np.abs(j).max())
