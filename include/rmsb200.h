@@ -316,8 +316,11 @@ int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
  * getspline, src/Tools.jl:46-85) handed over as [nt, ts[nt], values[nt], gamma[nt]] (gamma = second derivatives at the knots,
  * gamma[0] = gamma[nt-1] = 0; linear extrapolation outside the knots), one row per reactor (profile_stride = 1 + 3*nt) or one row
  * shared by all (0).  `cond` keeps its layout (its V / P entry is ignored).  domain_kind stays RMSB_DOMAIN_CONSTANT_V / _P.
+ * ParametrizedTPDomain (src/Domain.jl:241-320,1437-1512,2002-2004,2635-2725): domain_kind RMSB_DOMAIN_CONSTANT_TP with `profile` =
+ * the T table followed by the P table; y = [ns; V]; rate coefficients are evaluated on every call (vector thermo path) and
+ * p = [dG_i ; f_j] as for ConstantV (not the [G ; k] of ConstantTP).
  * t: evaluation time of every state for dydt / jac (NULL = 0); solve integrates from t = 0.
- * ParametrizedTPDomain and ParametrizedTConstantVDomain: not built. */
+ * ParametrizedTConstantVDomain: not built. */
 typedef struct rmsb_extras {
     int32_t struct_size;          /* = sizeof(rmsb_extras) */
     const double* interfaces;     /* boundary interfaces, see rmsb_dydt_batch_if; NULL = none */

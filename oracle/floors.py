@@ -61,7 +61,7 @@ def dydt_terms(domain, y, t=0.0, p=None):
     elif domain.kind in ("ConstantP", "ParametrizedP"):        # :1950-1953
         M[Ns] = np.dot(np.abs(th.Hs), M[:Ns]) / abs(th.N * (th.Cvave + R))
         M[Ns + 1] = np.sum(M[:Ns]) * R * th.T / th.P + M[Ns] * th.V / th.T
-    elif domain.kind == "ConstantTP":       # :1863-1866
+    elif domain.kind in ("ConstantTP", "ParametrizedTP"):       # :1863-1866
         M[Ns] = np.sum(M[:Ns]) * R * th.T / th.P
     for i in domain.constantspeciesinds:
         M[i] = 0.0
@@ -91,7 +91,7 @@ def closure_floor(domain, y, p, Jabs, t=0.0):
     Ns = domain.phase.Ns
     R = ro.R
     A = np.abs(Jabs[:Ns])
-    if domain.kind == "ConstantTP":
+    if domain.kind in ("ConstantTP", "ParametrizedTP"):
         return EPS * (A.sum(axis=0) * R * th.T / th.P)[None]
     if domain.kind in ("ConstantV", "ParametrizedV"):
         trow = np.abs(th.Us) @ A / abs(th.N * th.Cvave)
@@ -110,7 +110,7 @@ def species_block_magnitude(domain, y, p, t=0.0):
     yv = np.asarray(y, dtype=float)
     th = domain.calcthermo(yv, t, p)
     Ns = domain.phase.Ns
-    Vind = Ns if domain.kind == "ConstantTP" else (Ns + 1 if domain.kind in ("ConstantP", "ParametrizedP") else None)
+    Vind = Ns if domain.kind in ("ConstantTP", "ParametrizedTP") else (Ns + 1 if domain.kind in ("ConstantP", "ParametrizedP") else None)
     Jabs = np.zeros((len(yv), len(yv)))
 
     def abs_spread(jac, deriv, slots, col, sign):

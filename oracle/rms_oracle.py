@@ -1085,6 +1085,51 @@ class ParametrizedPDomain(ConstantPDomain):
             dydt[i] = 0.0
 
 
+class ParametrizedTPDomain(_Domain):
+    """src/Domain.jl:241-320 (ctor), :1437-1512 (calcthermo), :2002-2004 (derivatives), :2635-2725 (jacobiany!): temperature and pressure
+    follow time profiles, y = [ns; V].  A variable-k domain (vector thermo path, k's on every call); p = [dG; f]."""
+    kind = "ParametrizedTP"
+
+    def __init__(self, phase: Phase, initialconds: dict, constantspecies=()):
+        assert phase.kind == "gas"
+        ic = dict(initialconds)
+        ts, Ts, Ps = ic.pop("ts"), ic.pop("T"), ic.pop("P")
+        self.Tf, self.Pf = Spline(ts, Ts), Spline(ts, Ps)
+        _, ns = _initial(phase, ic, ())
+        N = ns.sum()
+        V = N * R * self.Tf(0.0) / self.Pf(0.0)
+        self.phase = phase
+        self.y0 = np.concatenate([ns, [V]])
+        self.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+        self.constantspeciesinds = self._constspc(constantspecies)
+        self.Ny = phase.Ns + 1
+        self.cond = np.array([self.Tf(0.0), self.Pf(0.0)])
+
+    def calcthermo(self, y, t=0.0, p=None) -> Thermo:
+        ph, Ns = self.phase, self.phase.Ns
+        T, P = self.Tf(t), self.Pf(t)
+        ns, V = y[:Ns], y[Ns]
+        N = P * V / (R * T)
+        cs = ns / V
+        C = N / V
+        cp, h, s = ph.calcHSCpdless(T)
+        if p is not None:
+            h = h + p[:Ns] / (R * T)
+        Gs = (h - s) * (R * T)
+        kfs, krevs = ph.getkfkrevs(T, P, C, N, ns, Gs, _EMPTY, V)
+        if p is not None:
+            kfs = kfs * p[Ns:Ns + ph.Nr]
+            krevs = krevs * p[Ns:Ns + ph.Nr]
+        return Thermo(ns, cs, T, P, V, C, N, 0.0, kfs, krevs, _EMPTY, _EMPTY, Gs, _EMPTY, 0.0, _EMPTY, 0.0, t)
+
+    def derivatives(self, dydt, th: Thermo):
+        Ns = self.phase.Ns
+        dydt[Ns] = (np.sum(dydt[:Ns]) * R * th.T / th.P + self.Tf.derivative(th.t) * th.V / th.T
+                    - self.Pf.derivative(th.t) * th.V / th.P)
+        for i in self.constantspeciesinds:
+            dydt[i] = 0.0
+
+
 class _ConstantKDomain(_Domain):
     def _setup_k(self, T, P, C, N, ns, V):
         ph = self.phase
@@ -1301,7 +1346,7 @@ def apply_interfaces(domain, dydt, th: Thermo, t, interfaces):
     """The interface loops of calcdomainderivatives! (src/Domain.jl:1843-1860 generic, 1868-1898 ConstantTP, 1907-1947 ConstantV,
     1957-1997 ConstantP), after the constant-species zeroing."""
     Ns = domain.phase.Ns
-    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP"}.get(domain.kind, domain.kind)   # same interface terms (Domain.jl:2007-2044,2052-2094)
+    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP", "ParametrizedTP": "ConstantTP"}.get(domain.kind, domain.kind)   # same interface terms (Domain.jl:2007-2094)
     T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
     for it in interfaces:
         if it.domain is not domain:
@@ -1460,7 +1505,7 @@ def _jac_interfaces(jac, domain, th: Thermo, t, interfaces):
     (ConstantTP), 2322-2448 (ConstantV), 2493-2628 (ConstantP), 3057-3088 (ConstantTV / ConstantTAPhi).  VolumeMaintainingOutlet has
     no analytic terms in the reference."""
     Ns = domain.phase.Ns
-    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP"}.get(domain.kind, domain.kind)
+    kind = {"ParametrizedV": "ConstantV", "ParametrizedP": "ConstantP", "ParametrizedTP": "ConstantTP"}.get(domain.kind, domain.kind)
     T, P, V, N, ns = th.T, th.P, th.V, th.N, th.ns
     for it in interfaces:
         if it.domain is not domain:
@@ -1556,10 +1601,12 @@ def jacobiany(domain, y, t=0.0, p=None, cstep=1e-30, interfaces=()):
     Ns = domain.phase.Ns
     jac = np.zeros((Ny, Ny))
     th = domain.calcthermo(y, t, p)
-    if domain.kind == "ConstantTP":
+    if domain.kind in ("ConstantTP", "ParametrizedTP"):
         jacobianynsderiv(jac, domain, th, Ns)
         for i in range(Ns + 1):
             jac[Ns, i] = np.sum(jac[:Ns, i]) * R * th.T / th.P
+        if domain.kind == "ParametrizedTP":                 # src/Domain.jl:2646
+            jac[Ns, Ns] += domain.Tf.derivative(t) / th.T - domain.Pf.derivative(t) / th.P
         for ind in domain.constantspeciesinds:
             jac[ind, :] = 0.0
         _jac_interfaces(jac, domain, th, t, interfaces)

@@ -958,8 +958,8 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
         if (MODE != 0 && MODE != 1) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles: dydt, Jacobian and solve only");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
-        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P)
-            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV) and ConstantP (ParametrizedP) domains only");
+        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P && a.domain_kind != RMSB_DOMAIN_CONSTANT_TP)
+            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV), ConstantP (ParametrizedP) and ConstantTP (ParametrizedTP) domains only");
     }
     if (a.Ny > 128) {
         if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
@@ -1059,8 +1059,8 @@ static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cu
     if (a.flow || a.ptab) {      // boundary interfaces / time profiles: the warp-per-reactor integrator (rhs_v / rhs_ck / jac_warp carry the terms)
         if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
-        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P)
-            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV) and ConstantP (ParametrizedP) domains only");
+        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P && a.domain_kind != RMSB_DOMAIN_CONSTANT_TP)
+            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV), ConstantP (ParametrizedP) and ConstantTP (ParametrizedTP) domains only");
     } else if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
     switch (rows_per_lane(a.Ny)) {
     case 1: return launch_solve_R<1>(h, a, want_wpb, st);
@@ -1106,7 +1106,7 @@ static BatchArgs make_batch(const rmsb_mech* h, int kind, int64_t n, const doubl
 
 // validated copy of the caller's rmsb_extras (NULL / short structs give the defaults)
 struct Extras { const double* ifs = nullptr; int64_t if_stride = 0; const double* prof = nullptr; int64_t prof_stride = 0; const double* t = nullptr; int64_t prof_len = 0; };
-static int check_extras(const rmsb_mech* h, const rmsb_extras* x, Extras* e) {
+static int check_extras(const rmsb_mech* h, int kind, const rmsb_extras* x, Extras* e) {
     *e = Extras();
     if (!x) return RMSB_OK;
     if (x->struct_size != (int32_t)sizeof(rmsb_extras)) return fail(RMSB_ERR_ARG, "rmsb_extras size mismatch (ABI)");
@@ -1117,8 +1117,13 @@ static int check_extras(const rmsb_mech* h, const rmsb_extras* x, Extras* e) {
         const int64_t nt = (int64_t)e->prof[0];
         if (nt < 2 || (double)nt != e->prof[0]) return fail(RMSB_ERR_ARG, "profile: the first entry is the number of knots (>= 2)");
         e->prof_len = 1 + 3 * nt;
-        if (e->prof_stride != 0 && e->prof_stride != e->prof_len) return fail(RMSB_ERR_ARG, "profile_stride must be 0 or 1 + 3*nt");
         for (int64_t k = 1; k < nt; ++k) if (!(e->prof[1 + k] > e->prof[k])) return fail(RMSB_ERR_ARG, "profile: knot times must increase");
+        if (kind == RMSB_DOMAIN_CONSTANT_TP) {                 // ParametrizedTP: the T table is followed by the P table
+            const int64_t nt2 = (int64_t)e->prof[e->prof_len];
+            if (nt2 < 2 || (double)nt2 != e->prof[e->prof_len]) return fail(RMSB_ERR_ARG, "profile: ParametrizedTP needs a T table followed by a P table");
+            e->prof_len += 1 + 3 * nt2;
+        }
+        if (e->prof_stride != 0 && e->prof_stride != e->prof_len) return fail(RMSB_ERR_ARG, "profile_stride must be 0 or the length of one reactor's table(s)");
     }
     return RMSB_OK;
 }
@@ -1313,7 +1318,7 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     int rc = check_common(h, kind, n, y, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     Extras ex;
-    if ((rc = check_extras(h, xtr, &ex)) != RMSB_OK) return rc;
+    if ((rc = check_extras(h, kind, xtr, &ex)) != RMSB_OK) return rc;
     if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
@@ -1432,7 +1437,7 @@ static int solve_host_impl(const rmsb_mech* h, int kind, int64_t n, const double
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     Extras ex;
-    if ((rc = check_extras(h, xtr, &ex)) != RMSB_OK) return rc;
+    if ((rc = check_extras(h, kind, xtr, &ex)) != RMSB_OK) return rc;
     const double* ifs = ex.ifs;
     const int64_t if_stride = ex.if_stride;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;

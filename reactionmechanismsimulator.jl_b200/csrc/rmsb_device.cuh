@@ -1088,6 +1088,94 @@ static __device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
 }
 
 // per-reactor constants the RHS reads from the workspace (call once per reactor, before the first RHS)
+// ParametrizedTPDomain (src/Domain.jl:241-320 ctor, 1437-1512 calcthermo, 2002-2004 derivatives): y = [ns; V], temperature and
+// pressure follow time profiles (d.ptab = [T table][P table]).  A variable-k domain: thermo through the vector path and every
+// rate coefficient on each call, exactly as rhs_v; closure dV/dt = sum(dn)*R*T/P + dT/dt*V/T - dP/dt*V/P.
+// p = [dG_i ; f_j] as for the other variable-k domains (h/RT += dG/(RT), k *= f).
+static __device__ __noinline__ void rhs_tp_param(DomainArgs d, Ws w, int lane, bool store_k) {
+    const DevMech& m = mech();
+    const int Ns = m.Ns, Nr = m.Nr;
+    const double* p = d.p;
+    const double* yb = w.ybuf();
+    double* cs = w.cs();
+    double* fb = w.fbuf();
+    double* qb = w.q();
+    double* gb = w.g();
+    double dTdt = 0.0, dPdt = 0.0;
+    const double T = profile_eval(d.ptab, d.t, &dTdt);
+    const double P = profile_eval(d.ptab + 1 + 3 * (int)d.ptab[0], d.t, &dPdt);
+    const double V = yb[Ns], invV = 1.0 / V;
+    TPow<double> tp(T);
+    const double RT = RMSB_R * T, invRT = tp.T4 * RMSB_INV_R;
+    const double Nt = P * V * invRT, C = P * invRT;
+    for (int s = lane; s < Ns; s += 32) {
+        double cp, h, sr;
+        nasa_hscp(s, tp, T, cp, h, sr);
+        if (p) h = h + p[s] * invRT;
+        gb[s] = h - sr;
+        cs[s] = yb[s] * invV;
+    }
+    __syncwarp();
+    KinEnv<double> e;
+    e.T = T; e.logT = tp.T6; e.RT = RT; e.invRT = invRT; e.P = P;
+    const double logC0 = RMSB_LOG_1E5_OVER_R - tp.T6;
+    for (int j = lane; j < Nr; j += 32) {
+        double kf;
+        if (G(m.ktype, j) == RMSB_KIN_ARRHENIUS_VEC) kf = arr_vec(m.kpar + G(m.koff, j), e);
+        else kf = eval_kin<double>(j, &e, ceff_of(j, C, yb, V), false);
+        double ex = 0.0;
+        for (int k = G(m.kc_ptr, j); k < G(m.kc_ptr, j + 1); ++k) ex = ex + G(m.kc_coef, k) * gb[G(m.kc_spc, k)];
+        ex = ex + G(m.nrp, j) * logC0;
+        double kr = kf * exp(-ex);
+        kf = kf * G(m.fwd, j); kr = kr * G(m.rev, j);
+        if (p) { kf = kf * p[Ns + j]; kr = kr * p[Ns + j]; }
+        if (store_k) { w.kf()[j] = kf; w.kr()[j] = kr; }
+        qb[j] = net_rate<double>(j, kf, kr, cs);
+    }
+    __syncwarp();
+    double nsum = 0.0;
+    for (int s = lane; s < Ns; s += 32) {
+        double acc = 0.0;
+        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+            int jr = G(m.sr_rxn, k);
+            double qv = qb[jr & 0x7fffffff];
+            acc = (jr < 0) ? acc - qv : acc + qv;
+        }
+        const double dn = acc * V;
+        fb[s] = dn;
+        nsum += dn;
+    }
+    const double dV = warp_sum(nsum) * RT / P + dTdt * V * tp.T4 - dPdt * V / P;
+    if (lane == 0) {
+        fb[Ns] = dV;
+        double* ax = w.aux();
+        ax[0] = T; ax[1] = P; ax[2] = V; ax[3] = Nt; ax[4] = C; ax[5] = dTdt; ax[6] = dPdt;
+    }
+    __syncwarp();
+    for (int k = lane; k < d.nconst; k += 32) fb[d.constspc[k] - 1] = 0.0;
+    __syncwarp();
+    if (d.flow) {                                        // src/Domain.jl:2007-2044: the ConstantTP interface terms at the current T, P
+        const double* fl = d.flow;
+        const double Fin = fl[IF_FIN], Fout = fl[IF_FOUT], Vin = fl[IF_VIN], Vout = fl[IF_VOUT];
+        const double iNt = 1.0 / Nt, rtp = RT / P;
+        for (int s = lane; s < Ns; s += 32) {
+            double v = fb[s];
+            v += fl[IF_Y + s] * Fin; v -= Fout * yb[s] * iNt; v += Vin * fl[IF_Y + Ns + s]; v -= Vout * yb[s] * invV;
+            fb[s] = v;
+        }
+        __syncwarp();
+        double dVi = fb[Ns] + Fin * rtp - Fout * rtp + Vin - Vout;
+        __syncwarp();
+        if (fl[IF_VM] != 0.0) {
+            const double flowm = P * dVi / RT;
+            for (int s = lane; s < Ns; s += 32) fb[s] -= flowm * yb[s] * iNt;
+            dVi -= dVi;
+        }
+        if (lane == 0) fb[Ns] = dVi;
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, int lane) {
     if (lane == 0) w.aux()[7] = (d.kind == RMSB_DOMAIN_CONSTANT_V) ? 1.0 / d.cond[0] : 0.0;
     __syncwarp();
@@ -1096,6 +1184,7 @@ __device__ __forceinline__ void rhs_prepare(const DomainArgs& d, const Ws& w, in
 __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int lane, bool store_k) {
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(d, w, lane, store_k);
     else if (d.kind == RMSB_DOMAIN_CONSTANT_P) rhs_v<double, true>(d, w, lane, store_k);
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_TP && d.ptab) rhs_tp_param(d, w, lane, store_k);
     else if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) rhs_coupled(d, w, lane);
     else rhs_ck(d, w, lane);
 }
@@ -1103,7 +1192,7 @@ __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int l
 // once per reactor for every domain whose rate coefficients are constants of the reactor
 __device__ __forceinline__ void setup_domain(const DomainArgs& d, const Ws& w, int lane) {
     if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) setup_coupled(d, w, lane);
-    else if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P) setup_constk(d, w, lane);
+    else if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P && !d.ptab) setup_constk(d, w, lane);   // ParametrizedTP: k's every call
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1201,7 +1290,9 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         for (int c = lane; c <= Ns; c += 32) {           // Domain.jl:2211-2214
             double a = 0.0;
             for (int i = 0; i < Ns; ++i) a += J[i + c * LD];
-            J[Ns + c * LD] = a * RMSB_R * aT / aP;
+            double v = a * RMSB_R * aT / aP;
+            if (d.ptab && c == Ns) v += ax[5] / aT - ax[6] / aP;     // ParametrizedTP: + dT/dt/T - dP/dt/P (Domain.jl:2646)
+            J[Ns + c * LD] = v;
         }
     } else if (d.kind == RMSB_DOMAIN_CONSTANT_V) {
         const double* us = w.us();

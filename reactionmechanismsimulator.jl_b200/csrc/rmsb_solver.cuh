@@ -593,7 +593,7 @@ __device__ void bdf_solve_warp(const SolveArgs& a, const Ws& w, int64_t ir, int 
 
     rhs_prepare(d, w, lane);
     // constant-k domains: rate coefficients once per reactor
-    if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P) {
+    if (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P && !d.ptab) {
         to_smem<R>(w.ybuf(), y, Ny, lane);
         setup_domain(d, w, lane);
     }

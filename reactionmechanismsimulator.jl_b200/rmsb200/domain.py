@@ -304,6 +304,28 @@ def ParametrizedVDomain(*, phase: Phase, initialconds: Dict[str, float], constan
     return dom, y0.copy(), dom.p.copy()
 
 
+def ParametrizedTPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """ParametrizedTPDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:257-320: temperature and pressure
+    follow profiles ("ts", "T", "P" arrays), y = [ns; V], p = [zeros(Ns); ones(Nr)].  On the device: the ConstantTP layout with a
+    T table followed by a P table; rate coefficients are evaluated on every call."""
+    from .profile import profile_value, spline_table
+    assert phase.kind == L.PHASE_GAS, "ParametrizedTPDomain needs an IdealGas phase"
+    ic = dict(initialconds)
+    ts = ic.pop("ts")
+    tabT, tabP = spline_table(ts, ic.pop("T")), spline_table(ts, ic.pop("P"))
+    _, ns = _parse(phase, ic, ())
+    T0, P0 = profile_value(tabT, 0.0), profile_value(tabP, 0.0)
+    V = float(ns.sum()) * R * T0 / P0
+    y0 = np.concatenate([ns, [V]])
+    dom = Domain(L.DOMAIN_CONSTANT_TP, phase, y0, np.array([T0, P0]), constantspecies)
+    dom.profile = np.concatenate([tabT, tabP])
+    dom.indexes = [1, phase.Ns, phase.Ns + 1]
+    dom.thermovariabledict = {"V": phase.Ns + 1}
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, y0.copy(), dom.p.copy()
+
+
 def ParametrizedPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
     """ParametrizedPDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:413-498: adiabatic reactor whose
     pressure follows a profile ("ts", "P" arrays).  y = [ns; T; V]; the ConstantP domain with a time profile on the device."""
