@@ -161,6 +161,44 @@ def jacp_magnitude(domain, y, p, t=0.0):
     return M
 
 
+def thermo_column_magnitude(domain, y, p, col, t=0.0, h=1e-30):
+    """Sum of the magnitudes of the terms of d(dn_i/dt)/d y[col] for a thermodynamic-variable column (T, or P of the ConstantV domain) of the
+    variable-k domains: every reaction's forward and reverse rate is differentiated on its own (complex step) and the magnitudes are
+    accumulated with the conditioning of the exponentials (see dydt_terms) -- the T / P columns of jacobiany! are the derivative of the
+    complete RHS (src/Reactor.jl:1469-1477), so their rounding floor is eps times this sum, not the spread under input perturbations."""
+    yc = np.asarray(y, dtype=complex).copy()
+    yc[col] += 1j * h
+    th = domain.calcthermo(yc, t, p)
+    ra = domain.phase.rxnarray
+    Ns = domain.phase.Ns
+    M = np.zeros(len(y))
+    RT = ro.R * th.T.real
+    for i in range(ra.shape[1]):
+        fR, rR = th.kfs[i], th.krevs[i]
+        for j in range(4):
+            if ra[j, i] < 0:
+                break
+            fR = fR * th.cs[ra[j, i]]
+        for j in range(4, 8):
+            if ra[j, i] < 0:
+                break
+            rR = rR * th.cs[ra[j, i]]
+        kf = abs(th.kfs[i])
+        kap_f = 2.0 + (abs(np.log(kf)) if kf != 0.0 else 0.0)
+        kap_r = kap_f + sum(abs(th.Gs[ra[j, i]]) for j in range(8) if ra[j, i] >= 0) / RT
+        mag = (kap_f * abs(fR.imag) + kap_r * abs(rR.imag)) / h
+        for j in range(8):
+            if ra[j, i] >= 0:
+                M[ra[j, i]] += mag
+    M[:Ns] *= abs(th.V.real if hasattr(th.V, "real") else th.V)
+    E = th.Us if domain.kind in ("ConstantV", "ParametrizedV") else th.Hs
+    den = abs(th.N * th.Cvave) if domain.kind in ("ConstantV", "ParametrizedV") else abs(th.N * (th.Cvave + ro.R))
+    M[Ns] = np.dot(np.abs(E), M[:Ns]) / den
+    M[Ns + 1] = (np.sum(M[:Ns]) * ro.R * abs(th.T) / abs(th.V) + abs(th.P / th.T) * M[Ns]) if domain.kind in ("ConstantV", "ParametrizedV") else \
+        (np.sum(M[:Ns]) * ro.R * abs(th.T) / abs(th.P) + abs(th.V / th.T) * M[Ns])
+    return M
+
+
 def jac_floor(fn, domain, y, p, t=0.0, **kw):
     """(ref, floor) for a Jacobian-like fn(y, p) -> Ny x ncol: conditioning floor (numeric_floor) plus the accumulation floor of the
     closure rows (closure_floor, with a factor for the number of summands' roundings)."""
@@ -173,6 +211,10 @@ def jac_floor(fn, domain, y, p, t=0.0, **kw):
         floor[:Ns] += 2.0 * EPS * mag[:Ns]                       # accumulation order of each entry's own terms
     if ref.shape[0] > Ns:
         floor[Ns:] += 4.0 * closure_floor(domain, y, p, np.maximum(np.abs(ref), mag) if mag is not None else ref, t)
+    if ref.shape[1] == ref.shape[0] and domain.kind in ("ConstantV", "ConstantP", "ParametrizedV", "ParametrizedP"):
+        cols = (Ns, Ns + 1) if domain.kind in ("ConstantV", "ParametrizedV") else (Ns,)
+        for col in cols:
+            floor[:, col] += EPS * thermo_column_magnitude(domain, y, p, col, t)
     # entries that are EXACTLY zero in the oracle because +d / -d pairs of one reaction cancel (a species on both sides, e.g. a
     # collider): another summation order leaves a residue of a few eps of the column's largest term
     zero = ref == 0.0

@@ -668,7 +668,16 @@ class Phase:
         if len(spcinds) == 2:
             a, b = spcinds
             return 4.0 * math.pi * (diffs[a] + diffs[b]) * (self.species[a].radius + self.species[b].radius) * Na
-        raise NotImplementedError(">2-body diffusion limit")
+        # generalised Smoluchowski rate for N >= 3 bodies, src/PhaseState.jl:92-101
+        D = np.array([diffs[i] for i in spcinds], dtype=float)
+        n = len(spcinds)
+        a = (3.0 * n - 5.0) / 2.0
+        Dinv = 1.0 / D
+        Dbar = 1.0 / np.cumsum(Dinv)[::-1]
+        Dhat = D + Dbar
+        deltaN = Dinv.sum() / sum(sum(1.0 / (D[i] * D[m]) for m in range(n - 1) if i > m) for i in range(1, n))
+        rsum = sum(self.species[i].radius for i in spcinds)
+        return np.prod(Dhat[1:] ** 1.5) * 4 * math.pi ** (a + 1) / math.gamma(a) * (rsum / math.sqrt(deltaN)) ** (2 * a) * Na ** (n - 1)
 
     def getkfkrev(self, rxn: Reaction, T, P, C, N, ns, Gs, diffs, V, kf=None, f=None):
         """src/PhaseState.jl:184-223."""

@@ -511,13 +511,26 @@ static __device__ __noinline__ double kc_scalar(int j, const double* G, double T
     return exp(-(dG) / (RMSB_R * T)) * pow(C0, (double)(npr - nre));
 }
 
-// getDiffusiveRate for 1 or 2 bodies (src/PhaseState.jl:87-93); >2-body form is out of scope
+// getDiffusiveRate (src/PhaseState.jl:87-103): Smoluchowski for 2 bodies, its generalisation for 3 and 4 (:92-101)
 __device__ __forceinline__ double diffusive_rate(int j, int side, const double* diffs) {
     const DevMech& m = mech();
     const int Nr = m.Nr;
-    int s0 = G(m.rx, (side * 4) * Nr + j), s1 = G(m.rx, (side * 4 + 1) * Nr + j);
-    if (s1 < 0) return INFINITY;
-    return 4.0 * RMSB_PI * (diffs[s0] + diffs[s1]) * (G(m.radius, s0) + G(m.radius, s1)) * RMSB_NA;
+    int sp[4];
+    int n = 0;
+    for (int k = 0; k < 4; ++k) { sp[k] = G(m.rx, (side * 4 + k) * Nr + j); if (sp[k] >= 0) ++n; else break; }
+    if (n < 2) return INFINITY;
+    if (n == 2) return 4.0 * RMSB_PI * (diffs[sp[0]] + diffs[sp[1]]) * (G(m.radius, sp[0]) + G(m.radius, sp[1])) * RMSB_NA;
+    double D[4], Dinv[4], csum[4];
+    double sinv = 0.0, rsum = 0.0;
+    for (int k = 0; k < n; ++k) { D[k] = diffs[sp[k]]; Dinv[k] = 1.0 / D[k]; sinv += Dinv[k]; csum[k] = sinv; rsum += G(m.radius, sp[k]); }
+    const double a = (3.0 * n - 5.0) / 2.0;
+    // Dbar = 1 ./ reverse(cumsum(Dinv)); Dhat = D .+ Dbar; kf ~ prod(Dhat[2:end].^1.5)
+    double prod = 1.0;
+    for (int k = 1; k < n; ++k) { const double Dhat = D[k] + 1.0 / csum[n - 1 - k]; prod *= Dhat * sqrt(Dhat); }
+    double pairs = 0.0;                                    // sum_{i=2..N} sum_{m<i, m<=N-1} 1/(D_i D_m)
+    for (int i = 1; i < n; ++i) for (int q = 0; q < i && q < n - 1; ++q) pairs += 1.0 / (D[i] * D[q]);
+    const double deltaN = sinv / pairs;
+    return prod * 4.0 * pow(RMSB_PI, a + 1.0) / tgamma(a) * pow(rsum / sqrt(deltaN), 2.0 * a) * pow(RMSB_NA, (double)(n - 1));
 }
 
 struct DomainArgs {

@@ -14,7 +14,7 @@ from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, Co
                      ConstantVDomain, ConstantVEnsemble, Domain, ParametrizedPDomain, ParametrizedTPDomain, ParametrizedVDomain)
 from .interfaces import Inlet, Outlet, VolumeMaintainingOutlet, VolumetricFlowRateInlet, VolumetricFlowRateOutlet, pack_interfaces
 from .ensemble import balanced_shards, shard_bounds, shard_domain, solve_sharded
-from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getspeciesradius, readinput)
+from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getmechdict, getspeciesradius, readinput, writeyml)
 from .profile import spline_table
 from .phase import IdealDiluteSolution, IdealGas, IdealSurface, Phase
 from .reactor import RMSB200, Reactor, Solution, solve, threadedsensitivities

@@ -235,3 +235,72 @@ def readinput(fname: str) -> dict:
         key = phases[0] if len(phases) == 1 else frozenset(phases)
         out.setdefault(key, {"Reactions": []})["Reactions"].append(r)
     return out
+
+
+# -- writing mechanisms back (src/yml.jl:14-16: writeyml(D; path) = YAML.write_file(path, D)) --------------------------
+def _kin_dict(k: dict, name_of: Dict[int, str]) -> dict:
+    """Inverse of _kin: kinetics as the .rms file spells them (efficiencies by species name, as eff rather than eff - 1)."""
+    t = k["type"]
+    if t in ("Arrhenius", "StickingCoefficient"):
+        return {"type": t, "A": float(k["A"]), "n": float(k["n"]), "Ea": float(k["Ea"])}
+    if t == "MultiArrhenius":
+        return {"type": t, "arrs": [_kin_dict(a, name_of) for a in k["arrs"]]}
+    if t == "PdepArrhenius":
+        return {"type": t, "Ps": [float(p) for p in k["Ps"]], "arrs": [_kin_dict(a, name_of) for a in k["arrs"]]}
+    if t == "MultiPdepArrhenius":
+        return {"type": t, "parrs": [_kin_dict(a, name_of) for a in k["parrs"]]}
+    if t in ("ThirdBody", "Lindemann", "Troe"):
+        out = {"type": t}
+        if t == "ThirdBody":
+            out["arr"] = _kin_dict(k["arr"], name_of)
+        else:
+            out["arrhigh"], out["arrlow"] = _kin_dict(k["arrhigh"], name_of), _kin_dict(k["arrlow"], name_of)
+        if t == "Troe":
+            out.update(a=float(k["a"]), T3=float(k["T3"]), T1=float(k["T1"]), T2=float(k["T2"]))
+        out["efficiencies"] = {name_of[i]: float(v) + 1.0 for i, v in k["efficiencies"].items()}
+        return out
+    if t == "Chebyshev":
+        return {"type": t, "coefs": [[float(v) for v in row] for row in np.asarray(k["coefs"])], "Tmin": float(k["Tmin"]), "Tmax": float(k["Tmax"]),
+                "Pmin": float(k["Pmin"]), "Pmax": float(k["Pmax"])}
+    raise NotImplementedError(t)
+
+
+def getmechdict(parsed: dict) -> dict:
+    """The mechanism dictionary of a `.rms` file ({"Units", "Phases", "Reactions", "Solvents"}) from what `readinput` returned --
+    the D that the reference hands to writeyml (src/yml.jl:14-36 builds the same layout from Chemkin objects)."""
+    D: dict = {"Units": {}, "Phases": [], "Reactions": []}
+    rxns: List[ElementaryReaction] = []
+    for key, val in parsed.items():
+        if key == "Solvents":
+            D["Solvents"] = [{"name": s.name, "type": "Solvent", "mu": dict(s.mu)} for s in val]
+            continue
+        rxns += val["Reactions"]
+        if isinstance(key, frozenset):
+            continue
+        phase = {"name": key, "Species": []}
+        for sp in val["Species"]:
+            d = {"name": sp.name, "type": "Species", "radicalelectrons": 0,
+                 "thermo": {"type": "NASA", "polys": [{"type": "NASApolynomial", "coefs": [float(c) for c in q.coefs], "Tmin": float(q.Tmin),
+                                                      "Tmax": float(q.Tmax)} for q in sp.thermo.polys]}}
+            if sp.smiles:
+                d["smiles"] = sp.smiles
+            elif sp.radius:
+                d["radius"] = float(sp.radius)
+            phase["Species"].append(d)
+        D["Phases"].append(phase)
+    for r in sorted(rxns, key=lambda x: x.index):
+        name_of = {s.index: s.name for s in r.reactants + r.products}
+        # efficiencies may name species outside the reaction: resolve through every phase
+        for val in parsed.values():
+            if isinstance(val, dict) and "Species" in val:
+                name_of.update({s.index: s.name for s in val["Species"]})
+        D["Reactions"].append({"type": "ElementaryReaction", "reactants": [s.name for s in r.reactants], "products": [s.name for s in r.products],
+                               "kinetics": _kin_dict(r.kinetics, name_of), "reversible": bool(r.reversible), "forwardable": bool(r.forwardable),
+                               "electronchange": int(r.electronchange), "radicalchange": 0})
+    return D
+
+
+def writeyml(D: dict, path: str = "chem.rms") -> None:
+    """writeyml(D; path="chem.rms")  src/yml.jl:14-16"""
+    with open(path, "w") as fh:
+        yaml.dump(D, fh, Dumper=getattr(yaml, "CSafeDumper", yaml.SafeDumper), default_flow_style=None, sort_keys=True)

@@ -98,7 +98,7 @@ def test_rapid_compression_trajectory_vs_scipy():
     s = rb.solve(rb.Reactor(ens, None, (0.0, 0.06), p=p).ode, abstol=1e-16, reltol=1e-6)
     assert np.all(s.status == 0)
     Tend = s.yend[:, Ns]
-    assert Tend[-1] > Tend[0] and np.all(np.diff(Tend) > -1.0)   # more compression, hotter end state
+    assert Tend[-1] > Tend[0] + 500.0 and Tend[0] < 1000.0        # the highest compression ratio ignites, the lowest only heats up
     k8 = int(np.argmin(np.abs(cr - 8.0)))
     one = rb.Domain(gdom.kind, ig, gdom.y0, gdom.cond)
     one.profile = tabs[k8]

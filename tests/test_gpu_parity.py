@@ -272,3 +272,41 @@ def test_device_resident_entry_points_match_host_ones():
                                         tf.data_ptr(), C.c_void_p(st)))
     torch.cuda.synchronize()
     assert np.array_equal(tf.cpu().numpy(), f_host)
+
+
+def test_three_body_diffusion_limits(tmp_path):
+    """Generalised Smoluchowski rate for three reacting bodies (getDiffusiveRate, src/PhaseState.jl:92-101) inside getkfkrev's
+    diffusion limits: the liquid octane fixture with a 3 -> 1, a 1 -> 3 and a 3 -> 3 reaction added; kf / krev, dydt and the Jacobian
+    against the oracle."""
+    import yaml
+    with open(cases.fixture("liquid_phase")) as fh:
+        doc = yaml.load(fh, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
+    extra = [(["octane", "oxygen", "OH(D)"], ["CCCCCCC(C)OO"], 3.0e2), (["CCCCC(CCC)OO"], ["octane", "oxygen", "[O]O"], 5.0e4),
+             (["octane", "[O]O", "OH(D)"], ["CC[CH]CCCCC", "oxygen", "CCCCCCC(C)OO"], 8.0e3)]
+    for re_, pr_, A in extra:
+        doc["Reactions"].append({"kinetics": {"A": A, "Ea": 2.0e4, "n": 0.3, "type": "Arrhenius"}, "products": pr_, "radicalchange": 0,
+                                 "reactants": re_, "type": "ElementaryReaction"})
+    path = str(tmp_path / "liquid3.rms")
+    with open(path, "w") as fh:
+        yaml.safe_dump(doc, fh)
+    ic = {"T": 450.0, "V": 1.0, "octane": 6154.0, "oxygen": 4.953}
+    d = rb.readinput(path)
+    ph = rb.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0], name="phase")
+    od = ro.readinput(path)
+    oph = ro.IdealDiluteSolution(od["phase"]["Species"], od["phase"]["Reactions"], od["Solvents"][0])
+    gdom, y0, p = rb.ConstantTVDomain(phase=ph, initialconds=ic, constantspecies=["oxygen"])
+    odom = ro.ConstantTVDomain(oph, ic, constantspecies=("oxygen",))
+    assert ph.Nr == 383
+    three = [j for j, r in enumerate(oph.reactions) if len(r.reactantinds) == 3 or len(r.productinds) == 3]
+    assert len(three) == 3
+    np.testing.assert_allclose(gdom.kfs[0], odom.kfs, rtol=1e-12)
+    np.testing.assert_allclose(gdom.krevs[0], odom.krevs, rtol=1e-12)
+    kf_nolimit = ro.ConstantTVDomain(ro.IdealDiluteSolution(od["phase"]["Species"], od["phase"]["Reactions"], od["Solvents"][0], diffusionlimited=False),
+                                     ic, constantspecies=("oxygen",)).kfs
+    assert np.any(np.abs(odom.kfs[three] - kf_nolimit[three]) > 1e-6 * kf_nolimit[three])     # the three-body limit bites
+    ys = cases.states("liquid_TV", odom.y0, oph.Ns, "ConstantTV")[:2]
+    ens = ensemble_of(gdom, ys)
+    f, J = ens.dydt(ys, p), ens.jacobiany(ys, p)
+    for k in range(len(ys)):
+        assert cases.err_dydt(f[k], ro.dydtreactor(odom, ys[k], 0.0, None)) < TOL
+        assert cases.err_jac(J[k], ro.jacobiany(odom, ys[k], 0.0, None)) < TOL

@@ -192,3 +192,29 @@ def test_pack_interfaces_merges_by_type_and_matches_oracle_enthalpy():
     assert rows.shape == (2, 7 + 2 * Ns) and rows[1, 0] == 5e-3 and rows[0, 1] == 2e-3
     with pytest.raises(NotImplementedError):
         rb.Outlet(gdom, lambda t: 1e-3 * (1.0 + t))
+
+
+@pytest.mark.parametrize("fx", ["superminimal", "ethane", "liquid_phase", "ch4o2cat"])
+def test_rms_writer_round_trip(fx, tmp_path):
+    """writeyml (src/yml.jl:14-16) round trip: readinput -> getmechdict -> writeyml -> readinput gives the same species, thermo,
+    reactions and kinetics (compared through the flattened descriptor tables the device receives)."""
+    a = rb.readinput(cases.fixture(fx))
+    path = str(tmp_path / f"{fx}_copy.rms")
+    rb.writeyml(rb.getmechdict(a), path)
+    b = rb.readinput(path)
+    assert set(map(str, a.keys())) == set(map(str, b.keys()))
+    for key in a:
+        if key == "Solvents":
+            assert [(s.name, s.mu) for s in a[key]] == [(s.name, s.mu) for s in b[key]]
+            continue
+        ra, rbb = a[key]["Reactions"], b[key]["Reactions"]
+        assert [str(r) for r in ra] == [str(r) for r in rbb]
+        for x, y in zip(ra, rbb):
+            tx, px = ph.pack_kinetics(x.kinetics, False) if x.kinetics["type"] != "StickingCoefficient" else (0, [x.kinetics["A"], x.kinetics["n"], x.kinetics["Ea"]])
+            ty, py = ph.pack_kinetics(y.kinetics, False) if y.kinetics["type"] != "StickingCoefficient" else (0, [y.kinetics["A"], y.kinetics["n"], y.kinetics["Ea"]])
+            assert tx == ty and px == py and x.kinetics.get("efficiencies") == y.kinetics.get("efficiencies")
+            assert (x.reversible, x.forwardable) == (y.reversible, y.forwardable)
+        if "Species" in a[key]:
+            for sx, sy in zip(a[key]["Species"], b[key]["Species"]):
+                assert sx.name == sy.name and sx.smiles == sy.smiles and sx.radius == sy.radius and sx.diffusion_r == sy.diffusion_r
+                assert [(q.coefs, q.Tmin, q.Tmax) for q in sx.thermo.polys] == [(q.coefs, q.Tmin, q.Tmax) for q in sy.thermo.polys]
