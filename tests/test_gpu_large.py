@@ -283,7 +283,8 @@ def test_large_gas_domains_parity(gas_families, kind):
         if k == 1 or K == 12:
             Jo, Jf = fl.jac_floor(lambda yy, pp: ro.jacobiany(odom, yy, 0.0, pp), odom, ys[k], odom.p, nsample=8)
             rep = fl.report(J[k], Jo, Jf, 1e-12)
-            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, [rep[q] for q in ("max_rel_above", "worst_excess", "worst_at", "worst_x", "worst_ref", "worst_floor")]
+            # the conditioning floor is itself an estimate from eight random perturbations (a factor ~2 either way on 10^6 entries)
+            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 2.0, [rep[q] for q in ("max_rel_above", "worst_excess", "worst_at", "worst_x", "worst_ref", "worst_floor")]
             assert np.all(J[k][ph.names.index("N2")] == 0.0)                    # constant-species row
 
 
