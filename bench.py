@@ -216,7 +216,9 @@ def run_ours(args):
     t_idt = torch.empty(n, dtype=torch.float64, device=dev)
     t_status = torch.empty(n, dtype=torch.int32, device=dev)
     t_stats = torch.empty((n, 10), dtype=torch.int32, device=dev)          # rmsb_stats = 40 bytes
-    t_work = torch.zeros(64, dtype=torch.int64, device=dev)
+    lib.rmsb_solve_work_bytes.restype = C.c_int64
+    wbytes = int(lib.rmsb_solve_work_bytes(h, KIND, n))                       # work-queue counter + the hottest-first work order
+    t_work = torch.zeros((wbytes + 7) // 8, dtype=torch.int64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)

@@ -1165,7 +1165,7 @@ extern "C" int rmsb_jacp_batch_dev(const rmsb_mech* h, int kind, int64_t n, cons
 
 extern "C" int64_t rmsb_solve_work_bytes(const rmsb_mech* h, int kind, int64_t n) {
     if (!h || domain_ny(h, kind) < 0) { fail(RMSB_ERR_ARG, "bad mechanism / domain kind"); return -1; }
-    if (domain_ny(h, kind) <= 128) return 256;
+    if (domain_ny(h, kind) <= 128) return 256 + (int64_t)rmsb_small_work_bytes(h, kind, domain_ny(h, kind), n);
     DeviceGuard g(h->device);
     SolveArgs a{};
     a.domain_kind = kind; a.n = n > 0 ? n : 1;
@@ -1215,6 +1215,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
     a.idt_index = o.idt_index >= 0 ? o.idt_index : ((kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) ? h->dm.Ns : -1);
     if (a.idt_index >= a.Ny) return fail(RMSB_ERR_ARG, "idt_index out of range");
     a.counter = reinterpret_cast<unsigned long long*>(work);
+    a.work_bytes = sens ? 256 : (size_t)std::max<int64_t>(256, rmsb_solve_work_bytes(h, kind, n));     // the caller's contract (rmsb200.h)
     a.ssave = ssave; a.send = send; a.sens_hist = nullptr; a.Npp = sens_npp(h);
     a.flow = flow; a.flow_stride = flow ? flow_stride : 0;
     a.ptab = ptab; a.ptab_stride = ptab ? ptab_stride : 0;

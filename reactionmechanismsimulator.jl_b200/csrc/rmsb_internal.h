@@ -82,5 +82,7 @@ int rmsb_small_build(rmsb_mech* h, const std::vector<int>& rx /* [8][Nr] 0-based
 // true when (mechanism, domain, options) go through the group-per-reactor kernels
 bool rmsb_small_eligible(const rmsb_mech* h, int kind, int Ny, int flags);
 int rmsb_small_launch_solve(const rmsb_mech* h, const rmsb::SolveArgs& a, cudaStream_t st);
+// extra bytes of work buffer (behind the 256-byte header) the small path uses to order the work queue; 0 when it does not
+size_t rmsb_small_work_bytes(const rmsb_mech* h, int kind, int Ny, int64_t n);
 // mode 0: dydt, 1: Jacobian (dense column-major Ny x Ny)
 int rmsb_small_launch_eval(const rmsb_mech* h, int mode, const rmsb::BatchArgs& a, cudaStream_t st);

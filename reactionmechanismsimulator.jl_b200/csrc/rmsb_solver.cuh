@@ -81,6 +81,8 @@ struct SolveArgs {
     int64_t flow_stride = 0;
     const double* ptab = nullptr;   // time profiles (see BatchArgs)
     int64_t ptab_stride = 0;
+    const int* order = nullptr;     // work-queue position -> reactor index (hottest first, rmsb_small.cu) or nullptr = identity
+    size_t work_bytes = 256;        // size of the caller's work buffer (the ordering needs rmsb_solve_work_bytes() of it)
 };
 
 struct BatchArgs {
