@@ -25,6 +25,7 @@
 #ifndef RMSB200_H
 #define RMSB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -368,6 +369,18 @@ int rmsb_large_info(const rmsb_mech* mech, int64_t info[8]);
 /* cycle counters of the block-per-reactor solver summed over blocks: [0] rhs, [1] Jacobian, [2] factorisation,
  * [3] triangular solves, [4] whole solves; reset != 0 clears them after reading. */
 int rmsb_large_profile(const rmsb_mech* mech, int reset, double cycles[8]);
+
+/* ---- kernels generated for the mechanism ---------------------------------------------------------
+ * For small all-Arrhenius gas mechanisms (n_species <= 32, n_reactions <= 128, no third bodies) on ConstantV / ConstantP, batches of
+ * >= 4096 states in rmsb_dydt_batch / rmsb_jac_batch run on CUDA kernels the library writes out for the mechanism (every table
+ * entry a literal, csrc/rmsb_spec.cu) and compiles with NVRTC (libnvrtc.so.12 of the CUDA toolkit, found through the dynamic
+ * loader or RMSB_NVRTC=path) on first use; the arithmetic and its order are those of the generic kernels.  Without NVRTC, or with
+ * RMSB_NO_SPEC=1 in the environment, the generic kernels run.
+ * rmsb_mech_specialized: 1 if such kernels are loaded for (mech, domain) -- compiling them now if need be -- else 0 with the reason
+ * in rmsb_last_error.  rmsb_spec_source_desc: the generated source (needs no device): writes at most cap bytes, NUL-terminated,
+ * to buf (may be NULL) and the full length to *need. */
+int rmsb_mech_specialized(const rmsb_mech* mech, int domain_kind);
+int rmsb_spec_source_desc(const rmsb_mech_desc* desc, int domain_kind, char* buf, size_t cap, size_t* need);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Launch counter: number of kernels this library has launched in this process (bench gpu_launches). */

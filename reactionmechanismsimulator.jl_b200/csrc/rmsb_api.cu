@@ -66,11 +66,12 @@ extern "C" int rmsb_mech_device(const rmsb_mech* m) { return m ? m->device : -1;
 extern "C" void rmsb_mech_destroy(rmsb_mech* h) {
     if (!h) return;
     DeviceGuard g(h->device);
+    rmsb_spec_release(h);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
 
-static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
+static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h, bool host_only = false) {
     const int Ns = d->n_species, Nr = d->n_reactions;
     DevMech& dm = h->dm;
     dm.Ns = Ns; dm.Nr = Nr;
@@ -263,6 +264,9 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h) {
     for (int k = 0; k < 5; ++k) dm.visc[k] = d->viscosity_params[k];
 
     int rc;
+    if ((rc = rmsb_spec_capture(h, rx, srptr, srrxn, kcptr, kcspc, kccoef, nrp, ktype, koff, kpar, fwd, rev, nr, nc, tmax, coef, maxr,
+                                dtrxn, dtmult, dtoth, jeptr, jerow, jecol, jtidx)) != RMSB_OK) return rc;
+    if (host_only) return RMSB_OK;         // rmsb_spec_source_desc: tables only, nothing on a device
 #define UP(vec, field) if ((rc = upload(h, vec, &dm.field)) != RMSB_OK) return rc
     UP(nr, nasa_nr); UP(nc, nasa_nc); UP(tmax, nasa_tmax); UP(coef, nasa_c);
     UP(rx, rx); UP(ktype, ktype); UP(koff, koff); UP(kpar, kpar);
@@ -367,6 +371,32 @@ extern "C" int rmsb_mech_create(const rmsb_mech_desc* desc, int device, rmsb_mec
     if (rc != RMSB_OK) { std::string keep = g_err; rmsb_mech_destroy(h); g_err = keep; return rc; }
     *out = h;
     return RMSB_OK;
+}
+
+// Generated CUDA source of the mechanism-specialised dydt / Jacobian kernels (rmsb_spec.cu), from the descriptor alone: needs no
+// device.  Writes at most cap bytes (NUL-terminated) and the full length (without NUL) to *need.
+extern "C" int rmsb_spec_source_desc(const rmsb_mech_desc* desc, int domain_kind, char* buf, size_t cap, size_t* need) {
+    if (!desc) return fail(RMSB_ERR_ARG, "null argument");
+    if (desc->struct_size != (int32_t)sizeof(rmsb_mech_desc)) return fail(RMSB_ERR_ARG, "rmsb_mech_desc size mismatch (ABI)");
+    if (desc->n_species < 1 || desc->n_reactions < 1) return fail(RMSB_ERR_ARG, "empty mechanism");
+    rmsb_mech tmp;
+    int rc = build_mech(desc, &tmp, true);
+    if (rc != RMSB_OK) return rc;
+    std::string src;
+    if ((rc = rmsb_spec_source(&tmp, domain_kind, &src)) != RMSB_OK) return rc;
+    if (need) *need = src.size();
+    if (buf && cap > 0) { size_t k = std::min(cap - 1, src.size()); std::memcpy(buf, src.data(), k); buf[k] = '\0'; }
+    return RMSB_OK;
+}
+
+// 1 when large dydt / Jacobian batches of this (mechanism, domain) run on kernels generated for the mechanism (compiles them on
+// first use), 0 when they run on the generic kernels (rmsb_last_error says why)
+extern "C" int rmsb_mech_specialized(const rmsb_mech* h, int domain_kind) {
+    if (!h) return 0;
+    std::string why;
+    int r = rmsb_spec_ready(h, domain_kind, &why);
+    if (!r) g_err = "generic kernels: " + why;
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -945,10 +975,7 @@ static int launch_solve_large(const rmsb_mech* h, const SolveArgs& a, cudaStream
 
 // RMSB_NO_TPR=1 in the environment routes large batches of small mechanisms to the lane-group kernels instead of the
 // thread-per-reactor ones (A/B measurements, scripts/prof_evals.py)
-static bool tpr_disabled() {
-    static const bool off = [] { const char* v = std::getenv("RMSB_NO_TPR"); return v && v[0] == '1'; }();
-    return off;
-}
+static bool tpr_disabled() { const char* v = std::getenv("RMSB_NO_TPR"); return v && v[0] == '1'; }
 
 template <int MODE>
 static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) {
@@ -965,6 +992,8 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
         return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: this evaluation is not built for the large-mechanism path");
     }
+    if ((MODE == 0 || MODE == 1) && a.n >= 4096 && !extras && !tpr_disabled() && rmsb_spec_ready(h, a.domain_kind, nullptr))
+        return rmsb_spec_launch_eval(h, MODE, a, st);          // straight-line kernels generated for this mechanism (rmsb_spec.cu)
     if (MODE == 0 && (a.domain_kind == RMSB_DOMAIN_CONSTANT_V || a.domain_kind == RMSB_DOMAIN_CONSTANT_P) &&
         h->dm.Ns <= TPR_MAXNS && h->dm.Nr <= TPR_MAXNR && a.n >= 4096 && !tpr_disabled() && !extras) {
         // small variable-k mechanisms, large batches: one thread per reactor

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,7 @@ cudaError_t rmsb_cached_props(int device, cudaDeviceProp* out);
 // ------------------------------------------------------------------------------------------------
 // mechanism handle
 // ------------------------------------------------------------------------------------------------
+struct rmsb_spec_state;            // rmsb_spec.cu: host tables + the run-time compiled kernels of a small all-Arrhenius mechanism
 struct rmsb_mech {
     int device = 0;
     rmsb::DevMech dm{};
@@ -56,6 +58,8 @@ struct rmsb_mech {
     long long large_factor_flops = 0;
     // small-mechanism path (group of 16 / 32 lanes per reactor, tables staged in shared memory): rmsb_small.cu
     rmsb::SmallTables st{};
+    // mechanism-specialised evaluation kernels (generated source, NVRTC): rmsb_spec.cu; null when the mechanism does not qualify
+    std::shared_ptr<rmsb_spec_state> spec;
 };
 
 template <class T>
@@ -86,3 +90,16 @@ int rmsb_small_launch_solve(const rmsb_mech* h, const rmsb::SolveArgs& a, cudaSt
 size_t rmsb_small_work_bytes(const rmsb_mech* h, int kind, int Ny, int64_t n);
 // mode 0: dydt, 1: Jacobian (dense column-major Ny x Ny)
 int rmsb_small_launch_eval(const rmsb_mech* h, int mode, const rmsb::BatchArgs& a, cudaStream_t st);
+
+// rmsb_spec.cu -------------------------------------------------------------------------------------
+// keep the host tables the source generator needs (no-op when the mechanism does not qualify)
+int rmsb_spec_capture(rmsb_mech* h, const std::vector<int>& rx, const std::vector<int>& srptr, const std::vector<int>& srrxn, const std::vector<int>& kcptr,
+                      const std::vector<int>& kcspc, const std::vector<double>& kccoef, const std::vector<double>& nrp, const std::vector<int>& ktype,
+                      const std::vector<int>& koff, const std::vector<double>& kpar, const std::vector<double>& fwd, const std::vector<double>& rev,
+                      const std::vector<int>& nasa_nr, const std::vector<int>& nasa_nc, const std::vector<double>& nasa_tmax, const std::vector<double>& nasa_coef,
+                      int maxr, const std::vector<int>& dtrxn, const std::vector<int>& dtmult, const std::vector<int>& dtoth, const std::vector<int>& jeptr,
+                      const std::vector<int>& jerow, const std::vector<int>& jecol, const std::vector<int>& jtidx);
+int rmsb_spec_source(const rmsb_mech* h, int kind, std::string* out);
+int rmsb_spec_ready(const rmsb_mech* h, int kind, std::string* why);
+int rmsb_spec_launch_eval(const rmsb_mech* h, int mode, const rmsb::BatchArgs& a, cudaStream_t st);
+void rmsb_spec_release(rmsb_mech* h);

@@ -412,9 +412,15 @@ __device__ __forceinline__ void stage_small(const DevMech& mp, const SmallTables
 #ifndef RMSB_SMALL_MINBLOCKS
 #define RMSB_SMALL_MINBLOCKS 4
 #endif
+#ifndef RMSB_SMALL_THREADS
+#define RMSB_SMALL_THREADS 128
+#endif
+#ifndef RMSB_SMALL_TICKSYNC
+#define RMSB_SMALL_TICKSYNC 0      // 1: the warps of a block start every tick together (experiment: shared instruction fetch)
+#endif
 
 template <int G>
-__global__ void __launch_bounds__(128, RMSB_SMALL_MINBLOCKS)
+__global__ void __launch_bounds__(RMSB_SMALL_THREADS, RMSB_SMALL_MINBLOCKS)
 small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SmallTables st, const __grid_constant__ SmallLayout lay,
                    const __grid_constant__ SolveArgs a) {
     stage_small(mp, st, lay);
@@ -459,7 +465,14 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
 #pragma unroll
     for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) D[j] = 0.0;
 
+#if RMSB_SMALL_TICKSYNC
+    bool warp_done = false;
+#endif
     for (;;) {
+#if RMSB_SMALL_TICKSYNC
+        if (__syncthreads_and(warp_done)) break;
+        if (warp_done) continue;
+#endif
         // ================================================================================ next reactor (cold)
         {
             const bool want = (phase == PH_FETCH);
@@ -500,7 +513,11 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                         phase = PH_INIT0;
                     }
                 }
+#if RMSB_SMALL_TICKSYNC
+                if (__all_sync(FULL, phase == PH_IDLE)) { warp_done = true; continue; }
+#else
                 if (__all_sync(FULL, phase == PH_IDLE)) break;
+#endif
             }
         }
         bool finish = false;
@@ -991,14 +1008,14 @@ static SmallLayout small_layout(const rmsb_mech* h, int Ny, int G, int groups, b
 }
 
 template <class K>
-static int small_config(K kernel, const rmsb_mech* h, const SmallLayout& lay, int groups, size_t* smem, int* bps, int* sms) {
+static int small_config(K kernel, const rmsb_mech* h, const SmallLayout& lay, int groups, size_t* smem, int* bps, int* sms, int threads = 128) {
     cudaDeviceProp prop;
     CU(rmsb_cached_props(h->device, &prop));
     *smem = sizeof(double) * ((size_t)lay.grp0 + (size_t)groups * lay.gstride);
     if (*smem > prop.sharedMemPerBlockOptin) return fail(RMSB_ERR_UNSUPPORTED, "small-mechanism path: shared memory");
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     int b = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 128, *smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, *smem));
     *bps = b < 1 ? 1 : b;
     *sms = prop.multiProcessorCount;
     return RMSB_OK;
@@ -1045,15 +1062,15 @@ static int small_solve_G(const rmsb_mech* h, const SolveArgs& a_in, cudaStream_t
         CU(cub::DeviceRadixSort::SortPairsDescending(base, tb, keys, keys_out, idx, order, (int)a.n, 0, 64, stream));
         a.order = order;
     }
-    const int groups = 128 / G;
+    const int groups = RMSB_SMALL_THREADS / G;
     const SmallLayout lay = small_layout(h, a.Ny, G, groups, true);
     size_t smem; int bps, sms;
-    int rc = small_config(small_solve_kernel<G>, h, lay, groups, &smem, &bps, &sms);
+    int rc = small_config(small_solve_kernel<G>, h, lay, groups, &smem, &bps, &sms, RMSB_SMALL_THREADS);
     if (rc != RMSB_OK) return rc;
     const int64_t resident = (int64_t)sms * bps, need = (a.n + groups - 1) / groups;
     const int grid = (int)std::max<int64_t>(1, std::min(resident, need));
     CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
-    small_solve_kernel<G><<<grid, 128, smem, stream>>>(h->dm, h->st, lay, a);
+    small_solve_kernel<G><<<grid, RMSB_SMALL_THREADS, smem, stream>>>(h->dm, h->st, lay, a);
     ++g_launches;
     CU(cudaGetLastError());
     return RMSB_OK;

@@ -203,6 +203,19 @@ class Phase:
             self._more_handles[device] = h
         return self._more_handles[device]
 
+    def spec_source(self, domain_kind: int) -> str:
+        """CUDA source of the kernels the library generates for this mechanism (large dydt / Jacobian batches of small
+        all-Arrhenius gas mechanisms, csrc/rmsb_spec.cu).  Needs no device; raises when the mechanism does not qualify."""
+        need = C.c_size_t(0)
+        L.check(L.lib().rmsb_spec_source_desc(C.byref(self.desc), int(domain_kind), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 1)
+        L.check(L.lib().rmsb_spec_source_desc(C.byref(self.desc), int(domain_kind), buf, need.value + 1, C.byref(need)))
+        return buf.value.decode()
+
+    def specialized(self, domain_kind: int) -> bool:
+        """True when large dydt / Jacobian batches of this mechanism run on kernels compiled for it (compiles them on first use)."""
+        return bool(L.lib().rmsb_mech_specialized(self.handle, int(domain_kind)))
+
     def __del__(self):
         try:
             if L._lib is not None:

@@ -28,6 +28,7 @@ tf = torch.empty((ne, Ny), dtype=torch.float64, device=dev)
 tJ = torch.empty((ne, Ny * Ny), dtype=torch.float64, device=dev)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 h = ig.handle
+print('specialised kernels:', ig.specialized(L.DOMAIN_CONSTANT_V), lib.rmsb_last_error().decode() if not ig.specialized(L.DOMAIN_CONSTANT_V) else '')
 for name, fn in (("dydt", lambda: lib.rmsb_dydt_batch_dev(h, L.DOMAIN_CONSTANT_V, ne, ty.data_ptr(), tv.data_ptr(), None, 0, None, 0, tf.data_ptr(), sp)),
                  ("jac", lambda: lib.rmsb_jac_batch_dev(h, L.DOMAIN_CONSTANT_V, ne, ty.data_ptr(), tv.data_ptr(), None, 0, None, 0, tJ.data_ptr(), sp))):
     for _ in range(reps):

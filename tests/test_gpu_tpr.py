@@ -1,5 +1,8 @@
 """The thread-per-reactor dydt / Jacobian kernels (batches >= 4096 of small ConstantV / ConstantP mechanisms) against the oracle and
-against the warp-per-reactor kernel that smaller batches use."""
+against the kernels that smaller batches use: both the kernels generated and compiled for the mechanism (csrc/rmsb_spec.cu) and the
+generic table-driven ones they replace (RMSB_NO_SPEC=1)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -21,8 +24,19 @@ def _states(y0, Ns, n, seed):
     return ys
 
 
+@pytest.fixture(params=["specialised", "generic"])
+def big_batch_kernels(request):
+    old = os.environ.get("RMSB_NO_SPEC")
+    os.environ["RMSB_NO_SPEC"] = "0" if request.param == "specialised" else "1"
+    yield request.param
+    if old is None:
+        os.environ.pop("RMSB_NO_SPEC", None)
+    else:
+        os.environ["RMSB_NO_SPEC"] = old
+
+
 @pytest.mark.parametrize("which", ["ConstantV", "ConstantP"])
-def test_thread_per_reactor_dydt(which):
+def test_thread_per_reactor_dydt(which, big_batch_kernels):
     assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
     ic = {"T": 1000.0, "P": 10e5, "H2": 0.67, "O2": 0.33, "N2": 0.5}
     d = rb.readinput(cases.fixture("superminimal"))
@@ -35,6 +49,8 @@ def test_thread_per_reactor_dydt(which):
     else:
         gdom, y0, p = rb.ConstantPDomain(phase=ig, initialconds=ic)
         odom = ro.ConstantPDomain(oig, ic)
+    # the run-time compiled kernels must really be the ones that run (NVRTC is part of the CUDA toolkit of the image)
+    assert ig.specialized(gdom.kind) == (big_batch_kernels == "specialised"), L.lib().rmsb_last_error().decode()
     n = 6000
     ys = _states(y0, ig.Ns, n, 3)
     ens = rb.Domain(gdom.kind, ig, ys, np.repeat(gdom.cond, n, axis=0), constantspecies=["N2"] if which == "ConstantV" else [])

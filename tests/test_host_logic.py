@@ -218,3 +218,28 @@ def test_rms_writer_round_trip(fx, tmp_path):
             for sx, sy in zip(a[key]["Species"], b[key]["Species"]):
                 assert sx.name == sy.name and sx.smiles == sy.smiles and sx.radius == sy.radius and sx.diffusion_r == sy.diffusion_r
                 assert [(q.coefs, q.Tmin, q.Tmax) for q in sx.thermo.polys] == [(q.coefs, q.Tmin, q.Tmax) for q in sy.thermo.polys]
+
+
+def test_generated_kernel_source_compiles_for_sm100a(tmp_path):
+    """csrc/rmsb_spec.cu: the CUDA source the library writes out for a small all-Arrhenius gas mechanism comes from the descriptor
+    alone (no device), holds both kernels, compiles for sm_100a, and mechanisms outside that class are refused by name."""
+    import shutil
+    import subprocess
+    d = rb.readinput(cases.fixture("superminimal"))
+    ig = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"], name="phase")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    for kind in (L.DOMAIN_CONSTANT_V, L.DOMAIN_CONSTANT_P):
+        src = ig.spec_source(kind)
+        assert "rmsb_spec_dydt" in src and "rmsb_spec_jac" in src
+        assert src.count("// reaction ") == ig.Nr                # value pass and dual-number pass share one template
+        f = tmp_path / f"spec_{kind}.cu"
+        f.write_text(src)
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-cubin", "-o", str(f.with_suffix(".cubin")), str(f)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+    with pytest.raises(L.RMSBError, match="ConstantV / ConstantP"):
+        ig.spec_source(L.DOMAIN_CONSTANT_TP)
+    d = rb.readinput(cases.fixture("ethane"))                        # falloff kinetics: generic kernels only
+    eg = rb.IdealGas(d["phase"]["Species"], d["phase"]["Reactions"], name="phase")
+    with pytest.raises(L.RMSBError, match="does not qualify"):
+        eg.spec_source(L.DOMAIN_CONSTANT_V)
