@@ -43,6 +43,7 @@ struct SpecKernels {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t dydt = nullptr, jac = nullptr;
     int ldt = 0, ldj = 0;          // shared-memory row strides (doubles) of the two kernels
+    int occ_dydt = 1, occ_jac = 1; // resident blocks per SM
 };
 
 }  // namespace
@@ -60,6 +61,8 @@ struct rmsb_spec_state {
 
 namespace {
 
+// Doubles are written as 17-digit literals.  (Collecting them in a __constant__ array instead -- K[i] operands, LDCU loads into
+// uniform registers -- was measured and lost: dydt -3 %, Jacobian 2.2x slower through uniform-register pressure and spills.)
 std::string lit(double v) {
     if (v != v) return "(0.0/0.0)";
     if (std::isinf(v)) return v > 0 ? "(1.0/0.0)" : "(-1.0/0.0)";
@@ -237,29 +240,43 @@ void emit_rhs(std::ostringstream& o, const rmsb_spec_state& m, bool isp) {
     o << "}\n\n";
 }
 
+// resident blocks per SM the kernels are compiled for (register budget = 65536 / (128 * blocks)); RMSB_SPEC_DYDT_BLOCKS /
+// RMSB_SPEC_JAC_BLOCKS override the defaults for tuning runs
+int env_blocks(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    int b = v ? std::atoi(v) : dflt;
+    return (b >= 0 && b <= 32) ? b : dflt;
+}
+
 void emit_dydt_kernel(std::ostringstream& o, const rmsb_spec_state& m, int ldt) {
     const int Ny = m.Ns + 2;
-    o << "extern \"C\" __global__ void __launch_bounds__(" << SPEC_THREADS << ", 3) rmsb_spec_dydt(const double* __restrict__ Y, const double* __restrict__ COND, int ncond,\n"
+    // every warp stages its own 32 states (coalesced global accesses, no block-wide barrier: the warps of a block drift apart and
+    // overlap each other's memory phases)
+    o << "extern \"C\" __global__ void __launch_bounds__(" << SPEC_THREADS << ", " << env_blocks("RMSB_SPEC_DYDT_BLOCKS", 3) << ") rmsb_spec_dydt(const double* __restrict__ Y, const double* __restrict__ COND, int ncond,\n"
          "        const double* __restrict__ PP, long long p_stride, const int* __restrict__ constspc, int nconst, long long n, double* __restrict__ OUT) {\n"
-         "    extern __shared__ double tile[];\n    const int tid = threadIdx.x;\n"
-         "    for (long long base = (long long)blockIdx.x * " << SPEC_THREADS << "; base < n; base += (long long)gridDim.x * " << SPEC_THREADS << ") {\n"
-         "        const int cnt = (int)((n - base < " << SPEC_THREADS << ") ? n - base : " << SPEC_THREADS << ");\n"
-         "        for (int i = tid; i < cnt * " << Ny << "; i += " << SPEC_THREADS << ") { int r = i / " << Ny << "; tile[r * " << ldt << " + (i - r * " << Ny << ")] = Y[base * " << Ny << " + i]; }\n"
-         "        __syncthreads();\n"
-         "        if (tid < cnt) {\n            const long long ir = base + tid;\n            double* row = tile + tid * " << ldt << ";\n"
+         "    extern __shared__ double tile[];\n    const int lane = threadIdx.x & 31;\n    double* wt = tile + (threadIdx.x >> 5) * (32 * " << ldt << ");\n"
+         "    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);\n"
+         "    for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n; base += nwarps * 32) {\n"
+         "        const int cnt = (int)((n - base < 32) ? n - base : 32);\n"
+         "        for (int i = lane; i < cnt * " << Ny << "; i += 32) { int r = i / " << Ny << "; wt[r * " << ldt << " + (i - r * " << Ny << ")] = Y[base * " << Ny << " + i]; }\n"
+         "        __syncwarp();\n"
+         "        if (lane < cnt) {\n            const long long ir = base + lane;\n            double* row = wt + lane * " << ldt << ";\n"
          "            double y[" << Ny << "], f[" << Ny << "];\n";
     for (int i = 0; i < Ny; ++i) o << "            y[" << i << "] = row[" << i << "];\n";
     o << "            Keep kp;\n            spec_rhs<double, false>(y, COND[ir * ncond], PP ? PP + ir * p_stride : nullptr, f, kp);\n";
     for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = f[" << i << "];\n";
-    o << "            for (int k = 0; k < nconst; ++k) row[constspc[k] - 1] = 0.0;\n        }\n        __syncthreads();\n"
-         "        for (int i = tid; i < cnt * " << Ny << "; i += " << SPEC_THREADS << ") { int r = i / " << Ny << "; OUT[base * " << Ny << " + i] = tile[r * " << ldt << " + (i - r * " << Ny << ")]; }\n"
-         "        __syncthreads();\n    }\n}\n\n";
+    o << "            for (int k = 0; k < nconst; ++k) row[constspc[k] - 1] = 0.0;\n        }\n        __syncwarp();\n"
+         "        for (int i = lane; i < cnt * " << Ny << "; i += 32) { int r = i / " << Ny << "; OUT[base * " << Ny << " + i] = wt[r * " << ldt << " + (i - r * " << Ny << ")]; }\n"
+         "        __syncwarp();\n    }\n}\n\n";
 }
 
 // ---- jacobiany!: jac_tpr_kernel (rmsb_api.cu) written out; columns are produced in pairs and leave through a shared-memory tile --
+// Order of work (chosen for short live ranges, the results do not depend on it): the dual-number pass over the complete RHS first
+// (T and P columns, src/Reactor.jl:1469-1477) -- for ConstantV those two columns leave at once --, then the value pass, then the
+// species columns with their derivative terms formed column by column (a term belongs to the column of the species it differentiates).
 void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, int ldj, int chunk) {
     const int Ns = m.Ns, Nr = m.Nr, Ny = Ns + 2;
-    o << "extern \"C\" __global__ void __launch_bounds__(" << SPEC_THREADS << ", 2) rmsb_spec_jac(const double* __restrict__ Y, const double* __restrict__ COND, int ncond,\n"
+    o << "extern \"C\" __global__ void __launch_bounds__(" << SPEC_THREADS << ", " << env_blocks("RMSB_SPEC_JAC_BLOCKS", 2) << ") rmsb_spec_jac(const double* __restrict__ Y, const double* __restrict__ COND, int ncond,\n"
          "        const double* __restrict__ PP, long long p_stride, const int* __restrict__ constspc, int nconst, long long n, double* __restrict__ OUT) {\n"
          "    extern __shared__ double tile[];\n    const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;\n"
          "    for (long long base = (long long)blockIdx.x * " << SPEC_THREADS << "; base < n; base += (long long)gridDim.x * " << SPEC_THREADS << ") {\n"
@@ -271,17 +288,42 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
          "        double y[" << Ny << "], f[" << Ny << "];\n";
     for (int i = 0; i < Ny; ++i) o << "        y[" << i << "] = tile[me * " << ldj << " + " << i << "];\n";
     o << "        __syncthreads();\n";
-    o << "        const double* p = PP ? PP + ir * p_stride : nullptr;\n        const double cond = COND[ir * ncond];\n"
-         "        Keep kp;\n        spec_rhs<double, true>(y, cond, p, f, kp);\n";
-    // (1) derivative terms
-    o << "        double dt[" << std::max(1, m.n_dt) << "];\n";
-    for (int t = 0; t < m.n_dt; ++t) {
-        const int jr = m.dtrxn[t], j = jr & 0x3fffffff;
-        std::string e = (jr >> 30) ? idx("kp.kr", j) : idx("kp.kf", j);
-        if (m.dtmult[t] != 1) e = lit((double)m.dtmult[t]) + " * " + e;
-        for (int k = 0; k < 3; ++k) { int s = m.dtoth[3 * t + k]; if (s < 0) break; e += " * " + idx("kp.cs", s); }
-        o << "        dt[" << t << "] = " << e << ";\n";
+    o << "        const double* p = PP ? PP + ir * p_stride : nullptr;\n        const double cond = COND[ir * ncond];\n        Keep kp;\n";
+    // (6) constant species rows, then the warp writes its 32 reactors' runs of `ncols` columns starting at column c0
+    auto emit_write = [&](int c0, int ncols) {
+        const int w = ncols * Ny;
+        o << "            for (int k = 0; k < nconst; ++k) { const int s = constspc[k] - 1; for (int cc = 0; cc < " << ncols << "; ++cc) row[cc * " << Ny << " + s] = 0.0; }\n"
+             "            __syncwarp();\n";
+        if (env_blocks("RMSB_SPEC_WRITER", 4) == 0) {
+            o << "            for (int r = 0; r < 32 && wbase + r < cnt; ++r) {\n"
+                 "                double* dst = OUT + (base + wbase + r) * " << Ny * Ny << " + " << c0 * Ny << ";\n"
+                 "                const double* src = tile + (wbase + r) * " << ldj << ";\n"
+                 "                for (int i = lane; i < " << w << "; i += 32) dst[i] = src[i];\n"
+                 "            }\n";
+        } else {
+            o << "            {\n"
+                 "                double* dst = OUT + (base + wbase) * " << Ny * Ny << " + " << c0 * Ny << " + lane;\n"
+                 "                const double* src = tile + wbase * " << ldj << " + lane;\n"
+                 "                const int nr = (cnt - wbase < 32) ? cnt - wbase : 32;\n"
+                 "#pragma unroll " << env_blocks("RMSB_SPEC_WRITER", 4) << "\n"
+                 "                for (int r = 0; r < nr; ++r)\n"
+                 "                    for (int i = 0; i < " << w << "; i += 32) if (lane + i < " << w << ") dst[r * " << Ny * Ny << " + i] = src[r * " << ldj << " + i];\n"
+                 "            }\n";
+        }
+        o << "            __syncwarp();\n";
+    };
+    // (7) T (and P) columns: derivative of the complete RHS
+    o << "        {\n            Dual2 fd[" << Ny << "];\n            spec_rhs<Dual2, false>(y, cond, p, fd, kp);\n";
+    if (!isp) {
+        for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = fd[" << i << "].a; row[" << Ny + i << "] = fd[" << i << "].b;\n";
+        if (chunk >= 2) emit_write(Ns, 2);
+        else { emit_write(Ns, 1); for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = fd[" << i << "].b;\n"; emit_write(Ns + 1, 1); }
+        o << "        }\n";
+    } else {
+        o << "            for (int i = 0; i < " << Ny << "; ++i) f[i] = fd[i].a;      // the T column waits for the V column next to it\n        }\n";
     }
+    if (isp) o << "        double tcol[" << Ny << "];\n        for (int i = 0; i < " << Ny << "; ++i) tcol[i] = f[i];\n";
+    o << "        spec_rhs<double, true>(y, cond, p, f, kp);\n";
     if (isp) {
         // per-reaction pieces of the V column (src/Reactor.jl:1368-1413)
         o << "        double dfv[" << Nr << "], drv[" << Nr << "];\n";
@@ -290,35 +332,43 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
             if (nre > 1) o << "        dfv[" << j << "] = -" << lit((double)(nre - 1)) << " * (" << side_product(m, j, false, idx("kp.kf", j), "kp.cs") << ");\n";
             if (npr > 1) o << "        drv[" << j << "] = -" << lit((double)(npr - 1)) << " * (" << side_product(m, j, true, idx("kp.kr", j), "kp.cs") << ");\n";
         }
+        o << "        const double aCp = kp.Cv + 8.314, dTdt = -kp.dotU / (kp.Nt * aCp);\n";
     }
-    // entries by column (the entry list is sorted by column, then row)
+    // entries by column (the entry list is sorted by column, then row); derivative terms by the column they belong to
     std::vector<std::vector<int>> col_entries(Ns);
     for (int e = 0; e < m.n_je; ++e) col_entries[m.jecol[e]].push_back(e);
-    bool dual_done = false;
-    auto emit_dual = [&]() {
-        if (dual_done) return;
-        dual_done = true;
-        o << "        Dual2 fd[" << Ny << "];\n        spec_rhs<Dual2, false>(y, cond, p, fd, kp);\n";
-    };
-    if (isp) o << "        const double aCp = kp.Cv + 8.314, dTdt = -kp.dotU / (kp.Nt * aCp);\n";
-    for (int c0 = 0; c0 < Ny; c0 += chunk) {
-        const int c1 = std::min(Ny, c0 + chunk);
+    // chunks: the species columns in groups of `chunk`; for ConstantP one more chunk {T column, V column}
+    std::vector<std::pair<int, int>> chunks;
+    for (int c0 = 0; c0 < Ns; c0 += chunk) chunks.push_back({c0, std::min(Ns, c0 + chunk)});
+    if (isp) { if (chunk >= 2) chunks.push_back({Ns, Ns + 2}); else { chunks.push_back({Ns, Ns + 1}); chunks.push_back({Ns + 1, Ns + 2}); } }
+    for (auto& ch : chunks) {
+        const int c0 = ch.first, c1 = ch.second;
         o << "        {   // columns " << c0 << " .. " << c1 - 1 << "\n";
         for (int c = c0; c < c1; ++c) {
             const int off = (c - c0) * Ny;
-            if (c == Ns || (!isp && c == Ns + 1)) {          // (7) T (and P) column: derivative of the complete RHS
-                emit_dual();
-                for (int i = 0; i < Ny; ++i) o << "            row[" << off + i << "] = fd[" << i << "]." << (c == Ns ? "a" : "b") << ";\n";
-                continue;
-            }
+            if (c == Ns) { for (int i = 0; i < Ny; ++i) o << "            row[" << off + i << "] = tcol[" << i << "];\n"; continue; }
             std::vector<std::string> nz(Ns);                 // expression name of the species rows of this column
             o << "            {\n";
             if (c < Ns) {
+                // (1) the derivative terms this column's entries gather (src/Reactor.jl:899-1366)
+                std::map<int, std::string> tname;
+                for (int e : col_entries[c])
+                    for (int k = m.jeptr[e]; k < m.jeptr[e + 1]; ++k) {
+                        const int t = m.jtidx[k] & 0x7fffffff;
+                        if (tname.count(t)) continue;
+                        const int jr = m.dtrxn[t], j = jr & 0x3fffffff;
+                        std::string ex = (jr >> 30) ? idx("kp.kr", j) : idx("kp.kf", j);
+                        if (m.dtmult[t] != 1) ex = lit((double)m.dtmult[t]) + " * " + ex;
+                        for (int q = 0; q < 3; ++q) { int sp = m.dtoth[3 * t + q]; if (sp < 0) break; ex += " * " + idx("kp.cs", sp); }
+                        tname[t] = "d" + std::to_string(t);
+                        o << "                const double d" << t << " = " << ex << ";\n";
+                    }
+                // (2) entries in the reference's accumulation order
                 for (int e : col_entries[c]) {
                     std::string acc;
                     for (int k = m.jeptr[e]; k < m.jeptr[e + 1]; ++k) {
                         const int ti = m.jtidx[k];
-                        const std::string v = idx("dt", ti & 0x7fffffff);
+                        const std::string v = tname[ti & 0x7fffffff];
                         if (acc.empty()) acc = (ti < 0 ? "-" : "") + v;
                         else acc += (ti < 0 ? " - " : " + ") + v;
                     }
@@ -326,7 +376,7 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
                     o << "                const double " << nm << " = " << (acc.empty() ? "0.0" : acc) << ";\n";
                     nz[m.jerow[e]] = nm;
                 }
-            } else {                                          // V column of the species block (ConstantP)
+            } else {                                          // (3) V column of the species block (ConstantP)
                 for (int s = 0; s < Ns; ++s) {
                     std::string acc;
                     for (int k = m.srptr[s]; k < m.srptr[s + 1]; ++k) {
@@ -341,7 +391,8 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
                     nz[s] = nm;
                 }
             }
-            // (5) thermodynamic-variable rows: weighted column sums in ascending row order (structural zeros add nothing)
+            // (5) thermodynamic-variable rows: weighted column sums in ascending row order (structural zeros add nothing);
+            //     a + b + c parses as (a + b) + c, the accumulation order of the generic kernel
             std::string sa, sm;
             for (int i = 0; i < Ns; ++i) {
                 if (nz[i].empty()) continue;
@@ -349,7 +400,6 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
                 sm += (sm.empty() ? "" : " + ") + nz[i];
             }
             if (sa.empty()) { sa = "0.0"; sm = "0.0"; }
-            // left-to-right sums: a + b + c parses as (a + b) + c, the accumulation order of the generic kernel
             o << "                const double sa = " << sa << ";\n                const double sm = " << sm << ";\n";
             if (!isp) {
                 o << "                const double dCv = kp.cp[" << c << "] * 8.314 / kp.Nt;\n"
@@ -364,15 +414,8 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
             for (int i = 0; i < Ns; ++i) o << "                row[" << off + i << "] = " << (nz[i].empty() ? std::string("0.0") : nz[i]) << ";\n";
             o << "                row[" << off + Ns << "] = jt; row[" << off + Ns + 1 << "] = jp;\n            }\n";
         }
-        const int w = (c1 - c0) * Ny;
-        // (6) constant species rows, then the warp writes its reactors' column runs
-        o << "            for (int k = 0; k < nconst; ++k) { const int s = constspc[k] - 1; for (int cc = 0; cc < " << (c1 - c0) << "; ++cc) row[cc * " << Ny << " + s] = 0.0; }\n"
-             "            __syncwarp();\n"
-             "            for (int r = 0; r < 32 && wbase + r < cnt; ++r) {\n"
-             "                double* dst = OUT + (base + wbase + r) * " << Ny * Ny << " + " << c0 * Ny << ";\n"
-             "                const double* src = tile + (wbase + r) * " << ldj << ";\n"
-             "                for (int i = lane; i < " << w << "; i += 32) dst[i] = src[i];\n"
-             "            }\n            __syncwarp();\n        }\n";
+        emit_write(c0, c1 - c0);
+        o << "        }\n";
     }
     o << "        __syncthreads();\n    }\n}\n";
 }
@@ -497,6 +540,9 @@ int rmsb_spec_ready(const rmsb_mech* h, int kind, std::string* why) {
             if (e == cudaSuccess) e = cudaLibraryGetKernel(&k.jac, k.lib, "rmsb_spec_jac");
             if (e == cudaSuccess && sizeof(double) * SPEC_THREADS * k.ldj > 48 * 1024)
                 e = cudaFuncSetAttribute((const void*)k.jac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * SPEC_THREADS * k.ldj));
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.occ_dydt, (const void*)k.dydt, SPEC_THREADS, sizeof(double) * SPEC_THREADS * k.ldt);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.occ_jac, (const void*)k.jac, SPEC_THREADS, sizeof(double) * SPEC_THREADS * k.ldj);
+            if (e == cudaSuccess && (k.occ_dydt < 1 || k.occ_jac < 1)) e = cudaErrorLaunchOutOfResources;
             if (e == cudaSuccess) k.state = 1;
             else { k.why = std::string("loading the specialised kernels: ") + cudaGetErrorString(e); cudaGetLastError(); }
         }
@@ -512,7 +558,8 @@ int rmsb_spec_launch_eval(const rmsb_mech* h, int mode, const BatchArgs& a, cuda
     CU(rmsb_cached_props(h->device, &prop));
     const int ld = mode == 0 ? k.ldt : k.ldj;
     const size_t smem = sizeof(double) * (size_t)SPEC_THREADS * ld;
-    const int64_t blocks = (a.n + SPEC_THREADS - 1) / SPEC_THREADS, cap = (int64_t)prop.multiProcessorCount * (mode == 0 ? 12 : 8);
+    // one resident wave of blocks striding over the batch: every block then does (nearly) the same number of tiles
+    const int64_t blocks = (a.n + SPEC_THREADS - 1) / SPEC_THREADS, cap = (int64_t)prop.multiProcessorCount * (mode == 0 ? k.occ_dydt : k.occ_jac) * env_blocks("RMSB_SPEC_WAVES", 1);
     const int grid = (int)std::max<int64_t>(1, std::min(blocks, cap));
     const double* Y = a.y; const double* COND = a.cond; int ncond = a.ncond; const double* PP = a.p; long long p_stride = a.p_stride;
     const int* cs = a.constspc; int nconst = a.nconst; long long n = a.n; double* OUT = a.out;
