@@ -75,41 +75,75 @@ std::string lit(double v) {
 }
 std::string idx(const char* a, int i) { return std::string(a) + "[" + std::to_string(i) + "]"; }
 
+// Dual numbers for the T and P columns (the in-kernel analogue of the reference's ForwardDiff pass, src/Reactor.jl:1469-1477).
+// D1 carries d/dT only: everything thermo and kinetics compute depends on T alone, so the d/dP parts the generic kernels carry
+// through those expressions are sums of exact zeros.  D2 (d/dT, d/dP) is used for the few quantities that see P: the total moles
+// P V / (R T), dT/dt and dP/dt (dV/dt).  A D1 converts to a D2 with a zero P part.
 const char* PRELUDE = R"SRC(
-struct Dual2 {
-    double v, a, b;
-    __device__ __forceinline__ Dual2() {}
-    __device__ __forceinline__ Dual2(double v_) : v(v_), a(0.0), b(0.0) {}
-    __device__ __forceinline__ Dual2(double v_, double a_, double b_) : v(v_), a(a_), b(b_) {}
+struct D1 {
+    double v, a;
+    __device__ __forceinline__ D1() {}
+    __device__ __forceinline__ D1(double v_) : v(v_), a(0.0) {}
+    __device__ __forceinline__ D1(double v_, double a_) : v(v_), a(a_) {}
 };
-__device__ __forceinline__ Dual2 operator+(Dual2 x, Dual2 y) { return Dual2(x.v + y.v, x.a + y.a, x.b + y.b); }
-__device__ __forceinline__ Dual2 operator+(Dual2 x, double y) { return Dual2(x.v + y, x.a, x.b); }
-__device__ __forceinline__ Dual2 operator+(double x, Dual2 y) { return Dual2(x + y.v, y.a, y.b); }
-__device__ __forceinline__ Dual2 operator-(Dual2 x, Dual2 y) { return Dual2(x.v - y.v, x.a - y.a, x.b - y.b); }
-__device__ __forceinline__ Dual2 operator-(Dual2 x, double y) { return Dual2(x.v - y, x.a, x.b); }
-__device__ __forceinline__ Dual2 operator-(double x, Dual2 y) { return Dual2(x - y.v, -y.a, -y.b); }
-__device__ __forceinline__ Dual2 operator-(Dual2 x) { return Dual2(-x.v, -x.a, -x.b); }
-__device__ __forceinline__ Dual2 operator*(Dual2 x, Dual2 y) { return Dual2(x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b); }
-__device__ __forceinline__ Dual2 operator*(Dual2 x, double y) { return Dual2(x.v * y, x.a * y, x.b * y); }
-__device__ __forceinline__ Dual2 operator*(double x, Dual2 y) { return Dual2(x * y.v, x * y.a, x * y.b); }
-__device__ __forceinline__ Dual2 operator/(Dual2 x, Dual2 y) {
+__device__ __forceinline__ D1 operator+(D1 x, D1 y) { return D1(x.v + y.v, x.a + y.a); }
+__device__ __forceinline__ D1 operator+(D1 x, double y) { return D1(x.v + y, x.a); }
+__device__ __forceinline__ D1 operator+(double x, D1 y) { return D1(x + y.v, y.a); }
+__device__ __forceinline__ D1 operator-(D1 x, D1 y) { return D1(x.v - y.v, x.a - y.a); }
+__device__ __forceinline__ D1 operator-(D1 x, double y) { return D1(x.v - y, x.a); }
+__device__ __forceinline__ D1 operator-(double x, D1 y) { return D1(x - y.v, -y.a); }
+__device__ __forceinline__ D1 operator-(D1 x) { return D1(-x.v, -x.a); }
+__device__ __forceinline__ D1 operator*(D1 x, D1 y) { return D1(x.v * y.v, x.a * y.v + x.v * y.a); }
+__device__ __forceinline__ D1 operator*(D1 x, double y) { return D1(x.v * y, x.a * y); }
+__device__ __forceinline__ D1 operator*(double x, D1 y) { return D1(x * y.v, x * y.a); }
+__device__ __forceinline__ D1 operator/(D1 x, D1 y) { double q = x.v / y.v, iy = 1.0 / y.v; return D1(q, (x.a - q * y.a) * iy); }
+__device__ __forceinline__ D1 operator/(D1 x, double y) { return D1(x.v / y, x.a / y); }
+__device__ __forceinline__ D1 operator/(double x, D1 y) { double q = x / y.v, s = -q / y.v; return D1(q, s * y.a); }
+struct D2 {
+    double v, a, b;
+    __device__ __forceinline__ D2() {}
+    __device__ __forceinline__ D2(double v_) : v(v_), a(0.0), b(0.0) {}
+    __device__ __forceinline__ D2(D1 x) : v(x.v), a(x.a), b(0.0) {}
+    __device__ __forceinline__ D2(double v_, double a_, double b_) : v(v_), a(a_), b(b_) {}
+};
+__device__ __forceinline__ D2 operator+(D2 x, D2 y) { return D2(x.v + y.v, x.a + y.a, x.b + y.b); }
+__device__ __forceinline__ D2 operator+(D2 x, double y) { return D2(x.v + y, x.a, x.b); }
+__device__ __forceinline__ D2 operator+(double x, D2 y) { return D2(x + y.v, y.a, y.b); }
+__device__ __forceinline__ D2 operator-(D2 x, D2 y) { return D2(x.v - y.v, x.a - y.a, x.b - y.b); }
+__device__ __forceinline__ D2 operator-(D2 x, double y) { return D2(x.v - y, x.a, x.b); }
+__device__ __forceinline__ D2 operator-(double x, D2 y) { return D2(x - y.v, -y.a, -y.b); }
+__device__ __forceinline__ D2 operator-(D2 x) { return D2(-x.v, -x.a, -x.b); }
+__device__ __forceinline__ D2 operator*(D2 x, D2 y) { return D2(x.v * y.v, x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b); }
+__device__ __forceinline__ D2 operator*(D2 x, double y) { return D2(x.v * y, x.a * y, x.b * y); }
+__device__ __forceinline__ D2 operator*(double x, D2 y) { return D2(x * y.v, x * y.a, x * y.b); }
+__device__ __forceinline__ D2 operator/(D2 x, D2 y) {
     double q = x.v / y.v, iy = 1.0 / y.v;
-    return Dual2(q, (x.a - q * y.a) * iy, (x.b - q * y.b) * iy);
+    return D2(q, (x.a - q * y.a) * iy, (x.b - q * y.b) * iy);
 }
-__device__ __forceinline__ Dual2 operator/(Dual2 x, double y) { return Dual2(x.v / y, x.a / y, x.b / y); }
-__device__ __forceinline__ Dual2 operator/(double x, Dual2 y) {
-    double q = x / y.v, s = -q / y.v;
-    return Dual2(q, s * y.a, s * y.b);
-}
-__device__ __forceinline__ Dual2 dexp(Dual2 x) { double e = exp(x.v); return Dual2(e, e * x.a, e * x.b); }
+__device__ __forceinline__ D2 operator/(D2 x, double y) { return D2(x.v / y, x.a / y, x.b / y); }
+__device__ __forceinline__ D2 operator/(double x, D2 y) { double q = x / y.v, s = -q / y.v; return D2(q, s * y.a, s * y.b); }
+// mixed D1 / D2 expressions promote the D1 operand
+__device__ __forceinline__ D2 operator+(D2 x, D1 y) { return x + D2(y); }
+__device__ __forceinline__ D2 operator+(D1 x, D2 y) { return D2(x) + y; }
+__device__ __forceinline__ D2 operator-(D2 x, D1 y) { return x - D2(y); }
+__device__ __forceinline__ D2 operator-(D1 x, D2 y) { return D2(x) - y; }
+__device__ __forceinline__ D2 operator*(D2 x, D1 y) { return x * D2(y); }
+__device__ __forceinline__ D2 operator*(D1 x, D2 y) { return D2(x) * y; }
+__device__ __forceinline__ D2 operator/(D2 x, D1 y) { return x / D2(y); }
+__device__ __forceinline__ D2 operator/(D1 x, D2 y) { return D2(x) / y; }
+__device__ __forceinline__ D1 dexp(D1 x) { double e = exp(x.v); return D1(e, e * x.a); }
 __device__ __forceinline__ double dexp(double x) { return exp(x); }
-__device__ __forceinline__ Dual2 dlog(Dual2 x) { double i = 1.0 / x.v; return Dual2(log(x.v), x.a * i, x.b * i); }
+__device__ __forceinline__ D1 dlog(D1 x) { double i = 1.0 / x.v; return D1(log(x.v), x.a * i); }
 __device__ __forceinline__ double dlog(double x) { return log(x); }
 __device__ __forceinline__ double val(double x) { return x; }
-__device__ __forceinline__ double val(Dual2 x) { return x.v; }
-template <class N> __device__ __forceinline__ N seed(double v, int which);
-template <> __device__ __forceinline__ double seed<double>(double v, int) { return v; }
-template <> __device__ __forceinline__ Dual2 seed<Dual2>(double v, int which) { return Dual2(v, which == 0 ? 1.0 : 0.0, which == 1 ? 1.0 : 0.0); }
+__device__ __forceinline__ double val(D1 x) { return x.v; }
+__device__ __forceinline__ double val(D2 x) { return x.v; }
+template <class N> __device__ __forceinline__ N seedT(double v);
+template <> __device__ __forceinline__ double seedT<double>(double v) { return v; }
+template <> __device__ __forceinline__ D1 seedT<D1>(double v) { return D1(v, 1.0); }
+template <class M> __device__ __forceinline__ M seedP(double v);
+template <> __device__ __forceinline__ double seedP<double>(double v) { return v; }
+template <> __device__ __forceinline__ D2 seedP<D2>(double v) { return D2(v, 0.0, 1.0); }
 )SRC";
 
 // ---- NASA polynomial of species s, range r, in the operation order of nasa_hscp (rmsb_device.cuh) ---------------------------
@@ -153,13 +187,14 @@ int side_count(const rmsb_spec_state& m, int j, bool products) {
 void emit_rhs(std::ostringstream& o, const rmsb_spec_state& m, bool isp) {
     const int Ns = m.Ns, Nr = m.Nr;
     o << "struct Keep { double kf[" << Nr << "], kr[" << Nr << "], us[" << Ns << "], cp[" << Ns << "], cs[" << Ns << "]; double T, P, V, Nt, C, Cv, dotU; };\n";
-    o << "template <class N, bool KEEP>\n__device__ __forceinline__ void spec_rhs(const double* y, const double cond, const double* __restrict__ p, N* f, Keep& kp) {\n";
+    // N: type of everything that depends on T only; M: type of what also sees P (value pass: double, double)
+    o << "template <class N, class M, bool KEEP>\n__device__ __forceinline__ void spec_rhs(const double* y, const double cond, const double* __restrict__ p, N* f, M& fT, M& fP, Keep& kp) {\n";
     o << "    const double V = " << (isp ? "y[" + std::to_string(Ns + 1) + "]" : std::string("cond")) << ";\n";
     o << "    const double invV = 1.0 / V;\n";
-    o << "    N T = seed<N>(y[" << Ns << "], 0), P = " << (isp ? std::string("N(cond)") : "seed<N>(y[" + std::to_string(Ns + 1) + "], 1)") << ";\n";
+    o << "    N T = seedT<N>(y[" << Ns << "]);\n    M P = " << (isp ? std::string("M(cond)") : "seedP<M>(y[" + std::to_string(Ns + 1) + "])") << ";\n";
     o << "    const double Tv = val(T);\n";
     o << "    N T0 = T, T1 = T * T, T2 = T1 * T, T3 = T2 * T, T4 = 1.0 / T, T5 = T4 * T4, T6 = dlog(T);\n";
-    o << "    N RT = 8.314 * T;\n    N invRT = T4 * (1.0 / 8.314);\n    N Nt = P * V * invRT, C = P * invRT;\n";
+    o << "    N RT = 8.314 * T;\n    N invRT = T4 * (1.0 / 8.314);\n    M Nt = P * V * invRT, C = P * invRT;\n";
     o << "    N cp[" << Ns << "], hh[" << Ns << "], sr[" << Ns << "];\n";
     // species grouped by their range boundaries: one branch chain per group (selectPoly: first range with T <= Tmax, else the last)
     std::map<std::vector<double>, std::vector<int>> groups;
@@ -232,9 +267,9 @@ void emit_rhs(std::ostringstream& o, const rmsb_spec_state& m, bool isp) {
         o << "    { N dn = (" << acc << ") * V; f[" << s << "] = dn; usum = usum + u[" << s << "] * dn; nsum = nsum + dn; }\n";
     }
     if (isp) {
-        o << "    N dT = -usum / (8.314 * cpsum);\n    f[" << Ns << "] = dT;\n    f[" << Ns + 1 << "] = nsum * RT / P + dT * V * T4;\n";
+        o << "    M dT = -usum / (8.314 * cpsum);\n    fT = dT;\n    fP = nsum * RT / P + dT * V * T4;\n";
     } else {
-        o << "    N dT = -usum / (8.314 * (cpsum - Nt));\n    f[" << Ns << "] = dT;\n    f[" << Ns + 1 << "] = nsum * RT * invV + P * T4 * dT;\n";
+        o << "    M dT = -usum / (8.314 * (cpsum - Nt));\n    fT = dT;\n    fP = nsum * RT * invV + P * T4 * dT;\n";
     }
     o << "    if (KEEP) { kp.T = val(T); kp.P = val(P); kp.V = V; kp.Nt = val(Nt); kp.C = val(C); kp.Cv = val(cpsum) * (8.314 / val(Nt)) - 8.314; kp.dotU = val(usum); }\n";
     o << "}\n\n";
@@ -263,7 +298,7 @@ void emit_dydt_kernel(std::ostringstream& o, const rmsb_spec_state& m, int ldt) 
          "        if (lane < cnt) {\n            const long long ir = base + lane;\n            double* row = wt + lane * " << ldt << ";\n"
          "            double y[" << Ny << "], f[" << Ny << "];\n";
     for (int i = 0; i < Ny; ++i) o << "            y[" << i << "] = row[" << i << "];\n";
-    o << "            Keep kp;\n            spec_rhs<double, false>(y, COND[ir * ncond], PP ? PP + ir * p_stride : nullptr, f, kp);\n";
+    o << "            Keep kp;\n            spec_rhs<double, double, false>(y, COND[ir * ncond], PP ? PP + ir * p_stride : nullptr, f, f[" << Ny - 2 << "], f[" << Ny - 1 << "], kp);\n";
     for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = f[" << i << "];\n";
     o << "            for (int k = 0; k < nconst; ++k) row[constspc[k] - 1] = 0.0;\n        }\n        __syncwarp();\n"
          "        for (int i = lane; i < cnt * " << Ny << "; i += 32) { int r = i / " << Ny << "; OUT[base * " << Ny << " + i] = wt[r * " << ldt << " + (i - r * " << Ny << ")]; }\n"
@@ -313,17 +348,24 @@ void emit_jac_kernel(std::ostringstream& o, const rmsb_spec_state& m, bool isp, 
         o << "            __syncwarp();\n";
     };
     // (7) T (and P) columns: derivative of the complete RHS
-    o << "        {\n            Dual2 fd[" << Ny << "];\n            spec_rhs<Dual2, false>(y, cond, p, fd, kp);\n";
     if (!isp) {
-        for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = fd[" << i << "].a; row[" << Ny + i << "] = fd[" << i << "].b;\n";
+        o << "        {\n            D1 fd[" << Ns << "]; D2 fT, fP;\n            spec_rhs<D1, D2, false>(y, cond, p, fd, fT, fP, kp);\n";
+        for (int i = 0; i < Ns; ++i) o << "            row[" << i << "] = fd[" << i << "].a; row[" << Ny + i << "] = 0.0;\n";
+        o << "            row[" << Ns << "] = fT.a; row[" << Ns + 1 << "] = fP.a; row[" << Ny + Ns << "] = fT.b; row[" << Ny + Ns + 1 << "] = fP.b;\n";
         if (chunk >= 2) emit_write(Ns, 2);
-        else { emit_write(Ns, 1); for (int i = 0; i < Ny; ++i) o << "            row[" << i << "] = fd[" << i << "].b;\n"; emit_write(Ns + 1, 1); }
+        else {
+            emit_write(Ns, 1);
+            for (int i = 0; i < Ns; ++i) o << "            row[" << i << "] = 0.0;\n";
+            o << "            row[" << Ns << "] = fT.b; row[" << Ns + 1 << "] = fP.b;\n";
+            emit_write(Ns + 1, 1);
+        }
         o << "        }\n";
     } else {
-        o << "            for (int i = 0; i < " << Ny << "; ++i) f[i] = fd[i].a;      // the T column waits for the V column next to it\n        }\n";
+        o << "        double tcol[" << Ny << "];      // the T column waits for the V column next to it\n"
+             "        {\n            D1 fd[" << Ns << "], fT, fP;\n            spec_rhs<D1, D1, false>(y, cond, p, fd, fT, fP, kp);\n"
+             "            for (int i = 0; i < " << Ns << "; ++i) tcol[i] = fd[i].a;\n            tcol[" << Ns << "] = fT.a; tcol[" << Ns + 1 << "] = fP.a;\n        }\n";
     }
-    if (isp) o << "        double tcol[" << Ny << "];\n        for (int i = 0; i < " << Ny << "; ++i) tcol[i] = f[i];\n";
-    o << "        spec_rhs<double, true>(y, cond, p, f, kp);\n";
+    o << "        spec_rhs<double, double, true>(y, cond, p, f, f[" << Ns << "], f[" << Ns + 1 << "], kp);\n";
     if (isp) {
         // per-reaction pieces of the V column (src/Reactor.jl:1368-1413)
         o << "        double dfv[" << Nr << "], drv[" << Nr << "];\n";
