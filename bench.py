@@ -317,6 +317,7 @@ def run_ours(args):
             tot += e0.elapsed_time(e1)
         return tot / k * 1e-3
 
+    generated = bool(lib.rmsb_mech_specialized(h, KIND))      # compiles the mechanism's own evaluation kernels now (csrc/rmsb_spec.cu)
     t_dydt = ev(lambda: L.check(lib.rmsb_dydt_batch_dev(h, KIND, ne, t_ye.data_ptr(), t_Ve.data_ptr(), None, 0, None, 0, t_f.data_ptr(), sp)))
     t_jac = ev(lambda: L.check(lib.rmsb_jac_batch_dev(h, KIND, ne, t_ye.data_ptr(), t_Ve.data_ptr(), None, 0, None, 0, t_J.data_ptr(), sp)))
     hbm_peak, peak_src = measured_peaks()
@@ -423,6 +424,8 @@ def run_ours(args):
                               "flops_per_solve": flops, "peak_source": "rmsb_fp64_peak_tflops (DFMA microbenchmark, this run)"},
             "roofline_issue": _issue_roofline(mean["n_steps"], n, t_kernel, clocks, local),
             "evals": {"n": ne,
+                      "kernels": ("rmsb_spec_dydt / rmsb_spec_jac: generated for the mechanism, compiled with NVRTC at first use" if generated
+                                  else "dydt_tpr_kernel / jac_tpr_kernel (generic; NVRTC unavailable or RMSB_NO_SPEC=1)"),
                       "dydt": {"evals_per_s": ne / t_dydt, "GBps": b_dydt * ne / t_dydt / 1e9, "frac_hbm": b_dydt * ne / t_dydt / 1e9 / hbm_peak,
                                "bytes_per_eval": b_dydt},
                       "jac": {"evals_per_s": ne / t_jac, "GBps": b_jac * ne / t_jac / 1e9, "frac_hbm": b_jac * ne / t_jac / 1e9 / hbm_peak,

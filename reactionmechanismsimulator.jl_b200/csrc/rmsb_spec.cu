@@ -35,7 +35,8 @@ using namespace rmsb;
 
 namespace {
 
-constexpr int SPEC_MAXNS = 32, SPEC_MAXNR = 128, SPEC_THREADS = 128;
+constexpr int SPEC_THREADS = 128;
+int spec_max(const char* name, int dflt) { const char* v = std::getenv(name); int b = v ? std::atoi(v) : dflt; return b > 0 ? b : dflt; }
 
 struct SpecKernels {
     int state = 0;                 // 0 not tried, 1 ready, -1 failed
@@ -544,7 +545,7 @@ int rmsb_spec_capture(rmsb_mech* h, const std::vector<int>& rx, const std::vecto
                       const std::vector<int>& jerow, const std::vector<int>& jecol, const std::vector<int>& jtidx) {
     const DevMech& dm = h->dm;
     h->spec.reset();
-    if (dm.Ns > SPEC_MAXNS || dm.Nr > SPEC_MAXNR || dm.Nr < 1 || dm.coupled || dm.difflim || dm.phase_kind != RMSB_PHASE_GAS || dm.n_effrxn > 0) return RMSB_OK;
+    if (dm.Ns > spec_max("RMSB_SPEC_MAXNS", 32) || dm.Nr > spec_max("RMSB_SPEC_MAXNR", 128) || dm.Nr < 1 || dm.coupled || dm.difflim || dm.phase_kind != RMSB_PHASE_GAS || dm.n_effrxn > 0) return RMSB_OK;
     for (int j = 0; j < dm.Nr; ++j) if (ktype[j] != RMSB_KIN_ARRHENIUS_VEC) return RMSB_OK;
     auto s = std::make_shared<rmsb_spec_state>();
     s->Ns = dm.Ns; s->Nr = dm.Nr; s->maxr = maxr; s->n_dt = (int)dtrxn.size(); s->n_je = (int)jerow.size();

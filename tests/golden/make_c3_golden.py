@@ -1,10 +1,11 @@
 """Golden trajectory for config C3 at its stated size (tests/test_gpu_large.py): the octane-family mechanism of
 tests/synth.py::write_octane_families (36 families, seed 20261019: 1015 species / 11 593 reactions), ConstantTV, T = 450 K, V = 1,
-oxygen held constant (the reference's C3 charge, src/TestReactors.jl:18-22), integrated by SciPy BDF at rtol 1e-10 / atol 1e-20.
-The right-hand side and the analytic Jacobian SciPy integrates are the oracle's: the C++ restatement (oracle/cpu/rms_cpu.cpp, strict
-build) for speed -- 3e4 evaluations -- after it has been checked here against the NumPy oracle (oracle/rms_oracle.py) on the initial and
-on perturbed states; the Jacobian is handed over as a sparse matrix.  Also stored: the NumPy oracle's dydt / kf / krev at three states.
-Writes tests/golden/c3_octane_families.npz.  Run from the repo root:  python tests/golden/make_c3_golden.py   (a few minutes)"""
+oxygen held constant (the reference's C3 charge, src/TestReactors.jl:18-22), integrated by SciPy BDF over the NumPy oracle
+(oracle/rms_oracle.py: dydtreactor + analytic jacobiany as a sparse matrix) at rtol 1e-9 / atol 1e-18.
+Writes tests/golden/c3_octane_families.npz (times, states, and the oracle's dydt / kf / krev at three perturbed states).
+Run from the repo root:  python tests/golden/make_c3_golden.py   (11 CPU-minutes; rtol 1e-10 / 1e-11, also with the C++ restatement
+supplying the callbacks, were stopped after 4 and 1 CPU-hours: the golden therefore carries SciPy's global error at rtol 1e-9, about
+1.2e-6 on the species above 1e-9 of the largest -- see the bars in tests/test_gpu_large.py)"""
 import sys
 import time
 from pathlib import Path
@@ -17,7 +18,6 @@ ROOT = Path(__file__).resolve().parents[2]
 for p in (ROOT, ROOT / "tests"):
     sys.path.insert(0, str(p))
 import synth  # noqa: E402
-from oracle import cpu_oracle as co  # noqa: E402
 from oracle import rms_oracle as ro  # noqa: E402
 
 K = 36
@@ -27,24 +27,16 @@ d = ro.readinput(path)
 ph = ro.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0])
 ic = {"T": 450.0, "V": 1.0, **synth.octane_family_moles(K)}
 dom = ro.ConstantTVDomain(ph, ic, constantspecies=("oxygen",))
-Ns = ph.Ns
-rng = np.random.default_rng(1)
-ys = np.stack([dom.y0, np.abs(dom.y0 + 10.0 ** rng.uniform(-3, 1, Ns)), np.abs(dom.y0 * rng.uniform(0.5, 1.5, Ns) + 1e-6)])
-f = np.stack([ro.dydtreactor(dom, y, 0.0, dom.p) for y in ys])
-cm = co.CpuMech(ph)
-cond, cs = dom.cond[None], dom.constantspeciesinds
-fc = cm.dydt("ConstantTV", ys, np.repeat(cond, 3, axis=0), dom.p, constspc=cs)
-scale = np.abs(f) + 1e-6 * np.abs(f).max(axis=1, keepdims=True)
-assert np.max(np.abs(fc - f) / scale) < 1e-12, "C++ restatement disagrees with the NumPy oracle"
-Jn = ro.jacobiany(dom, ys[2], 0.0, dom.p)
-Jc = cm.jac("ConstantTV", ys[2][None], cond, dom.p, constspc=cs)[0]
-assert np.max(np.abs(Jc - Jn) / (np.abs(Jn) + 1e-3 * np.abs(Jn).max(axis=0, keepdims=True) + 1e-300)) < 1e-12
 tq = np.array([1.0e3, 1.0e4, 5.0e4, 1.4e5])
 t0 = time.time()
-sol = solve_ivp(lambda t, y: cm.dydt("ConstantTV", y[None], cond, dom.p, constspc=cs)[0], (0.0, tq[-1]), dom.y0, method="BDF", rtol=1e-10, atol=1e-20,
-                jac=lambda t, y: csc_matrix(cm.jac("ConstantTV", y[None], cond, dom.p, constspc=cs)[0]), t_eval=tq)
+sol = solve_ivp(lambda t, y: ro.dydtreactor(dom, y, t, dom.p), (0.0, tq[-1]), dom.y0, method="BDF", rtol=1e-9, atol=1e-18,
+                jac=lambda t, y: csc_matrix(ro.jacobiany(dom, y, t, dom.p)), t_eval=tq)
 assert sol.status == 0
 print("SciPy BDF", time.time() - t0, "s", sol.nfev, sol.njev, sol.nlu)
+rng = np.random.default_rng(1)
+Ns = ph.Ns
+ys = np.stack([dom.y0, np.abs(dom.y0 + 10.0 ** rng.uniform(-3, 1, Ns)), np.abs(dom.y0 * rng.uniform(0.5, 1.5, Ns) + 1e-6)])
+f = np.stack([ro.dydtreactor(dom, y, 0.0, dom.p) for y in ys])
 np.savez_compressed(ROOT / "tests" / "golden" / "c3_octane_families.npz", tq=tq, yq=sol.y.T, ys=ys, f=f, kfs=dom.kfs, krevs=dom.krevs,
                     ns=Ns, nr=ph.Nr, names=np.array(ph.names))
 print("x(octane, family 0) at t_end:", sol.y[ph.names.index("F00_octane"), -1] / sol.y[:, -1].sum())

@@ -203,11 +203,22 @@ def test_c3_stated_size_dydt_jacobian_rates_parity(octane_families):
 def test_c3_stated_size_trajectory_vs_scipy_golden(octane_families):
     ph, oph, gdom, odom, y0, p, gold = octane_families
     tq, yq = gold["tq"], gold["yq"]
+    # The golden is SciPy's BDF at rtol 1e-9 over the NumPy oracle (11 CPU-minutes; tighter settings do not finish in hours), so it
+    # carries its own global error.  Measured (scripts/gpu_c3_golden_check.py): the GPU trajectory converges on itself -- rtol 1e-9 /
+    # 1e-10 / 1e-11 sit 4.9e-7 / 9e-8 / 6e-9 from the rtol 1e-12 run -- while its distance to the golden saturates at 1.15e-6 from
+    # rtol 1e-10 on: that distance is the golden's error.  Bars: 1e-6 between the GPU at rtol 1e-9 and at rtol 1e-11, 2e-6 to SciPy.
+    def dist(a, b):
+        out = 0.0
+        for k in range(len(tq)):
+            big = np.abs(b[k]) > 1e-9 * np.abs(b[k]).max()
+            out = max(out, float(np.max(np.abs(a[k] - b[k])[big] / np.abs(b[k])[big])))
+        return out
+
     sol = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-18, reltol=1e-9, saveat=tq)
-    assert sol.retcode == ["Success"]
-    for k in range(len(tq)):
-        big = np.abs(yq[k]) > 1e-9 * np.abs(yq[k]).max()
-        assert np.max(np.abs(sol.u[0, k] - yq[k])[big] / np.abs(yq[k])[big]) < 1e-6, tq[k]
+    sol11 = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-18, reltol=1e-11, saveat=tq)
+    assert sol.retcode == ["Success"] and sol11.retcode == ["Success"]
+    assert dist(sol.u[0], sol11.u[0]) < 1e-6
+    assert dist(sol11.u[0], yq) < 2e-6
     i_oct = ph.names.index("F00_octane")
     assert sol.u[0, -1, i_oct] < 0.5 * y0[i_oct]                               # the fuel is mostly converted by t_end: not a trivial trajectory
     # the reference's loose setting lands on the same solution
