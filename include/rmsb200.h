@@ -320,8 +320,11 @@ int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
  * ParametrizedTPDomain (src/Domain.jl:241-320,1437-1512,2002-2004,2635-2725): domain_kind RMSB_DOMAIN_CONSTANT_TP with `profile` =
  * the T table followed by the P table; y = [ns; V]; rate coefficients are evaluated on every call (vector thermo path) and
  * p = [dG_i ; f_j] as for ConstantV (not the [G ; k] of ConstantTP).
- * t: evaluation time of every state for dydt / jac (NULL = 0); solve integrates from t = 0.
- * ParametrizedTConstantVDomain: not built. */
+ * ParametrizedTConstantVDomain (src/Domain.jl:563-633,1372-1434; Jacobian of the constant-T family :3049-3055): domain_kind
+ * RMSB_DOMAIN_CONSTANT_TV with `profile` = the T table; y = ns; Gibbs energies through the vector thermo path, viscosity,
+ * diffusivities and the diffusion-limited kf / krev are evaluated at T(t) on every call; p = [dG_i ; f_j] (not the [G ; kf] of
+ * ConstantTV); cond = [T (ignored), V].
+ * t: evaluation time of every state for dydt / jac (NULL = 0); solve integrates from t = 0. */
 typedef struct rmsb_extras {
     int32_t struct_size;          /* = sizeof(rmsb_extras) */
     const double* interfaces;     /* boundary interfaces, see rmsb_dydt_batch_if; NULL = none */

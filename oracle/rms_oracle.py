@@ -1139,6 +1139,50 @@ class ParametrizedTPDomain(_Domain):
             dydt[i] = 0.0
 
 
+class ParametrizedTConstantVDomain(_Domain):
+    """src/Domain.jl:563-633 (ctor), :1372-1434 (calcthermo), jacobiany! of the constant-T family (:3049-3055): a liquid whose
+    temperature follows a time profile at constant volume.  y = ns; thermo through the vector path, viscosity, diffusivities and
+    the diffusion-limited kf / krev (per-reaction path) on every call; p = [dG; f]."""
+    kind = "ParametrizedTConstantV"
+
+    def __init__(self, phase: Phase, initialconds: dict, constantspecies=()):
+        assert phase.kind == "liquid"
+        ic = dict(initialconds)
+        assert "V" in ic and "P" not in ic, "ParametrizedTConstantVDomain needs V and cannot specify P"
+        self.Tf = Spline(ic.pop("ts"), ic.pop("T"))
+        vals, ns = _initial(phase, ic, ("V", "Phi"))
+        self.phase, self.V, self.phi = phase, vals["V"], vals["Phi"]
+        self.y0 = ns.copy()
+        self.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+        self.constantspeciesinds = self._constspc(constantspecies)
+        self.Ny = phase.Ns
+        self.cond = np.array([self.Tf(0.0), self.V])
+
+    def calcthermo(self, y, t=0.0, p=None) -> Thermo:
+        ph, Ns = self.phase, self.phase.Ns
+        T = self.Tf(t)
+        ns = y[:Ns]
+        N = np.sum(ns)
+        cs = ns / self.V
+        C = N / self.V
+        P = 1.0e8
+        mu = ph.solvent.viscosity(T)
+        cp, h, s = ph.calcHSCpdless(T)
+        if p is not None:
+            h = h + p[:Ns] / (R * T)
+        Gs = (h - s) * (R * T)
+        diffs = ph.diffusivities(T, mu) if ph.diffusionlimited else _EMPTY
+        kfs, krevs = ph.getkfkrevs(T, P, C, N, ns, Gs, diffs, self.V)
+        if p is not None:
+            kfs = kfs * p[Ns:Ns + ph.Nr]
+            krevs = krevs * p[Ns:Ns + ph.Nr]
+        return Thermo(ns, cs, T, P, self.V, C, N, mu, kfs, krevs, _EMPTY, _EMPTY, Gs, diffs, 0.0, _EMPTY, self.phi, t)
+
+    def derivatives(self, dydt, th: Thermo):
+        for i in self.constantspeciesinds:
+            dydt[i] = 0.0
+
+
 class _ConstantKDomain(_Domain):
     def _setup_k(self, T, P, C, N, ns, V):
         ph = self.phase

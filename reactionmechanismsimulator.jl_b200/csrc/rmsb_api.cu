@@ -985,8 +985,6 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
         if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
         if (MODE != 0 && MODE != 1) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles: dydt, Jacobian and solve only");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
-        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P && a.domain_kind != RMSB_DOMAIN_CONSTANT_TP)
-            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV), ConstantP (ParametrizedP) and ConstantTP (ParametrizedTP) domains only");
     }
     if (a.Ny > 128) {
         if (MODE <= 2 || MODE == 4) return launch_eval_large<((MODE <= 2 || MODE == 4) ? MODE : 0)>(h, a, st);
@@ -1088,8 +1086,6 @@ static int launch_solve(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cu
     if (a.flow || a.ptab) {      // boundary interfaces / time profiles: the warp-per-reactor integrator (rhs_v / rhs_ck / jac_warp carry the terms)
         if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
-        if (a.ptab && a.domain_kind != RMSB_DOMAIN_CONSTANT_V && a.domain_kind != RMSB_DOMAIN_CONSTANT_P && a.domain_kind != RMSB_DOMAIN_CONSTANT_TP)
-            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (ParametrizedV), ConstantP (ParametrizedP) and ConstantTP (ParametrizedTP) domains only");
     } else if (rmsb_small_eligible(h, a.domain_kind, a.Ny, a.flags)) return rmsb_small_launch_solve(h, a, st);   // lane group per reactor (rmsb_small.cu)
     switch (rows_per_lane(a.Ny)) {
     case 1: return launch_solve_R<1>(h, a, want_wpb, st);
@@ -1143,6 +1139,8 @@ static int check_extras(const rmsb_mech* h, int kind, const rmsb_extras* x, Extr
     e->prof = x->profile; e->prof_stride = x->profile ? x->profile_stride : 0; e->t = x->t;
     if (e->ifs && e->if_stride != 0 && e->if_stride != 7 + 2 * (int64_t)h->dm.Ns) return fail(RMSB_ERR_ARG, "if_stride must be 0 or 7 + 2*Ns");
     if (e->prof) {
+        if (kind != RMSB_DOMAIN_CONSTANT_V && kind != RMSB_DOMAIN_CONSTANT_P && kind != RMSB_DOMAIN_CONSTANT_TP && kind != RMSB_DOMAIN_CONSTANT_TV)
+            return fail(RMSB_ERR_UNSUPPORTED, "time profiles: ConstantV (V(t)), ConstantP (P(t)), ConstantTP (T(t), P(t)) and ConstantTV (T(t)) layouts only");
         const int64_t nt = (int64_t)e->prof[0];
         if (nt < 2 || (double)nt != e->prof[0]) return fail(RMSB_ERR_ARG, "profile: the first entry is the number of knots (>= 2)");
         e->prof_len = 1 + 3 * nt;

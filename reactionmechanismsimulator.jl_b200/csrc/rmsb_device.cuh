@@ -643,11 +643,25 @@ static __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
     const double* ns = w.ybuf();
     double* G = w.g();
     double* diffs = w.un();
-    const double T = d.cond[0];
+    // ParametrizedTConstantV (ConstantTV with a time profile, src/Domain.jl:1372-1434): T = T(t), Gibbs energies through the vector
+    // thermo path with p = [dG; f] (enthalpy shifts and rate factors) instead of the constant-k convention p = [Gs; kfs]
+    const bool param = d.ptab != nullptr;
+    double dTdt_unused;
+    const double T = param ? profile_eval(d.ptab, d.t, &dTdt_unused) : d.cond[0];
     double P, V;
     if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = ns[Ns]; }
     else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
-    for (int s = lane; s < Ns; s += 32) G[s] = p ? p[s] : gibbs_scalar(s, T);
+    if (param) {
+        const TPow<double> tp(T);
+        for (int s = lane; s < Ns; s += 32) {
+            double cp, h, sr;
+            nasa_hscp(s, tp, T, cp, h, sr);
+            if (p) h = h + p[s] / (RMSB_R * T);
+            G[s] = (h - sr) * (RMSB_R * T);
+        }
+    } else {
+        for (int s = lane; s < Ns; s += 32) G[s] = p ? p[s] : gibbs_scalar(s, T);
+    }
     if (m.difflim) {   // Stokes diffusivities, src/Calculators/Diffusion.jl:19, Viscosity.jl:24
         double mu = 0.0;
         if (m.visc_kind == RMSB_VISC_RIEDEL)
@@ -670,7 +684,8 @@ static __device__ __noinline__ void setup_constk(DomainArgs d, Ws w, int lane) {
     bool is_eff_dom = (d.kind == RMSB_DOMAIN_CONSTANT_TP);
     for (int j = lane; j < Nr; j += 32) {
         double kf, kr;
-        constk_rates(j, p, is_eff_dom, G, diffs, e, C0, logC0, C, ns, V, T, kf, kr);
+        constk_rates(j, param ? nullptr : p, is_eff_dom, G, diffs, e, C0, logC0, C, ns, V, T, kf, kr);
+        if (param && p) { kf *= p[Ns + j]; kr *= p[Ns + j]; }
         w.kf()[j] = kf * G(m.fwd, j);          // forwardability / reversibility masks (:220-221, :254-255)
         w.kr()[j] = kr * G(m.rev, j);
     }
@@ -835,7 +850,8 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     double* cs = w.cs();
     double* fb = w.fbuf();
     double* qb = w.q();
-    const double T = d.cond[0];
+    double dTdt_unused;
+    const double T = (d.kind == RMSB_DOMAIN_CONSTANT_TV && d.ptab) ? profile_eval(d.ptab, d.t, &dTdt_unused) : d.cond[0];
     double P, V;
     if (d.kind == RMSB_DOMAIN_CONSTANT_TP) { P = d.cond[1]; V = yb[Ns]; }
     else { P = (d.kind == RMSB_DOMAIN_CONSTANT_TV) ? 1.0e8 : 0.0; V = d.cond[1]; }
@@ -1198,6 +1214,7 @@ __device__ __forceinline__ void rhs_warp(const DomainArgs& d, const Ws& w, int l
     if (d.kind == RMSB_DOMAIN_CONSTANT_V) rhs_v<double>(d, w, lane, store_k);
     else if (d.kind == RMSB_DOMAIN_CONSTANT_P) rhs_v<double, true>(d, w, lane, store_k);
     else if (d.kind == RMSB_DOMAIN_CONSTANT_TP && d.ptab) rhs_tp_param(d, w, lane, store_k);
+    else if (d.kind == RMSB_DOMAIN_CONSTANT_TV && d.ptab) { setup_constk(d, w, lane); rhs_ck(d, w, lane); }   // ParametrizedTConstantV: k's at T(t)
     else if (d.kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) rhs_coupled(d, w, lane);
     else rhs_ck(d, w, lane);
 }

@@ -11,7 +11,8 @@ from ._lib import (DOMAIN_CONSTANT_P, DOMAIN_CONSTANT_TAPHI, DOMAIN_CONSTANT_TP,
 from .coupled import CoupledEnsemble, CoupledPhase, SystemSimulation, coupled_domain
 from .coupled import make_interface as ReactiveInternalInterfaceConstantTPhi
 from .domain import (ConstantPDomain, ConstantPEnsemble, ConstantTAPhiDomain, ConstantTPDomain, ConstantTPEnsemble, ConstantTVDomain, ConstantTVEnsemble,
-                     ConstantVDomain, ConstantVEnsemble, Domain, ParametrizedPDomain, ParametrizedTPDomain, ParametrizedVDomain)
+                     ConstantVDomain, ConstantVEnsemble, Domain, ParametrizedPDomain, ParametrizedTConstantVDomain, ParametrizedTPDomain,
+                     ParametrizedVDomain)
 from .interfaces import Inlet, Outlet, VolumeMaintainingOutlet, VolumetricFlowRateInlet, VolumetricFlowRateOutlet, pack_interfaces
 from .ensemble import balanced_shards, shard_bounds, shard_domain, solve_sharded
 from .mechanism import (ElementaryReaction, NASA, NASApolynomial, R, Solvent, Species, getmechdict, getspeciesradius, readinput, writeyml)

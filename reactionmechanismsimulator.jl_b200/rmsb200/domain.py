@@ -326,6 +326,27 @@ def ParametrizedTPDomain(*, phase: Phase, initialconds: Dict[str, float], consta
     return dom, y0.copy(), dom.p.copy()
 
 
+def ParametrizedTConstantVDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
+    """ParametrizedTConstantVDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:563-633: a liquid whose
+    temperature follows a profile ("ts", "T" arrays) at constant volume.  y = ns, p = [zeros(Ns); ones(Nr)].  On the device: the
+    ConstantTV layout with a T table; thermo, viscosity, diffusivities and the diffusion-limited rate coefficients are evaluated on
+    every call (src/Domain.jl:1372-1434)."""
+    from .profile import profile_value, spline_table
+    assert phase.kind == L.PHASE_LIQUID, "ParametrizedTConstantVDomain needs an IdealDiluteSolution phase"
+    ic = dict(initialconds)
+    assert "V" in ic and "P" not in ic, "ParametrizedTConstantVDomain needs V and cannot specify P"
+    tab = spline_table(ic.pop("ts"), ic.pop("T"))
+    vals, ns = _parse(phase, ic, ("V", "Phi"))
+    y0 = ns.copy()
+    dom = Domain(L.DOMAIN_CONSTANT_TV, phase, y0, np.array([profile_value(tab, 0.0), vals["V"]]), constantspecies)
+    dom.profile = tab
+    dom.indexes = [1, phase.Ns]
+    dom.thermovariabledict = {}
+    dom.p = np.concatenate([np.zeros(phase.Ns), np.ones(phase.Nr)])
+    dom._p_default = dom.p.copy()
+    return dom, y0.copy(), dom.p.copy()
+
+
 def ParametrizedPDomain(*, phase: Phase, initialconds: Dict[str, float], constantspecies: Sequence[str] = (), **_):
     """ParametrizedPDomain(; phase, initialconds, constantspecies) -> (domain, y0, p)  src/Domain.jl:413-498: adiabatic reactor whose
     pressure follows a profile ("ts", "P" arrays).  y = [ns; T; V]; the ConstantP domain with a time profile on the device."""

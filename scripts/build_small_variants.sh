@@ -9,6 +9,6 @@ C=reactionmechanismsimulator.jl_b200/csrc
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $flags -c -o build/variants/small_$name.o $C/rmsb_small.cu &&
-    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/lib_$name.so build/rmsb_api.o build/variants/small_$name.o && echo built $name ) &
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/lib_$name.so build/rmsb_api.o build/rmsb_spec.o build/variants/small_$name.o && echo built $name ) &
 done
 wait

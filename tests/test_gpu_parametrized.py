@@ -143,3 +143,85 @@ def test_parametrized_tp_parity_and_trajectory():
         yr = ref.y[:, k]
         big = np.abs(yr) > 1e-6 * np.abs(yr[:ig.Ns]).max()
         assert np.max(np.abs(sol.u[0, k] - yr)[big] / np.abs(yr)[big]) < 1e-6
+
+
+PTV_GOLDEN_BAR = 1e-6       # measured: GPU rtol 1e-9 vs 1e-11 1.4e-8, GPU rtol 1e-11 vs the SciPy golden 2.3e-8
+IC_TV = {"ts": [0.0, 600.0, 1200.0], "T": [450.0, 490.0, 500.0], "V": 1.0, "octane": 6154.0, "oxygen": 4.953}      # src/TestReactors.jl:150
+
+
+def test_parametrized_t_constant_v_parity_and_trajectory():
+    """ParametrizedTConstantVDomain on the reference's test inputs (src/TestReactors.jl:148-167): the liquid octane
+    mechanism with a temperature ramp at constant volume -- thermo, viscosity, diffusivities and diffusion-limited rate coefficients
+    on every call.  dydt / jacobiany against the oracle inside and beyond the profile's knots, the reference's analytic-vs-AD
+    criterion, non-default parameters p = [dG; f], the ramp trajectory against SciPy BDF, per-reactor ramps."""
+    assert L.lib().rmsb_device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    d = rb.readinput(cases.fixture("liquid_phase"))
+    liq = rb.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0], name="phase")
+    od = ro.readinput(cases.fixture("liquid_phase"))
+    oliq = ro.IdealDiluteSolution(od["phase"]["Species"], od["phase"]["Reactions"], od["Solvents"][0])
+    gdom, y0, p = rb.ParametrizedTConstantVDomain(phase=liq, initialconds=IC_TV, constantspecies=["oxygen"])
+    odom = ro.ParametrizedTConstantVDomain(oliq, IC_TV, constantspecies=("oxygen",))
+    np.testing.assert_array_equal(y0, odom.y0)
+    Ns, Nr = liq.Ns, liq.Nr
+    ys = cases.states("liquid_TV", odom.y0, Ns, "ConstantTV")[:3]
+    ts = np.array([0.0, 700.0, 32977.61568])                    # a knot, inside the ramp, the reference's test time (past the last knot)
+    rng = np.random.default_rng(5)
+    par = np.concatenate([rng.uniform(-2000.0, 2000.0, Ns), rng.uniform(0.5, 2.0, Nr)])
+    ens = rb.Domain(gdom.kind, liq, ys, np.repeat(gdom.cond, len(ys), axis=0), constantspecies=["oxygen"])
+    ens.profile = gdom.profile
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    for pp in (p, par):
+        f, J = ens.dydt(ys, pp, t=ts), ens.jacobiany(ys, pp, t=ts)
+        for k, y in enumerate(ys):
+            fo, M = fl.dydt_terms(odom, y, ts[k], pp)
+            rep = fl.report(f[k], fo, fl.EPS * (M + np.abs(fo)), 1e-12, slack=4.0)
+            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, (k, rep)
+            Jo, Jf = fl.jac_floor(lambda yy, qq: ro.jacobiany(odom, yy, ts[k], qq), odom, y, pp, t=ts[k])
+            rep = fl.report(J[k], Jo, Jf, 1e-12)
+            assert rep["max_rel_above"] <= 1e-12 and rep["worst_excess"] <= 1.0, (k, rep["worst_at"], rep["worst_excess"], rep["max_rel_above"])
+            Jc = ro.jacobiany_complexstep(odom, y, ts[k], pp)
+            assert not np.any(np.abs(J[k] - Jc) > 1e-4 * np.abs(Jc) + 1e-16 * np.abs(Jc).max())
+    # the ramp matters: 450 K at t = 0, 490 K at t = 600
+    plain = rb.Domain(gdom.kind, liq, ys, np.repeat(gdom.cond, len(ys), axis=0), constantspecies=["oxygen"])
+    plain.profile = gdom.profile
+    plain.p, plain._p_default = gdom.p, gdom._p_default
+    assert not np.allclose(plain.dydt(ys, p, t=np.zeros(3))[1], ens.dydt(ys, p, t=ts)[1], rtol=1e-2)
+    # trajectory through the ramp and one hour beyond it, against the committed SciPy-BDF golden (tests/golden/make_ptv_golden.py:
+    # 37 000 evaluations of the NumPy oracle, too slow to repeat here).  As for C3 (tests/test_gpu_large.py) the GPU run is also held
+    # to its own tighter run, which separates its error from the golden's.
+    gold = np.load(cases.ROOT / "tests" / "golden" / "ptv_liquid.npz")
+    tq, yq = gold["tq"], gold["yq"]
+
+    def dist(a, b):
+        out = 0.0
+        for k in range(len(tq)):
+            big = np.abs(b[k]) > 1e-9 * np.abs(b[k]).max()
+            out = max(out, float(np.max(np.abs(a[k] - b[k])[big] / np.abs(b[k])[big])))
+        return out
+
+    sol = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-20, reltol=1e-9, saveat=tq)
+    sol11 = rb.solve(rb.Reactor(gdom, y0, (0.0, float(tq[-1])), p=p).ode, abstol=1e-20, reltol=1e-11, saveat=tq)
+    assert sol.retcode == ["Success"] and sol11.retcode == ["Success"]
+    print("PTV trajectory: GPU rtol 1e-9 vs 1e-11 %.3e, GPU rtol 1e-11 vs SciPy golden %.3e" % (dist(sol.u[0], sol11.u[0]), dist(sol11.u[0], yq)))
+    assert dist(sol.u[0], sol11.u[0]) < 1e-6
+    assert dist(sol11.u[0], yq) < PTV_GOLDEN_BAR
+    # against the same charge held at 450 K, the ramp converts more fuel
+    cdom, cy0, cp = rb.ConstantTVDomain(phase=liq, initialconds={"T": 450.0, "V": 1.0, "octane": 6154.0, "oxygen": 4.953}, constantspecies=["oxygen"])
+    cold = rb.solve(rb.Reactor(cdom, cy0, (0.0, 4800.0), p=cp).ode, abstol=1e-18, reltol=1e-9)
+    io = liq.names.index("octane")
+    assert y0[io] - sol.u[0, -1, io] > 2.0 * (y0[io] - cold.yend[0, io])
+    # an ensemble of ramps through per-reactor profile rows: reactor k of the batch == the same ramp alone
+    n = 16
+    tabs = np.stack([rb.spline_table(IC_TV["ts"], [450.0, 450.0 + dT, 450.0 + 1.25 * dT]) for dT in np.linspace(0.0, 60.0, n)])
+    ens = rb.Domain(gdom.kind, liq, np.repeat(gdom.y0, n, axis=0), np.repeat(gdom.cond, n, axis=0), constantspecies=["oxygen"])
+    ens.profile = tabs
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    s = rb.solve(rb.Reactor(ens, None, (0.0, 2400.0), p=p).ode, abstol=1e-16, reltol=1e-6)
+    assert np.all(s.status == 0)
+    conv = y0[io] - s.yend[:, io]
+    assert np.all(np.diff(conv) > 0.0)                          # hotter ramps convert more
+    one = rb.Domain(gdom.kind, liq, gdom.y0, gdom.cond, constantspecies=["oxygen"])
+    one.profile = tabs[5]
+    one.p, one._p_default = gdom.p, gdom._p_default
+    s1 = rb.solve(rb.Reactor(one, None, (0.0, 2400.0), p=p).ode, abstol=1e-16, reltol=1e-6)
+    assert np.array_equal(s1.yend[0], s.yend[5])

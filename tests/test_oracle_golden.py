@@ -274,3 +274,25 @@ def test_parametrized_domains_analytic_jacobian_equals_ad(which):
     ja = ro.jacobiany(dom, y, 0.1, dom.p)
     j = ro.jacobiany_complexstep(dom, y, 0.1, dom.p)
     assert not np.any(np.abs(ja - j) > 1e-4 * np.abs(j) + 1e-16 * np.abs(j).max())
+
+
+def test_parametrized_t_constant_v_analytic_jacobian_equals_ad():
+    """src/TestReactors.jl:148-167: ParametrizedTConstantVDomain on the liquid octane mechanism with "ts" / "T" arrays, analytic
+    Jacobian vs the derivative of the full RHS at the reference's test time t = 32977.61568 (past the last knot: the profile
+    continues linearly) and inside the ramp; the rate coefficients really follow T(t)."""
+    d = ro.readinput(cases.fixture("liquid_phase"))
+    liq = ro.IdealDiluteSolution(d["phase"]["Species"], d["phase"]["Reactions"], d["Solvents"][0])
+    ic = {"ts": [0.0, 600.0, 1200.0], "T": [450.0, 490.0, 500.0], "V": 1.0, "octane": 6154.0, "oxygen": 4.953}
+    dom = ro.ParametrizedTConstantVDomain(liq, ic)
+    assert dom.Tf(0.0) == 450.0 and dom.Tf(600.0) == pytest.approx(490.0, rel=1e-14) and dom.Tf(32977.61568) > 500.0
+    np.testing.assert_array_equal(dom.p, np.concatenate([np.zeros(liq.Ns), np.ones(liq.Nr)]))
+    y = cases.states("liquid_TV", dom.y0, liq.Ns, "ConstantTV")[0]
+    for t in (300.0, 32977.61568):
+        ja = ro.jacobiany(dom, y, t, dom.p)
+        j = ro.jacobiany_complexstep(dom, y, t, dom.p)
+        assert not np.any(np.abs(ja - j) > 1e-4 * np.abs(j) + 1e-16)
+    # at the first knot the domain is the ConstantTV domain at 450 K (same Gibbs energies to rounding of the two thermo paths)
+    ctv = ro.ConstantTVDomain(liq, {"T": 450.0, "V": 1.0, "octane": 6154.0, "oxygen": 4.953})
+    np.testing.assert_allclose(ro.dydtreactor(dom, y, 0.0, dom.p), ro.dydtreactor(ctv, y, 0.0, ctv.p), rtol=1e-9, atol=1e-9 * np.abs(ro.dydtreactor(ctv, y, 0.0, ctv.p)).max())
+    k450, k490 = dom.calcthermo(y, 0.0).kfs, dom.calcthermo(y, 600.0).kfs
+    assert np.max(k490 / k450) > 2.0
