@@ -3,7 +3,7 @@
 set -u
 TAG=${1:-x}
 OUT=gpurun_out; mkdir -p $OUT
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-others"
 timeout 600 $CMD > $OUT/plain_$TAG.log 2>&1 && \
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 3 -c 1 -f -o $OUT/prof_solve_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log; tail -c 600 $OUT/plain_$TAG.log
