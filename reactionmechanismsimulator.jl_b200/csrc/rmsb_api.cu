@@ -411,11 +411,12 @@ __device__ __forceinline__ void stage_mech(const DevMech& mp) {
     __syncthreads();
 }
 
-__device__ __forceinline__ Ws make_ws(int warp, int ws_per_warp, int Ny, int mode = 0) {
+__device__ __forceinline__ Ws make_ws(int warp, int ws_per_warp, int Ny, int mode, int kind) {
     const DevMech& m = mech();
     Ws w;
-    w.off = MECH_DOUBLES + warp * ws_per_warp; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = m.n_dt; w.LD = Ny | 1;
-    w.jpo = ws_jp_offset(m.Ns, m.Nr, Ny, m.n_dt, mode);
+    w.off = MECH_DOUBLES + warp * ws_per_warp; w.Ns = m.Ns; w.Nr = m.Nr; w.Ny = Ny; w.ndt = ws_ndt_reserved(m.n_dt, mode); w.LD = Ny | 1;
+    w.tri = ws_tri(kind);
+    w.jpo = ws_jp_offset(m.Ns, m.Nr, Ny, m.n_dt, mode, w.tri);
     return w;
 }
 
@@ -424,7 +425,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ BatchArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const Ws w = make_ws(warp, ws_per_warp, a.Ny, MODE == 3 ? 3 : 0);
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny, MODE == 3 ? 3 : 0, a.domain_kind);
     const int Ny = a.Ny, Nr = w.Nr;
     const int64_t nw = (int64_t)gridDim.x * wpb;
     for (int64_t ir = (int64_t)blockIdx.x * wpb + warp; ir < a.n; ir += nw) {
@@ -486,7 +487,7 @@ template <int R>
 __global__ void __launch_bounds__(128, (R == 1 ? RMSB_SOLVE_MINBLOCKS : 1)) solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Ws w = make_ws(warp, ws_per_warp, a.Ny);
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny, 1, a.domain_kind);
     for (;;) {
         unsigned long long ir = 0;
         if (lane == 0) ir = atomicAdd(a.counter, 1ULL);     // dynamic work queue: one reactor per warp at a time
@@ -504,7 +505,7 @@ template <int R>
 __global__ void __launch_bounds__(128, (R == 1 ? RMSB_SENS_MINBLOCKS : 1)) sens_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ SolveArgs a, int ws_per_warp) {
     stage_mech(mp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Ws w = make_ws(warp, ws_per_warp, a.Ny, 2);
+    const Ws w = make_ws(warp, ws_per_warp, a.Ny, 2, a.domain_kind);
     for (;;) {
         unsigned long long ir = 0;
         if (lane == 0) ir = atomicAdd(a.counter, 1ULL);
@@ -888,10 +889,10 @@ cudaError_t rmsb_cached_props(int device, cudaDeviceProp* out) {
 struct LaunchCfg { int wpb; int ws; size_t smem; int blocks_per_sm; int sms; };
 
 template <class K>
-static int config_launch(K kernel, const rmsb_mech* h, int Ny, int mode, int want_wpb, LaunchCfg* cfg) {
+static int config_launch(K kernel, const rmsb_mech* h, int kind, int Ny, int mode, int want_wpb, LaunchCfg* cfg) {
     cudaDeviceProp prop;
     CU(rmsb_cached_props(h->device, &prop));
-    int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, mode);
+    int ws = ws_doubles(h->dm.Ns, h->dm.Nr, Ny, h->n_dt, mode, ws_tri(kind));
     size_t per_warp = (size_t)ws * sizeof(double);
     const size_t mech_bytes = (size_t)MECH_DOUBLES * sizeof(double);
     size_t max_smem = prop.sharedMemPerBlockOptin - mech_bytes;
@@ -1021,7 +1022,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
     }
     if ((MODE == 0 || MODE == 1) && !extras && rmsb_small_eligible(h, a.domain_kind, a.Ny, 0)) return rmsb_small_launch_eval(h, MODE, a, st);
     LaunchCfg cfg;
-    int rc = config_launch(eval_kernel<MODE>, h, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
+    int rc = config_launch(eval_kernel<MODE>, h, a.domain_kind, a.Ny, MODE == 3 ? 3 : 0, 4, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
     int64_t max_blocks = (int64_t)cfg.sms * cfg.blocks_per_sm * 8;   // grid-stride beyond 8 waves
@@ -1036,7 +1037,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
 template <int R>
 static int launch_solve_R(const rmsb_mech* h, const SolveArgs& a, int want_wpb, cudaStream_t st) {
     LaunchCfg cfg;
-    int rc = config_launch(solve_kernel<R>, h, a.Ny, 1, want_wpb, &cfg);
+    int rc = config_launch(solve_kernel<R>, h, a.domain_kind, a.Ny, 1, want_wpb, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t resident = (int64_t)cfg.sms * cfg.blocks_per_sm;
     int64_t blocks_needed = (a.n + cfg.wpb - 1) / cfg.wpb;
@@ -1054,9 +1055,9 @@ static int sens_npp(const rmsb_mech* h) { return (h->dm.Ns + h->dm.Nr + 31) & ~3
 
 // resident warps of the sensitivity kernel and the scratch they need; launches when `a` is given
 template <int R>
-static int sens_R(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
+static int sens_R(const rmsb_mech* h, int kind, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
     LaunchCfg cfg;
-    int rc = config_launch(sens_kernel<R>, h, Ny, 2, want_wpb, &cfg);
+    int rc = config_launch(sens_kernel<R>, h, kind, Ny, 2, want_wpb, &cfg);
     if (rc != RMSB_OK) return rc;
     int64_t resident = (int64_t)cfg.sms * cfg.blocks_per_sm;
     int64_t blocks_needed = (n + cfg.wpb - 1) / cfg.wpb;
@@ -1072,12 +1073,12 @@ static int sens_R(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, size_t* w
     return RMSB_OK;
 }
 
-static int sens_dispatch(const rmsb_mech* h, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
+static int sens_dispatch(const rmsb_mech* h, int kind, int Ny, int64_t n, int want_wpb, size_t* work_bytes, SolveArgs* a, cudaStream_t st) {
     switch (rows_per_lane(Ny)) {
-    case 1: return sens_R<1>(h, Ny, n, want_wpb, work_bytes, a, st);
-    case 2: return sens_R<2>(h, Ny, n, want_wpb, work_bytes, a, st);
-    case 3: return sens_R<3>(h, Ny, n, want_wpb, work_bytes, a, st);
-    case 4: return sens_R<4>(h, Ny, n, want_wpb, work_bytes, a, st);
+    case 1: return sens_R<1>(h, kind, Ny, n, want_wpb, work_bytes, a, st);
+    case 2: return sens_R<2>(h, kind, Ny, n, want_wpb, work_bytes, a, st);
+    case 3: return sens_R<3>(h, kind, Ny, n, want_wpb, work_bytes, a, st);
+    case 4: return sens_R<4>(h, kind, Ny, n, want_wpb, work_bytes, a, st);
     }
     return fail(RMSB_ERR_UNSUPPORTED, "Ny > 128: needs the sparse CTA-per-reactor path (not built yet, see DESIGN.md)");
 }
@@ -1250,7 +1251,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
     if (!sens) return launch_solve(h, a, o.warps_per_block, (cudaStream_t)stream);
     a.idt_index = -1; a.idt = nullptr;
     a.sens_hist = reinterpret_cast<double*>(static_cast<char*>(work) + SENS_WORK_HEADER);
-    return sens_dispatch(h, a.Ny, n, o.warps_per_block, nullptr, &a, (cudaStream_t)stream);
+    return sens_dispatch(h, a.domain_kind, a.Ny, n, o.warps_per_block, nullptr, &a, (cudaStream_t)stream);
 }
 
 extern "C" int rmsb_solve_batch_dev(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond,
@@ -1270,7 +1271,7 @@ extern "C" int64_t rmsb_sens_work_bytes(const rmsb_mech* h, int kind, int64_t n)
     size_t bytes = 0;
     for (int wpb = 0; wpb <= 4; ++wpb) {
         size_t b = 0;
-        if (sens_dispatch(h, domain_ny(h, kind), n > 0 ? n : 1, wpb, &b, nullptr, nullptr) != RMSB_OK) return -1;
+        if (sens_dispatch(h, kind, domain_ny(h, kind), n > 0 ? n : 1, wpb, &b, nullptr, nullptr) != RMSB_OK) return -1;
         if (b > bytes) bytes = b;
     }
     return (int64_t)bytes;

@@ -163,19 +163,22 @@ struct Ws {
     int off;                                  // offset (in doubles) of this warp's slice inside smem_ws
     int Ns, Nr, Ny, ndt, LD;
     int jpo;                                  // offset of the parameter-Jacobian tile inside the slice (mode 2: after LU; mode 3: on J)
+    int tri;                                  // 3: g / un / q / fbuf hold dual numbers (ConstantV / ConstantP run the dual pass), else 1
     __device__ __forceinline__ double* at(int o) const { return smem_ws + off + o; }
     __device__ __forceinline__ double* cs() const { return at(0); }                                 // [Ns]   concentrations
-    __device__ __forceinline__ double* g() const { return at(Ns); }                                 // [3Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
-    __device__ __forceinline__ double* un() const { return at(4 * Ns); }                            // [3Ns]  internal energies U_i (Dual2-capable) | diffusivities (liquid setup)
-    __device__ __forceinline__ double* q() const { return at(7 * Ns); }                             // [3Nr]  net rates (Dual2-capable)
-    __device__ __forceinline__ double* kf() const { return at(7 * Ns + 3 * Nr); }                   // [Nr]
-    __device__ __forceinline__ double* kr() const { return at(7 * Ns + 4 * Nr); }                   // [Nr]
-    __device__ __forceinline__ double* us() const { return at(7 * Ns + 5 * Nr); }                   // [Ns]   U_i values (Jacobian)
-    __device__ __forceinline__ double* cp() const { return at(8 * Ns + 5 * Nr); }                   // [Ns]   cp_i/R values (Jacobian)
-    __device__ __forceinline__ double* dterm() const { return at(9 * Ns + 5 * Nr); }                // [ndt]
-    __device__ __forceinline__ double* ybuf() const { return dterm() + ndt; }                       // [Ny]   RHS / Jacobian input state
-    __device__ __forceinline__ double* fbuf() const { return ybuf() + Ny; }                         // [3Ny]  RHS output (Dual2-capable)
-    __device__ __forceinline__ double* aux() const { return fbuf() + 3 * Ny; }                      // [8]    T P V N C Cv dot(U,dn) 1/V
+    __device__ __forceinline__ double* g() const { return at(Ns); }                                 // [tri*Ns]  G/(RT) (Dual2-capable) | absolute G (constant-k)
+    __device__ __forceinline__ double* un() const { return at((1 + tri) * Ns); }                    // [tri*Ns]  internal energies U_i (Dual2-capable) | diffusivities (liquid setup)
+    __device__ __forceinline__ double* q() const { return at((1 + 2 * tri) * Ns); }                 // [tri*Nr]  net rates (Dual2-capable)
+    __device__ __forceinline__ double* kf() const { return at((1 + 2 * tri) * Ns + tri * Nr); }     // [Nr]
+    __device__ __forceinline__ double* kr() const { return kf() + Nr; }                             // [Nr]
+    __device__ __forceinline__ double* us() const { return kf() + 2 * Nr; }                         // [Ns]   U_i values (Jacobian)
+    __device__ __forceinline__ double* cp() const { return kf() + 2 * Nr + Ns; }                    // [Ns]   cp_i/R values (Jacobian)
+    // Jacobian derivative terms [n_dt]: scratch of jac_warp / jac_coupled only.  In the solver slices (ndt == 0 here) they live on the
+    // LU region, which every Jacobian evaluation invalidates anyway (the factorisation follows it); evaluation slices reserve ndt doubles.
+    __device__ __forceinline__ double* dterm() const { return ndt ? kf() + 2 * Nr + 2 * Ns : LU(); }
+    __device__ __forceinline__ double* ybuf() const { return kf() + 2 * Nr + 2 * Ns + ndt; }        // [Ny]   RHS / Jacobian input state
+    __device__ __forceinline__ double* fbuf() const { return ybuf() + Ny; }                         // [tri*Ny]  RHS output (Dual2-capable)
+    __device__ __forceinline__ double* aux() const { return fbuf() + tri * Ny; }                    // [8]    T P V N C Cv dot(U,dn) 1/V
     __device__ __forceinline__ double* ru() const { return aux() + 8; }                             // [36]   change_D matrix
     __device__ __forceinline__ double* dinv() const { return ru() + 36; }                           // [Ny]   spare
     __device__ __forceinline__ double* xs() const { return dinv() + Ny; }                           // [Ny]   linear-solve vector
@@ -195,21 +198,27 @@ __device__ __forceinline__ const DevMech& mech() { return *reinterpret_cast<cons
 
 // mode 0: RHS / Jacobian evaluation, 1: solver (+ LU), 2: forward sensitivities (+ LU, Jp tile, work tile),
 // 3: parameter-Jacobian evaluation (the Jp tile takes the place of J)
-__host__ __device__ inline int ws_fixed_doubles(int Ns, int Nr, int Ny, int n_dt) {
-    return 9 * Ns + 5 * Nr + n_dt + Ny + 3 * Ny + 8 + 36 + Ny + Ny + (Ny + 1) / 2 + 1;
+// Dual2 capacity of the g / un / q / fbuf arrays: only the adiabatic gas domains run the dual-number pass (rhs_v<Dual2>); every other
+// domain gets the slimmer slice, i.e. more resident warps per SM for the 33..128-variable mechanisms whose slice is tens of KB
+__host__ __device__ inline int ws_tri(int kind) { return (kind == RMSB_DOMAIN_CONSTANT_V || kind == RMSB_DOMAIN_CONSTANT_P) ? 3 : 1; }
+__host__ __device__ inline int ws_fixed_doubles(int Ns, int Nr, int Ny, int n_dt, int tri) {
+    return (3 + 2 * tri) * Ns + (2 + tri) * Nr + n_dt + Ny + tri * Ny + 8 + 36 + Ny + Ny + (Ny + 1) / 2 + 1;
 }
-__host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, int mode) {
+// doubles of the derivative-term array reserved in the fixed part of the slice: none in the solver modes (see Ws::dterm)
+__host__ __device__ inline int ws_ndt_reserved(int n_dt, int mode) { return (mode == 1 || mode == 2) ? 0 : n_dt; }
+__host__ __device__ inline int ws_lu_doubles(int Ny, int n_dt) { int LD = Ny | 1; return Ny * LD > n_dt ? Ny * LD : n_dt; }
+__host__ __device__ inline int ws_doubles(int Ns, int Nr, int Ny, int n_dt, int mode, int tri) {
     int LD = Ny | 1;
-    int n = ws_fixed_doubles(Ns, Nr, Ny, n_dt);
+    int n = ws_fixed_doubles(Ns, Nr, Ny, ws_ndt_reserved(n_dt, mode), tri);
     if (mode == 3) n += (Ny * LD > Ny * 32) ? Ny * LD : Ny * 32;
     else n += Ny * LD;
-    if (mode == 1 || mode == 2) n += Ny * LD;
+    if (mode == 1 || mode == 2) n += ws_lu_doubles(Ny, n_dt);
     if (mode == 2) n += 2 * Ny * 32;
     return (n + 1) & ~1;
 }
-__host__ __device__ inline int ws_jp_offset(int Ns, int Nr, int Ny, int n_dt, int mode) {
+__host__ __device__ inline int ws_jp_offset(int Ns, int Nr, int Ny, int n_dt, int mode, int tri) {
     int LD = Ny | 1;
-    return ws_fixed_doubles(Ns, Nr, Ny, n_dt) + (mode == 2 ? 2 * Ny * LD : 0);
+    return ws_fixed_doubles(Ns, Nr, Ny, ws_ndt_reserved(n_dt, mode), tri) + (mode == 2 ? Ny * LD + ws_lu_doubles(Ny, n_dt) : 0);
 }
 
 // smem load/store of a possibly-dual value at logical index i of an array with Dual2 capacity

@@ -27,7 +27,7 @@ def _ens(gdom, ys):
 
 def _row(case, what, rep):
     ROWS.append(f"{case:18s} {what:5s} entries {rep['n']:6d}  above floor {rep['n_above']:6d}  max plain rel err above floor {rep['max_rel_above']:.2e}  "
-                f"worst |err| / (1e-12 |ref| + 8 floors) {rep['worst_excess']:.2e}")
+                f"worst |err| / (1e-12 |ref| + k floors) {rep['worst_excess']:.2e}   (k = 4 for dydt, 8 otherwise)")
     print(ROWS[-1])
 
 
