@@ -59,17 +59,18 @@ def measured_peaks():
 
 def _issue_roofline(mean_steps, n, t_kernel, clocks, device):
     """The bound that actually limits the solve kernel: warp-instruction issue.  Warp instructions per accepted step come from the
-    committed ncu capture (smsp__inst_executed.sum / reactors / steps, profiles/r02_small_solve_kernel_by_line_c.txt); the peak is
+    committed ncu capture of the bench workload (smsp__inst_executed.sum 1.264e11 / 100 000 reactors / 391.1 steps,
+    profiles/r02_small_solve_kernel_ncu_k.txt); the peak is
     SMs x 4 schedulers x one instruction per cycle at the SM clock sampled during the timed region."""
     try:
         import torch
         sms = torch.cuda.get_device_properties(device).multi_processor_count
         mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
-        per_step = 3316.0
+        per_step = 3232.0
         ach = per_step * mean_steps * n / t_kernel
         peak = sms * 4 * float(mhz) * 1e6
         return {"achieved_ginst_s": ach / 1e9, "peak_ginst_s": peak / 1e9, "frac": ach / peak, "warp_instructions_per_step": per_step,
-                "source": "profiles/r02_small_solve_kernel_by_line_c.txt (ncu source page)"}
+                "source": "profiles/r02_small_solve_kernel_ncu_k.txt (ncu --set full of this workload)"}
     except Exception as exc:
         return {"achieved_ginst_s": None, "peak_ginst_s": None, "frac": None, "source": f"unavailable: {exc}"}
 

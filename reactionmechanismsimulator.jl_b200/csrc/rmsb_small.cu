@@ -415,6 +415,9 @@ __device__ __forceinline__ void stage_small(const DevMech& mp, const SmallTables
 #ifndef RMSB_SMALL_THREADS
 #define RMSB_SMALL_THREADS 128
 #endif
+#ifndef RMSB_SMALL_HYST
+#define RMSB_SMALL_HYST 1.2        // step-size increases below this factor (at unchanged order) are not taken: no rescale, no refactorisation
+#endif
 #ifndef RMSB_SMALL_TICKSYNC
 #define RMSB_SMALL_TICKSYNC 0      // 1: the warps of a block start every tick together (experiment: shared instruction fetch)
 #endif
@@ -797,7 +800,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                         else if (f0 >= fp) { delta = 0; fmax_ = f0; }
                         else { delta = 1; fmax_ = fp; }
                         const double factor = fmin(BDF_MAX_FACTOR, safety * fmax_);
-                        if (!(hysteresis && delta == 0 && factor >= 1.0 && factor < 1.2)) {
+                        if (!(hysteresis && delta == 0 && factor >= 1.0 && factor < RMSB_SMALL_HYST)) {
                             order += delta; h_abs *= factor; pend = factor; n_equal = 0; lu_valid = false;
                         }
                     }
