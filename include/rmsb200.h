@@ -156,7 +156,8 @@ typedef struct rmsb_solve_opts {
     int32_t reserved;        /* integrator flags: 0 = defaults; bit 0 = scipy-style Newton test; bit 1 = no step hysteresis;
                               * bit 2 / bit 3 (diagnostics): do not impose the unit rows of inert species / recompute the step as
                               * fl(t+h)-t like SciPy; bit 4 (large-mechanism path): refactorise on every change of h instead of
-                              * keeping the factors while c = h/alpha stays within 30 % (CVODE's dgmax); bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
+                              * keeping the factors while c = h/alpha stays within 30 % (CVODE's dgmax); bit 6 (lane-group path): hand the reactors out in
+                              * the caller's order instead of hottest-first (for callers that sorted by a measured cost); bits 8-15 = v: Newton tolerance coefficient 0.1/2^(v-1) (0 = default 0.1/8) */
     /* ---- version 2 (struct_size >= 40; version-1 callers with struct_size 32 are still accepted) ---- */
     double* dysave;          /* rmsb_solve_batch only (host buffer, may be NULL): [n][nsave][Ny], dy/dt = dydtreactor!(u) at every
                               * saved state -- the `du` of sol.interp (src/Simulation.jl:27-34), so the caller's Hermite interpolation

@@ -1053,7 +1053,8 @@ size_t rmsb_small_work_bytes(const rmsb_mech* h, int kind, int Ny, int64_t n) {
 template <int G>
 static int small_solve_G(const rmsb_mech* h, const SolveArgs& a_in, cudaStream_t stream) {
     SolveArgs a = a_in;
-    if (a.n >= ORDER_MIN_N && a.n <= 0x7fffffff && a.work_bytes >= 256 + rmsb_small_work_bytes(h, a.domain_kind, a.Ny, a.n)) {
+    // flags bit 6: the caller has ordered the reactors itself (e.g. by the cost a previous sweep measured): keep that order
+    if (!(a.flags & 64) && a.n >= ORDER_MIN_N && a.n <= 0x7fffffff && a.work_bytes >= 256 + rmsb_small_work_bytes(h, a.domain_kind, a.Ny, a.n)) {
         char* base = reinterpret_cast<char*>(a.counter) + 256;
         int* order = reinterpret_cast<int*>(base); base += al256(4 * (size_t)a.n);
         unsigned long long* keys = reinterpret_cast<unsigned long long*>(base); base += al256(8 * (size_t)a.n);

@@ -209,6 +209,9 @@ def test_ensemble_properties_at_scale():
     rev = rb.ConstantVEnsemble(ig, T0[::-1].copy(), P0[::-1].copy(), ns[::-1].copy())
     sol2 = rb.solve(rb.Reactor(rev, None, (0.0, 0.1)), abstol=1e-16, reltol=1e-6)
     assert np.array_equal(sol2.yend[::-1], sol.yend) and np.array_equal(sol2.idt[::-1], sol.idt, equal_nan=True)
+    # ... and so does keeping the caller's order in the work queue (flags bit 6) instead of the library's hottest-first order
+    sol3 = rb.solve(rb.Reactor(ens, None, (0.0, 0.1)), rb.RMSB200(flags=64), abstol=1e-16, reltol=1e-6)
+    assert np.array_equal(sol3.yend, sol.yend) and np.array_equal(sol3.idt, sol.idt, equal_nan=True)
     # the ideal-gas law is an invariant of the ConstantV equations (dP/dt is derived from it, Domain.jl:1903):
     # P*V/(R*T) must track sum(ns) to integration accuracy (the CPU port drifts by 6e-7 at these tolerances).
     Ni = sol.yend[:, ig.Ns + 1] * ens.cond[:, 0] / (8.314 * sol.yend[:, ig.Ns])
