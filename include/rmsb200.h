@@ -311,6 +311,21 @@ int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
                         double* yend, double* idt, int32_t* status, rmsb_stats* stats,
                         const rmsb_solve_opts* opts);
 
+/* Parameter Jacobian and forward sensitivities with boundary interfaces (the reference's own tests run both on ConstantTP with an Inlet
+ * and an Outlet, src/TestReactors.jl:271-296).  jacobianp! gains terms only for an Inlet on the adiabatic domains
+ * (src/Domain.jl:3421-3430,3461-3470, reproduced as written); the sensitivity equations see the interfaces through the RHS and
+ * jacobiany!.  Time profiles are not accepted here. */
+int rmsb_jacp_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n, const double* y, const double* cond,
+                       const double* p, int64_t p_stride, const int32_t* const_species, int32_t n_const,
+                       const double* interfaces, int64_t if_stride, double* Jp);
+int rmsb_sens_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n, const double* y0, const double* cond,
+                       const double* p, int64_t p_stride, const int32_t* const_species, int32_t n_const,
+                       const double* interfaces, int64_t if_stride,
+                       const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                       double* ysave, double* ssave, double* yend, double* send, int32_t* status, rmsb_stats* stats,
+                       const rmsb_solve_opts* opts);
+
+
 /* ---- time profiles (ParametrizedVDomain / ParametrizedPDomain) and the general extended calls ---------
  * The reference's rapid-compression-machine / shock-tube domains (src/Domain.jl:331-498): the ConstantV domain whose volume
  * follows V(t), the ConstantP domain whose pressure follows P(t) -- dT/dt and dP/dt (dV/dt) gain the dV/dt (dP/dt) terms of

@@ -1723,10 +1723,12 @@ def jacobiany_complexstep(domain, y, t=0.0, p=None, h=1e-30, interfaces=()):
 # --------------------------------------------------------------------------------------
 # Parameter Jacobian: src/Domain.jl:3095-3485
 # --------------------------------------------------------------------------------------
-def jacobianp(domain, y, t=0.0, p=None):
+def jacobianp(domain, y, t=0.0, p=None, interfaces=()):
     """d(dy/dt)/dp, Ny x (Ns+Nr).  Columns 0..Ns-1: dG_i (enters through krev = kf/Kc);
     columns Ns+j: k_j (constant-k domains: the rate coefficient itself, or the multiplier for
-    efficiency reactions; variable-k domains: the multiplier).  src/Domain.jl:3095-3374."""
+    efficiency reactions; variable-k domains: the multiplier).  src/Domain.jl:3095-3374.
+    Boundary interfaces: the reference adds a term only for an Inlet on ConstantV / ConstantP (src/Domain.jl:3421-3430,3461-3470,
+    restated as written there); ConstantTP / TV / TAPhi ignore them (:3376-3392,3473-3485)."""
     y = np.asarray(y, dtype=float)
     ph = domain.phase
     Ns, Nr = ph.Ns, ph.Nr
@@ -1800,4 +1802,13 @@ def jacobianp(domain, y, t=0.0, p=None):
             jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.P + jacp[Ns, i] * th.V / th.T
     for ind in domain.constantspeciesinds:
         jacp[ind, :] = 0.0
+    if domain.kind in ("ConstantV", "ConstantP"):
+        for inter in interfaces:
+            if isinstance(inter, Inlet) and inter.domain is domain:
+                flow = _flow(inter.F, t)
+                Cx = th.Cvave if domain.kind == "ConstantV" else th.Cvave + R
+                for i in range(Ns):
+                    ddG = flow * (-th.ns[i] / th.N) / (th.N * Cx)
+                    jacp[Ns, i] += ddG
+                    jacp[Ns + 1, i] += th.P / th.T * ddG if domain.kind == "ConstantV" else ddG * th.V / th.T
     return jacp

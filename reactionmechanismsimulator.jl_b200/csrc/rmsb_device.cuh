@@ -1562,6 +1562,14 @@ static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int 
             col[(Ns + 1) * JP_CHUNK] = sm * RMSB_R * aT / aP + jt * aV / aT;
         }
         for (int k = 0; k < d.nconst; ++k) col[(d.constspc[k] - 1) * JP_CHUNK] = 0.0;
+        // boundary interfaces: the only parameter-Jacobian term the reference carries is the Inlet's on the T and P (V) rows of the
+        // dG columns of the adiabatic domains (src/Domain.jl:3421-3430,3461-3470, as written there); ConstantTP / TV / TAPhi: none
+        if (d.flow && c < Ns && (d.kind == RMSB_DOMAIN_CONSTANT_V || d.kind == RMSB_DOMAIN_CONSTANT_P)) {
+            const bool isp = d.kind == RMSB_DOMAIN_CONSTANT_P;
+            const double ddG = d.flow[IF_FIN] * (-w.ybuf()[c] / aN) / (aN * (isp ? aCv + RMSB_R : aCv));
+            col[Ns * JP_CHUNK] += ddG;
+            col[(Ns + 1) * JP_CHUNK] += isp ? ddG * aV / aT : aP / aT * ddG;
+        }
     }
     __syncwarp();
 }

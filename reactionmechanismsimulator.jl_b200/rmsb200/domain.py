@@ -165,15 +165,21 @@ class Domain:
                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], self.Ny, self.Ny).transpose(0, 2, 1)   # column-major -> [eqn, var]
 
-    def jacobianp(self, y=None, p=None):
-        """jacobianp! for every reactor -> [n][Ny][Ns+Nr] with Jp[r, eqn, par] (src/Domain.jl:3095-3485)."""
+    def jacobianp(self, y=None, p=None, interfaces=None):
+        """jacobianp! for every reactor -> [n][Ny][Ns+Nr] with Jp[r, eqn, par] (src/Domain.jl:3095-3485); `interfaces`: boundary
+        interfaces as for dydt / jacobiany (only an Inlet on ConstantV / ConstantP adds terms, src/Domain.jl:3421-3430)."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
         pp, ps = self._p_for_sens(p)
         Np = self.phase.Ns + self.phase.Nr
         out = np.empty((y.shape[0], Np * self.Ny))
         cs = self.constantspeciesinds
-        L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
-                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
+        fa, fs = self._interfaces_for(interfaces, y.shape[0])
+        if fa is not None:
+            L.check(L.lib().rmsb_jacp_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+        else:
+            L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
+                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], Np, self.Ny).transpose(0, 2, 1)      # column-major -> [eqn, par]
 
     def _p_for_sens(self, p):

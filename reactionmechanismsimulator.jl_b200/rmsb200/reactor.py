@@ -46,8 +46,6 @@ class Reactor:
 
     def __init__(self, domain: Domain, y0=None, tspan: Tuple[float, float] = (0.0, 1.0), interfaces: Sequence = (), p=None,
                  forwardsensitivities: bool = False):
-        if interfaces is not None and len(interfaces) > 0 and forwardsensitivities:
-            raise NotImplementedError("forward sensitivities with boundary interfaces (DESIGN.md, 'out of scope')")
         if forwardsensitivities and domain.kind == L.DOMAIN_COUPLED_TP_TAPHI:
             raise NotImplementedError("forward sensitivities of coupled gas-surface systems (DESIGN.md, 'next')")
         self.domain = domain
@@ -177,9 +175,18 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
         Np = dom.phase.Ns + dom.phase.Nr
         ssave = np.empty((n, nsave, Np, Ny)) if nsave else None
         send = np.empty((n, Np, Ny))
-        L.check(L.lib().rmsb_sens_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
-                                        L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
-                                        L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats), C.byref(opts)))
+        if getattr(dom, "profile", None) is not None:
+            raise NotImplementedError("forward sensitivities of the Parametrized* domains (time profiles)")
+        fa, fs = dom._interfaces_for(react.interfaces, n)           # boundary interfaces (src/TestReactors.jl:284-296)
+        if fa is not None:
+            L.check(L.lib().rmsb_sens_batch_if(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(te), reltol, abstol, nsave,
+                                               L.ptr(tsave), L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats),
+                                               C.byref(opts)))
+        else:
+            L.check(L.lib().rmsb_sens_batch(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(te), reltol, abstol, nsave, L.ptr(tsave),
+                                            L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats), C.byref(opts)))
         idt[:] = np.nan
         sol = Solution(react, tsave, ysave, yend, idt, status, stats, te, ssave, send)
         sol.kernel_ms = float(L.lib().rmsb_last_kernel_ms())

@@ -80,8 +80,9 @@ def test_jacobianp_parity(case):
 
 
 def sens_err(S, Sref):
-    """max over parameters of |S - Sref| / max_i |Sref[:, par]| (column scale)."""
-    sc = np.max(np.abs(Sref), axis=-1, keepdims=True) + 1e-300
+    """max over parameters of |S - Sref| / max_i |Sref[:, par]| (column scale; columns 1e-25 of the largest and below -- the
+    oracle's integration noise on the parameters of absent species, exact zeros on the GPU -- are measured against that floor)."""
+    sc = np.maximum(np.max(np.abs(Sref), axis=-1, keepdims=True), 1e-25 * np.max(np.abs(Sref))) + 1e-300
     return float(np.max(np.abs(S - Sref) / sc))
 
 
@@ -232,3 +233,54 @@ def test_sensitivity_launch_geometry_small_batches():
                 ref = sol
             assert np.array_equal(sol.sens_end, ref.sens_end) and np.array_equal(sol.yend, ref.yend)
         assert np.array_equal(ref.sens_end[0], ref.sens_end[-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Parameter Jacobian and forward sensitivities WITH boundary interfaces (src/TestReactors.jl:259-296: the reference runs both on the
+# ConstantTP reactor with an Inlet and an Outlet).  Oracle: oracle/sensitivity.py with the interfaces in the RHS, jacobiany and
+# jacobianp; goldens tests/golden/sens_if_vectors.npz (make_golden_sens_if.py, finite-difference spot check 3e-9).
+# ---------------------------------------------------------------------------------------------------------------------------------
+GIF = np.load(cases.ROOT / "tests" / "golden" / "sens_if_vectors.npz")
+IF_SETS = {"superminimal_TP": ([("Inlet", ({"H2": 0.67, "O2": 0.33, "T": 1000.0, "P": 1e5}, 0.001)), ("Outlet", (0.001,))], 150.11094),
+           "superminimal_V": ([("Inlet", ({"H2": 0.67, "O2": 0.33, "T": 900.0, "P": 1e5}, 0.002)), ("Outlet", (0.001,))], 0.02)}
+
+
+@pytest.mark.parametrize("case", list(IF_SETS))
+def test_jacobianp_and_sensitivities_with_interfaces(case):
+    spec, tend = IF_SETS[case]
+    gdom, y0, p = cases.product_domain(case)
+    gifs = [getattr(rb, nm)(gdom, *args) for nm, args in spec]
+    ys, Jpo = GIF[f"{case}/y"], GIF[f"{case}/Jp"]
+    ens = rb.Domain(gdom.kind, gdom.phase, ys, np.repeat(gdom.cond, len(ys), axis=0))
+    ens.p, ens._p_default = gdom.p, gdom._p_default
+    row = rb.pack_interfaces(gdom, gifs)
+    Jp = ens.jacobianp(ys, p, interfaces=row)
+    for k in range(len(ys)):
+        assert cases.err_jac(Jp[k], Jpo[k]) < 1e-12, (case, k)
+    plain = ens.jacobianp(ys, p)
+    if case == "superminimal_TP":
+        assert np.array_equal(Jp, plain)                          # src/Domain.jl:3376-3392: no interface terms
+    else:
+        Ns = gdom.phase.Ns
+        assert np.array_equal(Jp[:, :Ns], plain[:, :Ns]) and not np.array_equal(Jp[:, Ns:, :Ns], plain[:, Ns:, :Ns])
+    # forward sensitivities through the reference's call sequence: Reactor(domain, y0, tspan, interfaces; p, forwardsensitivities=true)
+    tq, yq, Sq = GIF[f"{case}/tq"], GIF[f"{case}/yq"], GIF[f"{case}/Sq"]
+    react = rb.Reactor(gdom, y0, (0.0, tend), gifs, p=p, forwardsensitivities=True)
+    sol = rb.solve(react.ode, abstol=1e-20, reltol=1e-8, saveat=tq)
+    assert sol.retcode[0] == "Success"
+    big = np.abs(yq) > 1e-10 * np.max(np.abs(yq), axis=1, keepdims=True)
+    assert np.max(np.abs(sol.u[0] - yq)[big] / np.abs(yq)[big]) < 1e-5
+    for k in range(len(tq)):
+        assert sens_err(sol.sens[0, k], Sq[k]) < 1e-4, (case, k, sens_err(sol.sens[0, k], Sq[k]))
+    # the interfaces matter: the closed reactor's sensitivities are different
+    closed = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-8, saveat=tq)
+    assert sens_err(closed.sens[0, -1], Sq[-1]) > 1e-3            # ten times the bar above (0.4 % over the 20 ms of the ConstantV case)
+    # an ensemble of residence times through per-reactor interface rows: row k alone == row k of the batch
+    n = 8
+    rows = np.stack([rb.pack_interfaces(gdom, [getattr(rb, nm)(gdom, *(args[:-1] + (args[-1] * f,))) for nm, args in spec]) for f in np.linspace(0.5, 2.0, n)])
+    ensr = rb.Domain(gdom.kind, gdom.phase, np.repeat(gdom.y0, n, axis=0), np.repeat(gdom.cond, n, axis=0))
+    ensr.p, ensr._p_default = gdom.p, gdom._p_default
+    sb = rb.solve(rb.Reactor(ensr, None, (0.0, tend), rows, p=p, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-8)
+    assert np.all(sb.status == 0)
+    one = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), rows[3], p=p, forwardsensitivities=True).ode, abstol=1e-20, reltol=1e-8)
+    assert np.array_equal(one.sens_end[0], sb.sens_end[3]) and np.array_equal(one.yend[0], sb.yend[3])

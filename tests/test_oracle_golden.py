@@ -209,6 +209,36 @@ def test_jacobianp_vs_complexstep():
         assert np.all(np.abs(Jp[:, cols] - num[:, cols]) <= 1e-4 * np.abs(num[:, cols]) + 1e-9 * scale + 1e-16)
 
 
+def test_jacobianp_with_interfaces_reference_criterion():
+    """src/TestReactors.jl:277-279: jacobianp(y, p, t, domain, interfaces) of the ConstantTP reactor with an Inlet and an Outlet equals
+    the derivative of the RHS (with interfaces) w.r.t. p; and it equals the interface-free jacobianp, as src/Domain.jl:3376-3392 says.
+    ConstantV: the Inlet adds the reference's terms to the T and P rows of the dG columns and nothing else (:3421-3430)."""
+    dom = cases.oracle_domain("superminimal_TP")
+    ifs = [ro.Inlet(dom, {"H2": 0.67, "O2": 0.33, "T": 1000.0, "P": 1e5}, 0.001), ro.Outlet(dom, 0.001)]
+    y = np.load(cases.ROOT / "tests" / "golden" / "parity_vectors.npz")["superminimal_TP/y"][0]
+    Jp = ro.jacobianp(dom, y, 20.44002454, dom.p, ifs)
+    np.testing.assert_array_equal(Jp, ro.jacobianp(dom, y, 20.44002454, dom.p))
+    Ns = dom.phase.Ns
+    num = np.zeros_like(Jp)
+    for k in range(Ns, Jp.shape[1]):                  # rate-coefficient columns (the dG columns of a constant-k domain are not smooth in p)
+        pc = dom.p.astype(complex)
+        pc[k] += 1e-30j
+        num[:, k] = ro.dydtreactor(dom, y.astype(complex), 20.44002454, pc, ifs).imag / 1e-30
+    scale = np.max(np.abs(num[:, Ns:]), axis=0, keepdims=True)
+    assert np.all(np.abs(Jp[:, Ns:] - num[:, Ns:]) <= 1e-4 * np.abs(num[:, Ns:]) + 1e-9 * scale + 1e-16)
+    dv = cases.oracle_domain("superminimal_V")
+    iv = [ro.Inlet(dv, {"H2": 0.67, "O2": 0.33, "T": 900.0, "P": 1e5}, 0.002), ro.Outlet(dv, 0.001)]
+    yv = np.load(cases.ROOT / "tests" / "golden" / "parity_vectors.npz")["superminimal_V/y"][0]
+    J0 = ro.jacobianp(dv, yv, 0.0, dv.p)
+    d = ro.jacobianp(dv, yv, 0.0, dv.p, iv) - J0
+    Nv = dv.phase.Ns
+    assert np.all(d[:Nv] == 0.0) and np.all(d[:, Nv:] == 0.0) and np.all(d[Nv, :Nv] != 0.0)
+    th = dv.calcthermo(yv, 0.0, dv.p)
+    term = 0.002 * (-yv[:Nv] / th.N) / (th.N * th.Cvave)        # the difference of two Jacobians carries their rounding
+    np.testing.assert_allclose(d[Nv, :Nv], term, rtol=1e-9, atol=8 * np.finfo(float).eps * np.abs(J0[Nv, :Nv]).max())
+    np.testing.assert_allclose(d[Nv + 1, :Nv], th.P / th.T * term, rtol=1e-9, atol=8 * np.finfo(float).eps * np.abs(J0[Nv + 1, :Nv]).max())
+
+
 # ---------------------------------------------------------------------------------------------
 # trajectories (the reference's pinned reactor results)
 # ---------------------------------------------------------------------------------------------
