@@ -314,7 +314,7 @@ int rmsb_solve_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n,
 /* Parameter Jacobian and forward sensitivities with boundary interfaces (the reference's own tests run both on ConstantTP with an Inlet
  * and an Outlet, src/TestReactors.jl:271-296).  jacobianp! gains terms only for an Inlet on the adiabatic domains
  * (src/Domain.jl:3421-3430,3461-3470, reproduced as written); the sensitivity equations see the interfaces through the RHS and
- * jacobiany!.  Time profiles are not accepted here. */
+ * jacobiany!. */
 int rmsb_jacp_batch_if(const rmsb_mech* mech, int domain_kind, int64_t n, const double* y, const double* cond,
                        const double* p, int64_t p_stride, const int32_t* const_species, int32_t n_const,
                        const double* interfaces, int64_t if_stride, double* Jp);
@@ -362,6 +362,20 @@ int rmsb_solve_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n,
                         int32_t nsave, const double* tsave, double* ysave,
                         double* yend, double* idt, int32_t* status, rmsb_stats* stats,
                         const rmsb_solve_opts* opts);
+
+/* Parameter Jacobian and forward sensitivities with interfaces and / or the time profile of a Parametrized* domain (the reference tests jacobianp of all
+ * four, src/TestReactors.jl:163-165,423-425,444-446,465-467); jacobianp! of a Parametrized domain is the variable-k one
+ * (p = [dG; f]) whatever its layout (src/Domain.jl:3204-3233). */
+int rmsb_jacp_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n, const double* y, const double* cond,
+                       const double* p, int64_t p_stride, const int32_t* const_species, int32_t n_const,
+                       const rmsb_extras* extras, double* Jp);
+int rmsb_sens_batch_ex(const rmsb_mech* mech, int domain_kind, int64_t n, const double* y0, const double* cond,
+                       const double* p, int64_t p_stride, const int32_t* const_species, int32_t n_const,
+                       const rmsb_extras* extras,
+                       const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave,
+                       double* ysave, double* ssave, double* yend, double* send, int32_t* status, rmsb_stats* stats,
+                       const rmsb_solve_opts* opts);
+
 
 /* ---- one host process, several GPUs -------------------------------------------------------------
  * rmsb_solve_batch over n_mech handles of the SAME mechanism created on different devices: the reactors are split into

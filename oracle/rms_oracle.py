@@ -1776,10 +1776,10 @@ def jacobianp(domain, y, t=0.0, p=None, interfaces=()):
             for q in ps:
                 jacp[q, s] += -sign * gderiv
     jacp *= th.V
-    if domain.kind == "ConstantTP":
+    if domain.kind in ("ConstantTP", "ParametrizedTP"):        # src/Domain.jl:3376-3392
         for i in range(Ns + Nr):
             jacp[Ns, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.P
-    elif domain.kind == "ConstantV":
+    elif domain.kind in ("ConstantV", "ParametrizedV"):        # src/Domain.jl:3394-3431
         dydt = np.zeros(Ny)
         addreactionratecontributions(dydt, ra, th.cs, th.kfs, th.krevs)
         dydt *= th.V
@@ -1789,7 +1789,7 @@ def jacobianp(domain, y, t=0.0, p=None, interfaces=()):
         for i in range(Ns, Ns + Nr):
             jacp[Ns, i] = -np.dot(th.Us, jacp[:Ns, i]) / (th.N * th.Cvave)
             jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.V + th.P / th.T * jacp[Ns, i]
-    elif domain.kind == "ConstantP":          # src/Domain.jl:3433-3460
+    elif domain.kind in ("ConstantP", "ParametrizedP"):        # src/Domain.jl:3433-3471
         dydt = np.zeros(Ny)
         addreactionratecontributions(dydt, ra, th.cs, th.kfs, th.krevs)
         dydt *= th.V
@@ -1802,13 +1802,14 @@ def jacobianp(domain, y, t=0.0, p=None, interfaces=()):
             jacp[Ns + 1, i] = np.sum(jacp[:Ns, i]) * R * th.T / th.P + jacp[Ns, i] * th.V / th.T
     for ind in domain.constantspeciesinds:
         jacp[ind, :] = 0.0
-    if domain.kind in ("ConstantV", "ConstantP"):
+    if domain.kind in ("ConstantV", "ConstantP", "ParametrizedV", "ParametrizedP"):
         for inter in interfaces:
             if isinstance(inter, Inlet) and inter.domain is domain:
                 flow = _flow(inter.F, t)
-                Cx = th.Cvave if domain.kind == "ConstantV" else th.Cvave + R
+                isv = domain.kind in ("ConstantV", "ParametrizedV")
+                Cx = th.Cvave if isv else th.Cvave + R
                 for i in range(Ns):
                     ddG = flow * (-th.ns[i] / th.N) / (th.N * Cx)
                     jacp[Ns, i] += ddG
-                    jacp[Ns + 1, i] += th.P / th.T * ddG if domain.kind == "ConstantV" else ddG * th.V / th.T
+                    jacp[Ns + 1, i] += th.P / th.T * ddG if isv else ddG * th.V / th.T
     return jacp

@@ -984,7 +984,7 @@ static int launch_eval(const rmsb_mech* h, const BatchArgs& a, cudaStream_t st) 
     if (extras) {
         // boundary interfaces / time profiles are evaluated by the warp-per-reactor routines (rhs_v / rhs_ck / jac_warp)
         if (a.Ny > 128) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles on the large-mechanism path (Ny > 128) are not built");
-        if (MODE != 0 && MODE != 1 && !(MODE == 3 && !a.ptab)) return fail(RMSB_ERR_UNSUPPORTED, "time profiles: dydt, Jacobian and solve only; boundary interfaces: also the parameter Jacobian");
+        if (MODE != 0 && MODE != 1 && MODE != 3) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces / time profiles: dydt, Jacobian, parameter Jacobian and solve only");
         if (a.domain_kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "boundary interfaces on the coupled gas-surface system are not built");
     }
     if (a.Ny > 128) {
@@ -1174,9 +1174,9 @@ extern "C" int rmsb_jac_batch_dev(const rmsb_mech* h, int kind, int64_t n, const
     return launch_eval<1>(h, make_batch(h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr), (cudaStream_t)stream);
 }
 
-static int check_jacp(const rmsb_mech* h, int kind, const double* p) {
+static int check_jacp(const rmsb_mech* h, int kind, const double* p, bool profile = false) {
     if (kind == RMSB_DOMAIN_COUPLED_TP_TAPHI) return fail(RMSB_ERR_UNSUPPORTED, "parameter Jacobian of the coupled gas-surface system is not built");
-    if (kind == RMSB_DOMAIN_CONSTANT_TV && !p) return fail(RMSB_ERR_ARG, "ConstantTV parameter Jacobian needs the explicit parameter vector p (chain rule through the diffusion limit)");
+    if (kind == RMSB_DOMAIN_CONSTANT_TV && !p && !profile) return fail(RMSB_ERR_ARG, "ConstantTV parameter Jacobian needs the explicit parameter vector p (chain rule through the diffusion limit)");
     (void)h;
     return RMSB_OK;
 }
@@ -1226,8 +1226,7 @@ static int solve_dev_impl(bool sens, const rmsb_mech* h, int kind, int64_t n, co
                           const double* ptab = nullptr, int64_t ptab_stride = 0) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
-    if (sens && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
-    if (sens && ptab) return fail(RMSB_ERR_UNSUPPORTED, "forward sensitivities with time profiles are not built");
+    if (sens && (rc = check_jacp(h, kind, p, ptab != nullptr)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!t_end || !status || !work) return fail(RMSB_ERR_ARG, "t_end, status and work buffers are required");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(RMSB_ERR_ARG, "rtol must be > 0 and atol >= 0");
@@ -1348,7 +1347,7 @@ static int eval_host(int mode, const rmsb_mech* h, int kind, int64_t n, const do
     if (rc != RMSB_OK) return rc;
     Extras ex;
     if ((rc = check_extras(h, kind, xtr, &ex)) != RMSB_OK) return rc;
-    if (mode == 3 && (rc = check_jacp(h, kind, p)) != RMSB_OK) return rc;
+    if (mode == 3 && (rc = check_jacp(h, kind, p, ex.prof != nullptr)) != RMSB_OK) return rc;
     if ((rc = check_const_species(h, cs, ncs)) != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
     if (!out || (mode == 2 && !out2)) return fail(RMSB_ERR_ARG, "null output buffer");
@@ -1417,6 +1416,10 @@ extern "C" int rmsb_dydt_batch_ex(const rmsb_mech* h, int kind, int64_t n, const
 extern "C" int rmsb_jac_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras, double* J) {
     return eval_host(1, h, kind, n, y, cond, p, p_stride, cs, ncs, J, nullptr, extras);
+}
+extern "C" int rmsb_jacp_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
+                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras, double* Jp) {
+    return eval_host(3, h, kind, n, y, cond, p, p_stride, cs, ncs, Jp, nullptr, extras);
 }
 extern "C" int rmsb_dydt_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y, const double* cond, const double* p,
                                   int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride, double* dydt) {
@@ -1623,7 +1626,7 @@ extern "C" int rmsb_solve_batch_multi(const rmsb_mech* const* mechs, int32_t n_m
 static int sens_host_impl(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
                           int64_t p_stride, const int32_t* cs, int32_t ncs, const double* t_end, double rtol, double atol,
                           int32_t nsave, const double* tsave, double* ysave, double* ssave, double* yend, double* send,
-                          int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts, const double* ifs, int64_t if_stride) {
+                          int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts, const rmsb_extras* xtr) {
     int rc = check_common(h, kind, n, y0, cond, p_stride, p);
     if (rc != RMSB_OK) return rc;
     if (n == 0) return RMSB_OK;
@@ -1657,18 +1660,23 @@ static int sens_host_impl(const rmsb_mech* h, int kind, int64_t n, const double*
     CU(dwork.alloc((size_t)wb));
     EventPair ev;
     CU(ev.start(sg.st));
-    DevBuf dif(sg.st);
-    if (ifs) {
-        if (if_stride != 0 && if_stride != 7 + 2 * (int64_t)h->dm.Ns) return fail(RMSB_ERR_ARG, "if_stride must be 0 or 7 + 2*Ns");
-        const size_t nif = (size_t)(if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
-        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ifs, sizeof(double) * nif);
+    Extras ex;
+    if ((rc = check_extras(h, kind, xtr, &ex)) != RMSB_OK) return rc;
+    DevBuf dif(sg.st), dpr(sg.st);
+    if (ex.ifs) {
+        const size_t nif = (size_t)(ex.if_stride ? n : 1) * (7 + 2 * (size_t)h->dm.Ns);
+        CU(dif.alloc(sizeof(double) * nif)); H2D(dif.p, ex.ifs, sizeof(double) * nif);
+    }
+    if (ex.prof) {
+        const size_t np = (size_t)(ex.prof_stride ? n : 1) * (size_t)ex.prof_len;
+        CU(dpr.alloc(sizeof(double) * np)); H2D(dpr.p, ex.prof, sizeof(double) * np);
     }
     rc = solve_dev_impl(true, h, kind, n, dy.as<double>(), dc.as<double>(), p ? dp.as<double>() : nullptr, p_stride,
                         (cs && ncs > 0) ? dcs.as<int32_t>() : nullptr, ncs, dte.as<double>(), rtol, atol, nsave,
                         nsave > 0 ? dts.as<double>() : nullptr, (nsave > 0 && ysave) ? dys.as<double>() : nullptr,
                         (nsave > 0 && ssave) ? dss.as<double>() : nullptr, yend ? dye.as<double>() : nullptr,
                         send ? dse.as<double>() : nullptr, nullptr, dst.as<int32_t>(), stats ? dstats.as<rmsb_stats>() : nullptr, opts,
-                        dwork.p, sg.st, ifs ? dif.as<double>() : nullptr, if_stride);
+                        dwork.p, sg.st, ex.ifs ? dif.as<double>() : nullptr, ex.if_stride, ex.prof ? dpr.as<double>() : nullptr, ex.prof_stride);
     if (rc != RMSB_OK) return rc;
     CU(ev.stop(sg.st));
     if (nsave > 0 && ysave) D2H(ysave, dys.p, sizeof(double) * n * nsave * Ny);
@@ -1687,14 +1695,22 @@ extern "C" int rmsb_sens_batch(const rmsb_mech* h, int kind, int64_t n, const do
                                int32_t nsave, const double* tsave, double* ysave, double* ssave, double* yend, double* send,
                                int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts) {
     return sens_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, t_end, rtol, atol, nsave, tsave, ysave, ssave, yend, send, status, stats,
-                          opts, nullptr, 0);
+                          opts, nullptr);
+}
+extern "C" int rmsb_sens_batch_ex(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
+                                  int64_t p_stride, const int32_t* cs, int32_t ncs, const rmsb_extras* extras,
+                                  const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave, double* ysave,
+                                  double* ssave, double* yend, double* send, int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    return sens_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, t_end, rtol, atol, nsave, tsave, ysave, ssave, yend, send, status, stats,
+                          opts, extras);
 }
 extern "C" int rmsb_sens_batch_if(const rmsb_mech* h, int kind, int64_t n, const double* y0, const double* cond, const double* p,
                                   int64_t p_stride, const int32_t* cs, int32_t ncs, const double* ifs, int64_t if_stride,
                                   const double* t_end, double rtol, double atol, int32_t nsave, const double* tsave, double* ysave,
                                   double* ssave, double* yend, double* send, int32_t* status, rmsb_stats* stats, const rmsb_solve_opts* opts) {
+    rmsb_extras x = extras_of_interfaces(ifs, if_stride);
     return sens_host_impl(h, kind, n, y0, cond, p, p_stride, cs, ncs, t_end, rtol, atol, nsave, tsave, ysave, ssave, yend, send, status, stats,
-                          opts, ifs, if_stride);
+                          opts, &x);
 }
 
 extern "C" int rmsb_large_info(const rmsb_mech* h, int64_t* out) {

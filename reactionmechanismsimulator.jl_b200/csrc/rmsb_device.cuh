@@ -1496,7 +1496,9 @@ static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int 
     const double* ax = w.aux();
     const double aT = ax[0], aP = ax[1], aV = ax[2], aN = ax[3], aCv = ax[5];
     const double RTinv = 1.0 / (RMSB_R * aT);
-    const bool constk = (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P);
+    // the Parametrized* domains are variable-k domains whatever their layout (ParametrizedTP on the ConstantTP layout,
+    // ParametrizedTConstantV on the ConstantTV one): jacobianpnsderiv! of src/Domain.jl:3204-3233, p = [dG; f]
+    const bool constk = (d.kind != RMSB_DOMAIN_CONSTANT_V && d.kind != RMSB_DOMAIN_CONSTANT_P && !d.ptab);
     const int c = c0 + lane;
     for (int i = 0; i < Ny; ++i) col[i * JP_CHUNK] = 0.0;
     if (c < Np) {
@@ -1509,7 +1511,7 @@ static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int 
             for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pp *= cs[sp]; }
             const bool eff = G(m.eff_ptr, j + 1) > G(m.eff_ptr, j);
             double fderiv, rderiv;
-            if (d.kind == RMSB_DOMAIN_CONSTANT_TV) {            // Domain.jl:3290-3317: chain rule through the diffusion limit
+            if (d.kind == RMSB_DOMAIN_CONSTANT_TV && !d.ptab) { // Domain.jl:3290-3317: chain rule through the diffusion limit
                 double pk = d.p[Ns + j];
                 fderiv = kfb[j] * kfb[j] / (pk * pk) * pr;
                 rderiv = kfb[j] * krb[j] / (pk * pk) * pp;

@@ -75,7 +75,7 @@ EXPORTS = [
     "rmsb_sens_work_bytes", "rmsb_sens_batch_dev", "rmsb_kfs_batch", "rmsb_large_info", "rmsb_large_profile",
     "rmsb_solve_batch_multi", "rmsb_last_kernel_ms", "rmsb_dydt_batch_if", "rmsb_jac_batch_if", "rmsb_solve_batch_if",
     "rmsb_dydt_batch_ex", "rmsb_jac_batch_ex", "rmsb_solve_batch_ex", "rmsb_spec_source_desc", "rmsb_mech_specialized",
-    "rmsb_jacp_batch_if", "rmsb_sens_batch_if",
+    "rmsb_jacp_batch_if", "rmsb_sens_batch_if", "rmsb_jacp_batch_ex", "rmsb_sens_batch_ex",
 ]
 
 
@@ -128,6 +128,8 @@ def lib():
     L.rmsb_jac_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp]
     L.rmsb_solve_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
     L.rmsb_jacp_batch_if.argtypes = common + [vp, i32, vp, i64, vp]
+    L.rmsb_jacp_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp]
+    L.rmsb_sens_batch_ex.argtypes = common + [vp, i32, C.POINTER(Extras), vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
     L.rmsb_sens_batch_if.argtypes = common + [vp, i32, vp, i64, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOpts)]
     L.rmsb_spec_source_desc.argtypes = [C.POINTER(MechDesc), C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rmsb_mech_specialized.argtypes = [vp, C.c_int]

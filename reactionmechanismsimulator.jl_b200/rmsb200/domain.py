@@ -165,7 +165,7 @@ class Domain:
                                            L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))
         return out.reshape(y.shape[0], self.Ny, self.Ny).transpose(0, 2, 1)   # column-major -> [eqn, var]
 
-    def jacobianp(self, y=None, p=None, interfaces=None):
+    def jacobianp(self, y=None, p=None, interfaces=None, t=None):
         """jacobianp! for every reactor -> [n][Ny][Ns+Nr] with Jp[r, eqn, par] (src/Domain.jl:3095-3485); `interfaces`: boundary
         interfaces as for dydt / jacobiany (only an Inlet on ConstantV / ConstantP adds terms, src/Domain.jl:3421-3430)."""
         y = self.y0 if y is None else np.ascontiguousarray(np.atleast_2d(y), dtype=float)
@@ -173,10 +173,12 @@ class Domain:
         Np = self.phase.Ns + self.phase.Nr
         out = np.empty((y.shape[0], Np * self.Ny))
         cs = self.constantspeciesinds
-        fa, fs = self._interfaces_for(interfaces, y.shape[0])
-        if fa is not None:
-            L.check(L.lib().rmsb_jacp_batch_if(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
-                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(out)))
+        xtr, keep = self._extras(interfaces, y.shape[0], t)          # boundary interfaces and / or the profile of a Parametrized* domain
+        if xtr is not None:
+            if getattr(self, "profile", None) is not None:
+                pp, ps = self._p_for_device(p)                        # variable-k parameters [dG; f] whatever the layout
+            L.check(L.lib().rmsb_jacp_batch_ex(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, C.byref(xtr), L.ptr(out)))
         else:
             L.check(L.lib().rmsb_jacp_batch(self.phase.handle, self.kind, y.shape[0], L.ptr(y), L.ptr(self._cond_for(y.shape[0])), L.ptr(pp), ps,
                                             L.ptr(cs) if cs.size else None, cs.size, L.ptr(out)))

@@ -175,12 +175,12 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
         Np = dom.phase.Ns + dom.phase.Nr
         ssave = np.empty((n, nsave, Np, Ny)) if nsave else None
         send = np.empty((n, Np, Ny))
-        if getattr(dom, "profile", None) is not None:
-            raise NotImplementedError("forward sensitivities of the Parametrized* domains (time profiles)")
-        fa, fs = dom._interfaces_for(react.interfaces, n)           # boundary interfaces (src/TestReactors.jl:284-296)
-        if fa is not None:
-            L.check(L.lib().rmsb_sens_batch_if(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
-                                               L.ptr(cs) if cs.size else None, cs.size, L.ptr(fa), fs, L.ptr(te), reltol, abstol, nsave,
+        xtr, keep = dom._extras(react.interfaces, n)               # boundary interfaces (src/TestReactors.jl:284-296) / time profile
+        if xtr is not None:
+            if getattr(dom, "profile", None) is not None:
+                pp, ps = dom._p_for_device(react.p)
+            L.check(L.lib().rmsb_sens_batch_ex(dom.phase.handle, dom.kind, n, L.ptr(y0), L.ptr(dom.cond), L.ptr(pp), ps,
+                                               L.ptr(cs) if cs.size else None, cs.size, C.byref(xtr), L.ptr(te), reltol, abstol, nsave,
                                                L.ptr(tsave), L.ptr(ysave), L.ptr(ssave), L.ptr(yend), L.ptr(send), L.ptr(status), L.ptr(stats),
                                                C.byref(opts)))
         else:
