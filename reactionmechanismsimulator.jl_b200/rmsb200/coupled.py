@@ -129,6 +129,12 @@ def CoupledEnsemble(inter_phase: CoupledPhase, T, P, A, ns_gas, ns_surf) -> Doma
 class SystemSimulation:
     """SystemSimulation(sol, domains, interfaces, p) (src/Simulation.jl:92-134): accessors over the coupled solution."""
 
+    def __new__(cls, sol, domains=None, interfaces=(), p=None, r: int = 0):
+        if type(sol).__name__ == "MultiDomainSolution":          # domains without interfaces: one Simulation per domain
+            from .multidomain import MultiDomainSimulation
+            return MultiDomainSimulation(sol, domains, interfaces, p)
+        return object.__new__(cls)
+
     def __init__(self, sol, domains, interfaces, p=None, r: int = 0):
         from .simulation import Simulation
         self.sol, self.domains, self.interfaces, self.r = sol, domains, interfaces, r

@@ -32,6 +32,11 @@ class Reactor:
         ConstantTAPhi surface domain and one ReactiveInternalInterfaceConstantTPhi."""
         if isinstance(domain, (tuple, list)):
             from .coupled import ReactiveInternalInterfaceConstantTPhi, coupled_domain
+            if interfaces is None or len(interfaces) == 0:
+                # domains without interfaces (src/TestReactors.jl:470-531): a block-diagonal system, each block solved by its own call
+                from .multidomain import MultiDomainReactor
+                mr = MultiDomainReactor(domain, y0, tspan, p, forwardsensitivities=bool(kw.get("forwardsensitivities", False)))
+                return mr, mr.y0.copy(), mr.p
             if len(domain) != 2 or len(interfaces) != 1 or not isinstance(interfaces[0], ReactiveInternalInterfaceConstantTPhi):
                 raise NotImplementedError("multi-domain systems other than gas(TP) + surface(TAPhi) + ReactiveInternalInterfaceConstantTPhi "
                                           "are outside the accelerated hot path (DESIGN.md)")
@@ -154,6 +159,10 @@ def solve(react: Reactor, alg: Optional[RMSB200] = None, *, abstol: float = 1e-6
     save_derivatives: also return du at the saved states (what sol.interp.du holds in the reference) from the same call.
     devices: GPU ordinals to shard the ensemble over from this one process (rmsb_solve_batch_multi: contiguous blocks by
     reactor index, one host thread per device); None = the device of the phase's handle."""
+    if type(react).__name__ == "MultiDomainReactor":
+        from .multidomain import solve_multidomain
+        kw = dict(abstol=abstol, reltol=reltol, saveat=saveat, save_derivatives=save_derivatives)
+        return solve_multidomain(react, alg, **kw)
     alg = alg or react.recommendedsolver
     dom = react.domain
     y0 = react.y0
