@@ -428,7 +428,8 @@ __device__ __forceinline__ void change_D(double (&D)[BDF_MAX_ORDER + 3][R], int 
 // ---- forward sensitivities: staggered direct corrector --------------------------------------------------
 // S = dy/dp obeys dS/dt = J(y) S + Jp(y), S(0) = 0 (what ODEForwardSensitivityProblem appends to the state in the
 // reference, src/Reactor.jl:63-75; per-parameter form in src/ThreadedSensitivities.jl:59-67).  Its BDF corrector is
-// linear: with S_new = S_pred + dS,  (I - c J(y_new)) dS = c (J(y_new) S_pred + Jp(y_new)) - psi_S, solved exactly
+// linear: with S_new = S_pred + dS,  (I - c J(y_new)) dS = c (J(y_new) S_pred + Jp(y_new)) - psi_S, i.e.
+// (I - c J(y_new)) S_new = S_pred + c Jp(y_new) - psi_S, solved exactly
 // with a fresh Jacobian/LU after every accepted state step.  One lane per parameter column; the backward-difference
 // history of S (same step/order sequence as the state) lives in global scratch [j][row][par], L2-resident.
 struct SensHist {
@@ -472,15 +473,14 @@ static __device__ __noinline__ void sens_change_D(Ws w, SensHist sh, int order, 
 // predictor and history update of one parameter column at a compile-time order (no predicated loads; same operations in the
 // same order as the generic loops they replace)
 template <int ORDER>
-__device__ __forceinline__ void sens_predict(const SensHist& sh, int Ny, int pc, double c, double inv_alpha, double* b, double* x) {
+__device__ __forceinline__ void sens_predict(const SensHist& sh, int Ny, int pc, double c, double inv_alpha, double* b) {
     const double* Dp = sh.D + pc;
     for (int i = 0; i < Ny; ++i) {
         const double* q = Dp + (size_t)i * sh.Npp;
         double sp = 0.0, ps = 0.0;
 #pragma unroll
         for (int j = 0; j <= ORDER; ++j) { const double v = q[(size_t)j * sh.plane]; sp += v; ps += c_gamma[j] * v; }
-        x[i * JP_CHUNK] = sp;
-        b[i * JP_CHUNK] = c * b[i * JP_CHUNK] - ps * inv_alpha;
+        b[i * JP_CHUNK] = sp + (c * b[i * JP_CHUNK] - ps * inv_alpha);      // right-hand side of (I - cJ) S_new = S_pred + c Jp - psi_S
     }
 }
 template <int ORDER>
@@ -488,10 +488,13 @@ __device__ __forceinline__ void sens_update(const SensHist& sh, int Ny, int pc, 
     double* Dp = sh.D + pc;
     for (int i = 0; i < Ny; ++i) {
         double* q = Dp + (size_t)i * sh.Npp;
-        const double ds = x[i * JP_CHUNK];
         double dv[ORDER + 3];
 #pragma unroll
         for (int j = 0; j <= ORDER + 1; ++j) dv[j] = q[(size_t)j * sh.plane];
+        double sp = 0.0;                                                     // the predictor, summed exactly as sens_predict does
+#pragma unroll
+        for (int j = 0; j <= ORDER; ++j) sp += dv[j];
+        const double ds = x[i * JP_CHUNK] - sp;                              // x holds S_new
         dv[ORDER + 2] = ds - dv[ORDER + 1];
         dv[ORDER + 1] = ds;
 #pragma unroll
@@ -508,7 +511,6 @@ __device__ __noinline__ bool sens_step(DomainArgs d, Ws w, SensHist sh, int orde
     jac_warp(d, w, lane);
     const int Ny = w.Ny, LD = w.LD;
     const bool ok = lu_factor_warp<R>(w, c, lane);
-    const double* J = w.J();
     const double* A = w.LU();
     const double* dinv = w.dinv();
     const int* perm = w.perm();
@@ -520,19 +522,14 @@ __device__ __noinline__ bool sens_step(DomainArgs d, Ws w, SensHist sh, int orde
         const int pc = c0 + lane;
         // predictor S_pred = sum_j D_j, psi_S = sum_j gamma_j D_j / alpha;  b = c*Jp - psi_S
         switch (order) {
-        case 1: sens_predict<1>(sh, Ny, pc, c, inv_alpha, b, x); break;
-        case 2: sens_predict<2>(sh, Ny, pc, c, inv_alpha, b, x); break;
-        case 3: sens_predict<3>(sh, Ny, pc, c, inv_alpha, b, x); break;
-        case 4: sens_predict<4>(sh, Ny, pc, c, inv_alpha, b, x); break;
-        default: sens_predict<5>(sh, Ny, pc, c, inv_alpha, b, x); break;
+        case 1: sens_predict<1>(sh, Ny, pc, c, inv_alpha, b); break;
+        case 2: sens_predict<2>(sh, Ny, pc, c, inv_alpha, b); break;
+        case 3: sens_predict<3>(sh, Ny, pc, c, inv_alpha, b); break;
+        case 4: sens_predict<4>(sh, Ny, pc, c, inv_alpha, b); break;
+        default: sens_predict<5>(sh, Ny, pc, c, inv_alpha, b); break;
         }
-        // b += c * J * S_pred
-        for (int i = 0; i < Ny; ++i) {
-            double acc = 0.0;
-            for (int k = 0; k < Ny; ++k) acc += J[i + k * LD] * x[k * JP_CHUNK];
-            b[i * JP_CHUNK] += c * acc;
-        }
-        // x = (I - cJ)^-1 b with the pivoted LU factors: every lane substitutes its own column
+        // x = S_new = (I - cJ)^-1 b with the pivoted LU factors: every lane substitutes its own column.  (Solving for S_new instead of
+        // the correction dS = S_new - S_pred saves the J * S_pred mat-vec: (I - cJ) dS = c (J S_pred + Jp) - psi_S is the same equation.)
         for (int i = 0; i < Ny; ++i) x[i * JP_CHUNK] = b[perm[i] * JP_CHUNK];
         for (int i = 1; i < Ny; ++i) {
             double acc = x[i * JP_CHUNK];
