@@ -418,6 +418,9 @@ __device__ __forceinline__ void stage_small(const DevMech& mp, const SmallTables
 #ifndef RMSB_SMALL_HYST
 #define RMSB_SMALL_HYST 1.2        // step-size increases below this factor (at unchanged order) are not taken: no rescale, no refactorisation
 #endif
+#ifndef RMSB_SMALL_DGMAX
+#define RMSB_SMALL_DGMAX 0.0       // > 0: keep the LU factors while c = h/alpha stays within this fraction of the factorised value (CVODE's
+#endif                             // dgmax = 0.3, corrections scaled by 2/(1 + c/c_lu)); measured, see DESIGN 5.1
 #ifndef RMSB_SMALL_TICKSYNC
 #define RMSB_SMALL_TICKSYNC 0      // 1: the warps of a block start every tick together (experiment: shared instruction fetch)
 #endif
@@ -464,6 +467,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
     int order = 1, n_equal = 0, kiter = 0, isave = 0, status = RMSB_SOLVE_OK;
     int n_rhs = 0, n_jac = 0, n_lu = 0, n_steps = 0, n_nfail = 0, n_efail = 0;
     bool lu_valid = false, current_jac = false, jac_pending = false, jac_from_y = false, lu_ok = true, new_step = true;
+    double c_lu = 0.0, nscale = 1.0;      // RMSB_SMALL_DGMAX: c of the factors in place (0: they do not belong to the Jacobian in place)
     int phase = PH_FETCH;
 #pragma unroll
     for (int j = 0; j < BDF_MAX_ORDER + 3; ++j) D[j] = 0.0;
@@ -505,6 +509,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                         n_rhs = n_jac = n_lu = n_steps = n_nfail = n_efail = 0;
                         crate = 1.0; c_jac = 0.0; idt_best = -INFINITY; idt_time = NAN; pend = 1.0;
                         lu_valid = false; current_jac = false; jac_pending = false; jac_from_y = false; lu_ok = true; new_step = true;
+                        c_lu = 0.0; nscale = 1.0;
                         isave = 0;
                         if (a.nsave > 0) {
                             double* ysave = a.ysave ? a.ysave + (size_t)ir * a.nsave * Ny : nullptr;
@@ -575,7 +580,9 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                             // a Jacobian from a step size 100x away is refreshed before it is factorised again (see bdf_solve_warp)
                             if (c_jac == 0.0) c_jac = c;
                             else if (!current_jac && (c > JAC_REFRESH_RATIO * c_jac || c * JAC_REFRESH_RATIO < c_jac)) jac_pending = true;
+                            if (RMSB_SMALL_DGMAX > 0.0 && !jac_pending && lu_ok && c_lu > 0.0 && fabs(c / c_lu - 1.0) <= RMSB_SMALL_DGMAX) lu_valid = true;
                         }
+                        nscale = (RMSB_SMALL_DGMAX > 0.0 && lu_valid && c_lu > 0.0 && c != c_lu) ? 2.0 / (1.0 + c / c_lu) : 1.0;
                         kiter = 0;
                         phase = PH_NEWTON;
                     }
@@ -592,7 +599,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                 if (jn) {
                     ++n_jac;
                     if (!jac_from_y) { current_jac = true; c_jac = c; }
-                    jac_pending = false; jac_from_y = false; lu_valid = false;
+                    jac_pending = false; jac_from_y = false; lu_valid = false; c_lu = 0.0;
                 }
             }
         }
@@ -605,7 +612,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                     lu_ok = ok != 0;
                     myperm = act ? perm[gl] : gl;
                     dinv = act ? dinvs[gl] : 1.0;
-                    lu_valid = true; ++n_lu; crate = 1.0;
+                    lu_valid = true; ++n_lu; crate = 1.0; c_lu = c; nscale = 1.0;
                 }
             }
         }
@@ -629,7 +636,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
                 const double xk = __shfl_sync(FULL, b, k, G);
                 if (gl < k) b -= *col * xk;
             }
-            dy = unit_row ? dy : b;              // unit rows keep their right-hand side exactly (see bdf_solve_warp)
+            dy = unit_row ? dy : (RMSB_SMALL_DGMAX > 0.0 ? b * nscale : b);      // unit rows keep their right-hand side exactly (see bdf_solve_warp)
         }
         const double qn = act ? dy * iw : 0.0;
         const double dy_norm = sqrt(gsum<G>(FULL, qn * qn) * inv_ny);
@@ -658,7 +665,7 @@ small_solve_kernel(const __grid_constant__ DevMech mp, const __grid_constant__ S
             }
             if (outcome == 2) {
                 if (current_jac) {             // the Jacobian is current: halve the step
-                    ++n_nfail; h_abs *= 0.5; pend = 0.5; n_equal = 0; lu_valid = false; phase = PH_ATTEMPT;
+                    ++n_nfail; h_abs *= 0.5; pend = 0.5; n_equal = 0; lu_valid = false; c_lu = 0.0; phase = PH_ATTEMPT;
                 } else {                        // new Jacobian at the predicted state, same step
                     jac_pending = true; kiter = 0; dvec = 0.0; ynew = ypred; dy_norm_old = -1.0;
                 }
