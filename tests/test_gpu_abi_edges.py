@@ -99,3 +99,44 @@ def test_result_does_not_depend_on_launch_geometry(dom):
             continue
         assert np.array_equal(sol.yend, ref.yend) and np.array_equal(sol.u, ref.u)
         assert np.array_equal(sol.stats["n_steps"], ref.stats["n_steps"]) and np.array_equal(sol.stats["n_rhs"], ref.stats["n_rhs"])
+
+
+def test_round2_entry_points_reject_what_they_cannot_do(dom):
+    """Extended entry points (interfaces / profiles / generated kernels): bad strides, profiles on layouts without one, kernels of a
+    mechanism outside the generated class."""
+    gdom, y0, p = dom
+    lib = L.lib()
+    Ns, Nr = gdom.phase.Ns, gdom.phase.Nr
+    y = np.ascontiguousarray(gdom.y0)
+    Jp = np.empty((1, (Ns + Nr) * gdom.Ny))
+    row = np.zeros(7 + 2 * Ns)
+    assert lib.rmsb_jacp_batch_if(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(row), 5, L.ptr(Jp)) == -1
+    assert b"if_stride" in lib.rmsb_last_error()
+    assert lib.rmsb_jacp_batch_if(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(row), 0, L.ptr(Jp)) == 0
+    plain = np.empty_like(Jp)
+    assert lib.rmsb_jacp_batch(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, L.ptr(plain)) == 0
+    assert np.array_equal(Jp, plain)                                    # an all-zero interface row changes nothing
+    # a time profile on the surface layout is refused by name; a malformed table too
+    x = L.Extras()
+    x.struct_size = C.sizeof(L.Extras)
+    tab = rb.spline_table([0.0, 1.0, 2.0], [1.0, 2.0, 3.0])
+    x.profile, x.profile_stride = tab.ctypes.data, 0
+    out = np.empty_like(y)
+    assert lib.rmsb_dydt_batch_ex(gdom.phase.handle, L.DOMAIN_CONSTANT_TAPHI, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, C.byref(x), L.ptr(out)) != 0
+    bad = tab.copy(); bad[2] = bad[1]                                  # knot times must increase
+    x.profile = bad.ctypes.data
+    assert lib.rmsb_dydt_batch_ex(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, C.byref(x), L.ptr(out)) == -1
+    assert b"knot times" in lib.rmsb_last_error()
+    x.struct_size = 8
+    assert lib.rmsb_dydt_batch_ex(gdom.phase.handle, gdom.kind, 1, L.ptr(y), L.ptr(gdom.cond), None, 0, None, 0, C.byref(x), L.ptr(out)) == -1
+    assert b"rmsb_extras size" in lib.rmsb_last_error()
+    # generated kernels: only ConstantV / ConstantP of an all-Arrhenius gas mechanism; everything else runs on the generic kernels
+    assert lib.rmsb_mech_specialized(gdom.phase.handle, L.DOMAIN_CONSTANT_V) == 1
+    assert lib.rmsb_mech_specialized(gdom.phase.handle, L.DOMAIN_CONSTANT_TP) == 0 and b"generic kernels" in lib.rmsb_last_error()
+    edom, _, _ = cases.product_domain("ethane_V")                      # Troe / PLOG / Chebyshev kinetics
+    assert lib.rmsb_mech_specialized(edom.phase.handle, L.DOMAIN_CONSTANT_V) == 0 and b"does not qualify" in lib.rmsb_last_error()
+    n = 4608
+    ys = np.repeat(edom.y0, n, axis=0)
+    f = rb.Domain(edom.kind, edom.phase, ys, np.repeat(edom.cond, n, axis=0)).dydt(ys)       # large batch: the generic thread-per-reactor kernel
+    f1 = edom.dydt(edom.y0)
+    assert np.allclose(f[0], f1[0], rtol=1e-11, atol=1e-11 * np.abs(f1).max()) and np.array_equal(f[0], f[-1])
