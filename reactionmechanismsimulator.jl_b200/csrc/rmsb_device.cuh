@@ -1525,9 +1525,14 @@ static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int 
             for (int q = G(m.sr_ptr, c); q < G(m.sr_ptr, c + 1); ++q) {
                 const int jr = G(m.sr_rxn, q);
                 const int j = jr & 0x7fffffff;
+                int sl[8];                                   // the reaction's slots, read once for the products and the scatter below
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sl[k] = G(m.rx, k * Nr + j);
                 double pr = 1.0, pp = 1.0;
-                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pr *= cs[sp]; }
-                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; pp *= cs[sp]; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { if (sl[k] < 0) break; pr *= cs[sl[k]]; }
+#pragma unroll
+                for (int k = 4; k < 8; ++k) { if (sl[k] < 0) break; pp *= cs[sl[k]]; }
                 const double net = kfb[j] * pr - krb[j] * pp;
                 raw = (jr < 0) ? raw - net : raw + net;
                 // gderiv = d(reverse flux)/dG = krev*prod(c_products)/RT (the reference reaches it through rderiv*kfs*RTinv in
@@ -1537,8 +1542,10 @@ static __device__ __noinline__ void jacp_warp(DomainArgs d, Ws w, int lane, int 
                 if (constk && eff && d.kind != RMSB_DOMAIN_CONSTANT_TV) gderiv *= kfb[j];
                 gderiv *= aV;
                 const double sg = (jr < 0) ? gderiv : -gderiv;      // reactant slot: reactant rows -= g, product rows += g
-                for (int k = 0; k < 4; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] -= sg; }
-                for (int k = 4; k < 8; ++k) { int sp = G(m.rx, k * Nr + j); if (sp < 0) break; col[sp * JP_CHUNK] += sg; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { if (sl[k] < 0) break; col[sl[k] * JP_CHUNK] -= sg; }
+#pragma unroll
+                for (int k = 4; k < 8; ++k) { if (sl[k] < 0) break; col[sl[k] * JP_CHUNK] += sg; }
             }
         }
         // thermodynamic-variable rows

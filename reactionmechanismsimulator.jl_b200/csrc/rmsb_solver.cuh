@@ -533,12 +533,18 @@ __device__ __noinline__ bool sens_step(DomainArgs d, Ws w, SensHist sh, int orde
         for (int i = 0; i < Ny; ++i) x[i * JP_CHUNK] = b[perm[i] * JP_CHUNK];
         for (int i = 1; i < Ny; ++i) {
             double acc = x[i * JP_CHUNK];
-            for (int k = 0; k < i; ++k) acc -= A[i + k * LD] * x[k * JP_CHUNK];
+            const double* a = A + i;                 // row i of L, column by column (broadcast reads); my column of x
+            const double* xk = x;
+#pragma unroll 4
+            for (int k = 0; k < i; ++k, a += LD, xk += JP_CHUNK) acc -= *a * *xk;
             x[i * JP_CHUNK] = acc;
         }
         for (int i = Ny - 1; i >= 0; --i) {
             double acc = x[i * JP_CHUNK];
-            for (int k = i + 1; k < Ny; ++k) acc -= A[i + k * LD] * x[k * JP_CHUNK];
+            const double* a = A + i + (i + 1) * LD;
+            const double* xk = x + (i + 1) * JP_CHUNK;
+#pragma unroll 4
+            for (int k = i + 1; k < Ny; ++k, a += LD, xk += JP_CHUNK) acc -= *a * *xk;
             x[i * JP_CHUNK] = acc * dinv[i];
         }
         // history update, as for the state: D[o+2] = dS - D[o+1]; D[o+1] = dS; D[j] += D[j+1], j = o..0
