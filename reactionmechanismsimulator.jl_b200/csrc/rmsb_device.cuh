@@ -1274,18 +1274,25 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
     const int Vcol = (d.kind == RMSB_DOMAIN_CONSTANT_P) ? Ns + 1 : Ns;      // column of the volume in y
     // (3) V column of the ns block (src/Reactor.jl:1368-1413) -- lanes over species rows
     if (hasV) {
+        // per-reaction pieces once (one lane per reaction), kept on the derivative-term array, which (1)-(2) are done with and which
+        // holds at least 2 Nr entries (one term per direction and distinct species); the species sums then only gather
+        double* dfv = dterm;
+        double* drv = dterm + Nr;
+        for (int j = lane; j < Nr; j += 32) {
+            int nre = 0, npr = 0;
+            double pf = kfb[j], pr = krb[j];
+            for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; ++nre; }
+            for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; ++npr; }
+            dfv[j] = (nre > 1) ? -(double)(nre - 1) * pf : 0.0;
+            drv[j] = (npr > 1) ? -(double)(npr - 1) * pr : 0.0;
+        }
+        __syncwarp();
         for (int s = lane; s < Ns; s += 32) {
             double acc = 0.0;
             for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
-                int jr = G(m.sr_rxn, k);
-                int j = jr & 0x7fffffff;
-                double df = 0.0, dr = 0.0;
-                int nre = 0, npr = 0;
-                double pf = kfb[j], pr = krb[j];
-                for (int q = 0; q < 4; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pf *= cs[sp]; ++nre; }
-                for (int q = 4; q < 8; ++q) { int sp = G(m.rx, q * Nr + j); if (sp < 0) break; pr *= cs[sp]; ++npr; }
-                if (nre > 1) df = -(double)(nre - 1) * pf;
-                if (npr > 1) dr = -(double)(npr - 1) * pr;
+                const int jr = G(m.sr_rxn, k);
+                const int j = jr & 0x7fffffff;
+                const double df = dfv[j], dr = drv[j];
                 if (jr < 0) { acc -= df; acc += dr; } else { acc += df; acc -= dr; }
             }
             J[s + Vcol * LD] = acc;
