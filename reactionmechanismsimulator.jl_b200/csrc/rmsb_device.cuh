@@ -889,17 +889,37 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     }
     for (int j = lane; j < Nr; j += 32) qb[j] = net_rate<double>(j, kfb[j], krb[j], cs);
     __syncwarp();
+    // dn_s/dt = V * sum over the species' reaction slots of +-q_j.  A species that takes part in most reactions (O2, ROO. in the
+    // liquid oxidation mechanisms: hundreds of slots against an average of 40) would serialise the warp behind its lane: rows longer
+    // than COOP_ROW are summed by the whole warp (tree order; the short rows keep the reference's sequential order) -- ncu on C3_35:
+    // this gather was 35 % of the kernel's instructions
     double nsum = 0.0;
-    for (int s = lane; s < Ns; s += 32) {
-        double acc = 0.0;
-        for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
-            int jr = G(m.sr_rxn, k);
-            double qv = qb[jr & 0x7fffffff];
-            acc = (jr < 0) ? acc - qv : acc + qv;
+    for (int s0 = 0; s0 < Ns; s0 += 32) {
+        const int s = s0 + lane;
+        int k0 = 0, k2 = 0;
+        if (s < Ns) { k0 = G(m.sr_ptr, s); k2 = G(m.sr_ptr, s + 1); }
+        const bool heavy = (k2 - k0) > COOP_ROW;
+        if (s < Ns && !heavy) {
+            double acc = 0.0;
+            for (int k = k0; k < k2; ++k) {
+                int jr = G(m.sr_rxn, k);
+                double qv = qb[jr & 0x7fffffff];
+                acc = (jr < 0) ? acc - qv : acc + qv;
+            }
+            double dn = acc * V;
+            fb[s] = dn;
+            nsum += dn;
         }
-        double dn = acc * V;
-        fb[s] = dn;
-        nsum += dn;
+        unsigned hv = __ballot_sync(FULL, heavy);
+        while (hv) {
+            const int src = __ffs(hv) - 1;
+            hv &= hv - 1;
+            const int h0 = __shfl_sync(FULL, k0, src), h2 = __shfl_sync(FULL, k2, src);
+            double a = 0.0;
+            for (int k = h0 + lane; k < h2; k += 32) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; a = (jr < 0) ? a - qv : a + qv; }
+            const double dn = warp_sum(a) * V;
+            if (lane == 0) { fb[s0 + src] = dn; nsum += dn; }
+        }
     }
     if (d.kind == RMSB_DOMAIN_CONSTANT_TP) {
         double dV = warp_sum(nsum) * RMSB_R * T / P;     // Domain.jl:1864
