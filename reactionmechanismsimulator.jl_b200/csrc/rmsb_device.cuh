@@ -891,7 +891,7 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     __syncwarp();
     // dn_s/dt = V * sum over the species' reaction slots of +-q_j.  A species that takes part in most reactions (O2, ROO. in the
     // liquid oxidation mechanisms: hundreds of slots against an average of 40) would serialise the warp behind its lane: rows longer
-    // than COOP_ROW are summed by the whole warp (tree order; the short rows keep the reference's sequential order) -- ncu on C3_35:
+    // than COOP_ROW are summed by the whole warp (32 contiguous pieces, then a tree; the short rows keep the reference's sequential order) -- ncu on C3_35:
     // this gather was 35 % of the kernel's instructions
     double nsum = 0.0;
     for (int s0 = 0; s0 < Ns; s0 += 32) {
@@ -915,8 +915,10 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
             const int src = __ffs(hv) - 1;
             hv &= hv - 1;
             const int h0 = __shfl_sync(FULL, k0, src), h2 = __shfl_sync(FULL, k2, src);
+            const int chunk = (h2 - h0 + 31) >> 5;                  // contiguous pieces of the list, each in the reference's order
+            const int kb = h0 + lane * chunk, ke = min(h2, kb + chunk);
             double a = 0.0;
-            for (int k = h0 + lane; k < h2; k += 32) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; a = (jr < 0) ? a - qv : a + qv; }
+            for (int k = kb; k < ke; ++k) { int jr = G(m.sr_rxn, k); double qv = qb[jr & 0x7fffffff]; a = (jr < 0) ? a - qv : a + qv; }
             const double dn = warp_sum(a) * V;
             if (lane == 0) { fb[s0 + src] = dn; nsum += dn; }
         }
@@ -1279,10 +1281,31 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
         dterm[t] = v;
     }
     __syncwarp();
-    // (2) gather into entries, in the reference's accumulation order
-    for (int e = lane; e < m.n_je; e += 32) {
+    // (2) gather into entries, in the reference's accumulation order; entries with more than COOP_ROW terms (the diagonal and the
+    //     O2 / ROO. rows and columns of the oxidation mechanisms) are summed by the whole warp, as the long species rows of rhs_ck are
+    for (int e0 = 0; e0 < m.n_je; e0 += 32) {
+        const int e = e0 + lane;
+        int k0 = 0, k2 = 0;
+        if (e < m.n_je) { k0 = G(m.je_ptr, e); k2 = G(m.je_ptr, e + 1); }
+        const bool heavy = (k2 - k0) > COOP_ROW;
+        unsigned hv = __ballot_sync(FULL, heavy);
+        while (hv) {
+            const int src = __ffs(hv) - 1;
+            hv &= hv - 1;
+            const int h0 = __shfl_sync(FULL, k0, src), h2 = __shfl_sync(FULL, k2, src);
+            // every lane sums a CONTIGUOUS piece of the list in the reference's order: the +d / -d pairs a species on both sides of a
+            // reaction contributes sit next to each other and must cancel inside one partial sum (dealt round-robin they left
+            // O(d) partial sums whose rounding cost the propane case 38 % more steps after ignition)
+            const int chunk = (h2 - h0 + 31) >> 5;
+            const int kb = h0 + lane * chunk, ke = min(h2, kb + chunk);
+            double a = 0.0;
+            for (int k = kb; k < ke; ++k) { int ti = G(m.jt_idx, k); double v = dterm[ti & 0x7fffffff]; a = (ti < 0) ? a - v : a + v; }
+            a = warp_sum(a);
+            if (lane == 0) J[G(m.je_row, e0 + src) + G(m.je_col, e0 + src) * LD] = a;
+        }
+        if (e >= m.n_je || heavy) continue;
         double acc = 0.0;
-        for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
+        for (int k = k0; k < k2; ++k) {
             int ti = G(m.jt_idx, k);
             double v = dterm[ti & 0x7fffffff];
             acc = (ti < 0) ? acc - v : acc + v;
