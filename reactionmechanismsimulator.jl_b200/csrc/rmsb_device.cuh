@@ -1111,8 +1111,10 @@ static __device__ __noinline__ void jac_coupled(DomainArgs d, Ws w, int lane) {
             const int src = __ffs(hv) - 1;
             hv &= hv - 1;
             const int h0 = __shfl_sync(FULL, k0, src), h1 = __shfl_sync(FULL, k1, src), hp = __shfl_sync(FULL, pos, src);
+            const int chunk = (h1 - h0 + 31) >> 5;                  // contiguous pieces in the reference's order (see jac_warp)
+            const int kb = h0 + lane * chunk, ke = min(h1, kb + chunk);
             double acc = 0.0;
-            for (int k = h0 + lane; k < h1; k += 32) { int ti = G(m.jt_idx, k); double v = dterm[ti & 0x7fffffff]; acc = (ti < 0) ? acc - v : acc + v; }
+            for (int k = kb; k < ke; ++k) { int ti = G(m.jt_idx, k); double v = dterm[ti & 0x7fffffff]; acc = (ti < 0) ? acc - v : acc + v; }
             acc = warp_sum(acc);
             if (lane == 0) J[hp] = acc;
         }
