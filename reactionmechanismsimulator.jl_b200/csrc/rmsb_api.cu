@@ -222,6 +222,9 @@ static int build_mech(const rmsb_mech_desc* d, rmsb_mech* h, bool host_only = fa
         for (int v : kv.second) jtidx.push_back(v);
         jeptr.push_back((int)jtidx.size());
     }
+    dm.heavy_sr = 0; dm.heavy_je = 0;
+    for (int s2 = 0; s2 < Ns; ++s2) if (srptr[s2 + 1] - srptr[s2] > COOP_ROW) dm.heavy_sr = 1;
+    for (size_t e = 0; e + 1 < jeptr.size(); ++e) if (jeptr[e + 1] - jeptr[e] > COOP_ROW) dm.heavy_je = 1;
     dm.n_dt = h->n_dt = (int)dtrxn.size();
     dm.n_je = h->n_je = (int)jerow.size();
     dm.n_effrxn = (int)effrxn.size();

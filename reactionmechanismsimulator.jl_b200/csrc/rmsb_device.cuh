@@ -88,6 +88,8 @@ struct DevMech {
     const double* nrp2;      // [Nr] surface-phase exponent of C0 in Kc (nrp is the bulk-phase exponent)
     const int* sr_mid;       // [Ns] first interface entry of the species' slot list
     const int* inert;        // [Ns] 1 = no reaction changes the species (absent, or written on both sides everywhere): dn/dt == 0 exactly
+    int heavy_sr, heavy_je;  // 1 = some species row / Jacobian entry list is longer than COOP_ROW: the warp-cooperative sums are compiled in
+                             // for those mechanisms only (their ballots cost the 12-species mechanisms 10 %)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -894,6 +896,19 @@ static __device__ __noinline__ void rhs_ck(DomainArgs d, Ws w, int lane) {
     // than COOP_ROW are summed by the whole warp (32 contiguous pieces, then a tree; the short rows keep the reference's sequential order) -- ncu on C3_35:
     // this gather was 35 % of the kernel's instructions
     double nsum = 0.0;
+    if (!m.heavy_sr) {
+        for (int s = lane; s < Ns; s += 32) {
+            double acc = 0.0;
+            for (int k = G(m.sr_ptr, s); k < G(m.sr_ptr, s + 1); ++k) {
+                int jr = G(m.sr_rxn, k);
+                double qv = qb[jr & 0x7fffffff];
+                acc = (jr < 0) ? acc - qv : acc + qv;
+            }
+            double dn = acc * V;
+            fb[s] = dn;
+            nsum += dn;
+        }
+    } else
     for (int s0 = 0; s0 < Ns; s0 += 32) {
         const int s = s0 + lane;
         int k0 = 0, k2 = 0;
@@ -1285,6 +1300,17 @@ static __device__ __noinline__ void jac_warp(DomainArgs d, Ws w, int lane) {
     __syncwarp();
     // (2) gather into entries, in the reference's accumulation order; entries with more than COOP_ROW terms (the diagonal and the
     //     O2 / ROO. rows and columns of the oxidation mechanisms) are summed by the whole warp, as the long species rows of rhs_ck are
+    if (!m.heavy_je) {
+        for (int e = lane; e < m.n_je; e += 32) {
+            double acc = 0.0;
+            for (int k = G(m.je_ptr, e); k < G(m.je_ptr, e + 1); ++k) {
+                int ti = G(m.jt_idx, k);
+                double v = dterm[ti & 0x7fffffff];
+                acc = (ti < 0) ? acc - v : acc + v;
+            }
+            J[G(m.je_row, e) + G(m.je_col, e) * LD] = acc;
+        }
+    } else
     for (int e0 = 0; e0 < m.n_je; e0 += 32) {
         const int e = e0 + lane;
         int k0 = 0, k2 = 0;
