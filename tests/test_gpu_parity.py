@@ -154,6 +154,31 @@ def test_ensemble_vs_cpu_oracle_idt():
     assert np.max(np.abs(sol.yend - ref["yend"])[big] / np.abs(ref["yend"])[big]) < 1e-6
 
 
+def test_c2_subsample_vs_scipy():
+    """The same 64 conditions against SciPy BDF over the NumPy oracle (tests/golden/make_c2_scipy_subsample.py, rtol 1e-10 /
+    atol 1e-20): an integrator and a right-hand side that share nothing with the CUDA path or the C++ port.  Ignition delay within
+    0.1 % (north_star), final state within 1e-6 on every significant species; and at the throughput tolerances the delay still
+    within 0.1 %."""
+    gold = np.load(cases.ROOT / "tests" / "golden" / "c2_scipy_subsample.npz")
+    gdom, _, _ = cases.product_domain("superminimal_V")
+    ig = gdom.phase
+    T0, P0, ns = sweep(ig, 64)
+    ens = rb.ConstantVEnsemble(ig, T0, P0, ns)
+    np.testing.assert_allclose(ens.y0, gold["y0"], rtol=1e-13)
+    np.testing.assert_allclose(ens.cond, gold["cond"].reshape(ens.cond.shape), rtol=1e-13)
+    sol = rb.solve(rb.Reactor(ens, None, (0.0, 0.1)), abstol=1e-20, reltol=1e-10)
+    assert np.all(sol.status == 0)
+    yr = gold["yend"]
+    ign = (yr[:, ig.Ns] - ens.y0[:, ig.Ns]) > 400.0
+    assert ign.sum() > 10
+    np.testing.assert_allclose(sol.idt[ign], gold["idt"][ign], rtol=1e-3)
+    scale = np.max(np.abs(yr[:, :ig.Ns]), axis=1, keepdims=True)
+    big = np.abs(yr) > 1e-9 * scale
+    assert np.max(np.abs(sol.yend - yr)[big] / np.abs(yr)[big]) < 1e-6
+    loose = rb.solve(rb.Reactor(ens, None, (0.0, 0.1)), abstol=1e-16, reltol=1e-6)
+    np.testing.assert_allclose(loose.idt[ign], gold["idt"][ign], rtol=1e-3)
+
+
 def test_ensemble_loose_tolerance_vs_tight_cpu_oracle():
     """2 000 conditions at the THROUGHPUT tolerances (rtol 1e-6, atol 1e-16) against the C++ CPU oracle at rtol 1e-10:
     ignition delay within 0.1 % (north_star), final temperature within 1e-4."""
