@@ -96,12 +96,15 @@ def test_forward_sensitivities_vs_oracle(case, tend):
     yq, Sq = G[f"{case}/yq"], G[f"{case}/Sq"]
     big = np.abs(yq) > 1e-10 * np.max(np.abs(yq), axis=1, keepdims=True)
     assert np.max(np.abs(sol.u[0] - yq)[big] / np.abs(yq)[big]) < 1e-5
+    # C5 against its golden (SciPy, rtol 1e-9): 1.2e-5 / 9.8e-7 / 1.9e-7 / 4.5e-8 / 7.9e-9 of the column scale at rtol 1e-6 ... 1e-10
+    # (scripts/gpu_sens_convergence.py); the ConstantV golden is itself an rtol 1e-8 run through the induction period
+    tol = 1e-6 if case == "superminimal_TP" else 1e-4
     for k in range(len(tq)):
-        assert sens_err(sol.sens[0, k], Sq[k]) < 1e-4, (k, sens_err(sol.sens[0, k], Sq[k]))
+        assert sens_err(sol.sens[0, k], Sq[k]) < tol, (k, sens_err(sol.sens[0, k], Sq[k]))
     x, dp = sol.extract_local_sensitivities(float(tq[-1]))
     assert np.allclose(np.array(dp), sol.sens[0, -1])
     xe, dpe = sol.extract_local_sensitivities()
-    assert sens_err(np.array(dpe), Sq[-1]) < 1e-4
+    assert sens_err(np.array(dpe), Sq[-1]) < tol
     # the state computed alongside the sensitivities is the plain solve's state
     plain = rb.solve(rb.Reactor(gdom, y0, (0.0, tend), p=p).ode, abstol=1e-20, reltol=1e-8, saveat=tq)
     assert np.max(np.abs(plain.u[0] - sol.u[0])[big] / np.abs(yq)[big]) < 1e-5
